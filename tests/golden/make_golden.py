@@ -1,0 +1,235 @@
+"""Generate the golden vectors in tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+
+Everything written here is produced by executing reference code (FrameProcessor,
+PenaltyCalculator, ProtrusionDetector, the vendored ultralytics ops.py) or by reading reference
+data files (the 13 `*_grids.npy` inputs and the `*_processed.png` known-answer renders) - the
+oracle in oracle/ is NOT used, so the vectors pin the oracle as well as the CUDA path.
+
+Files:
+  fixtures.npz      13 reference occupancy fixtures (utilities/generate_testing_grids/examples)
+                    + reference penalties / peaks for them + per-cell LUT colour index read from
+                    the 5 live `*_processed.png` renders.
+  polygons.npz      seeded random polygons through reference FrameProcessor._extract_grid_information
+                    -> _calculate_penalties -> ProtrusionDetector (list rows, attrs, flags, penalties, peaks).
+  mask_assembly.npz seeded synthetic head outputs through the vendored ops.process_mask
+                    (cropped logits + packed binary masks).
+  frames.npz        seeded synthetic frames through the whole reference chain
+                    process_mask -> masks2segments -> scale_coords -> FrameProcessor -> penalties -> peaks.
+"""
+from __future__ import annotations
+
+import inspect
+import os
+import sys
+import textwrap
+
+import cv2
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import polygen  # noqa: E402
+import refharness  # noqa: E402
+from vision_assist_b200 import synth  # noqa: E402
+
+RMAX, CMAX, PMAX = 80, 100, 48
+LUT_KEYS = [1.0, 0.9166, 0.8333, 0.75, 0.6666, 0.5833, 0.5, 0.4166, 0.3333, 0.1666, 0.0833, 0.0]
+
+
+def ref_state_arrays(fp, ref, H, W):
+    """Dump a reference FrameProcessor's grid state (+penalties, peaks) into fixed-size arrays."""
+    R = len(fp.grids)
+    C = len(fp.grids[0]) if R else 0
+    assert R <= RMAX and C <= CMAX
+    rows_y = np.full(RMAX, -1, np.int32)
+    rows_attr = np.full(RMAX, -1, np.int32)
+    occ = np.zeros((RMAX, CMAX), np.uint8)
+    pen = np.full((RMAX, CMAX), np.nan)
+    peaks = np.full((PMAX, 2), -1, np.int32)
+    x0 = fp.grids[0][0].coords.x if R else 0
+    npk = 0
+    if R:
+        fp._calculate_penalties()
+        for r, row in enumerate(fp.grids):
+            rows_y[r] = row[0].coords.y
+            rows_attr[r] = row[0].row
+            for c, g in enumerate(row):
+                occ[r, c] = (0 if g.empty else 1) | (2 if g.artificial else 0)
+                if not g.empty:
+                    pen[r, c] = float(g.penalty)
+        pk = fp.protrusion_detector(fp.frame, fp.grids, fp.grid_lookup)
+        npk = len(pk)
+        for k, p in enumerate(pk):
+            peaks[k] = (p.x, p.y)
+    return dict(R=R, C=C, x0=x0, rows_y=rows_y, rows_attr=rows_attr, occ=occ, pen=pen, peaks=peaks, npk=npk)
+
+
+def gen_fixtures(ref):
+    exdir = os.path.join(refharness.REFERENCE_ROOT, "utilities/generate_testing_grids/examples")
+    names = sorted(f[:-len("_grids.npy")] for f in os.listdir(exdir) if f.endswith("_grids.npy"))
+    live_png = ["insane_case2", "obstacle_on_path", "outrageous_case", "right_turn_on_path", "right_turn"]
+    # the fixture loader, executed from the reference source with the reference's own models
+    src_path = os.path.join(refharness.REFERENCE_ROOT, "utilities/generate_testing_grids/run_on_main.py")
+    src = open(src_path).read()
+    start = src.index("def convert_npy_to_grid_info")
+    end = src.index("class SingleSavedFrameFrameProcessor")
+    ns = {"np": np, "Coordinate": ref.models.Coordinate, "Grid": ref.models.Grid, "print": lambda *a, **k: None}
+    exec(compile(src[start:end], src_path, "exec"), ns)
+    convert = ns["convert_npy_to_grid_info"]
+    out = {"names": np.array(names), "live_png": np.array(live_png)}
+    for nm in names:
+        path = os.path.join(exdir, nm + "_grids.npy")
+        g = np.load(path)
+        out[f"{nm}/grid"] = g.astype(np.uint8)
+        fp = refharness.new_frame_processor(ref)
+        H, W = g.shape[0] * 20, g.shape[1] * 20
+        fp.frame = np.zeros((H, W, 3), np.uint8)
+        fp.grids, fp.grid_lookup = convert(path)
+        # run_on_main never sets np_grids -> pure traversal (use_easy=False in the oracle)
+        a = ref_state_arrays(fp, ref, H, W)
+        out[f"{nm}/pen_traversal"] = a["pen"][:a["R"], :a["C"]]
+        out[f"{nm}/occ"] = a["occ"][:a["R"], :a["C"]]
+        out[f"{nm}/rows_y"] = a["rows_y"][:a["R"]]
+        out[f"{nm}/rows_attr"] = a["rows_attr"][:a["R"]]
+        out[f"{nm}/peaks"] = a["peaks"][:a["npk"]]
+        # also with easy segments (what FrameProcessor.__call__ would do with np_grids set)
+        fp2 = refharness.new_frame_processor(ref)
+        fp2.frame = fp.frame
+        fp2.grids, fp2.grid_lookup = convert(path)
+        fp2.np_grids = np.array([[0 if q.empty else 1 for q in row] for row in fp2.grids], dtype=np.uint8)
+        a2 = ref_state_arrays(fp2, ref, H, W)
+        out[f"{nm}/pen_easy"] = a2["pen"][:a2["R"], :a2["C"]]
+        if nm in live_png:
+            img = cv2.imread(os.path.join(exdir, "outputs", nm + "_processed.png"))
+            assert img is not None and img.shape[:2] == (H, W), (nm, None if img is None else img.shape)
+            lut = ref.config.penalty_colour_gradient
+            keys = list(lut.keys())
+            assert [round(k, 4) for k in keys] == LUT_KEYS
+            col = np.full(g.shape, -1, np.int8)
+            for r in range(a["R"]):
+                for c in range(a["C"]):
+                    if a["occ"][r, c] & 1:
+                        y, x = a["rows_y"][r] + 10, a["x0"] + c * 20 + 10
+                        bgr = tuple(int(v) for v in img[y, x])
+                        hits = [i for i, k in enumerate(keys) if lut[k] == bgr]
+                        assert len(hits) == 1, (nm, r, c, bgr)
+                        col[r, c] = hits[0]
+            out[f"{nm}/png_colour_idx"] = col
+    np.savez_compressed(os.path.join(HERE, "fixtures.npz"), **out)
+    print("fixtures.npz:", len(names), "fixtures,", len(live_png), "live PNG answers")
+
+
+def gen_polygons(ref, n_cases=172):
+    rng = np.random.default_rng(20261018)
+    cfgs = [(640, 640, 20)] * 110 + [(720, 1280, 20)] * 20 + [(640, 640, 16)] * 10 + \
+           [(640, 640, 32)] * 10 + [(384, 640, 8)] * 10 + [(650, 650, 20)] * 12
+    out = {}
+    keep = dict(H=[], W=[], gs=[], err=[], R=[], C=[], x0=[], npk=[])
+    arrs = dict(rows_y=[], rows_attr=[], occ=[], pen=[], peaks=[])
+    polys_all, poly_off = [], [0]
+    case_poly = []
+    for H, W, gs in cfgs[:n_cases]:
+        for modname in ("FrameProcessor", "PenaltyCalculator", "ProtrusionDetector", "models"):
+            setattr(getattr(ref, modname), "grid_size", gs)        # config.grid_size is imported by value
+        k = int(rng.integers(1, 4))
+        polys = [polygen.random_polygon(rng, H, W) for _ in range(k)]
+        fp = refharness.new_frame_processor(ref)
+        fp.frame = np.zeros((H, W, 3), np.uint8)
+        err = 0
+        try:
+            fp._extract_grid_information([refharness.FakeResult(polys)])
+            a = ref_state_arrays(fp, ref, H, W)
+        except IndexError as e:
+            err = 1 if "out of bounds" in str(e) else 2
+            fp.grids = []
+            a = ref_state_arrays(fp, ref, H, W)
+        case_poly.append(k)
+        for p in polys:
+            polys_all.append(p)
+            poly_off.append(poly_off[-1] + len(p))
+        for key, v in dict(H=H, W=W, gs=gs, err=err, R=a["R"], C=a["C"], x0=a["x0"], npk=a["npk"]).items():
+            keep[key].append(v)
+        for key in arrs:
+            arrs[key].append(a[key if key != "pen" else "pen"])
+    for modname in ("FrameProcessor", "PenaltyCalculator", "ProtrusionDetector", "models"):
+        setattr(getattr(ref, modname), "grid_size", 20)
+    out.update({k: np.array(v, np.int32) for k, v in keep.items()})
+    out.update({k: np.stack(v) for k, v in arrs.items()})
+    out["poly_pts"] = np.concatenate(polys_all).astype(np.float32)
+    out["poly_off"] = np.array(poly_off, np.int64)
+    out["case_npoly"] = np.array(case_poly, np.int32)
+    np.savez_compressed(os.path.join(HERE, "polygons.npz"), **out)
+    print("polygons.npz:", len(keep["H"]), "cases; errors:", int((out["err"] > 0).sum()),
+          "empty:", int((out["R"] == 0).sum()))
+
+
+MASK_CASES = [  # (frame_idx, n, H, W, mh, mw, family)
+    (0, 4, 160, 160, 40, 40, "sidewalk"),
+    (1, 3, 160, 160, 40, 40, "noise"),
+    (2, 2, 640, 640, 160, 160, "sidewalk"),
+    (3, 2, 640, 640, 160, 160, "noise"),
+    (4, 3, 270, 480, 40, 40, "noise"),          # anisotropic non-integer scale (6.75 x 12)
+    (5, 2, 384, 640, 96, 160, "sidewalk"),
+]
+
+
+def gen_mask_assembly(ref):
+    out = {"cases": np.array([c[:6] for c in MASK_CASES], np.int32),
+           "families": np.array([c[6] for c in MASK_CASES])}
+    for i, (f, n, H, W, mh, mw, fam) in enumerate(MASK_CASES):
+        p, c, b = synth.make_frame(f, n, H, W, mh, mw, 32, fam)
+        m = ref.ops.process_mask(p, c, b, (H, W), upsample=True)
+        lo = ref.ops.process_mask(p, c, b, (H, W), upsample=False)          # sign of cropped logits
+        cl = ref.ops.crop_mask((c @ p.view(32, -1)).view(-1, mh, mw),
+                               b * torch.tensor([mw / W, mh / H, mw / W, mh / H]))
+        out[f"{i}/masks_packed"] = np.packbits(m.numpy().astype(np.uint8), axis=-1)
+        out[f"{i}/cropped_logits"] = cl.numpy()
+        out[f"{i}/lowres_packed"] = np.packbits(lo.numpy().astype(np.uint8), axis=-1)
+    np.savez_compressed(os.path.join(HERE, "mask_assembly.npz"), **out)
+    print("mask_assembly.npz:", len(MASK_CASES), "cases")
+
+
+FRAME_CASES = [(640, 640, 160, 160, 8, 20, "sidewalk", 100, 24),
+               (640, 640, 160, 160, 3, 20, "noise", 200, 6),
+               (1080, 1920, 160, 160, 4, 20, "sidewalk", 300, 2)]
+
+
+def gen_frames(ref):
+    out = {"cases": np.array([c[:6] + c[7:] for c in FRAME_CASES], np.int32),
+           "families": np.array([c[6] for c in FRAME_CASES])}
+    for ci, (H, W, mh, mw, n, gs, fam, first, count) in enumerate(FRAME_CASES):
+        acc = dict(R=[], C=[], x0=[], npk=[], rows_y=[], rows_attr=[], occ=[], pen=[], peaks=[], areas=[])
+        for f in range(first, first + count):
+            p, c, b = synth.make_frame(f, n, H, W, mh, mw, 32, fam)
+            masks = ref.ops.process_mask(p, c, b, (H, W), upsample=True)
+            segs = ref.ops.masks2segments(masks)
+            xy = [ref.ops.scale_coords((H, W), s, (H, W), normalize=False) for s in segs]
+            fp = refharness.new_frame_processor(ref)
+            fp.frame = np.zeros((H, W, 3), np.uint8)
+            fp._extract_grid_information([refharness.FakeResult(xy)])
+            a = ref_state_arrays(fp, ref, H, W)
+            for k in ("R", "C", "x0", "npk", "rows_y", "rows_attr", "occ", "pen", "peaks"):
+                acc[k].append(a[k])
+            acc["areas"].append(masks.reshape(n, -1).sum(1).numpy().astype(np.int64))
+        for k, v in acc.items():
+            out[f"{ci}/{k}"] = np.array(v) if np.ndim(v[0]) == 0 else np.stack(v)
+    np.savez_compressed(os.path.join(HERE, "frames.npz"), **out)
+    print("frames.npz:", sum(c[-1] for c in FRAME_CASES), "frames")
+
+
+if __name__ == "__main__":
+    ref = refharness.load()
+    torch.set_num_threads(1)
+    gen_fixtures(ref)
+    gen_polygons(ref)
+    gen_mask_assembly(ref)
+    gen_frames(ref)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -1,0 +1,102 @@
+"""CPU, build container only: the oracle against the UNMODIFIED reference imported from
+/root/reference (skipped on the GPU box, where only the golden vectors travel)."""
+import numpy as np
+import pytest
+import torch
+
+import polygen
+import refharness
+from oracle import grid as og
+from oracle import mask_assembly as oma
+from oracle import penalty as open_
+from oracle import pipeline as opl
+from oracle import protrusion as oprot
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refharness.load()
+
+
+def _set_gs(ref, gs):
+    for m in ("FrameProcessor", "PenaltyCalculator", "ProtrusionDetector", "models"):
+        setattr(getattr(ref, m), "grid_size", gs)
+
+
+@pytest.mark.parametrize("H,W,gs,n", [(640, 640, 20, 220), (720, 1280, 20, 40), (640, 640, 8, 12),
+                                      (650, 650, 20, 30), (1080, 1920, 20, 6)])
+def test_grid_penalty_peaks_match_reference(ref, H, W, gs, n):
+    rng = np.random.default_rng(H * 7 + gs)
+    _set_gs(ref, gs)
+    try:
+        for it in range(n):
+            polys = [polygen.random_polygon(rng, H, W) for _ in range(int(rng.integers(1, 4)))]
+            fp = refharness.new_frame_processor(ref)
+            fp.frame = np.zeros((H, W, 3), np.uint8)
+            rerr = oerr = None
+            try:
+                fp._extract_grid_information([refharness.FakeResult(polys)])
+            except IndexError as e:
+                rerr = "centre" if "out of bounds" in str(e) else "list"
+            try:
+                st = og.extract_grid_from_polygons(polys, H, W, gs)
+            except IndexError as e:
+                oerr = "centre" if "centre" in str(e) else "list"
+            assert rerr == oerr
+            if rerr:
+                continue
+            assert len(fp.grids) == len(st.grids)
+            if not fp.grids:
+                continue
+            for rr, ro in zip(fp.grids, st.grids):
+                for gr, go in zip(rr, ro):
+                    assert (gr.coords.x, gr.coords.y, gr.centre.x, gr.centre.y, gr.row, gr.col, gr.empty,
+                            gr.artificial) == (go.x, go.y, go.x + gs // 2, go.y + gs // 2, go.row, go.col,
+                                               go.empty, go.artificial)
+            assert set(fp.grid_lookup) == set(st.lookup)
+            for key, g in fp.grid_lookup.items():
+                o = st.lookup[key]
+                assert (g.empty, g.artificial, g.row) == (o.empty, o.artificial, o.row)
+            assert np.array_equal(fp.np_grids, st.np_grids)
+            fp._calculate_penalties()
+            pen = open_.calculate_penalties(st)
+            for r, rr in enumerate(fp.grids):
+                for c, g in enumerate(rr):
+                    if g.empty:
+                        assert g.penalty is None and np.isnan(pen[r, c])
+                    else:
+                        assert float(g.penalty) == pen[r, c]
+            want = [(p.x, p.y) for p in fp.protrusion_detector(fp.frame, fp.grids, fp.grid_lookup)]
+            res = opl.state_to_result(st)
+            assert want == oprot.peaks_raster(st.grids, H, W, gs) == [tuple(p) for p in res["peaks"].tolist()]
+    finally:
+        _set_gs(ref, 20)
+
+
+def test_penalty_colour_lut(ref):
+    pc = ref.PenaltyCalculator.penalty_calculator
+    for p in np.linspace(0, 1.2, 241):
+        assert pc.get_penalty_colour(float(p)) == open_.get_penalty_colour(float(p))
+
+
+def test_process_mask_matches_vendored_ops(ref):
+    torch.manual_seed(3)
+    for (mh, mw, ih, iw, n) in [(160, 160, 640, 640, 5), (40, 40, 270, 480, 3), (96, 160, 384, 640, 2)]:
+        protos = torch.randn(32, mh, mw)
+        coefs = torch.randn(n, 32)
+        x1 = torch.rand(n) * iw * 0.5
+        y1 = torch.rand(n) * ih * 0.5
+        boxes = torch.stack([x1, y1, x1 + torch.rand(n) * iw * 0.5, y1 + torch.rand(n) * ih * 0.5], 1)
+        want = ref.ops.process_mask(protos, coefs, boxes, (ih, iw), upsample=True)
+        assert torch.equal(want, oma.process_mask(protos, coefs, boxes, (ih, iw)))
+        got_np = oma.process_mask_np(protos.numpy(), coefs.numpy(), boxes.numpy(), (ih, iw))
+        # numpy matmul may sum in a different order than torch: allow flips only at |logit| ~ 0
+        assert (got_np != want.numpy().astype(np.uint8)).mean() < 1e-5
+        segs_ref = ref.ops.masks2segments(want)
+        segs = oma.masks2segments(want.numpy())
+        assert all(np.array_equal(a, b) for a, b in zip(segs_ref, segs))
+        for s in segs:
+            a = ref.ops.scale_coords((ih, iw), s.copy(), (720, 1280))
+            assert np.array_equal(a, oma.scale_coords((ih, iw), s, (720, 1280)))

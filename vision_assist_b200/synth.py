@@ -1,0 +1,111 @@
+"""Deterministic synthetic inputs for the mask -> grid -> penalty -> protrusion path.
+
+There are no weights in the reference repository (`model/.MISSING_LARGE_BLOBS`) and no network,
+so every test / bench frame is synthesised: YOLOv8-seg head outputs (prototype maps, per-instance
+mask coefficients, xyxy boxes) whose assembled masks look like sidewalk segmentations.
+
+Per frame the seed is 0xB2000000 + frame_idx, generated with a CPU torch.Generator so
+the build container, the GPU box and the committed golden vectors all see identical tensors.
+
+  family "sidewalk" : instance 0 is a sheared trapezoid that widens towards the bottom of the frame
+                      (channel 0 is its signed-distance-like field), instances 1.. are small discs
+                      (channels 1..3), channels 4..K-1 are smooth noise that roughens the outlines.
+                      Masks are (almost always) single hole-free blobs, instance 0 has the largest area.
+  family "noise"    : every channel is smooth noise, coefficients N(0,1): masks with many components
+                      and holes - used for logit / binary-mask parity and the non-simple-mask flag.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+SEED_BASE = 0xB2000000
+N_DISC_CH = 3
+
+
+def _smooth_noise(g: torch.Generator, ch: int, mh: int, mw: int) -> torch.Tensor:
+    z = torch.randn(1, ch, 6, 6, generator=g)
+    return F.interpolate(z, (mh, mw), mode="bicubic", align_corners=False)[0]
+
+
+def make_frame(frame_idx: int, n: int, H: int, W: int, mh: int, mw: int, K: int = 32,
+               family: str = "sidewalk"):
+    """-> protos [K,mh,mw] f32, coefs [n,K] f32, boxes [n,4] f32 (xyxy, frame pixels)."""
+    g = torch.Generator().manual_seed(SEED_BASE + int(frame_idx))
+    sx, sy = W / mw, H / mh
+    if family == "noise":
+        protos = _smooth_noise(g, K, mh, mw)
+        coefs = torch.randn(n, K, generator=g)
+        c = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.6, H * 0.6])
+        wh = (0.2 + 0.6 * torch.rand(n, 2, generator=g)) * torch.tensor([float(W), float(H)])
+        boxes = torch.cat([c, torch.minimum(c + wh, torch.tensor([W - 1.0, H - 1.0]))], 1)
+        return protos.contiguous(), coefs.contiguous(), boxes.contiguous()
+
+    u = torch.rand(16, generator=g)
+    nrm = torch.randn(8, generator=g)
+    ys = torch.arange(mh, dtype=torch.float32)[:, None]
+    xs = torch.arange(mw, dtype=torch.float32)[None, :]
+    cx0 = mw / 2 + nrm[0] * mw / 8
+    y_top = mh * (0.125 + 0.375 * u[0])
+    hw_top = mw * (1 / 16 + u[1] / 8)
+    hw_bot = mw * (0.25 + 0.25 * u[2])
+    shear = 0.3 * nrm[1]
+    t = ((ys - y_top) / max(mh - 1 - float(y_top), 1.0)).clamp(0, 1)
+    halfw = hw_top + (hw_bot - hw_top) * t
+    cx = cx0 + shear * (ys - y_top)
+    field = torch.minimum(halfw - (xs - cx).abs(), ys - y_top + 0.5)
+
+    protos = torch.zeros(K, mh, mw)
+    protos[0] = field
+    disc = []
+    for d in range(N_DISC_CH):
+        dcx = mw * (0.1 + 0.8 * u[3 + 2 * d])
+        dcy = mh * (0.1 + 0.8 * u[4 + 2 * d])
+        rad = mw * (1 / 16 + u[9 + d] / 16)
+        protos[1 + d] = rad - ((xs - dcx) ** 2 + (ys - dcy) ** 2).sqrt()
+        disc.append((float(dcx), float(dcy), float(rad)))
+    n_noise = K - 1 - N_DISC_CH
+    protos[1 + N_DISC_CH:] = 0.3 * _smooth_noise(g, n_noise, mh, mw)
+
+    coefs = torch.zeros(n, K)
+    boxes = torch.zeros(n, 4)
+    jit = torch.rand(n, 4, generator=g) * 8.0
+    for i in range(n):
+        coefs[i, 1 + N_DISC_CH:] = 0.3 * torch.randn(n_noise, generator=g)
+        if i == 0:
+            coefs[i, 0] = 1.0
+            pos = (field > -1.0).nonzero()
+            if pos.numel() == 0:
+                x1 = y1 = 0.0
+                x2, y2 = W - 1.0, H - 1.0
+            else:
+                y1, x1 = (pos.min(0).values.float() * torch.tensor([sy, sx])).tolist()
+                y2, x2 = ((pos.max(0).values.float() + 1) * torch.tensor([sy, sx])).tolist()
+        else:
+            d = (i - 1) % N_DISC_CH
+            coefs[i, 1 + d] = 0.75 + 0.5 * float(torch.rand(1, generator=g))
+            dcx, dcy, rad = disc[d]
+            shrink = 1.0 / (1 + (i - 1) // N_DISC_CH)       # later instances: smaller boxes
+            x1, x2 = (dcx - rad * shrink) * sx, (dcx + rad * shrink) * sx
+            y1, y2 = (dcy - rad * shrink) * sy, (dcy + rad * shrink) * sy
+        b = torch.tensor([x1 - jit[i, 0], y1 - jit[i, 1], x2 + jit[i, 2], y2 + jit[i, 3]])
+        b[0::2] = b[0::2].clamp(0, W - 1.0)
+        b[1::2] = b[1::2].clamp(0, H - 1.0)
+        boxes[i] = b
+    return protos.contiguous(), coefs.contiguous(), boxes.contiguous()
+
+
+def make_batch(first_idx: int, B: int, n: int, H: int, W: int, mh: int, mw: int, K: int = 32,
+               family: str = "sidewalk", max_n: int | None = None, pin: bool = False):
+    """-> protos [B,K,mh,mw], coefs [B,max_n,K], boxes [B,max_n,4], counts [B] int32 (CPU tensors)."""
+    max_n = max_n or n
+    protos = torch.empty(B, K, mh, mw, pin_memory=pin)
+    coefs = torch.zeros(B, max_n, K, pin_memory=pin)
+    boxes = torch.zeros(B, max_n, 4, pin_memory=pin)
+    counts = torch.full((B,), n, dtype=torch.int32)
+    for b in range(B):
+        p, c, bx = make_frame(first_idx + b, n, H, W, mh, mw, K, family)
+        protos[b] = p
+        coefs[b, :n] = c
+        boxes[b, :n] = bx
+    return protos, coefs, boxes, counts
