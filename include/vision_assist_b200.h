@@ -1,0 +1,186 @@
+/*
+ * vision_assist_b200.h - C ABI of libva_sm100.so
+ *
+ * B200-native (sm_100a) implementation of Vision Assist's per-frame data-parallel stage:
+ *
+ *   YOLOv8-seg mask assembly   ultralytics.utils.ops.process_mask, vendored in the reference at
+ *                              testing/old/segmenting_using_tflite/ops.py:707-737 (+ crop_mask :688-704)
+ *   mask -> occupancy grid     FrameProcessor._extract_grid_information     FrameProcessor.py:50-171
+ *   penalty map                PenaltyCalculator                            PenaltyCalculator.py:26-142
+ *                              (driver FrameProcessor._calculate_penalties  FrameProcessor.py:173-182)
+ *   top-edge (protrusion) scan ProtrusionDetector.__call__/_find_peak       ProtrusionDetector.py:38-158,419-535
+ *
+ * The reference has no FFI layer (it is pure Python); these entry points are what a ctypes
+ * binding inside the reference's FrameProcessor / PenaltyCalculator / ProtrusionDetector would
+ * call (INTEGRATION.md shows that binding).  Conventions:
+ *
+ *   - plain C, no exceptions: every call returns VA_OK (0) or a negative VA_ERR_* code and
+ *     va_last_error() describes the failure;
+ *   - device entry points take raw DEVICE pointers (e.g. torch.Tensor.data_ptr()) and the
+ *     caller's CUDA stream (cudaStream_t passed as void*; NULL = legacy default stream); they
+ *     enqueue work and return without synchronising;  *_host entry points take HOST pointers,
+ *     do their own H2D/D2H copies and return after the results are in host memory;
+ *   - the caller owns every buffer; the library owns only the context's scratch memory;
+ *   - a context is bound to one device and is not thread-safe (one context per stream);
+ *   - there is NO CPU fallback: without a CUDA device va_create fails with VA_ERR_CUDA.
+ */
+#ifndef VISION_ASSIST_B200_H
+#define VISION_ASSIST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VA_ABI_VERSION 1
+#if defined(__GNUC__)
+#define VA_API __attribute__((visibility("default")))
+#else
+#define VA_API
+#endif
+
+enum {
+  VA_OK = 0,
+  VA_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  VA_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  VA_ERR_CAPACITY = -3,  /* batch or instance count above what the context was created for */
+  VA_ERR_UNSUPPORTED = -4
+};
+
+/* va_config.flags */
+enum {
+  VA_CFG_CHECK_SIMPLE = 1,  /* also compute the Euler number of the selected mask (extra H*W read
+                               per frame) and set VA_FLAG_NON_SIMPLE when it is not one hole-free blob */
+  VA_CFG_NO_TENSOR_CORE = 2 /* debug: force the CUDA-core (FFMA) contraction instead of tcgen05 */
+};
+
+/* va_frame_header.flags */
+enum {
+  VA_FLAG_EMPTY = 1,       /* no grid: reference returns [] (FrameProcessor.py:99-101, :328-332) */
+  VA_FLAG_CENTRE_OOB = 2,  /* reference raises IndexError at FrameProcessor.py:97 (cell centre outside frame) */
+  VA_FLAG_LIST_OOB = 4,    /* reference raises IndexError at FrameProcessor.py:163 (negative list index) */
+  VA_FLAG_NON_SIMPLE = 8,  /* selected mask is not a single hole-free 8-connected blob */
+  VA_FLAG_OVERFLOW = 16    /* record capacity exceeded (cannot happen for frames the context was sized for) */
+};
+
+typedef struct va_ctx va_ctx;
+
+typedef struct va_config {
+  int32_t device;    /* CUDA device ordinal */
+  int32_t H, W;      /* frame (= network input) height / width in pixels */
+  int32_t mh, mw;    /* prototype map height / width */
+  int32_t K;         /* number of prototypes (32) */
+  int32_t max_n;     /* instance capacity per frame (<= 32) */
+  int32_t gs;        /* grid cell size in pixels (config.py:1 grid_size = 20) */
+  int32_t max_batch; /* frames per call capacity */
+  int32_t flags;     /* VA_CFG_* */
+} va_config;
+
+/* Per-frame result record: one contiguous blob of layout.record_bytes bytes.
+ *   header   : va_frame_header (64 B)
+ *   row_y    : int32 [rmax]        pixel y of list row k        (Grid.coords.y)
+ *   row_attr : int32 [rmax]        Grid.row attribute of row k  (differs from k under the
+ *                                  duplicate-row / gap-compression / negative-index quirks)
+ *   penalty  : double[rmax][cmax]  Grid.penalty, NaN where the cell is empty (None in the reference)
+ *   peaks    : int32 [pmax][2]     (x, y) of ProtrusionDetector's returned Coordinates
+ *   occ      : uint8 [rmax][cmax]  bit0 = not Grid.empty, bit1 = Grid.artificial
+ * Rows [0, n_rows) are FrameProcessor.grids in list order (np_grids = occ & 1); rows
+ * [n_rows, n_rows + n_orphans) are rows that are only reachable through grid_lookup.
+ * Cell (k, c) has Grid.coords = (x0 + c*gs, row_y[k]) and Grid.col = c. */
+typedef struct va_frame_header {
+  int32_t flags;      /* VA_FLAG_* */
+  int32_t sel;        /* selected instance (largest pixel area, first max), -1 if none */
+  int32_t x0, y0;     /* snapped bbox origin (FrameProcessor.py:79-80) */
+  int32_t n_cols;     /* C */
+  int32_t n_rows;     /* R = len(FrameProcessor.grids) */
+  int32_t n_orphans;
+  int32_t n_peaks;
+  int32_t area;       /* pixel area of the selected mask */
+  int32_t n_mask_rows;
+  int32_t minx, miny, maxx, maxy; /* pixel bbox of the selected mask */
+  int32_t euler;      /* Euler number when VA_CFG_CHECK_SIMPLE, else 0 */
+  int32_t reserved;
+} va_frame_header;
+
+typedef struct va_layout {
+  int32_t record_bytes;
+  int32_t rmax, cmax, pmax;
+  int32_t off_header, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ;
+  int32_t lat_rows, lat_cols; /* cell-centre lattice sampled from the masks */
+  int32_t algorithmic_bytes_per_frame_n1; /* SURVEY 8(d) with n = 1 masks written; informational */
+  int32_t reserved[3];
+} va_layout;
+
+/* Grid-mode input header for va_grid_to_penalty_peaks (PenaltyCalculator / ProtrusionDetector
+ * drop-ins and the reference's *_grids.npy fixtures).  All coordinates are multiples of gs. */
+typedef struct va_grid_input {
+  int32_t x0;       /* Grid.coords.x of column 0 */
+  int32_t n_cols;   /* C <= cmax */
+  int32_t n_rows;   /* list rows R <= rmax */
+  int32_t n_plane;  /* number of grid_lookup rows given (0 = derive the lookup from the list rows,
+                       later rows overriding earlier ones with the same y) */
+  int32_t use_easy; /* 1 = _pre_compute_easy_segments(np_grids, grids) as FrameProcessor does;
+                       0 = empty np_grids (run_on_main.py fixture path: pure traversal) */
+  int32_t reserved[3];
+} va_grid_input;
+
+VA_API int va_abi_version(void);
+
+/* Create / destroy a context.  Replaces: FrameProcessor.__init__ (FrameProcessor.py:29-42) state. */
+VA_API int va_create(va_ctx** out, const va_config* cfg);
+VA_API void va_destroy(va_ctx* ctx);
+VA_API const char* va_last_error(const va_ctx* ctx); /* ctx may be NULL: error of the last failed va_create */
+VA_API int va_get_layout(const va_ctx* ctx, va_layout* out);
+
+/* Mask assembly only.  Replaces ops.process_mask(protos[b], coefs[b,:n], boxes[b,:n], (H,W),
+ * upsample=True) for every frame b (ops.py:707-737).
+ *   protos [B][K][mh][mw] f32, coefs [B][max_n][K] f32, boxes [B][max_n][4] f32 xyxy in (H,W)
+ *   pixels, counts [B] i32 (instances per frame, <= max_n).
+ *   masks_out  [B][max_n][H][W] u8 in {0,1}, or NULL
+ *   logits_out [B][max_n][mh][mw] f32 (cropped proto-resolution logits, ops.py:734), or NULL */
+VA_API int va_assemble_masks(va_ctx* ctx, const float* protos, const float* coefs, const float* boxes,
+                      const int32_t* counts, int32_t B, uint8_t* masks_out, float* logits_out,
+                      void* stream);
+
+/* Whole path in one call: mask assembly -> grid -> penalties -> peaks.
+ * Replaces model.predict()'s process_mask + FrameProcessor._extract_grid_information +
+ * _calculate_penalties + ProtrusionDetector.__call__ (FrameProcessor.py:322-341).
+ *   masks_out may be NULL ("grid-only" mode: masks never touch HBM).
+ *   records_out [B][record_bytes] */
+VA_API int va_run_fused(va_ctx* ctx, const float* protos, const float* coefs, const float* boxes,
+                 const int32_t* counts, int32_t B, uint8_t* masks_out, uint8_t* records_out,
+                 void* stream);
+
+/* Same as va_run_fused with HOST buffers: copies inputs H2D in chunks overlapped with compute,
+ * copies records (and masks when h_masks_out != NULL) back, returns when they are in host memory.
+ * Pinned host memory is recommended (pageable works, slower). */
+VA_API int va_run_fused_host(va_ctx* ctx, const float* h_protos, const float* h_coefs, const float* h_boxes,
+                      const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out);
+
+/* Binary masks -> records.  Replaces FrameProcessor._extract_grid_information (+ penalties, peaks)
+ * when the masks come from elsewhere (e.g. cv2.fillPoly of a polygon model output).
+ *   masks [B][max_n][H][W] u8 (non-zero = inside), counts [B]
+ *   rects [B][4] i32 = cv2.boundingRect (x, y, w, h) override of the selected instance's pixel
+ *   bbox, or NULL; sel [B] i32 = instance to use, or NULL (largest area). */
+VA_API int va_mask_to_records(va_ctx* ctx, const uint8_t* masks, const int32_t* counts, int32_t B,
+                       const int32_t* rects, const int32_t* sel, uint8_t* records_out, void* stream);
+
+/* Occupancy grids -> penalties + peaks.  Replaces PenaltyCalculator._pre_compute_easy_segments +
+ * calculate_penalty for every cell (PenaltyCalculator.py:26-142) and ProtrusionDetector.__call__.
+ *   hdr [B]; row_y/row_attr [B][rmax] i32; occ [B][rmax][cmax] u8 (bit0 non-empty, bit1 artificial);
+ *   plane_y [B][rmax] i32 and plane_occ [B][rmax][cmax] u8 (bit0 non-empty) when n_plane > 0, else NULL.
+ *   records_out [B][record_bytes] (same record as va_run_fused). */
+VA_API int va_grid_to_penalty_peaks(va_ctx* ctx, const va_grid_input* hdr, const int32_t* row_y,
+                             const int32_t* row_attr, const uint8_t* occ, const int32_t* plane_y,
+                             const uint8_t* plane_occ, int32_t B, uint8_t* records_out, void* stream);
+
+/* Introspection for benchmarks: number of kernels launched by the last call, and which
+ * contraction path the context uses (1 = tcgen05/TMEM, 0 = CUDA-core FFMA). */
+VA_API int va_last_launch_count(const va_ctx* ctx);
+VA_API int va_uses_tensor_core(const va_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISION_ASSIST_B200_H */

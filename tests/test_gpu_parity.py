@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden vectors.  Bit-exact for grids / penalties / peaks; binary masks bit-exact except pixels
+whose reference logit is within 1e-4 of the threshold (counted); logits within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+import goldenio
+import polygen
+from gpucommon import assert_record_equals_oracle, band_mismatch_report, to_dev
+from oracle import grid as og
+from oracle import mask_assembly as oma
+from oracle import penalty as open_
+from oracle import pipeline as opl
+from oracle import protrusion as oprot
+
+pytestmark = pytest.mark.gpu
+
+from vision_assist_b200 import synth  # noqa: E402
+from vision_assist_b200.engine import MaskGridEngine  # noqa: E402
+
+PATHS = [pytest.param(False, id="cuda-core"), pytest.param(True, id="tcgen05")]
+
+
+def make_engine(tc, **kw):
+    e = MaskGridEngine(tensor_core=tc, **kw)
+    if tc and not e.uses_tensor_core:
+        pytest.fail("tcgen05 plan unavailable: " + e.lib.va_last_error(e._ctx).decode())
+    return e
+
+
+@pytest.mark.parametrize("tc", PATHS)
+@pytest.mark.parametrize("H,W,mh,mw,n,family", [(640, 640, 160, 160, 8, "sidewalk"), (640, 640, 160, 160, 5, "noise"),
+                                                (160, 160, 40, 40, 3, "noise"), (384, 640, 96, 160, 2, "sidewalk")])
+def test_logits_and_masks_vs_oracle(tc, H, W, mh, mw, n, family):
+    B = 3
+    eng = make_engine(tc, H=H, W=W, mh=mh, mw=mw, max_n=8, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(1000, B, n, H, W, mh, mw, family=family, max_n=8)
+    masks, logits = eng.assemble_masks(*to_dev(protos, coefs, boxes, counts), want_logits=True)
+    torch.cuda.synchronize()
+    masks, logits = masks.cpu().numpy(), logits.cpu().numpy()
+    total_diff = 0
+    for b in range(B):
+        cl = oma.cropped_logits(protos[b], coefs[b, :n], boxes[b, :n], (H, W)).numpy()
+        got = logits[b, :n]
+        assert np.array_equal(cl == 0, got == 0), "crop pattern"
+        scale = np.abs(cl).max()
+        assert np.abs(got - cl).max() <= 1e-3 * scale, "logits within 1e-3 relative"
+        assert np.abs(got - cl).max() <= 2e-5 * scale, "fp32-class accuracy expected"
+        up = oma.upsampled_logits(protos[b], coefs[b, :n], boxes[b, :n], (H, W)).numpy()
+        nd, nout = band_mismatch_report(masks[b, :n], up)
+        assert nout == 0, f"{nout} mask pixels differ outside the 1e-4 band"
+        total_diff += nd
+        # identical logits in -> bit-identical upsample arithmetic
+        spec = (oma.bilinear_upsample_np(got, (H, W)) > 0).astype(np.uint8)
+        assert np.array_equal(spec, masks[b, :n]), "upsample arithmetic differs from the specification"
+    print(f"[parity] {family} {H}x{W}: {total_diff} mask pixels inside the 1e-4 band differ")
+
+
+@pytest.mark.parametrize("tc", PATHS)
+def test_mask_assembly_golden(tc):
+    z = goldenio.load("mask_assembly.npz")
+    for i, (f, n, H, W, mh, mw) in enumerate(z["cases"].tolist()):
+        fam = str(z["families"][i])
+        if H < 8 or W < 16:
+            continue
+        eng = make_engine(tc, H=H, W=W, mh=mh, mw=mw, max_n=8, gs=20 if min(H, W) >= 80 else 8, max_batch=1)
+        protos, coefs, boxes, counts = synth.make_batch(f, 1, n, H, W, mh, mw, family=fam, max_n=8)
+        masks = eng.assemble_masks(*to_dev(protos, coefs, boxes, counts)).cpu().numpy()[0, :n]
+        gold = np.unpackbits(z[f"{i}/masks_packed"], axis=-1)[..., :W]
+        up = oma.bilinear_upsample_np(z[f"{i}/cropped_logits"], (H, W))
+        nd, nout = band_mismatch_report(masks, up)
+        assert nout == 0 and nd <= 8, (i, nd, nout)
+        assert (masks != gold).sum() == nd
+
+
+@pytest.mark.parametrize("tc", PATHS)
+def test_frames_golden(tc):
+    z = goldenio.load("frames.npz")
+    for ci, (H, W, mh, mw, n, gs, first, count) in enumerate(z["cases"].tolist()):
+        fam = str(z["families"][ci])
+        eng = make_engine(tc, H=H, W=W, mh=mh, mw=mw, max_n=8, gs=gs, max_batch=count, check_simple=True)
+        protos, coefs, boxes, counts = synth.make_batch(first, count, n, H, W, mh, mw, family=fam, max_n=8)
+        records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+        recs = eng.decode(records)
+        for k, rec in enumerate(recs):
+            assert rec.area == int(z[f"{ci}/areas"][k].max())
+            R, C = int(z[f"{ci}/R"][k]), int(z[f"{ci}/C"][k])
+            case = dict(R=R, C=C, x0=int(z[f"{ci}/x0"][k]), rows_y=z[f"{ci}/rows_y"][k][:R],
+                        rows_attr=z[f"{ci}/rows_attr"][k][:R], occ=z[f"{ci}/occ"][k][:R, :C],
+                        pen=z[f"{ci}/pen"][k][:R, :C], peaks=z[f"{ci}/peaks"][k][:int(z[f"{ci}/npk"][k])])
+            if fam == "sidewalk":      # single hole-free blobs: the reference's contour route == ours
+                assert not (rec.flags & opl.FLAG_NON_SIMPLE)
+                goldenio.assert_result_matches(rec.as_dict(), case, f"golden frame {ci}/{k}")
+
+
+@pytest.mark.parametrize("tc", PATHS)
+@pytest.mark.parametrize("family", ["sidewalk", "noise"])
+def test_run_fused_vs_oracle(tc, family):
+    H = W = 640
+    B, n = 24, 8
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=8, gs=20, max_batch=B, check_simple=True)
+    protos, coefs, boxes, counts = synth.make_batch(5000, B, n, H, W, 160, 160, family=family, max_n=8)
+    counts[3] = 0          # a frame without detections
+    counts[5] = 1
+    counts[7] = 3
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    n_contour_diff = 0
+    for b in range(B):
+        nb = int(counts[b])
+        res = opl.frame_from_masks(masks[b, :nb], 20, "direct")        # same masks: grid path must be bit-exact
+        assert_record_equals_oracle(recs[b], res, f"{family} frame {b}")
+        assert bool(recs[b].flags & opl.FLAG_NON_SIMPLE) == bool(res["flags"] & opl.FLAG_NON_SIMPLE)
+        if nb:
+            assert recs[b].sel == res["sel"]
+        full = opl.frame_from_tensors(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W), 20, "contour")
+        assert (masks[b, :nb] != full["masks"]).sum() <= 4
+        try:
+            assert_record_equals_oracle(recs[b], full)
+        except AssertionError:
+            n_contour_diff += 1
+            assert family == "noise"
+    print(f"[parity] {family}: {n_contour_diff}/{B} frames differ from the reference's contour route")
+
+
+@pytest.mark.parametrize("tc", PATHS)
+def test_cfg1_full_batch_256(tc):
+    """BASELINE config 1: 256 synthetic 640x640 frames, bit-exact grid / penalty / peaks check."""
+    H = W = 640
+    B, n = 256, 8
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=8, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(0, B, n, H, W, 160, 160, max_n=8)
+    dev = to_dev(protos, coefs, boxes, counts)
+    records, masks = eng.run(*dev)
+    recs = eng.decode(records)
+    band_pixels = 0
+    for b in range(B):
+        full = opl.frame_from_tensors(protos[b], coefs[b], boxes[b], (H, W), 20, "contour")
+        assert_record_equals_oracle(recs[b], full, f"cfg1 frame {b}")
+        if b % 16 == 0:
+            band_pixels += int((masks[b].cpu().numpy() != full["masks"]).sum())
+    print(f"[parity] cfg1: 256/256 records bit-exact; {band_pixels} differing mask pixels in 16 sampled frames")
+    # size-independent properties: idempotence (scratch reset), batch-split invariance, grid-only mode
+    records2, _ = eng.run(*dev)
+    assert torch.equal(records, records2)
+    half = [t[:128].contiguous() for t in dev]
+    r_half, _ = eng.run(*half)
+    assert torch.equal(r_half, records[:128])
+    r_nomask, none = eng.run(*dev, write_masks=False)
+    assert none is None and torch.equal(r_nomask, records)
+
+
+@pytest.mark.parametrize("tc", PATHS)
+def test_cfg2_1080p_generic_scale(tc):
+    H, W, B, n = 1080, 1920, 2, 32
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(7000, B, n, H, W, 160, 160, max_n=32)
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    for b in range(B):
+        up = oma.upsampled_logits(protos[b], coefs[b], boxes[b], (H, W)).numpy()
+        nd, nout = band_mismatch_report(masks[b], up)
+        assert nout == 0 and nd < 50, (nd, nout)
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], 20, "direct"), f"1080p frame {b}")
+
+
+@pytest.mark.parametrize("tc", PATHS)
+@pytest.mark.parametrize("gs", [4, 8, 16, 32])
+def test_cfg4_cell_size_sweep(tc, gs):
+    H = W = 640
+    B, n = 4, 8
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=8, gs=gs, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(8000, B, n, H, W, 160, 160, max_n=8)
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    for b in range(B):
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], gs, "direct"), f"gs={gs} frame {b}")
+
+
+@pytest.mark.parametrize("tc", PATHS)
+@pytest.mark.parametrize("m,n", [(192, 8), (224, 8), (256, 32), (320, 8)])
+def test_cfg4_proto_sweep(tc, m, n):
+    H = W = 4 * m
+    B = 2
+    eng = make_engine(tc, H=H, W=W, mh=m, mw=m, max_n=n, gs=20 if H % 20 == 0 else 16, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(9000, B, n, H, W, m, m, max_n=n)
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    for b in range(B):
+        up = oma.upsampled_logits(protos[b], coefs[b], boxes[b], (H, W)).numpy()
+        nd, nout = band_mismatch_report(masks[b], up)
+        assert nout == 0, (m, nd, nout)
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], eng.gs, "direct"), f"proto {m} frame {b}")
+
+
+def test_host_buffer_path_matches_device_path():
+    H = W = 640
+    B, n = 70, 8                   # > 2 host chunks
+    eng = MaskGridEngine(H=H, W=W, mh=160, mw=160, max_n=8, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(100, B, n, H, W, 160, 160, max_n=8, pin=True)
+    rec_host = eng.run_host(protos, coefs, boxes, counts)
+    rec_dev, _ = eng.run(*to_dev(protos, coefs, boxes, counts), write_masks=False)
+    assert np.array_equal(rec_host.numpy(), rec_dev.cpu().numpy())
+    masks_h = torch.empty((B, 8, H, W), dtype=torch.uint8, pin_memory=True)
+    rec_host2 = eng.run_host(protos, coefs, boxes, counts, masks_out=masks_h)
+    _, masks_d = eng.run(*to_dev(protos, coefs, boxes, counts))
+    assert np.array_equal(rec_host2.numpy(), rec_dev.cpu().numpy())
+    assert np.array_equal(masks_h.numpy(), masks_d.cpu().numpy())
+
+
+def test_polygon_route_golden():
+    """ultralytics-style masks.xy polygons: host fillPoly + boundingRect, device grid/penalty/peaks."""
+    import cv2
+    engines = {}
+    n = 0
+    for case in goldenio.polygon_cases():
+        H, W, gs = case["H"], case["W"], case["gs"]
+        key = (H, W, gs)
+        if key not in engines:
+            engines[key] = MaskGridEngine(H=H, W=W, mh=H // 4 // 4 * 4 or 4, mw=max(4, W // 4 // 4 * 4), max_n=1, gs=gs, max_batch=1)
+        eng = engines[key]
+        poly = og.select_polygon(case["polys"])
+        pts = np.int32([poly])
+        rect = cv2.boundingRect(pts)
+        raster = np.zeros((H, W), np.uint8)
+        cv2.fillPoly(raster, pts, 1)
+        m = torch.from_numpy(raster)[None, None].cuda()
+        rec = eng.decode(eng.masks_to_records(m, torch.tensor([1], dtype=torch.int32).cuda(),
+                                              rects=torch.tensor([list(rect)], dtype=torch.int32).cuda(),
+                                              sel=torch.tensor([0], dtype=torch.int32).cuda()))[0]
+        err = 1 if rec.flags & opl.FLAG_CENTRE_OOB else 2 if rec.flags & opl.FLAG_LIST_OOB else 0
+        assert err == case["err"], case["idx"]
+        goldenio.assert_result_matches(rec.as_dict(), case, f"polygon case {case['idx']}")
+        n += 1
+    assert n >= 150
+
+
+def test_reference_fixtures_grid_mode():
+    """The reference's 13 *_grids.npy fixtures and 5 live PNG known answers through va_grid_to_penalty_peaks."""
+    z = goldenio.load("fixtures.npz")
+    eng = MaskGridEngine(H=720, W=1280, mh=180, mw=320, max_n=1, gs=20, max_batch=32)
+    keys = list(open_.PENALTY_COLOUR_GRADIENT.keys())
+    for use_easy, key in ((0, "pen_traversal"), (1, "pen_easy")):
+        inputs = [dict(x0=0, rows_y=z[f"{nm}/rows_y"], rows_attr=z[f"{nm}/rows_attr"], occ=z[f"{nm}/occ"], use_easy=use_easy)
+                  for nm in z["names"]]
+        recs = eng.decode(eng.grids_to_records(inputs))
+        for nm, rec in zip(z["names"], recs):
+            gold = z[f"{nm}/{key}"]
+            assert np.array_equal(np.isnan(rec.penalty), np.isnan(gold)), nm
+            assert np.array_equal(rec.penalty[~np.isnan(gold)].view(np.uint64), gold[~np.isnan(gold)].view(np.uint64)), nm
+            assert np.array_equal(rec.peaks, z[f"{nm}/peaks"]), nm
+            if nm in z["live_png"] and not use_easy:
+                col = z[f"{nm}/png_colour_idx"]
+                for r in range(rec.R):
+                    for c in range(rec.C):
+                        if rec.occ[r, c] & 1:
+                            want = open_.PENALTY_COLOUR_GRADIENT[keys[int(col[r, c])]]
+                            assert open_.get_penalty_colour(rec.penalty[r, c]) == want, (nm, r, c)
+
+
+def test_random_grids_grid_mode_vs_oracle():
+    rng = np.random.default_rng(77)
+    gs = 20
+    eng = MaskGridEngine(H=720, W=1280, mh=180, mw=320, max_n=1, gs=gs, max_batch=64)
+    done = 0
+    for it in range(12):
+        inputs, want = [], []
+        for k in range(64):
+            R, C = int(rng.integers(1, 37)), int(rng.integers(1, 65))
+            g = polygen.random_occupancy(rng, R, C)
+            st = og.grid_from_npy(np.pad(g, ((0, 36 - R), (0, 64 - C))))
+            use_easy = bool(rng.integers(0, 2))
+            pen = open_.calculate_penalties(st, use_easy=use_easy)
+            rows_y = np.array([r[0].y for r in st.grids], np.int32)
+            occ = np.array([[(0 if q.empty else 1) | (2 if q.artificial else 0) for q in r] for r in st.grids], np.uint8)
+            inputs.append(dict(x0=0, rows_y=rows_y, rows_attr=np.array([r[0].row for r in st.grids], np.int32), occ=occ,
+                               use_easy=int(use_easy)))
+            want.append((pen, oprot.peaks_closed_form(rows_y, (occ & 1).astype(bool), 0, st.W, gs)))
+        recs = eng.decode(eng.grids_to_records(inputs))
+        for rec, (pen, pk) in zip(recs, want):
+            assert np.array_equal(np.isnan(rec.penalty), np.isnan(pen))
+            assert np.array_equal(rec.penalty[~np.isnan(pen)].view(np.uint64), pen[~np.isnan(pen)].view(np.uint64))
+            assert [tuple(p) for p in rec.peaks.tolist()] == pk
+            done += 1
+    assert done == 768
+
+
+def test_capacity_and_argument_errors():
+    from vision_assist_b200 import _lib
+    eng = MaskGridEngine(H=640, W=640, mh=160, mw=160, max_n=8, gs=20, max_batch=2)
+    protos, coefs, boxes, counts = synth.make_batch(0, 3, 2, 640, 640, 160, 160, max_n=8)
+    with pytest.raises(ValueError):
+        eng.run(*to_dev(protos, coefs, boxes, counts))
+    with pytest.raises(ValueError):
+        eng.run(protos, coefs, boxes, counts)          # CPU tensors on the device API
+    with pytest.raises(_lib.VaError):
+        MaskGridEngine(H=640, W=640, mh=160, mw=160, max_n=64)
+    r0, _ = eng.run(*[t[:0] for t in to_dev(protos, coefs, boxes, counts)])
+    assert r0.shape[0] == 0

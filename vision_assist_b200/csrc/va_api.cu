@@ -1,0 +1,365 @@
+// C ABI of libva_sm100.so (include/vision_assist_b200.h): context, record layout, launch plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "va_common.cuh"
+
+using namespace va;
+
+struct va_ctx {
+  va_config cfg;
+  Dims d;
+  va_layout layout;
+  Scratch scratch;
+  int logits_chunk;            // frames of logits scratch (CUDA-core path)
+  FusedPlan* plan;             // tcgen05 path, nullptr when unavailable / disabled
+  int last_launches;
+  char err[512];
+  // host-buffer pipeline (va_run_fused_host), created lazily
+  bool host_ready;
+  int host_chunk;
+  cudaStream_t s_in, s_compute, s_out;
+  cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+  float* d_protos[2];
+  float* d_coefs[2];
+  float* d_boxes[2];
+  int* d_counts[2];
+  uint8_t* d_records[2];
+  uint8_t* d_masks[2];
+};
+
+static char g_create_err[512] = "";
+
+static void set_err(va_ctx* c, const char* fmt, ...) {
+  char* dst = c ? c->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+}
+
+#define VA_CUDA(ctx, call)                                                              \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return VA_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+static int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, size_t n) {
+  if (c.K != kProtoK) { snprintf(why, n, "K must be %d (got %d)", kProtoK, c.K); return false; }
+  if (c.max_n < 1 || c.max_n > kMaxInst) { snprintf(why, n, "max_n must be in [1,%d]", kMaxInst); return false; }
+  if (c.H < 8 || c.W < 16 || c.mh < 2 || c.mw < 4 || (c.mw % 4) != 0) {
+    snprintf(why, n, "unsupported geometry H=%d W=%d mh=%d mw=%d (mw must be a multiple of 4)", c.H, c.W, c.mh, c.mw);
+    return false;
+  }
+  if (c.gs < 4 || c.gs > c.H || c.gs > c.W) { snprintf(why, n, "gs must be in [4, min(H,W)]"); return false; }
+  if (c.max_batch < 1 || c.max_batch > 65535) { snprintf(why, n, "max_batch must be in [1,65535]"); return false; }
+  memset(&d, 0, sizeof(d));
+  d.H = c.H; d.W = c.W; d.mh = c.mh; d.mw = c.mw; d.K = c.K; d.max_n = c.max_n; d.gs = c.gs;
+  d.flags = c.flags;
+  const int half = c.gs / 2;
+  d.lat_rows = ceil_div(c.H - half, c.gs);
+  d.lat_cols = ceil_div(c.W - half, c.gs);
+  d.lat_words = ceil_div(d.lat_cols, 32);
+  d.plane_rows = ceil_div(c.H, c.gs);
+  int s = (int)((long long)c.H * 7 / 8);                   // int(H * 0.875), FrameProcessor.py:126
+  s = s + (c.gs - s % c.gs) % c.gs;                        // :127
+  d.band_start = s;
+  const int nband = (s < c.H) ? ceil_div(c.H - s, c.gs) : 0;
+  d.rmax = ceil_div(c.H, c.gs) + nband + 2;
+  d.cmax = ceil_div(c.W, c.gs);
+  d.cwords = ceil_div(d.cmax, 32);
+  d.pmax = (d.cmax + 1) / 2 + 1;
+  int o = 0;
+  L.off_header = o; o += 64;
+  d.off_row_y = o; o += 4 * d.rmax;
+  d.off_row_attr = o; o += 4 * d.rmax;
+  o = align_up(o, 8);
+  d.off_penalty = o; o += 8 * d.rmax * d.cmax;
+  d.off_peaks = o; o += 8 * d.pmax;
+  d.off_occ = o; o += d.rmax * d.cmax;
+  d.record_bytes = align_up(o, 16);
+  d.wr = (float)((double)c.mw / (double)c.W);              // python float ratio cast to fp32 by torch
+  d.hr = (float)((double)c.mh / (double)c.H);
+  d.sx = (float)c.mw / (float)c.W;                         // ATen: static_cast<float>(in) / out
+  d.sy = (float)c.mh / (float)c.H;
+  memset(&L, 0, sizeof(L));
+  L.record_bytes = d.record_bytes; L.rmax = d.rmax; L.cmax = d.cmax; L.pmax = d.pmax;
+  L.off_header = 0; L.off_row_y = d.off_row_y; L.off_row_attr = d.off_row_attr; L.off_penalty = d.off_penalty;
+  L.off_peaks = d.off_peaks; L.off_occ = d.off_occ; L.lat_rows = d.lat_rows; L.lat_cols = d.lat_cols;
+  L.algorithmic_bytes_per_frame_n1 = 4 * c.K * c.mh * c.mw + 4 * c.K + 16 + c.H * c.W + d.rmax * d.cmax * 9 + 64;
+  return true;
+}
+
+extern "C" int va_abi_version(void) { return VA_ABI_VERSION; }
+
+extern "C" int va_create(va_ctx** out, const va_config* cfg) {
+  if (!out || !cfg) { set_err(nullptr, "va_create: null argument"); return VA_ERR_INVALID; }
+  *out = nullptr;
+  va_ctx* c = new (std::nothrow) va_ctx();
+  if (!c) { set_err(nullptr, "out of host memory"); return VA_ERR_INVALID; }
+  memset(c, 0, sizeof(*c));
+  c->cfg = *cfg;
+  char why[256];
+  if (!compute_dims(*cfg, c->d, c->layout, why, sizeof(why))) {
+    set_err(nullptr, "va_create: %s", why);
+    delete c;
+    return VA_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    set_err(nullptr, "va_create: no usable CUDA device %d (%s); this library has no CPU fallback", cfg->device,
+            e == cudaSuccess ? "device ordinal out of range" : cudaGetErrorString(e));
+    delete c;
+    return VA_ERR_CUDA;
+  }
+#define VA_CREATE_CUDA(call)                                                      \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      set_err(nullptr, "va_create: %s failed: %s", #call, cudaGetErrorString(e__)); \
+      va_destroy(c);                                                              \
+      return VA_ERR_CUDA;                                                         \
+    }                                                                             \
+  } while (0)
+  VA_CREATE_CUDA(cudaSetDevice(cfg->device));
+  const Dims& d = c->d;
+  const size_t ns = (size_t)cfg->max_batch * d.max_n;
+  VA_CREATE_CUDA(cudaMalloc(&c->scratch.stats, ns * sizeof(InstStats)));
+  VA_CREATE_CUDA(cudaMalloc(&c->scratch.lattice, ns * d.lat_rows * d.lat_words * sizeof(unsigned)));
+  VA_CREATE_CUDA(launch_init_scratch(d, cfg->max_batch, c->scratch.stats, c->scratch.lattice, 0));
+  // logits scratch for the CUDA-core path: keep one chunk (<= ~48 MB) so that it stays L2-resident
+  const size_t per_frame = (size_t)d.max_n * d.mh * d.mw * sizeof(float);
+  int chunk = (int)((48u << 20) / per_frame);
+  if (chunk < 1) chunk = 1;
+  if (chunk > cfg->max_batch) chunk = cfg->max_batch;
+  c->logits_chunk = chunk;
+  VA_CREATE_CUDA(cudaMalloc(&c->scratch.logits, per_frame * chunk));
+  c->plan = nullptr;
+  if (!(cfg->flags & VA_CFG_NO_TENSOR_CORE)) {
+    char perr[256] = "";
+    c->plan = fused_plan_create(d, cfg->device, perr, sizeof(perr));
+    if (!c->plan) snprintf(c->err, sizeof(c->err), "tensor-core plan unavailable: %s", perr);
+  }
+  VA_CREATE_CUDA(cudaDeviceSynchronize());
+  *out = c;
+  return VA_OK;
+}
+
+static void host_pipeline_destroy(va_ctx* c) {
+  if (!c->host_ready) return;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->d_protos[i]); cudaFree(c->d_coefs[i]); cudaFree(c->d_boxes[i]); cudaFree(c->d_counts[i]);
+    cudaFree(c->d_records[i]); cudaFree(c->d_masks[i]);
+    cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_out[i]);
+  }
+  cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_out);
+  c->host_ready = false;
+}
+
+extern "C" void va_destroy(va_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  host_pipeline_destroy(c);
+  if (c->plan) fused_plan_destroy(c->plan);
+  cudaFree(c->scratch.stats);
+  cudaFree(c->scratch.lattice);
+  cudaFree(c->scratch.logits);
+  delete c;
+}
+
+extern "C" const char* va_last_error(const va_ctx* c) { return c ? c->err : g_create_err; }
+
+extern "C" int va_get_layout(const va_ctx* c, va_layout* out) {
+  if (!c || !out) return VA_ERR_INVALID;
+  *out = c->layout;
+  return VA_OK;
+}
+
+extern "C" int va_last_launch_count(const va_ctx* c) { return c ? c->last_launches : 0; }
+extern "C" int va_uses_tensor_core(const va_ctx* c) { return (c && c->plan) ? 1 : 0; }
+
+static int check_batch(va_ctx* c, int B, const void* a, const void* b, const void* cc, const void* dd) {
+  if (!c) return VA_ERR_INVALID;
+  if (!a || !b || !cc || !dd) { set_err(c, "null input pointer"); return VA_ERR_INVALID; }
+  if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
+  return VA_OK;
+}
+
+// mask assembly for frames [0, B): tcgen05 path when available, else logits + upsample in
+// L2-sized chunks.  Leaves stats / lattice filled for the tail.
+static int assemble(va_ctx* c, const float* protos, const float* coefs, const float* boxes, const int* counts, int B,
+                    uint8_t* masks, float* logits_out, cudaStream_t st) {
+  const Dims& d = c->d;
+  if (c->plan && !logits_out) {
+    char perr[256] = "";
+    cudaError_t e = launch_fused(c->plan, d, protos, coefs, boxes, counts, B, masks, nullptr, c->scratch.stats,
+                                 c->scratch.lattice, st, perr, sizeof(perr));
+    if (e != cudaSuccess) { set_err(c, "fused kernel launch failed: %s %s", cudaGetErrorString(e), perr); return VA_ERR_CUDA; }
+    c->last_launches += 1;
+    return VA_OK;
+  }
+  const size_t P = (size_t)d.mh * d.mw;
+  const size_t fr_protos = (size_t)d.K * P, fr_coefs = (size_t)d.max_n * d.K, fr_boxes = (size_t)d.max_n * 4;
+  const size_t fr_logits = (size_t)d.max_n * P, fr_masks = (size_t)d.max_n * d.H * d.W;
+  const int step = logits_out ? B : c->logits_chunk;
+  for (int b0 = 0; b0 < B; b0 += step) {
+    const int nb = (B - b0 < step) ? B - b0 : step;
+    float* lg = logits_out ? logits_out + b0 * fr_logits : c->scratch.logits;
+    VA_CUDA(c, launch_logits(d, protos + b0 * fr_protos, coefs + b0 * fr_coefs, boxes + b0 * fr_boxes, counts + b0, nb, lg, st));
+    VA_CUDA(c, launch_upsample(d, lg, counts + b0, nb, masks ? masks + b0 * fr_masks : nullptr,
+                               c->scratch.stats + (size_t)b0 * d.max_n,
+                               c->scratch.lattice + (size_t)b0 * d.max_n * d.lat_rows * d.lat_words, st));
+    c->last_launches += 2;
+  }
+  return VA_OK;
+}
+
+extern "C" int va_assemble_masks(va_ctx* c, const float* protos, const float* coefs, const float* boxes,
+                                 const int32_t* counts, int32_t B, uint8_t* masks_out, float* logits_out, void* stream) {
+  int rc = check_batch(c, B, protos, coefs, boxes, counts);
+  if (rc != VA_OK) return rc;
+  if (B == 0) return VA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  c->last_launches = 0;
+  rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, logits_out, st);
+  if (rc != VA_OK) return rc;
+  // masks-only call: the reductions are not consumed by a tail, reset them
+  VA_CUDA(c, launch_init_scratch(c->d, B, c->scratch.stats, c->scratch.lattice, st));
+  c->last_launches += 1;
+  return VA_OK;
+}
+
+extern "C" int va_run_fused(va_ctx* c, const float* protos, const float* coefs, const float* boxes,
+                            const int32_t* counts, int32_t B, uint8_t* masks_out, uint8_t* records_out, void* stream) {
+  int rc = check_batch(c, B, protos, coefs, boxes, counts);
+  if (rc != VA_OK) return rc;
+  if (!records_out) { set_err(c, "records_out is null"); return VA_ERR_INVALID; }
+  if (B == 0) return VA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  c->last_launches = 0;
+  rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, nullptr, st);
+  if (rc != VA_OK) return rc;
+  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, masks_out, nullptr, nullptr, records_out, st));
+  c->last_launches += 1;
+  return VA_OK;
+}
+
+extern "C" int va_mask_to_records(va_ctx* c, const uint8_t* masks, const int32_t* counts, int32_t B,
+                                  const int32_t* rects, const int32_t* sel, uint8_t* records_out, void* stream) {
+  if (!c) return VA_ERR_INVALID;
+  if (!masks || !counts || !records_out) { set_err(c, "null pointer"); return VA_ERR_INVALID; }
+  if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
+  if (B == 0) return VA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  c->last_launches = 0;
+  VA_CUDA(c, launch_mask_stats(c->d, masks, counts, B, c->scratch.stats, c->scratch.lattice, st));
+  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, masks, rects, sel, records_out, st));
+  c->last_launches = 2;
+  return VA_OK;
+}
+
+extern "C" int va_grid_to_penalty_peaks(va_ctx* c, const va_grid_input* hdr, const int32_t* row_y,
+                                        const int32_t* row_attr, const uint8_t* occ, const int32_t* plane_y,
+                                        const uint8_t* plane_occ, int32_t B, uint8_t* records_out, void* stream) {
+  if (!c) return VA_ERR_INVALID;
+  if (!hdr || !row_y || !row_attr || !occ || !records_out) { set_err(c, "null pointer"); return VA_ERR_INVALID; }
+  if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
+  if (B == 0) return VA_OK;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_CUDA(c, launch_grid_mode(c->d, hdr, row_y, row_attr, occ, plane_y, plane_occ, B, records_out, (cudaStream_t)stream));
+  c->last_launches = 1;
+  return VA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline
+// ---------------------------------------------------------------------------------------------
+static int host_pipeline_init(va_ctx* c) {
+  if (c->host_ready) return VA_OK;
+  const Dims& d = c->d;
+  const size_t P = (size_t)d.mh * d.mw;
+  const size_t fr_in = (size_t)d.K * P * 4;
+  int chunk = (int)((96u << 20) / fr_in);          // ~96 MB of prototypes per chunk
+  if (chunk < 1) chunk = 1;
+  if (chunk > c->cfg.max_batch) chunk = c->cfg.max_batch;
+  c->host_chunk = chunk;
+  VA_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  VA_CUDA(c, cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+  VA_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    VA_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    VA_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    VA_CUDA(c, cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    VA_CUDA(c, cudaMalloc(&c->d_protos[i], fr_in * chunk));
+    VA_CUDA(c, cudaMalloc(&c->d_coefs[i], (size_t)d.max_n * d.K * 4 * chunk));
+    VA_CUDA(c, cudaMalloc(&c->d_boxes[i], (size_t)d.max_n * 16 * chunk));
+    VA_CUDA(c, cudaMalloc(&c->d_counts[i], sizeof(int) * chunk));
+    VA_CUDA(c, cudaMalloc(&c->d_records[i], (size_t)d.record_bytes * chunk));
+    c->d_masks[i] = nullptr;
+  }
+  c->host_ready = true;
+  return VA_OK;
+}
+
+extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* h_coefs, const float* h_boxes,
+                                 const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out) {
+  int rc = check_batch(c, B, h_protos, h_coefs, h_boxes, h_counts);
+  if (rc != VA_OK) return rc;
+  if (!h_records_out) { set_err(c, "h_records_out is null"); return VA_ERR_INVALID; }
+  if (B == 0) return VA_OK;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  rc = host_pipeline_init(c);
+  if (rc != VA_OK) return rc;
+  const Dims& d = c->d;
+  const size_t P = (size_t)d.mh * d.mw;
+  const size_t fr_protos = (size_t)d.K * P, fr_coefs = (size_t)d.max_n * d.K, fr_boxes = (size_t)d.max_n * 4;
+  const size_t fr_masks = (size_t)d.max_n * d.H * d.W;
+  const int chunk = c->host_chunk;
+  if (h_masks_out) {
+    for (int i = 0; i < 2; ++i)
+      if (!c->d_masks[i]) VA_CUDA(c, cudaMalloc(&c->d_masks[i], fr_masks * chunk));
+  }
+  int launches = 0;
+  int k = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
+    const int nb = (B - b0 < chunk) ? B - b0 : chunk;
+    const int s = k & 1;
+    if (k >= 2) VA_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_done[s], 0));     // input slot consumed
+    VA_CUDA(c, cudaMemcpyAsync(c->d_protos[s], h_protos + b0 * fr_protos, fr_protos * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
+    VA_CUDA(c, cudaMemcpyAsync(c->d_coefs[s], h_coefs + b0 * fr_coefs, fr_coefs * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
+    VA_CUDA(c, cudaMemcpyAsync(c->d_boxes[s], h_boxes + b0 * fr_boxes, fr_boxes * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
+    VA_CUDA(c, cudaMemcpyAsync(c->d_counts[s], h_counts + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, c->s_in));
+    VA_CUDA(c, cudaEventRecord(c->ev_in[s], c->s_in));
+    VA_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_in[s], 0));
+    if (k >= 2) VA_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_out[s], 0)); // output slot drained
+    c->last_launches = 0;
+    rc = assemble(c, c->d_protos[s], c->d_coefs[s], c->d_boxes[s], c->d_counts[s], nb,
+                  h_masks_out ? c->d_masks[s] : nullptr, nullptr, c->s_compute);
+    if (rc != VA_OK) return rc;
+    VA_CUDA(c, launch_tail(d, c->d_counts[s], nb, c->scratch.stats, c->scratch.lattice,
+                           h_masks_out ? c->d_masks[s] : nullptr, nullptr, nullptr, c->d_records[s], c->s_compute));
+    launches += c->last_launches + 1;
+    VA_CUDA(c, cudaEventRecord(c->ev_done[s], c->s_compute));
+    VA_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_done[s], 0));
+    VA_CUDA(c, cudaMemcpyAsync(h_records_out + (size_t)b0 * d.record_bytes, c->d_records[s], (size_t)d.record_bytes * nb,
+                               cudaMemcpyDeviceToHost, c->s_out));
+    if (h_masks_out)
+      VA_CUDA(c, cudaMemcpyAsync(h_masks_out + b0 * fr_masks, c->d_masks[s], fr_masks * nb, cudaMemcpyDeviceToHost, c->s_out));
+    VA_CUDA(c, cudaEventRecord(c->ev_out[s], c->s_out));
+  }
+  VA_CUDA(c, cudaStreamSynchronize(c->s_out));
+  VA_CUDA(c, cudaStreamSynchronize(c->s_compute));
+  c->last_launches = launches;
+  return VA_OK;
+}

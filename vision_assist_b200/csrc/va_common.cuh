@@ -1,0 +1,83 @@
+// Shared definitions for the sm_100a kernels of libva_sm100.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vision_assist_b200.h"
+
+namespace va {
+
+constexpr int kMaxInst = 32;   // instance capacity (va_config.max_n upper bound)
+constexpr int kProtoK = 32;    // prototypes
+
+// Per-(frame, instance) reduction of the binary mask, produced by the mask kernels and consumed
+// (then reset to this state) by the tail kernel.
+struct InstStats {
+  unsigned int area;   // pixels set
+  int minx, miny;      // init INT_MAX
+  int maxx, maxy;      // init -1
+  int euler4;          // 4 * Euler number partial sums (optional)
+  int pad0, pad1;
+};
+static_assert(sizeof(InstStats) == 32, "InstStats is 32 B");
+
+// Everything a kernel needs to know about the problem geometry (passed by value).
+struct Dims {
+  int H, W, mh, mw, K, max_n, gs;
+  int lat_rows, lat_cols, lat_words;   // cell-centre lattice: point (gs*lx+gs/2, gs*ly+gs/2)
+  int plane_rows;                      // ceil(H/gs): rows of the grid_lookup plane
+  int rmax, cmax, pmax, cwords;        // record capacity; cwords = ceil(cmax/32)
+  int record_bytes, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ;
+  int band_start;                      // FrameProcessor.py:126-127 starting_y
+  int flags;                           // VA_CFG_*
+  float wr, hr;                        // fl32(mw/W), fl32(mh/H): box scale, ops.py:725-732
+  float sx, sy;                        // fl32(mw)/W, fl32(mh)/H: bilinear scales (ATen area_pixel_compute_scale)
+};
+
+struct Scratch {
+  InstStats* stats;        // [max_batch][max_n]
+  unsigned int* lattice;   // [max_batch][max_n][lat_rows][lat_words]
+  float* logits;           // [max_batch][max_n][mh][mw] (CUDA-core path only)
+};
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Python floor division for possibly negative numerators (b > 0).
+__host__ __device__ inline int floor_div(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers (one per translation unit)
+// ---------------------------------------------------------------------------------------------
+// CUDA-core contraction + crop: logits[b][i][mh][mw] (ops.py:724-734)
+cudaError_t launch_logits(const Dims& d, const float* protos, const float* coefs, const float* boxes,
+                          const int* counts, int B, float* logits, cudaStream_t st);
+// bilinear upsample + threshold (+ stats / lattice) from proto-resolution logits (ops.py:736-737)
+cudaError_t launch_upsample(const Dims& d, const float* logits, const int* counts, int B, uint8_t* masks,
+                            InstStats* stats, unsigned int* lattice, cudaStream_t st);
+// stats / lattice from caller-provided binary masks
+cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, InstStats* stats,
+                              unsigned int* lattice, cudaStream_t st);
+cudaError_t launch_init_scratch(const Dims& d, int max_batch, InstStats* stats, unsigned int* lattice,
+                                cudaStream_t st);
+// selection -> grid -> penalties -> peaks -> record; resets stats / lattice
+cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned int* lattice,
+                        const uint8_t* masks, const int* rects, const int* sel, uint8_t* records,
+                        cudaStream_t st);
+cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,
+                             const uint8_t* occ, const int* plane_y, const uint8_t* plane_occ, int B,
+                             uint8_t* records, cudaStream_t st);
+size_t tail_smem_bytes(const Dims& d);
+
+// tcgen05 / TMA fused kernel (va_fused_tc.cu)
+struct FusedPlan;  // opaque, owned by the context
+FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen);
+void fused_plan_destroy(FusedPlan* p);
+cudaError_t launch_fused(FusedPlan* p, const Dims& d, const float* protos, const float* coefs, const float* boxes,
+                         const int* counts, int B, uint8_t* masks, float* logits_dbg, InstStats* stats,
+                         unsigned int* lattice, cudaStream_t st, char* err, size_t errlen);
+
+}  // namespace va

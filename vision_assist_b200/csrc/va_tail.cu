@@ -1,0 +1,567 @@
+// Frame tail: instance selection -> occupancy grid -> penalty map -> top-edge peaks -> record.
+//
+// One CTA per frame.  Input is the per-instance reduction written by the mask kernels (pixel
+// area, pixel bbox, cell-centre lattice bits); nothing here touches the full-resolution mask
+// (except the optional Euler-number check).  Reference semantics reproduced bit-for-bit:
+//
+//   FrameProcessor._extract_grid_information   FrameProcessor.py:50-171   (bbox snap :79-83, centre
+//       sampling :88-97, artificial band :126-165 incl. the `row_idx < len-1 ? replace : append`
+//       duplicate-row / gap-compression / negative-index behaviour :162-165)
+//   PenaltyCalculator._pre_compute_easy_segments :26-55, _calculate_segment_penalty :57-110,
+//       calculate_penalty :112-142 (float64, the reference's operation order, no FMA contraction)
+//   ProtrusionDetector._create_binary_image / _find_peak / __call__  :38-158, :419-535 in the
+//       grid-level closed form (oracle/protrusion.py::peaks_closed_form)
+//
+// Rows are bit masks (32 columns per word): run extents along a row are clz/ffs operations, the
+// vertical walks read one broadcast word per step.
+#include <climits>
+#include <cmath>
+
+#include "va_common.cuh"
+
+namespace va {
+
+constexpr int kTailThreads = 128;
+
+struct TailSmem {
+  // "created rows" table: ids [0, 2*rmax)
+  int* row_y;        // [T]
+  int* row_attr;     // [T]
+  unsigned* occ;     // [T][cwords]
+  unsigned* art;     // [T][cwords]
+  int* list_ids;     // [rmax]   FrameProcessor.grids (list order) -> created id
+  int* plane_owner;  // [PL]     grid_lookup row y/gs -> created id, -1 = no such row
+  int* erow_first;   // [rmax]   easy_rows[k]: first / last column, first = -1 when not easy
+  int* erow_last;    // [rmax]
+  int* ecol_first;   // [cmax]   easy_cols[c]: first / last LIST index
+  int* ecol_last;    // [cmax]
+  int* orphan_ids;   // [rmax]
+  int* sc;           // scalars, see enum
+};
+enum { S_FLAGS, S_SEL, S_X0, S_Y0, S_C, S_R, S_NORPH, S_NPEAKS, S_AREA, S_RM, S_MINX, S_MINY, S_MAXX, S_MAXY,
+       S_EULER, S_NCREATED, S_USE_EASY, S_COUNT };
+
+__host__ __device__ inline int plane_cap(const Dims& d) { return 2 * d.rmax; }
+
+__host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, unsigned char* base) {
+  const int T = 2 * d.rmax, PL = plane_cap(d);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
+  const size_t o_y = take(sizeof(int) * T), o_a = take(sizeof(int) * T);
+  const size_t o_occ = take(sizeof(unsigned) * T * d.cwords), o_art = take(sizeof(unsigned) * T * d.cwords);
+  const size_t o_l = take(sizeof(int) * d.rmax), o_p = take(sizeof(int) * PL);
+  const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * d.rmax);
+  const size_t o_cf = take(sizeof(int) * d.cmax), o_cl = take(sizeof(int) * d.cmax);
+  const size_t o_or = take(sizeof(int) * d.rmax), o_sc = take(sizeof(int) * S_COUNT);
+  if (s) {
+    s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a);
+    s->occ = (unsigned*)(base + o_occ); s->art = (unsigned*)(base + o_art);
+    s->list_ids = (int*)(base + o_l); s->plane_owner = (int*)(base + o_p);
+    s->erow_first = (int*)(base + o_ef); s->erow_last = (int*)(base + o_el);
+    s->ecol_first = (int*)(base + o_cf); s->ecol_last = (int*)(base + o_cl);
+    s->orphan_ids = (int*)(base + o_or); s->sc = (int*)(base + o_sc);
+  }
+  return o;
+}
+
+size_t tail_smem_bytes(const Dims& d) { return tail_smem_layout(d, nullptr, nullptr); }
+
+__device__ __forceinline__ bool bit_at(const unsigned* row, int c) { return (row[c >> 5] >> (c & 31)) & 1u; }
+
+// first column of the run of set bits that contains c (bit c itself is not tested)
+__device__ __forceinline__ int run_left(const unsigned* row, int c) {
+  int w = c >> 5;
+  // zeros strictly below c in word w
+  unsigned z = ~row[w] & ((c & 31) ? (0xffffffffu >> (32 - (c & 31))) : 0u);
+  while (true) {
+    if (z) return (w << 5) + (32 - __clz(z));
+    if (w == 0) return 0;
+    --w;
+    z = ~row[w];
+  }
+}
+// last column of the run of set bits that contains c; C = number of columns (bits >= C are 0)
+__device__ __forceinline__ int run_right(const unsigned* row, int c, int C) {
+  int w = c >> 5;
+  const int nw = (C + 31) >> 5;
+  unsigned z = ~row[w] & (((c & 31) == 31) ? 0u : (0xffffffffu << ((c & 31) + 1)));
+  while (true) {
+    if (z) return min((w << 5) + (__ffs(z) - 1) - 1, C - 1);
+    if (w == nw - 1) return C - 1;
+    ++w;
+    z = ~row[w];
+  }
+}
+
+__device__ __forceinline__ double seg_penalty(int pos, int lo, int hi) {
+  // PenaltyCalculator.py:98-110
+  const int den = hi - lo;
+  const double ratio = (den == 0) ? 0.5 : __ddiv_rn((double)(pos - lo), (double)den);
+  return __dmul_rn(2.0, fabs(__dsub_rn(ratio, 0.5)));
+}
+
+__device__ __forceinline__ double blend_penalty(double rp, double cp) {
+  // PenaltyCalculator.py:127-142
+  if (rp > 0.99 || cp > 0.99) return 1.0;
+  const double tot = __dadd_rn(rp, cp);
+  if (tot == 0.0) return 0.0;
+  const double dom = __ddiv_rn(fabs(__dsub_rn(rp, cp)), tot);
+  const double rw = __dadd_rn(0.5, (rp > cp) ? __dmul_rn(0.25, dom) : __dmul_rn(-0.25, dom));
+  const double cw = __dsub_rn(1.0, rw);
+  return __dadd_rn(__dmul_rn(rp, rw), __dmul_rn(cp, cw));
+}
+
+// ---------------------------------------------------------------------------------------------
+// phases shared by the mask-driven and the grid-mode kernels (list / plane already in smem)
+// ---------------------------------------------------------------------------------------------
+__device__ void easy_segments(const Dims& d, const TailSmem& s) {
+  const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords;
+  const bool use = s.sc[S_USE_EASY] != 0;
+  for (int k = threadIdx.x; k < d.rmax; k += kTailThreads) {
+    int first = -1, last = -1, cnt = 0;
+    if (use && k < R) {
+      const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
+      for (int w = 0; w < cw; ++w) {
+        const unsigned v = row[w];
+        if (v) {
+          if (first < 0) first = (w << 5) + __ffs(v) - 1;
+          last = (w << 5) + 31 - __clz(v);
+          cnt += __popc(v);
+        }
+      }
+      if (!(cnt > 0 && last - first == cnt - 1)) first = -1;
+    }
+    s.erow_first[k] = first;
+    s.erow_last[k] = last;
+  }
+  for (int c = threadIdx.x; c < d.cmax; c += kTailThreads) {
+    int first = -1, last = -1, cnt = 0;
+    if (use && c < C) {
+      for (int k = 0; k < R; ++k) {
+        if (bit_at(s.occ + (size_t)s.list_ids[k] * cw, c)) {
+          if (first < 0) first = k;
+          last = k;
+          ++cnt;
+        }
+      }
+      if (!(cnt > 0 && last - first == cnt - 1)) first = -1;
+    }
+    s.ecol_first[c] = first;
+    s.ecol_last[c] = last;
+  }
+}
+
+__device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
+  const int norph = s.sc[S_NORPH];
+  const int PL = plane_cap(d);
+  double* pen = reinterpret_cast<double*>(rec + d.off_penalty);
+  uint8_t* occ_out = rec + d.off_occ;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int cells = d.rmax * d.cmax;
+  for (int t = threadIdx.x; t < cells; t += kTailThreads) {
+    const int k = t / d.cmax, c = t - k * d.cmax;
+    double p = qnan;
+    uint8_t ob = 0;
+    if (k < R + norph && c < C) {
+      const int id = (k < R) ? s.list_ids[k] : s.orphan_ids[k - R];
+      const unsigned* own = s.occ + (size_t)id * cw;
+      const bool filled = bit_at(own, c);
+      ob = (filled ? 1 : 0) | (bit_at(s.art + (size_t)id * cw, c) ? 2 : 0);
+      if (filled && k < R) {
+        const int y = s.row_y[id], attr = s.row_attr[id], x = x0 + c * gs;
+        const int ly = y / gs;
+        // ---- row direction (PenaltyCalculator.py:68-69, else :73-95 on grid_lookup) ----
+        int lo, hi;
+        if (attr >= 0 && attr < R && s.erow_first[attr] >= 0) {
+          lo = x0 + s.erow_first[attr] * gs;
+          hi = x0 + s.erow_last[attr] * gs;
+        } else {
+          const unsigned* prow = s.occ + (size_t)s.plane_owner[ly] * cw;
+          lo = x0 + run_left(prow, c) * gs;
+          hi = x0 + run_right(prow, c, C) * gs;
+        }
+        const double rp = seg_penalty(x, lo, hi);
+        // ---- column direction ----
+        if (s.ecol_first[c] >= 0) {
+          lo = s.row_y[s.list_ids[s.ecol_first[c]]];
+          hi = s.row_y[s.list_ids[s.ecol_last[c]]];
+        } else {
+          int a = ly, b = ly;
+          while (a - 1 >= 0 && s.plane_owner[a - 1] >= 0 && bit_at(s.occ + (size_t)s.plane_owner[a - 1] * cw, c)) --a;
+          while (b + 1 < PL && s.plane_owner[b + 1] >= 0 && bit_at(s.occ + (size_t)s.plane_owner[b + 1] * cw, c)) ++b;
+          lo = a * gs;
+          hi = b * gs;
+        }
+        const double cp = seg_penalty(y, lo, hi);
+        p = blend_penalty(rp, cp);
+      }
+    }
+    pen[t] = p;
+    occ_out[t] = ob;
+  }
+  int* ry = reinterpret_cast<int*>(rec + d.off_row_y);
+  int* ra = reinterpret_cast<int*>(rec + d.off_row_attr);
+  for (int k = threadIdx.x; k < d.rmax; k += kTailThreads) {
+    int y = 0, a = 0;
+    if (k < R + norph) {
+      const int id = (k < R) ? s.list_ids[k] : s.orphan_ids[k - R];
+      y = s.row_y[id];
+      a = s.row_attr[id];
+    }
+    ry[k] = y;
+    ra[k] = a;
+  }
+}
+
+// ProtrusionDetector closed form; one thread (C <= a few hundred bits).
+__device__ void find_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  int* peaks = reinterpret_cast<int*>(rec + d.off_peaks);
+  const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
+  int ytop = INT_MAX;
+  for (int k = 0; k < R; ++k) {
+    const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
+    bool any = false;
+    for (int w = 0; w < cw; ++w) any |= (row[w] != 0);
+    if (any) ytop = min(ytop, s.row_y[s.list_ids[k]]);
+  }
+  int np = 0;
+  if (ytop != INT_MAX) {
+    int c = 0;
+    while (c < C) {
+      bool on = false;
+      for (int k = 0; k < R && !on; ++k)
+        if (s.row_y[s.list_ids[k]] == ytop) on = bit_at(s.occ + (size_t)s.list_ids[k] * cw, c);
+      if (!on) { ++c; continue; }
+      int c1 = c;
+      while (c1 + 1 < C) {
+        bool on1 = false;
+        for (int k = 0; k < R && !on1; ++k)
+          if (s.row_y[s.list_ids[k]] == ytop) on1 = bit_at(s.occ + (size_t)s.list_ids[k] * cw, c1 + 1);
+        if (!on1) break;
+        ++c1;
+      }
+      const int xa = x0 + c * gs;
+      const int xb = min(x0 + c1 * gs + gs, d.W - 1);
+      if (np < d.pmax) {
+        peaks[2 * np] = xa + (xb - xa + 1) / 2;
+        peaks[2 * np + 1] = ytop;
+      }
+      ++np;
+      c = c1 + 1;
+    }
+  }
+  if (np > d.pmax) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW; np = d.pmax; }
+  for (int q = np; q < d.pmax; ++q) { peaks[2 * q] = 0; peaks[2 * q + 1] = 0; }
+  s.sc[S_NPEAKS] = np;
+}
+
+__device__ void write_header(const TailSmem& s, uint8_t* rec) {
+  va_frame_header h;
+  h.flags = s.sc[S_FLAGS]; h.sel = s.sc[S_SEL]; h.x0 = s.sc[S_X0]; h.y0 = s.sc[S_Y0];
+  h.n_cols = s.sc[S_C]; h.n_rows = s.sc[S_R]; h.n_orphans = s.sc[S_NORPH]; h.n_peaks = s.sc[S_NPEAKS];
+  h.area = s.sc[S_AREA]; h.n_mask_rows = s.sc[S_RM];
+  h.minx = s.sc[S_MINX]; h.miny = s.sc[S_MINY]; h.maxx = s.sc[S_MAXX]; h.maxy = s.sc[S_MAXY];
+  h.euler = s.sc[S_EULER]; h.reserved = 0;
+  *reinterpret_cast<va_frame_header*>(rec) = h;
+}
+
+// list rows no longer in the list but still owning their grid_lookup row
+__device__ void collect_orphans(const Dims& d, const TailSmem& s) {
+  const int R = s.sc[S_R], n = s.sc[S_NCREATED];
+  int no = 0;
+  for (int id = 0; id < n; ++id) {
+    bool in_list = false;
+    for (int k = 0; k < R && !in_list; ++k) in_list = (s.list_ids[k] == id);
+    if (in_list) continue;
+    const int ly = s.row_y[id] / d.gs;
+    if (ly >= 0 && ly < plane_cap(d) && s.plane_owner[ly] == id && R + no < d.rmax) s.orphan_ids[no++] = id;
+  }
+  s.sc[S_NORPH] = no;
+}
+
+__device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  // common tail once list / plane / scalars are in shared memory
+  __syncthreads();
+  if (s.sc[S_FLAGS] & (VA_FLAG_EMPTY | VA_FLAG_CENTRE_OOB | VA_FLAG_LIST_OOB)) {
+    if (threadIdx.x == 0) { s.sc[S_R] = 0; s.sc[S_C] = 0; s.sc[S_NORPH] = 0; s.sc[S_NPEAKS] = 0; s.sc[S_FLAGS] |= VA_FLAG_EMPTY; }
+    __syncthreads();
+  } else {
+    if (threadIdx.x == 0) collect_orphans(d, s);
+    easy_segments(d, s);
+    __syncthreads();
+  }
+  penalties_and_record(d, s, rec);
+  if (threadIdx.x == 0) {
+    find_peaks(d, s, rec);
+    write_header(s, rec);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask-driven tail
+// ---------------------------------------------------------------------------------------------
+__device__ int euler_number(const Dims& d, const uint8_t* m) {
+  // 8-connectivity Euler number by bit-quad counting (Gray): (Q1 - Q3 - 2*QD) / 4 over the
+  // zero-padded image.
+  int acc = 0;
+  const int total = (d.H + 1) * (d.W + 1);
+  for (int t = threadIdx.x; t < total; t += kTailThreads) {
+    const int y = t / (d.W + 1) - 1, x = t % (d.W + 1) - 1;
+    const int a = (y >= 0 && x >= 0) ? (m[(size_t)y * d.W + x] != 0) : 0;
+    const int b = (y >= 0 && x + 1 < d.W) ? (m[(size_t)y * d.W + x + 1] != 0) : 0;
+    const int c = (y + 1 < d.H && x >= 0) ? (m[(size_t)(y + 1) * d.W + x] != 0) : 0;
+    const int e = (y + 1 < d.H && x + 1 < d.W) ? (m[(size_t)(y + 1) * d.W + x + 1] != 0) : 0;
+    const int sum = a + b + c + e;
+    if (sum == 1) acc += 1;
+    else if (sum == 3) acc -= 1;
+    else if (sum == 2 && a == e) acc -= 2;
+  }
+  __shared__ int s_red;
+  if (threadIdx.x == 0) s_red = 0;
+  __syncthreads();
+  atomicAdd(&s_red, acc);
+  __syncthreads();
+  return s_red / 4;
+}
+
+__global__ void __launch_bounds__(kTailThreads)
+tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stats, unsigned* __restrict__ lattice,
+            const uint8_t* __restrict__ masks, const int* __restrict__ rects, const int* __restrict__ sel_in,
+            uint8_t* __restrict__ records) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TailSmem s;
+  tail_smem_layout(d, &s, smem_raw);
+  const int b = blockIdx.x;
+  uint8_t* rec = records + (size_t)b * d.record_bytes;
+  InstStats* st = stats + (size_t)b * d.max_n;
+  const int n = min(counts[b], d.max_n);
+  const int gs = d.gs, cw = d.cwords;
+  const int T = 2 * d.rmax, PL = plane_cap(d);
+
+  for (int t = threadIdx.x; t < PL; t += kTailThreads) s.plane_owner[t] = -1;
+  for (int t = threadIdx.x; t < T * cw; t += kTailThreads) { s.occ[t] = 0; s.art[t] = 0; }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
+    s.sc[S_USE_EASY] = 1;
+    // ---- instance selection: largest pixel area, first maximum (FrameProcessor.py:71-73 uses
+    //      cv2.contourArea of the polygon; see DESIGN.md "selection") ----
+    int sel = -1;
+    unsigned best = 0;
+    if (sel_in) {
+      sel = sel_in[b];
+      if (sel < 0 || sel >= n) sel = -1; else best = st[sel].area;
+    } else {
+      for (int i = 0; i < n; ++i) if (st[i].area > best) { best = st[i].area; sel = i; }
+      if (sel < 0 && n > 0) sel = 0;
+    }
+    s.sc[S_SEL] = sel;
+    s.sc[S_AREA] = (int)best;
+    int flags = 0;
+    if (sel < 0 || best == 0) {
+      flags = VA_FLAG_EMPTY;
+    } else {
+      int x, y, w, h;
+      if (rects) { x = rects[4 * b]; y = rects[4 * b + 1]; w = rects[4 * b + 2]; h = rects[4 * b + 3]; }
+      else { x = st[sel].minx; y = st[sel].miny; w = st[sel].maxx - x + 1; h = st[sel].maxy - y + 1; }
+      s.sc[S_MINX] = x; s.sc[S_MINY] = y; s.sc[S_MAXX] = x + w - 1; s.sc[S_MAXY] = y + h - 1;
+      x -= x % gs;                                   // FrameProcessor.py:79
+      y -= y % gs;                                   // :80
+      if (w % gs != 0) w += gs - w % gs;             // :81
+      if (w > d.W) w = d.W;                          // :82
+      if (h % gs != 0) h += gs - h % gs;             // :83
+      const int C = ceil_div(w, gs), Rm = ceil_div(h, gs);   // len(arange(x, x+w, gs))
+      s.sc[S_X0] = x; s.sc[S_Y0] = y; s.sc[S_C] = C; s.sc[S_RM] = Rm;
+      if (C <= 0 || Rm <= 0) flags = VA_FLAG_EMPTY;
+      else if (y + (Rm - 1) * gs + gs / 2 >= d.H || x + (C - 1) * gs + gs / 2 >= d.W) flags = VA_FLAG_CENTRE_OOB;  // :97
+      else if (C > d.cmax || Rm > d.rmax) flags = VA_FLAG_OVERFLOW | VA_FLAG_EMPTY;
+    }
+    s.sc[S_FLAGS] = flags;
+  }
+  __syncthreads();
+
+  const int sel = s.sc[S_SEL];
+  if (!(s.sc[S_FLAGS] & (VA_FLAG_EMPTY | VA_FLAG_CENTRE_OOB))) {
+    // ---- centre sampling (FrameProcessor.py:88-97): shift the lattice rows of the selected
+    //      instance so that column 0 is x0 ----
+    const int C = s.sc[S_C], Rm = s.sc[S_RM];
+    const int lx0 = s.sc[S_X0] / gs, ly0 = s.sc[S_Y0] / gs;
+    const unsigned* lat = lattice + ((size_t)b * d.max_n + sel) * d.lat_rows * d.lat_words;
+    int any = 0;
+    for (int t = threadIdx.x; t < Rm * cw; t += kTailThreads) {
+      const int r = t / cw, w = t - r * cw;
+      const unsigned* lrow = lat + (size_t)(ly0 + r) * d.lat_words;
+      const int bitpos = lx0 + 32 * w;
+      const int wi = bitpos >> 5, sh = bitpos & 31;
+      const unsigned lo = (wi < d.lat_words) ? lrow[wi] : 0u;
+      const unsigned hi = (wi + 1 < d.lat_words) ? lrow[wi + 1] : 0u;
+      unsigned v = __funnelshift_r(lo, hi, sh);
+      const int rem = C - 32 * w;
+      if (rem < 32) v &= (rem <= 0) ? 0u : (0xffffffffu >> (32 - rem));
+      s.occ[(size_t)r * cw + w] = v;
+      any |= (v != 0);
+    }
+    for (int r = threadIdx.x; r < Rm; r += kTailThreads) {
+      s.row_y[r] = s.sc[S_Y0] + r * gs;
+      s.row_attr[r] = r;
+      s.list_ids[r] = r;
+      s.plane_owner[ly0 + r] = r;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) {
+      if (!any) {
+        s.sc[S_FLAGS] |= VA_FLAG_EMPTY;              // FrameProcessor.py:99-101
+      } else {
+        // ---- artificial band (FrameProcessor.py:126-165), replayed literally ----
+        int list_len = Rm, ncreated = Rm;
+        const int base = d.W / 2 - 8 * gs;
+        for (int i = d.band_start; i < d.H; i += gs) {
+          const int ly = i / gs;
+          const int row_idx = floor_div(i - s.sc[S_Y0], gs);
+          if (ncreated >= T || ly >= PL) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW; break; }
+          const int id = ncreated++;
+          const int prev = s.plane_owner[ly];
+          for (int w = 0; w < cw; ++w) {
+            unsigned am = 0;
+            for (int q = 0; q < 32; ++q) {
+              const int c = 32 * w + q;
+              if (c >= C) break;
+              const int delta = s.sc[S_X0] + c * gs - base;
+              if (delta >= 0 && delta % gs == 0 && delta / gs <= 16) am |= 1u << q;
+            }
+            const unsigned pv = (prev >= 0) ? s.occ[(size_t)prev * cw + w] : 0u;
+            s.occ[(size_t)id * cw + w] = pv | am;
+            s.art[(size_t)id * cw + w] = ~pv & am;
+          }
+          s.row_y[id] = i;
+          s.row_attr[id] = row_idx;
+          s.plane_owner[ly] = id;
+          if (row_idx < list_len - 1) {
+            int idx = row_idx;
+            if (idx < 0) idx += list_len;
+            if (idx < 0) { s.sc[S_FLAGS] |= VA_FLAG_LIST_OOB; break; }     // IndexError, :163
+            s.list_ids[idx] = id;
+          } else {
+            if (list_len >= d.rmax) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW; break; }
+            s.list_ids[list_len++] = id;
+          }
+        }
+        s.sc[S_R] = list_len;
+        s.sc[S_NCREATED] = ncreated;
+      }
+    }
+  }
+  __syncthreads();
+  if ((d.flags & VA_CFG_CHECK_SIMPLE) && masks && sel >= 0 && s.sc[S_AREA] > 0) {
+    const int e = euler_number(d, masks + ((size_t)b * d.max_n + sel) * (size_t)d.H * d.W);
+    if (threadIdx.x == 0) {
+      s.sc[S_EULER] = e;
+      if (e != 1) s.sc[S_FLAGS] |= VA_FLAG_NON_SIMPLE;
+    }
+  }
+  finish_record(d, s, rec);
+
+  // ---- reset the reduction scratch for the next call ----
+  __syncthreads();
+  for (int i = threadIdx.x; i < d.max_n; i += kTailThreads) {
+    InstStats z;
+    z.area = 0; z.minx = INT_MAX; z.miny = INT_MAX; z.maxx = -1; z.maxy = -1; z.euler4 = 0; z.pad0 = 0; z.pad1 = 0;
+    st[i] = z;
+  }
+  unsigned* latb = lattice + (size_t)b * d.max_n * d.lat_rows * d.lat_words;
+  for (int t = threadIdx.x; t < d.max_n * d.lat_rows * d.lat_words; t += kTailThreads) latb[t] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid mode: list rows (+ optional lookup rows) given by the caller
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTailThreads)
+grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __restrict__ row_y,
+                 const int* __restrict__ row_attr, const uint8_t* __restrict__ occ, const int* __restrict__ plane_y,
+                 const uint8_t* __restrict__ plane_occ, uint8_t* __restrict__ records) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TailSmem s;
+  tail_smem_layout(d, &s, smem_raw);
+  const int b = blockIdx.x;
+  uint8_t* rec = records + (size_t)b * d.record_bytes;
+  const va_grid_input h = hdr[b];
+  const int cw = d.cwords, T = 2 * d.rmax, PL = plane_cap(d), gs = d.gs;
+  const int R = min(max(h.n_rows, 0), d.rmax), C = min(max(h.n_cols, 0), d.cmax);
+  const int NP = (plane_y && plane_occ) ? min(max(h.n_plane, 0), d.rmax) : 0;
+
+  for (int t = threadIdx.x; t < PL; t += kTailThreads) s.plane_owner[t] = -1;
+  for (int t = threadIdx.x; t < T * cw; t += kTailThreads) { s.occ[t] = 0; s.art[t] = 0; }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
+    s.sc[S_USE_EASY] = h.use_easy;
+    s.sc[S_SEL] = -1;
+    s.sc[S_X0] = h.x0; s.sc[S_C] = C; s.sc[S_R] = R; s.sc[S_RM] = R;
+    s.sc[S_NCREATED] = R + NP;
+    int flags = (R == 0 || C == 0) ? VA_FLAG_EMPTY : 0;
+    if (h.n_rows > d.rmax || h.n_cols > d.cmax || h.n_plane > d.rmax) flags |= VA_FLAG_OVERFLOW | VA_FLAG_EMPTY;
+    s.sc[S_FLAGS] = flags;
+  }
+  __syncthreads();
+  // bit-pack rows: one thread per (row, word)
+  for (int t = threadIdx.x; t < (R + NP) * cw; t += kTailThreads) {
+    const int id = t / cw, w = t - id * cw;
+    const uint8_t* src = (id < R) ? occ + ((size_t)b * d.rmax + id) * d.cmax
+                                  : plane_occ + ((size_t)b * d.rmax + (id - R)) * d.cmax;
+    unsigned vo = 0, va_ = 0;
+    for (int q = 0; q < 32; ++q) {
+      const int c = 32 * w + q;
+      if (c >= C) break;
+      const uint8_t v = src[c];
+      vo |= (unsigned)(v & 1u) << q;
+      va_ |= (unsigned)((v >> 1) & 1u) << q;
+    }
+    s.occ[t] = vo;
+    s.art[t] = va_;
+  }
+  for (int id = threadIdx.x; id < R + NP; id += kTailThreads) {
+    s.row_y[id] = (id < R) ? row_y[(size_t)b * d.rmax + id] : plane_y[(size_t)b * d.rmax + (id - R)];
+    s.row_attr[id] = (id < R) ? row_attr[(size_t)b * d.rmax + id] : -1;
+    if (id < R) s.list_ids[id] = id;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // grid_lookup rows: explicit plane rows, else the list rows in order (later rows override)
+    const int lo = NP ? R : 0, hi = NP ? R + NP : R;
+    for (int id = lo; id < hi; ++id) {
+      const int y = s.row_y[id];
+      if (y < 0 || y % gs != 0 || y / gs >= PL) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW | VA_FLAG_EMPTY; break; }
+      s.plane_owner[y / gs] = id;
+    }
+    for (int id = 0; id < R && NP; ++id) {   // every list row must have a lookup row
+      const int y = s.row_y[id];
+      if (y < 0 || y % gs != 0 || y / gs >= PL || s.plane_owner[y / gs] < 0) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW | VA_FLAG_EMPTY; break; }
+    }
+  }
+  finish_record(d, s, rec);
+}
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice,
+                        const uint8_t* masks, const int* rects, const int* sel, uint8_t* records, cudaStream_t st) {
+  const size_t smem = tail_smem_bytes(d);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  tail_kernel<<<B, kTailThreads, smem, st>>>(d, counts, stats, lattice, masks, rects, sel, records);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,
+                             const uint8_t* occ, const int* plane_y, const uint8_t* plane_occ, int B,
+                             uint8_t* records, cudaStream_t st) {
+  const size_t smem = tail_smem_bytes(d);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(grid_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  grid_mode_kernel<<<B, kTailThreads, smem, st>>>(d, hdr, row_y, row_attr, occ, plane_y, plane_occ, records);
+  return cudaGetLastError();
+}
+
+}  // namespace va

@@ -1,0 +1,408 @@
+// Bilinear upsample (align_corners=False) of cropped proto-resolution logits to frame resolution,
+// threshold > 0, u8 mask store, and the per-instance reductions the grid stage needs
+// (pixel area, pixel bbox, cell-centre lattice samples).
+//
+// Follows ops.process_mask lines :736-737 (F.interpolate bilinear + gt_(0.0)); the 4-tap blend is
+// implemented with exactly the roundings torch's CPU kernel performs (oracle/mask_assembly.py
+// `bilinear_upsample_np`):   top = fma(a, l0x, fl(b*l1x)) ; out = fma(top, l0y, fl(bot*l1y))
+// and the source index  src = max(fma(scale, dst+0.5, -0.5), 0).
+//
+// Two kernels: an exact-4x specialisation (H = 4*mh, W = 4*mw: every YOLOv8-seg head at its native
+// input size) whose weights are the constants {.125,.375,.625,.875}, and a generic-scale kernel.
+// Both are HBM-store bound: n*H*W bytes out per frame, logits re-read from L2.
+#include <climits>
+
+#include "va_common.cuh"
+
+namespace va {
+
+// ---------------------------------------------------------------------------------------------
+// shared helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pack4(float a, float b, float c, float d) {
+  return (a > 0.f ? 1u : 0u) | (b > 0.f ? 0x100u : 0u) | (c > 0.f ? 0x10000u : 0u) | (d > 0.f ? 0x1000000u : 0u);
+}
+
+struct ThreadStats {
+  unsigned acc = 0;                 // four byte-lane counters (<= 255 rows*words per lane between flushes)
+  unsigned area = 0;
+  unsigned orw[4] = {0, 0, 0, 0};   // OR of all rows' mask words (x extent)
+  int miny = INT_MAX, maxy = -1;
+  // rows must be added in increasing Y; at most 63 rows between flush() calls
+  __device__ __forceinline__ void add_row(const uint4& w, int Y) {
+    const unsigned any = w.x | w.y | w.z | w.w;
+    if (any) {
+      acc += (w.x + w.y) + (w.z + w.w);
+      orw[0] |= w.x; orw[1] |= w.y; orw[2] |= w.z; orw[3] |= w.w;
+      if (miny == INT_MAX) miny = Y;
+      maxy = Y;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    area += (acc & 0xffu) + ((acc >> 8) & 0xffu) + ((acc >> 16) & 0xffu) + (acc >> 24);
+    acc = 0;
+  }
+};
+
+// Reduce over the warp (all lanes belong to the same (frame, instance)) and publish with atomics.
+__device__ __forceinline__ void publish_stats(const ThreadStats& t, int xbase, InstStats* dst) {
+  int minx = INT_MAX, maxx = -1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (t.orw[q]) {
+      const int lo = (__ffs(t.orw[q]) - 1) >> 3, hi = (31 - __clz(t.orw[q])) >> 3;
+      minx = min(minx, xbase + 4 * q + lo);
+      maxx = max(maxx, xbase + 4 * q + hi);
+    }
+  }
+  unsigned area = t.area + (t.acc & 0xffu) + ((t.acc >> 8) & 0xffu) + ((t.acc >> 16) & 0xffu) + (t.acc >> 24);
+  int miny = t.miny, maxy = t.maxy;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    area += __shfl_xor_sync(0xffffffffu, area, o);
+    minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+    miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+    maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+    maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+  }
+  if ((threadIdx.x & 31) == 0 && area) {
+    atomicAdd(&dst->area, area);
+    atomicMin(&dst->minx, minx);
+    atomicMin(&dst->miny, miny);
+    atomicMax(&dst->maxx, maxx);
+    atomicMax(&dst->maxy, maxy);
+  }
+}
+
+// Sample the cell-centre lattice points that fall into this thread's 16 pixels of row Y.
+__device__ __forceinline__ void lattice_row(const uint4& w, int Y, int xbase, const Dims& d, unsigned* lat) {
+  const int half = d.gs >> 1;
+  const int ly = (Y - half) / d.gs;
+  const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+  int lx = (xbase - half + d.gs - 1) / d.gs;
+  if (lx < 0) lx = 0;
+  for (; lx < d.lat_cols; ++lx) {
+    const int pos = d.gs * lx + half - xbase;
+    if (pos > 15) break;
+    if ((ww[pos >> 2] >> (8 * (pos & 3))) & 1u) atomicOr(&lat[ly * d.lat_words + (lx >> 5)], 1u << (lx & 31));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact 4x kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kStrip = 8;           // proto row pairs per thread
+constexpr int kUpThreads = 128;
+
+// horizontal pass for one proto row: 6 source values (cols 4g-1 .. 4g+4, clamped) -> 16 outputs
+__device__ __forceinline__ void hinterp4(const float (&s)[6], float (&h)[16], bool left_edge) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = s[k], b = s[k + 1], c = s[k + 2];
+    h[4 * k + 0] = fmaf(a, 0.375f, __fmul_rn(b, 0.625f));
+    h[4 * k + 1] = fmaf(a, 0.125f, __fmul_rn(b, 0.875f));
+    h[4 * k + 2] = fmaf(b, 0.875f, __fmul_rn(c, 0.125f));
+    h[4 * k + 3] = fmaf(b, 0.625f, __fmul_rn(c, 0.375f));
+  }
+  if (left_edge) {   // dst x = 0,1: src clamps to 0 -> l0 = 1, l1 = 0 -> a + b*0 = a
+    h[0] = fmaf(s[1], 1.0f, __fmul_rn(s[2], 0.0f));
+    h[1] = h[0];
+  }
+}
+
+__device__ __forceinline__ void load6(const float* __restrict__ row, int g, int mw, float (&s)[6], float& mn, float& mx) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(row + 4 * g));
+  s[1] = v.x; s[2] = v.y; s[3] = v.z; s[4] = v.w;
+  s[0] = (g > 0) ? __ldg(row + 4 * g - 1) : v.x;
+  s[5] = (4 * g + 4 < mw) ? __ldg(row + 4 * g + 4) : v.w;
+  mn = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(s[4], s[5]));
+  mx = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), fmaxf(s[4], s[5]));
+}
+
+struct RowState {
+  float s[6];
+  float h[16];
+  float mn, mx;
+  bool hvalid;
+};
+
+__device__ __forceinline__ uint4 vblend(const float (&hA)[16], const float (&hB)[16], float l0, float l1) {
+  float o[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) o[x] = fmaf(hA[x], l0, __fmul_rn(hB[x], l1));
+  return make_uint4(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]), pack4(o[8], o[9], o[10], o[11]),
+                    pack4(o[12], o[13], o[14], o[15]));
+}
+
+constexpr float kTiny = 1e-30f;   // below this a positive product could underflow: take the exact path
+
+template <bool kWriteMasks>
+__global__ void __launch_bounds__(kUpThreads, 3)
+upsample4x_kernel(Dims d, const float* __restrict__ logits, const int* __restrict__ counts, uint8_t* __restrict__ masks,
+                  InstStats* __restrict__ stats, unsigned* __restrict__ lattice) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  if (i >= min(counts[b], d.max_n)) return;
+  const int NG = d.W >> 4;                        // 16-px groups per row
+  const int NG8 = ceil_div(NG, 8);
+  const int NS4 = ceil_div(d.mh, 4 * kStrip);
+  const int wt = blockIdx.x * (kUpThreads / 32) + (threadIdx.x >> 5);
+  if (wt >= NG8 * NS4) return;
+  const int lane = threadIdx.x & 31;
+  const int g = (wt % NG8) * 8 + (lane & 7);
+  const int strip = (wt / NG8) * 4 + (lane >> 3);
+  const int r_begin = strip * kStrip;
+  const int r_end = min(r_begin + kStrip, d.mh);
+  const bool active = (g < NG) && (r_begin < d.mh);
+
+  const size_t inst = (size_t)b * d.max_n + i;
+  const float* L = logits + inst * d.mh * d.mw;
+  uint8_t* M = kWriteMasks ? masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
+  unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
+  const int half = d.gs >> 1;
+  ThreadStats ts;
+
+  if (active) {
+    const bool left = (g == 0);
+    RowState A, Bq;
+    load6(L + (size_t)r_begin * d.mw, g, d.mw, A.s, A.mn, A.mx);
+    A.hvalid = false;
+
+    // rows are emitted in increasing Y: keep the next cell-centre row instead of a modulo per row
+    const int Yfirst = (r_begin == 0) ? 0 : 4 * r_begin + 2;
+    int next_lat = (Yfirst <= half) ? half : half + ceil_div(Yfirst - half, d.gs) * d.gs;
+    auto emit = [&](const uint4& w, int Y) {
+      if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
+      ts.add_row(w, Y);
+      if (Y == next_lat) {
+        next_lat += d.gs;
+        if (w.x | w.y | w.z | w.w) lattice_row(w, Y, 16 * g, d, lat);
+      }
+    };
+    const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    const uint4 zeros = make_uint4(0, 0, 0, 0);
+
+    if (r_begin == 0) {   // dst rows 0,1: src y clamps to 0 -> l0 = 1, l1 = 0 -> value = h(row 0)
+      uint4 w;
+      if (A.mn > kTiny) w = ones;
+      else if (A.mx <= 0.f) w = zeros;
+      else {
+        hinterp4(A.s, A.h, left);
+        A.hvalid = true;
+        w = make_uint4(pack4(A.h[0], A.h[1], A.h[2], A.h[3]), pack4(A.h[4], A.h[5], A.h[6], A.h[7]),
+                       pack4(A.h[8], A.h[9], A.h[10], A.h[11]), pack4(A.h[12], A.h[13], A.h[14], A.h[15]));
+      }
+      emit(w, 0);
+      emit(w, 1);
+    }
+
+    auto step = [&](RowState& P, RowState& Q, int r) {
+      // pair (r, r+1): dst rows 4r+2 .. 4r+5
+      load6(L + (size_t)(r + 1) * d.mw, g, d.mw, Q.s, Q.mn, Q.mx);
+      Q.hvalid = false;
+      const float mn = fminf(P.mn, Q.mn), mx = fmaxf(P.mx, Q.mx);
+      const int Y0 = 4 * r + 2;
+      if (mn > kTiny) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) emit(ones, Y0 + j);
+      } else if (mx <= 0.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) emit(zeros, Y0 + j);
+      } else {
+        if (!P.hvalid) { hinterp4(P.s, P.h, left); P.hvalid = true; }
+        hinterp4(Q.s, Q.h, left);
+        Q.hvalid = true;
+        emit(vblend(P.h, Q.h, 0.875f, 0.125f), Y0);
+        emit(vblend(P.h, Q.h, 0.625f, 0.375f), Y0 + 1);
+        emit(vblend(P.h, Q.h, 0.375f, 0.625f), Y0 + 2);
+        emit(vblend(P.h, Q.h, 0.125f, 0.875f), Y0 + 3);
+      }
+    };
+    auto last_step = [&](RowState& P) {
+      // bottom edge r = mh-1: src row r+1 clamps to r, only dst rows 4r+2, 4r+3 exist
+      const int Y0 = 4 * (d.mh - 1) + 2;
+      if (P.mn > kTiny) { emit(ones, Y0); emit(ones, Y0 + 1); }
+      else if (P.mx <= 0.f) { emit(zeros, Y0); emit(zeros, Y0 + 1); }
+      else {
+        if (!P.hvalid) { hinterp4(P.s, P.h, left); P.hvalid = true; }
+        emit(vblend(P.h, P.h, 0.875f, 0.125f), Y0);
+        emit(vblend(P.h, P.h, 0.625f, 0.375f), Y0 + 1);
+      }
+    };
+    const int r_pairs_end = min(r_end, d.mh - 1);   // pairs with a real second row
+    int r = r_begin;
+    for (; r + 1 < r_pairs_end; r += 2) {
+      step(A, Bq, r);
+      step(Bq, A, r + 1);
+    }
+    if (r < r_pairs_end) {
+      step(A, Bq, r);
+      if (r_end == d.mh) last_step(Bq);
+    } else if (r_end == d.mh) {
+      last_step(A);
+    }
+  }
+  publish_stats(ts, 16 * g, stats + inst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic-scale kernel: one thread = 16 consecutive dst pixels of one dst row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
+  src = fmaxf(src, 0.f);
+  i0 = min((int)src, in_size - 1);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+  l0 = 1.0f - l1;
+}
+
+template <bool kWriteMasks>
+__global__ void __launch_bounds__(kUpThreads)
+upsample_generic_kernel(Dims d, const float* __restrict__ logits, const int* __restrict__ counts,
+                        uint8_t* __restrict__ masks, InstStats* __restrict__ stats, unsigned* __restrict__ lattice) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  if (i >= min(counts[b], d.max_n)) return;
+  const int NG = ceil_div(d.W, 16);
+  const int NG8 = ceil_div(NG, 8);
+  const int NY4 = ceil_div(d.H, 4);
+  const int wt = blockIdx.x * (kUpThreads / 32) + (threadIdx.x >> 5);
+  if (wt >= NG8 * NY4) return;
+  const int lane = threadIdx.x & 31;
+  const int g = (wt % NG8) * 8 + (lane & 7);
+  const int Y = (wt / NG8) * 4 + (lane >> 3);
+  const size_t inst = (size_t)b * d.max_n + i;
+  const float* L = logits + inst * d.mh * d.mw;
+  unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
+  ThreadStats ts;
+  if (g < NG && Y < d.H) {
+    int y0, y1;
+    float ly0, ly1;
+    src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
+    const float* r0 = L + (size_t)y0 * d.mw;
+    const float* r1 = L + (size_t)y1 * d.mw;
+    const int X0 = 16 * g, X1 = min(X0 + 15, d.W - 1);
+    int xa, xb, t0;
+    float f0, f1;
+    src_index(d.sx, X0, d.mw, xa, t0, f0, f1);
+    src_index(d.sx, X1, d.mw, t0, xb, f0, f1);
+    float mn = INFINITY, mx = -INFINITY;
+    for (int x = xa; x <= xb; ++x) {
+      const float u = __ldg(r0 + x), v = __ldg(r1 + x);
+      mn = fminf(mn, fminf(u, v));
+      mx = fmaxf(mx, fmaxf(u, v));
+    }
+    unsigned ww[4] = {0, 0, 0, 0};
+    if (mn > kTiny) {
+      for (int px = 0; px <= X1 - X0; ++px) ww[px >> 2] |= 1u << (8 * (px & 3));
+    } else if (mx > 0.f) {
+      for (int px = 0; px <= X1 - X0; ++px) {
+        int x0, x1;
+        float lx0, lx1;
+        src_index(d.sx, X0 + px, d.mw, x0, x1, lx0, lx1);
+        const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
+        const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
+        const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
+        if (o > 0.f) ww[px >> 2] |= 1u << (8 * (px & 3));
+      }
+    }
+    const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+    if (kWriteMasks) {
+      uint8_t* M = masks + inst * (size_t)d.H * d.W + (size_t)Y * d.W + X0;
+      if (X0 + 15 < d.W && (d.W & 15) == 0) *reinterpret_cast<uint4*>(M) = w;
+      else for (int px = 0; px <= X1 - X0; ++px) M[px] = (ww[px >> 2] >> (8 * (px & 3))) & 1u;
+    }
+    ts.add_row(w, Y);
+    const int t = Y - (d.gs >> 1);
+    if (t >= 0 && t % d.gs == 0 && (ww[0] | ww[1] | ww[2] | ww[3])) lattice_row(w, Y, X0, d, lat);
+  }
+  publish_stats(ts, 16 * g, stats + inst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stats from caller-provided u8 masks (va_mask_to_records)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kUpThreads)
+mask_stats_kernel(Dims d, const uint8_t* __restrict__ masks, const int* __restrict__ counts,
+                  InstStats* __restrict__ stats, unsigned* __restrict__ lattice) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  if (i >= min(counts[b], d.max_n)) return;
+  const int NG = ceil_div(d.W, 16);
+  const int NG8 = ceil_div(NG, 8);
+  const int NY4 = ceil_div(d.H, 4);
+  const int wt = blockIdx.x * (kUpThreads / 32) + (threadIdx.x >> 5);
+  if (wt >= NG8 * NY4) return;
+  const int lane = threadIdx.x & 31;
+  const int g = (wt % NG8) * 8 + (lane & 7);
+  const int Y = (wt / NG8) * 4 + (lane >> 3);
+  const size_t inst = (size_t)b * d.max_n + i;
+  unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
+  ThreadStats ts;
+  if (g < NG && Y < d.H) {
+    const uint8_t* M = masks + inst * (size_t)d.H * d.W + (size_t)Y * d.W + 16 * g;
+    unsigned ww[4] = {0, 0, 0, 0};
+    const int npx = min(16, d.W - 16 * g);
+    if (npx == 16 && (d.W & 15) == 0) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(M));
+      const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // normalise non-zero bytes to 1
+        unsigned t = vv[q];
+        t |= t >> 4; t |= t >> 2; t |= t >> 1;
+        ww[q] = t & 0x01010101u;
+      }
+    } else {
+      for (int px = 0; px < npx; ++px) if (M[px]) ww[px >> 2] |= 1u << (8 * (px & 3));
+    }
+    const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+    ts.add_row(w, Y);
+    const int t = Y - (d.gs >> 1);
+    if (t >= 0 && t % d.gs == 0 && (ww[0] | ww[1] | ww[2] | ww[3])) lattice_row(w, Y, 16 * g, d, lat);
+  }
+  publish_stats(ts, 16 * g, stats + inst);
+}
+
+__global__ void init_scratch_kernel(InstStats* stats, size_t n_stats, unsigned* lattice, size_t n_lat) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = t; k < n_stats; k += stride) {
+    InstStats s;
+    s.area = 0; s.minx = INT_MAX; s.miny = INT_MAX; s.maxx = -1; s.maxy = -1; s.euler4 = 0; s.pad0 = 0; s.pad1 = 0;
+    stats[k] = s;
+  }
+  for (size_t k = t; k < n_lat; k += stride) lattice[k] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_upsample(const Dims& d, const float* logits, const int* counts, int B, uint8_t* masks,
+                            InstStats* stats, unsigned* lattice, cudaStream_t st) {
+  const bool x4 = (d.H == 4 * d.mh) && (d.W == 4 * d.mw) && (d.mw % 4 == 0);
+  if (x4) {
+    const int warps = ceil_div(d.W >> 4, 8) * ceil_div(d.mh, 4 * kStrip);
+    dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
+    if (masks) upsample4x_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
+    else upsample4x_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
+  } else {
+    const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4);
+    dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
+    if (masks) upsample_generic_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
+    else upsample_generic_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, InstStats* stats,
+                              unsigned* lattice, cudaStream_t st) {
+  const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4);
+  dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
+  mask_stats_kernel<<<grid, kUpThreads, 0, st>>>(d, masks, counts, stats, lattice);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_init_scratch(const Dims& d, int max_batch, InstStats* stats, unsigned* lattice, cudaStream_t st) {
+  const size_t ns = (size_t)max_batch * d.max_n;
+  const size_t nl = ns * d.lat_rows * d.lat_words;
+  init_scratch_kernel<<<256, 256, 0, st>>>(stats, ns, lattice, nl);
+  return cudaGetLastError();
+}
+
+}  // namespace va

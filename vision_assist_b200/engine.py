@@ -1,0 +1,239 @@
+"""Batched host API above the C ABI: device buffers in, per-frame records out.
+
+`MaskGridEngine` owns one `va_ctx` (one CUDA device, one geometry).  torch is used only for
+device memory, streams and pinned host buffers; all compute is in libva_sm100.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass
+class FrameRecord:
+    """Decoded per-frame record (numpy views into the record blob, list order; see the C header)."""
+    flags: int
+    sel: int
+    x0: int
+    y0: int
+    C: int
+    R: int
+    n_orphans: int
+    area: int
+    bbox: tuple
+    euler: int
+    rows_y: np.ndarray      # int32 [R]
+    rows_attr: np.ndarray   # int32 [R]
+    occ: np.ndarray         # uint8 [R, C]   bit0 = non-empty, bit1 = artificial
+    penalty: np.ndarray     # float64 [R, C] NaN where empty
+    peaks: np.ndarray       # int32 [n_peaks, 2]
+    orphan_y: np.ndarray    # int32 [n_orphans]
+    orphan_occ: np.ndarray  # uint8 [n_orphans, C]
+
+    @property
+    def np_grids(self) -> np.ndarray:
+        """FrameProcessor.np_grids (FrameProcessor.py:168-171)."""
+        return (self.occ & 1).astype(np.uint8)
+
+    def as_dict(self) -> dict:
+        return dict(flags=self.flags, sel=self.sel, x0=self.x0, y0=self.y0, C=self.C, R=self.R,
+                    rows_y=self.rows_y, rows_attr=self.rows_attr, occ=self.occ, penalty=self.penalty,
+                    peaks=self.peaks, orphan_y=self.orphan_y, orphan_occ=self.orphan_occ)
+
+    def raise_reference_errors(self) -> None:
+        """Re-raise what the reference raises for this frame."""
+        if self.flags & _lib.VA_FLAG_CENTRE_OOB:
+            raise IndexError("index out of bounds: cell centre outside the frame (FrameProcessor.py:97)")
+        if self.flags & _lib.VA_FLAG_LIST_OOB:
+            raise IndexError("list assignment index out of range (FrameProcessor.py:163)")
+        if self.flags & _lib.VA_FLAG_OVERFLOW:
+            raise RuntimeError("record capacity exceeded")
+
+
+class MaskGridEngine:
+    def __init__(self, H: int, W: int, mh: int, mw: int, max_n: int = 8, gs: int = 20, max_batch: int = 256,
+                 device: int | None = None, K: int = 32, check_simple: bool = False, tensor_core: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vision_assist_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        flags = (_lib.VA_CFG_CHECK_SIMPLE if check_simple else 0) | (0 if tensor_core else _lib.VA_CFG_NO_TENSOR_CORE)
+        self.cfg = _lib.VaConfig(self.device, H, W, mh, mw, K, max_n, gs, max_batch, flags)
+        ctx = C.c_void_p()
+        torch.cuda.init()
+        rc = self.lib.va_create(C.byref(ctx), C.byref(self.cfg))
+        if rc != 0:
+            raise _lib.VaError(rc, self.lib.va_last_error(None).decode())
+        self._ctx = ctx
+        self.layout = _lib.VaLayout()
+        self._check(self.lib.va_get_layout(self._ctx, C.byref(self.layout)))
+        self.H, self.W, self.mh, self.mw, self.K, self.max_n, self.gs, self.max_batch = H, W, mh, mw, K, max_n, gs, max_batch
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.va_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise _lib.VaError(rc, self.lib.va_last_error(self._ctx).decode())
+
+    @property
+    def record_bytes(self) -> int:
+        return self.layout.record_bytes
+
+    @property
+    def uses_tensor_core(self) -> bool:
+        return bool(self.lib.va_uses_tensor_core(self._ctx))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.va_last_launch_count(self._ctx))
+
+    def algorithmic_bytes_per_frame(self, n: int, write_masks: bool = True) -> int:
+        """protos in + coefs + boxes + u8 masks out + grid/penalty record + header."""
+        L = self.layout
+        return (4 * self.K * self.mh * self.mw + 4 * n * self.K + 16 * n + (n * self.H * self.W if write_masks else 0)
+                + L.rmax * L.cmax * 9 + 64)
+
+    def _dev(self, t: torch.Tensor, dtype, shape_tail):
+        if not (t.is_cuda and t.device.index == self.device and t.dtype == dtype and t.is_contiguous()):
+            raise ValueError(f"expected contiguous {dtype} CUDA tensor on device {self.device}, got {t.dtype} {t.device}")
+        if tuple(t.shape[1:]) != tuple(shape_tail):
+            raise ValueError(f"expected trailing shape {tuple(shape_tail)}, got {tuple(t.shape)}")
+        return C.c_void_p(t.data_ptr())
+
+    def _inputs(self, protos, coefs, boxes, counts):
+        B = protos.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        return (B, self._dev(protos, torch.float32, (self.K, self.mh, self.mw)),
+                self._dev(coefs, torch.float32, (self.max_n, self.K)), self._dev(boxes, torch.float32, (self.max_n, 4)),
+                self._dev(counts, torch.int32, ()))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- device-buffer API ---------------------------------------------------------------------
+    def assemble_masks(self, protos, coefs, boxes, counts, want_logits: bool = False):
+        """ops.process_mask for a batch -> masks u8 [B,max_n,H,W] (+ cropped logits [B,max_n,mh,mw])."""
+        B, p, c, b, n = self._inputs(protos, coefs, boxes, counts)
+        masks = torch.empty((B, self.max_n, self.H, self.W), dtype=torch.uint8, device=protos.device)
+        logits = torch.empty((B, self.max_n, self.mh, self.mw), dtype=torch.float32, device=protos.device) if want_logits else None
+        self._check(self.lib.va_assemble_masks(self._ctx, p, c, b, n, B, C.c_void_p(masks.data_ptr()),
+                                               C.c_void_p(logits.data_ptr()) if want_logits else None, self._stream()))
+        return (masks, logits) if want_logits else masks
+
+    def run(self, protos, coefs, boxes, counts, masks_out: torch.Tensor | None = None,
+            records_out: torch.Tensor | None = None, write_masks: bool = True):
+        """Whole path; returns (records u8 [B, record_bytes], masks or None), all on the device."""
+        B, p, c, b, n = self._inputs(protos, coefs, boxes, counts)
+        if records_out is None:
+            records_out = torch.empty((B, self.record_bytes), dtype=torch.uint8, device=protos.device)
+        if write_masks and masks_out is None:
+            masks_out = torch.empty((B, self.max_n, self.H, self.W), dtype=torch.uint8, device=protos.device)
+        mptr = C.c_void_p(masks_out.data_ptr()) if (write_masks and masks_out is not None) else None
+        self._check(self.lib.va_run_fused(self._ctx, p, c, b, n, B, mptr, C.c_void_p(records_out.data_ptr()), self._stream()))
+        return records_out, (masks_out if write_masks else None)
+
+    def masks_to_records(self, masks, counts, rects: torch.Tensor | None = None, sel: torch.Tensor | None = None):
+        B = masks.shape[0]
+        m = self._dev(masks, torch.uint8, (self.max_n, self.H, self.W))
+        n = self._dev(counts, torch.int32, ())
+        rec = torch.empty((B, self.record_bytes), dtype=torch.uint8, device=masks.device)
+        r = self._dev(rects, torch.int32, (4,)) if rects is not None else None
+        s = self._dev(sel, torch.int32, ()) if sel is not None else None
+        self._check(self.lib.va_mask_to_records(self._ctx, m, n, B, r, s, C.c_void_p(rec.data_ptr()), self._stream()))
+        return rec
+
+    def grids_to_records(self, grids: list[dict]):
+        """grids: [{x0, rows_y, rows_attr, occ[R,C] u8, use_easy, plane_y?, plane_occ?}] -> records (device)."""
+        B = len(grids)
+        L = self.layout
+        hdr = (_lib.VaGridInput * B)()
+        row_y = np.zeros((B, L.rmax), np.int32)
+        row_attr = np.zeros((B, L.rmax), np.int32)
+        occ = np.zeros((B, L.rmax, L.cmax), np.uint8)
+        plane_y = np.zeros((B, L.rmax), np.int32)
+        plane_occ = np.zeros((B, L.rmax, L.cmax), np.uint8)
+        any_plane = False
+        for i, g in enumerate(grids):
+            o = np.asarray(g["occ"], np.uint8)
+            R, Cc = o.shape
+            if R > L.rmax or Cc > L.cmax:
+                raise ValueError(f"grid {R}x{Cc} exceeds engine capacity {L.rmax}x{L.cmax}")
+            npl = 0
+            if g.get("plane_y") is not None:
+                po = np.asarray(g["plane_occ"], np.uint8)
+                npl = po.shape[0]
+                if npl > L.rmax:
+                    raise ValueError("too many lookup rows")
+                plane_y[i, :npl] = g["plane_y"]
+                plane_occ[i, :npl, :Cc] = po
+                any_plane = True
+            hdr[i] = _lib.VaGridInput(int(g.get("x0", 0)), Cc, R, npl, int(g.get("use_easy", 1)))
+            row_y[i, :R] = g["rows_y"]
+            row_attr[i, :R] = g["rows_attr"]
+            occ[i, :R, :Cc] = o
+        dev = torch.device("cuda", self.device)
+        d_hdr = torch.frombuffer(bytearray(bytes(hdr)), dtype=torch.uint8).to(dev)
+        d_y, d_a, d_o = (torch.from_numpy(a).to(dev) for a in (row_y, row_attr, occ))
+        d_py, d_po = (torch.from_numpy(a).to(dev) for a in (plane_y, plane_occ)) if any_plane else (None, None)
+        rec = torch.empty((B, self.record_bytes), dtype=torch.uint8, device=dev)
+        self._check(self.lib.va_grid_to_penalty_peaks(
+            self._ctx, C.c_void_p(d_hdr.data_ptr()), C.c_void_p(d_y.data_ptr()), C.c_void_p(d_a.data_ptr()),
+            C.c_void_p(d_o.data_ptr()), C.c_void_p(d_py.data_ptr()) if any_plane else None,
+            C.c_void_p(d_po.data_ptr()) if any_plane else None, B, C.c_void_p(rec.data_ptr()), self._stream()))
+        return rec
+
+    # -- host-buffer API -----------------------------------------------------------------------
+    def run_host(self, protos, coefs, boxes, counts, records_out: torch.Tensor | None = None,
+                 masks_out: torch.Tensor | None = None):
+        """Host tensors in (pinned recommended), records (and optionally masks) back in host memory."""
+        for t, dt in ((protos, torch.float32), (coefs, torch.float32), (boxes, torch.float32), (counts, torch.int32)):
+            if t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("run_host expects contiguous CPU tensors (f32 / i32)")
+        B = protos.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        if records_out is None:
+            records_out = torch.empty((B, self.record_bytes), dtype=torch.uint8, pin_memory=True)
+        self._check(self.lib.va_run_fused_host(
+            self._ctx, C.c_void_p(protos.data_ptr()), C.c_void_p(coefs.data_ptr()), C.c_void_p(boxes.data_ptr()),
+            C.c_void_p(counts.data_ptr()), B, C.c_void_p(masks_out.data_ptr()) if masks_out is not None else None,
+            C.c_void_p(records_out.data_ptr())))
+        return records_out
+
+    # -- decoding ------------------------------------------------------------------------------
+    def decode(self, records) -> list[FrameRecord]:
+        """records: u8 [B, record_bytes] torch (any device) or numpy -> list of FrameRecord."""
+        if isinstance(records, torch.Tensor):
+            records = records.cpu().numpy()
+        return [decode_record(records[i], self.layout) for i in range(records.shape[0])]
+
+
+def decode_record(blob: np.ndarray, L) -> FrameRecord:
+    blob = np.ascontiguousarray(blob)
+    h = blob[:64].view(np.int32)
+    flags, sel, x0, y0, Cc, R, norph, npk, area, rm, minx, miny, maxx, maxy, euler = (int(v) for v in h[:15])
+    ry = blob[L.off_row_y:L.off_row_y + 4 * L.rmax].view(np.int32)
+    ra = blob[L.off_row_attr:L.off_row_attr + 4 * L.rmax].view(np.int32)
+    pen = blob[L.off_penalty:L.off_penalty + 8 * L.rmax * L.cmax].view(np.float64).reshape(L.rmax, L.cmax)
+    pk = blob[L.off_peaks:L.off_peaks + 8 * L.pmax].view(np.int32).reshape(L.pmax, 2)
+    occ = blob[L.off_occ:L.off_occ + L.rmax * L.cmax].reshape(L.rmax, L.cmax)
+    return FrameRecord(flags=flags, sel=sel, x0=x0, y0=y0, C=Cc, R=R, n_orphans=norph, area=area,
+                       bbox=(minx, miny, maxx, maxy), euler=euler, rows_y=ry[:R].copy(), rows_attr=ra[:R].copy(),
+                       occ=occ[:R, :Cc].copy(), penalty=pen[:R, :Cc].copy(), peaks=pk[:npk].copy(),
+                       orphan_y=ry[R:R + norph].copy(), orphan_occ=occ[R:R + norph, :Cc].copy())
