@@ -18,7 +18,7 @@ VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG
 
 EXPORTS = ["va_abi_version", "va_create", "va_destroy", "va_last_error", "va_get_layout", "va_assemble_masks",
            "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks",
-           "va_last_launch_count", "va_uses_tensor_core"]
+           "va_last_launch_count", "va_uses_tensor_core", "va_profile_enable", "va_profile_read"]
 
 
 class VaConfig(C.Structure):
@@ -69,6 +69,8 @@ def load() -> C.CDLL:
     lib.va_grid_to_penalty_peaks.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.va_last_launch_count.argtypes = [vp]
     lib.va_uses_tensor_core.argtypes = [vp]
+    lib.va_profile_enable.argtypes = [vp, i32]
+    lib.va_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i32)]
     for name in EXPORTS:
         getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
     _lib = lib

@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OBJS=()
 mkdir -p "$HERE/build"
 for f in va_logits va_upsample va_tail va_fused_tc va_api; do
-  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/va_common.cuh" -nt "$HERE/build/$f.o" ] \
+  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/va_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/va_up_common.cuh" -nt "$HERE/build/$f.o" ] \
      || [ "$HERE/../../include/vision_assist_b200.h" -nt "$HERE/build/$f.o" ]; then
     "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/build/$f.o" 2> "$HERE/build/$f.ptxas.log" || { cat "$HERE/build/$f.ptxas.log"; exit 1; }
   fi

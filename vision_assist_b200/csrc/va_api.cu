@@ -8,6 +8,8 @@
 
 using namespace va;
 
+constexpr int kProfMax = 512;
+
 struct va_ctx {
   va_config cfg;
   Dims d;
@@ -17,6 +19,9 @@ struct va_ctx {
   FusedPlan* plan;             // tcgen05 path, nullptr when unavailable / disabled
   int last_launches;
   char err[512];
+  // optional per-call device timing (va_profile_enable): events on the caller's stream
+  int prof_on, prof_count;
+  cudaEvent_t prof_ev[kProfMax][3];
   // host-buffer pipeline (va_run_fused_host), created lazily
   bool host_ready;
   int host_chunk;
@@ -172,6 +177,9 @@ extern "C" void va_destroy(va_ctx* c) {
   cudaFree(c->scratch.stats);
   cudaFree(c->scratch.lattice);
   cudaFree(c->scratch.logits);
+  if (c->prof_ev[0][0])
+    for (int i = 0; i < kProfMax; ++i)
+      for (int j = 0; j < 3; ++j) cudaEventDestroy(c->prof_ev[i][j]);
   delete c;
 }
 
@@ -183,11 +191,41 @@ extern "C" int va_get_layout(const va_ctx* c, va_layout* out) {
   return VA_OK;
 }
 
+extern "C" int va_profile_enable(va_ctx* c, int on) {
+  if (!c) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  if (on && !c->prof_ev[0][0]) {
+    for (int i = 0; i < kProfMax; ++i)
+      for (int j = 0; j < 3; ++j) VA_CUDA(c, cudaEventCreate(&c->prof_ev[i][j]));
+  }
+  c->prof_on = on ? 1 : 0;
+  c->prof_count = 0;
+  return VA_OK;
+}
+
+extern "C" int va_profile_read(va_ctx* c, float* assemble_ms, float* tail_ms, int32_t* calls) {
+  if (!c || !assemble_ms || !tail_ms || !calls) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  float a = 0.f, t = 0.f;
+  for (int i = 0; i < c->prof_count; ++i) {
+    float ms = 0.f;
+    VA_CUDA(c, cudaEventSynchronize(c->prof_ev[i][2]));
+    VA_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[i][0], c->prof_ev[i][1]));
+    a += ms;
+    VA_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[i][1], c->prof_ev[i][2]));
+    t += ms;
+  }
+  *assemble_ms = a; *tail_ms = t; *calls = c->prof_count;
+  c->prof_count = 0;
+  return VA_OK;
+}
+
 extern "C" int va_last_launch_count(const va_ctx* c) { return c ? c->last_launches : 0; }
 extern "C" int va_uses_tensor_core(const va_ctx* c) { return (c && c->plan) ? 1 : 0; }
 
 static int check_batch(va_ctx* c, int B, const void* a, const void* b, const void* cc, const void* dd) {
   if (!c) return VA_ERR_INVALID;
+  if (B == 0) return VA_OK;
   if (!a || !b || !cc || !dd) { set_err(c, "null input pointer"); return VA_ERR_INVALID; }
   if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
   return VA_OK;
@@ -198,9 +236,9 @@ static int check_batch(va_ctx* c, int B, const void* a, const void* b, const voi
 static int assemble(va_ctx* c, const float* protos, const float* coefs, const float* boxes, const int* counts, int B,
                     uint8_t* masks, float* logits_out, cudaStream_t st) {
   const Dims& d = c->d;
-  if (c->plan && !logits_out) {
+  if (c->plan) {
     char perr[256] = "";
-    cudaError_t e = launch_fused(c->plan, d, protos, coefs, boxes, counts, B, masks, nullptr, c->scratch.stats,
+    cudaError_t e = launch_fused(c->plan, d, protos, coefs, boxes, counts, B, masks, logits_out, c->scratch.stats,
                                  c->scratch.lattice, st, perr, sizeof(perr));
     if (e != cudaSuccess) { set_err(c, "fused kernel launch failed: %s %s", cudaGetErrorString(e), perr); return VA_ERR_CUDA; }
     c->last_launches += 1;
@@ -242,14 +280,19 @@ extern "C" int va_run_fused(va_ctx* c, const float* protos, const float* coefs, 
                             const int32_t* counts, int32_t B, uint8_t* masks_out, uint8_t* records_out, void* stream) {
   int rc = check_batch(c, B, protos, coefs, boxes, counts);
   if (rc != VA_OK) return rc;
-  if (!records_out) { set_err(c, "records_out is null"); return VA_ERR_INVALID; }
   if (B == 0) return VA_OK;
+  if (!records_out) { set_err(c, "records_out is null"); return VA_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   VA_CUDA(c, cudaSetDevice(c->cfg.device));
   c->last_launches = 0;
+  const bool prof = c->prof_on && c->prof_count < kProfMax;
+  cudaEvent_t* ev = prof ? c->prof_ev[c->prof_count] : nullptr;
+  if (prof) VA_CUDA(c, cudaEventRecord(ev[0], st));
   rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, nullptr, st);
   if (rc != VA_OK) return rc;
+  if (prof) VA_CUDA(c, cudaEventRecord(ev[1], st));
   VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, masks_out, nullptr, nullptr, records_out, st));
+  if (prof) { VA_CUDA(c, cudaEventRecord(ev[2], st)); c->prof_count++; }
   c->last_launches += 1;
   return VA_OK;
 }

@@ -212,6 +212,9 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
     ry[k] = y;
     ra[k] = a;
   }
+  // alignment padding: keep every byte of the record deterministic
+  for (int t = d.off_row_attr + 4 * d.rmax + threadIdx.x; t < d.off_penalty; t += kTailThreads) rec[t] = 0;
+  for (int t = d.off_occ + d.rmax * d.cmax + threadIdx.x; t < d.record_bytes; t += kTailThreads) rec[t] = 0;
 }
 
 // ProtrusionDetector closed form; one thread (C <= a few hundred bits).

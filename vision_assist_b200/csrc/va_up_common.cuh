@@ -1,0 +1,130 @@
+// Device helpers shared by the stand-alone upsample kernels (va_upsample.cu) and the fused
+// TMA + tcgen05 kernel (va_fused_tc.cu): 0/1 byte packing, per-thread mask reductions, lattice
+// sampling and the exact-4x bilinear arithmetic (see va_upsample.cu for the numerics contract).
+#pragma once
+
+#include <climits>
+
+#include "va_common.cuh"
+
+namespace va {
+
+// ---------------------------------------------------------------------------------------------
+// shared helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pack4(float a, float b, float c, float d) {
+  return (a > 0.f ? 1u : 0u) | (b > 0.f ? 0x100u : 0u) | (c > 0.f ? 0x10000u : 0u) | (d > 0.f ? 0x1000000u : 0u);
+}
+
+struct ThreadStats {
+  unsigned acc = 0;                 // four byte-lane counters (<= 255 rows*words per lane between flushes)
+  unsigned area = 0;
+  unsigned orw[4] = {0, 0, 0, 0};   // OR of all rows' mask words (x extent)
+  int miny = INT_MAX, maxy = -1;
+  // rows must be added in increasing Y; at most 63 rows between flush() calls
+  __device__ __forceinline__ void add_row(const uint4& w, int Y) {
+    const unsigned any = w.x | w.y | w.z | w.w;
+    if (any) {
+      acc += (w.x + w.y) + (w.z + w.w);
+      orw[0] |= w.x; orw[1] |= w.y; orw[2] |= w.z; orw[3] |= w.w;
+      if (miny == INT_MAX) miny = Y;
+      maxy = Y;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    area += (acc & 0xffu) + ((acc >> 8) & 0xffu) + ((acc >> 16) & 0xffu) + (acc >> 24);
+    acc = 0;
+  }
+};
+
+// Reduce over the warp (all lanes belong to the same (frame, instance)) and publish with atomics.
+__device__ __forceinline__ void publish_stats(const ThreadStats& t, int xbase, InstStats* dst) {
+  int minx = INT_MAX, maxx = -1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (t.orw[q]) {
+      const int lo = (__ffs(t.orw[q]) - 1) >> 3, hi = (31 - __clz(t.orw[q])) >> 3;
+      minx = min(minx, xbase + 4 * q + lo);
+      maxx = max(maxx, xbase + 4 * q + hi);
+    }
+  }
+  unsigned area = t.area + (t.acc & 0xffu) + ((t.acc >> 8) & 0xffu) + ((t.acc >> 16) & 0xffu) + (t.acc >> 24);
+  int miny = t.miny, maxy = t.maxy;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    area += __shfl_xor_sync(0xffffffffu, area, o);
+    minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+    miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+    maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+    maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+  }
+  if ((threadIdx.x & 31) == 0 && area) {
+    atomicAdd(&dst->area, area);
+    atomicMin(&dst->minx, minx);
+    atomicMin(&dst->miny, miny);
+    atomicMax(&dst->maxx, maxx);
+    atomicMax(&dst->maxy, maxy);
+  }
+}
+
+// Sample the cell-centre lattice points that fall into this thread's 16 pixels of row Y.
+__device__ __forceinline__ void lattice_row(const uint4& w, int Y, int xbase, const Dims& d, unsigned* lat) {
+  const int half = d.gs >> 1;
+  const int ly = (Y - half) / d.gs;
+  const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+  int lx = (xbase - half + d.gs - 1) / d.gs;
+  if (lx < 0) lx = 0;
+  for (; lx < d.lat_cols; ++lx) {
+    const int pos = d.gs * lx + half - xbase;
+    if (pos > 15) break;
+    if ((ww[pos >> 2] >> (8 * (pos & 3))) & 1u) atomicOr(&lat[ly * d.lat_words + (lx >> 5)], 1u << (lx & 31));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact 4x kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kStrip = 8;           // proto row pairs per thread
+constexpr int kUpThreads = 128;
+
+// horizontal pass for one proto row: 6 source values (cols 4g-1 .. 4g+4, clamped) -> 16 outputs
+__device__ __forceinline__ void hinterp4(const float (&s)[6], float (&h)[16], bool left_edge) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = s[k], b = s[k + 1], c = s[k + 2];
+    h[4 * k + 0] = fmaf(a, 0.375f, __fmul_rn(b, 0.625f));
+    h[4 * k + 1] = fmaf(a, 0.125f, __fmul_rn(b, 0.875f));
+    h[4 * k + 2] = fmaf(b, 0.875f, __fmul_rn(c, 0.125f));
+    h[4 * k + 3] = fmaf(b, 0.625f, __fmul_rn(c, 0.375f));
+  }
+  if (left_edge) {   // dst x = 0,1: src clamps to 0 -> l0 = 1, l1 = 0 -> a + b*0 = a
+    h[0] = fmaf(s[1], 1.0f, __fmul_rn(s[2], 0.0f));
+    h[1] = h[0];
+  }
+}
+
+__device__ __forceinline__ void load6(const float* __restrict__ row, int g, int mw, float (&s)[6], float& mn, float& mx) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(row + 4 * g));
+  s[1] = v.x; s[2] = v.y; s[3] = v.z; s[4] = v.w;
+  s[0] = (g > 0) ? __ldg(row + 4 * g - 1) : v.x;
+  s[5] = (4 * g + 4 < mw) ? __ldg(row + 4 * g + 4) : v.w;
+  mn = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(s[4], s[5]));
+  mx = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), fmaxf(s[4], s[5]));
+}
+
+constexpr float kTiny = 1e-30f;   // below this a positive product could underflow: take the exact path
+
+__device__ __forceinline__ uint4 vblend(const float (&hA)[16], const float (&hB)[16], float l0, float l1) {
+  float o[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) o[x] = fmaf(hA[x], l0, __fmul_rn(hB[x], l1));
+  return make_uint4(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]), pack4(o[8], o[9], o[10], o[11]),
+                    pack4(o[12], o[13], o[14], o[15]));
+}
+
+__device__ __forceinline__ uint4 hpack(const float (&h)[16]) {
+  return make_uint4(pack4(h[0], h[1], h[2], h[3]), pack4(h[4], h[5], h[6], h[7]), pack4(h[8], h[9], h[10], h[11]),
+                    pack4(h[12], h[13], h[14], h[15]));
+}
+
+}  // namespace va

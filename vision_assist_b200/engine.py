@@ -102,6 +102,16 @@ class MaskGridEngine:
     def last_launch_count(self) -> int:
         return int(self.lib.va_last_launch_count(self._ctx))
 
+    def profile(self, on: bool = True) -> None:
+        """Record CUDA events around the assembly and tail kernels of every run() (C ABI va_profile_enable)."""
+        self._check(self.lib.va_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """-> (assemble_ms_total, tail_ms_total, calls) since the last read; synchronises."""
+        a, t, n = C.c_float(), C.c_float(), C.c_int32()
+        self._check(self.lib.va_profile_read(self._ctx, C.byref(a), C.byref(t), C.byref(n)))
+        return a.value, t.value, n.value
+
     def algorithmic_bytes_per_frame(self, n: int, write_masks: bool = True) -> int:
         """protos in + coefs + boxes + u8 masks out + grid/penalty record + header."""
         L = self.layout
