@@ -186,16 +186,19 @@ __device__ __forceinline__ int chunk_last_row(const FusedParams& p, const Item& 
   return min((c + 1) * p.pr, it.nrows - 1);
 }
 
-struct SmemLayout {
-  uint8_t* hi;        // [kStagesHi][16 KB]   TMA staging, [32 k][128 px]
-  uint8_t* lo;        // [kStagesLo][A_hi 16 KB | A_lo 16 KB]   K-major SW128 operand tiles, 1024 B aligned
-  uint8_t* bt;        // [2 parity][hi, lo][kNPad * 128 B]
-  float* chunks;      // [kChunkBufs][chunk_floats]
-  float* box;         // [4 items ring][kMaxInstTc][4]   (the epilogue lags the front by < 4 items)
-  int* stat;          // [kMaxInstTc][8]  area, minx, miny, maxx, maxy
-  short* latrow;      // [H]  lattice row index of dst row Y, -1 if none
-  uint64_t* bars;
-  uint32_t* tmem_slot;
+// Shared-memory map as byte OFFSETS from the 1024 B-aligned base; all hot accesses go through
+// explicit ld.shared / st.shared on 32-bit shared addresses (no generic-space LD/ST).
+struct SmemMap {
+  uint32_t hi;        // [kStagesHi][16 KB]   TMA staging, [32 k][128 px]
+  uint32_t op;        // [kStagesLo][A_hi 16 KB | A_lo 16 KB]   K-major SW128 operand tiles
+  uint32_t bt;        // [2 parity][hi, lo][kNPad * 128 B]
+  uint32_t chunks;    // [kChunkBufs][chunk_floats] f32
+  uint32_t box;       // [4 items ring][kMaxInstTc][4] f32
+  uint32_t stat;      // [kMaxInstTc][8] i32: area, minx, miny, maxx, maxy
+  uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
+  uint32_t bars;      // [BAR_COUNT] u64
+  uint32_t tmem_slot;
+  uint32_t total;
 };
 enum {
   BAR_HI_FULL = 0,
@@ -211,62 +214,124 @@ enum {
   BAR_COUNT = BAR_CH_EMPTY + kChunkBufs
 };
 
-__host__ __device__ inline size_t fused_smem_layout(int chunk_floats, int H, SmemLayout* s, uint8_t* base) {
-  size_t o = 0;
-  auto take = [&](size_t bytes, size_t align) { o = (o + align - 1) / align * align; size_t r = o; o += bytes; return r; };
-  const size_t o_hi = take((size_t)kStagesHi * kTileBytes, 1024);
-  const size_t o_lo = take((size_t)kStagesLo * 2 * kTileBytes, 1024);
-  const size_t o_bt = take((size_t)2 * 2 * kNPad * 128, 1024);
-  const size_t o_ch = take((size_t)kChunkBufs * chunk_floats * 4, 16);
-  const size_t o_box = take((size_t)4 * kMaxInstTc * 4 * 4, 16);
-  const size_t o_st = take((size_t)kMaxInstTc * 8 * 4, 16);
-  const size_t o_lr = take((size_t)H * 2, 16);
-  const size_t o_bar = take((size_t)BAR_COUNT * 8, 8);
-  const size_t o_tm = take(16, 16);
-  if (s) {
-    s->hi = base + o_hi; s->lo = base + o_lo; s->bt = base + o_bt; s->chunks = (float*)(base + o_ch);
-    s->box = (float*)(base + o_box); s->stat = (int*)(base + o_st); s->latrow = (short*)(base + o_lr);
-    s->bars = (uint64_t*)(base + o_bar); s->tmem_slot = (uint32_t*)(base + o_tm);
-  }
-  return o;
+__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H) {
+  SmemMap m;
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes, uint32_t align) { o = (o + align - 1) / align * align; uint32_t r = o; o += bytes; return r; };
+  m.hi = take(kStagesHi * kTileBytes, 1024);
+  m.op = take(kStagesLo * 2 * kTileBytes, 1024);
+  m.bt = take(2 * 2 * kNPad * 128, 1024);
+  m.chunks = take((uint32_t)kChunkBufs * chunk_floats * 4, 16);
+  m.box = take(4 * kMaxInstTc * 4 * 4, 16);
+  m.stat = take(kMaxInstTc * 8 * 4, 16);
+  m.latrow = take((uint32_t)H * 2, 16);
+  m.bars = take(BAR_COUNT * 8, 8);
+  m.tmem_slot = take(16, 16);
+  m.total = o;
+  return m;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s16(uint32_t a) { short v; asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_s16(uint32_t a, short v) { asm volatile("st.shared.s16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void atoms_add(uint32_t a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void atoms_min(uint32_t a, int v) { asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void atoms_max(uint32_t a, int v) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// barrier helpers on 32-bit shared addresses
+__device__ __forceinline__ void bar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void bar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t a, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bar_commit(uint32_t a) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+template <int kN>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[kN]);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+
+__device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  kNI = instances handled per accumulator read (8 or 16 TMEM columns)
 // ---------------------------------------------------------------------------------------------
-template <bool kWriteMasks>
+template <bool kWriteMasks, int kNI>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
-  extern __shared__ uint8_t smem_dyn[];
-  // dynamic shared memory is only guaranteed 16 B aligned: align to 1024 for the 128B-swizzle tiles
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  SmemLayout s;
-  fused_smem_layout(p.chunk_floats, p.d.H, &s, base);
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  // dynamic shared memory is only guaranteed 16 B aligned: round the shared address up to 1024
+  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const SmemMap sm = fused_smem_map(p.chunk_floats, p.d.H);
   const Dims& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + sm.bars;
+  auto BAR = [&](int idx) { return bars + 8u * (uint32_t)idx; };
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStagesHi; ++i) { mbar_init(&s.bars[BAR_HI_FULL + i], 1); mbar_init(&s.bars[BAR_HI_EMPTY + i], kWarpsSplit); }
-    for (int i = 0; i < kStagesLo; ++i) { mbar_init(&s.bars[BAR_LO_FULL + i], kWarpsSplit); mbar_init(&s.bars[BAR_LO_EMPTY + i], 1); }
-    for (int i = 0; i < kAcc; ++i) { mbar_init(&s.bars[BAR_ACC_FULL + i], 1); mbar_init(&s.bars[BAR_ACC_EMPTY + i], kWarpsSplit); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.bars[BAR_B_FULL + i], kWarpsSplit); mbar_init(&s.bars[BAR_B_EMPTY + i], 1); }
-    for (int i = 0; i < kChunkBufs; ++i) { mbar_init(&s.bars[BAR_CH_FULL + i], kWarpsSplit); mbar_init(&s.bars[BAR_CH_EMPTY + i], kWarpsUp); }
+    for (int i = 0; i < kStagesHi; ++i) { bar_init(BAR(BAR_HI_FULL + i), 1); bar_init(BAR(BAR_HI_EMPTY + i), kWarpsSplit); }
+    for (int i = 0; i < kStagesLo; ++i) { bar_init(BAR(BAR_LO_FULL + i), kWarpsSplit); bar_init(BAR(BAR_LO_EMPTY + i), 1); }
+    for (int i = 0; i < kAcc; ++i) { bar_init(BAR(BAR_ACC_FULL + i), 1); bar_init(BAR(BAR_ACC_EMPTY + i), kWarpsSplit); }
+    for (int i = 0; i < 2; ++i) { bar_init(BAR(BAR_B_FULL + i), kWarpsSplit); bar_init(BAR(BAR_B_EMPTY + i), 1); }
+    for (int i = 0; i < kChunkBufs; ++i) { bar_init(BAR(BAR_CH_FULL + i), kWarpsSplit); bar_init(BAR(BAR_CH_EMPTY + i), kWarpsUp); }
     fence_barrier_init();
   }
   for (int y = threadIdx.x; y < d.H; y += kThreads) {
     const int t = y - (d.gs >> 1);
-    s.latrow[y] = (t >= 0 && t % d.gs == 0) ? (short)(t / d.gs) : (short)-1;
+    sts_s16(sbase + sm.latrow + 2 * y, (t >= 0 && t % d.gs == 0) ? (short)(t / d.gs) : (short)-1);
   }
   for (int t = threadIdx.x; t < kMaxInstTc * 8; t += kThreads) {
     const int f = t & 7;
-    s.stat[t] = (f == 1 || f == 2) ? INT_MAX : (f == 3 || f == 4) ? -1 : 0;
+    sts_s32(sbase + sm.stat + 4 * t, (f == 1 || f == 2) ? INT_MAX : (f == 3 || f == 4) ? -1 : 0);
   }
-  if (warp == 1) tmem_alloc(s.tmem_slot, kTmemCols);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + sm.tmem_slot), "r"((uint32_t)kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s.tmem_slot;
+  const uint32_t tmem_base = lds_u32(sbase + sm.tmem_slot);
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -278,9 +343,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int px0 = it.pa * d.mw;
         for (int t = 0; t < it.ntiles; ++t, ++g) {
           const int st = g % kStagesHi;
-          mbar_wait(&s.bars[BAR_HI_EMPTY + st], ((g / kStagesHi) & 1) ^ 1);
-          mbar_arrive_expect_tx(&s.bars[BAR_HI_FULL + st], kTileBytes);
-          tma_load_3d(s.hi + (size_t)st * kTileBytes, &tmap, &s.bars[BAR_HI_FULL + st], px0 + t * kTileM, 0, it.b);
+          bar_wait(BAR(BAR_HI_EMPTY + st), ((g / kStagesHi) & 1) ^ 1);
+          bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
+          tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), px0 + t * kTileM, 0, it.b);
         }
       }
     }
@@ -293,15 +358,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const Item it = get_item(p, k);
         if (!it.valid) break;
         const int par = k & 1;
-        mbar_wait(&s.bars[BAR_B_FULL + par], (k >> 1) & 1);
-        const uint32_t b_hi = smem_u32(s.bt + (size_t)(par * 2 + 0) * kNPad * 128);
-        const uint32_t b_lo = smem_u32(s.bt + (size_t)(par * 2 + 1) * kNPad * 128);
+        bar_wait(BAR(BAR_B_FULL + par), (k >> 1) & 1);
+        const uint32_t b_hi = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
+        const uint32_t b_lo = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
         for (int t = 0; t < it.ntiles; ++t, ++g) {
           const int sl = g % kStagesLo, ac = g % kAcc;
-          mbar_wait(&s.bars[BAR_ACC_EMPTY + ac], ((g / kAcc) & 1) ^ 1);
-          mbar_wait(&s.bars[BAR_LO_FULL + sl], (g / kStagesLo) & 1);
+          bar_wait(BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
+          bar_wait(BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(s.lo + (size_t)sl * 2 * kTileBytes);
+          const uint32_t a_hi = sbase + sm.op + sl * 2 * kTileBytes;
           const uint32_t a_lo = a_hi + kTileBytes;
           const uint32_t dcol = tmem_base + ac * kNPad;
           // K-major SW128 operands: rows (pixels / instances) are 128 B, 8-row groups 1024 B apart (SBO),
@@ -315,88 +380,88 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_tf32(dcol, make_smem_desc(a_lo + ks * 32, 16, 1024), make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, 1);
-          umma_commit(&s.bars[BAR_LO_EMPTY + sl]);
-          umma_commit(&s.bars[BAR_ACC_FULL + ac]);
+          bar_commit(BAR(BAR_LO_EMPTY + sl));
+          bar_commit(BAR(BAR_ACC_FULL + ac));
         }
-        umma_commit(&s.bars[BAR_B_EMPTY + par]);
+        bar_commit(BAR(BAR_B_EMPTY + par));
       }
     }
   } else if (warp < 2 + kWarpsSplit) {
     // =========================== split (front) + epilogue (back) ===========================
     const int sw = warp - 2;                 // 0..3
-    const int st_tid = sw * 32 + lane;       // 0..127
+    const int st_tid = sw * 32 + lane;       // 0..127 = pixel row of the tile this thread transposes
     const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are accessible to this warp
-    // front iterator
-    int fk = 0, ft = 0;
+    const int ep_px = quarter * 32 + lane;   // tile pixel this thread reads back from TMEM
+    int fk = 0, ft = 0;                      // front iterator (item, tile)
     Item fit = get_item(p, 0);
     uint32_t fg = 0;
-    // back iterator
-    int bk = 0, bt = 0;
+    int bk = 0, bt = 0;                      // back iterator
     Item bit = get_item(p, 0);
     uint32_t bg = 0;
     uint32_t chunk_base = 0;                 // global chunk index of chunk 0 of the back item
     int acquired = 0, completed = 0;         // chunks of the back item acquired for writing / signalled full
     int lagged = 0;
+    int brow = ep_px / d.mw, bcol = ep_px - brow * d.mw;   // band-local (row, col) of this thread's pixel in the back tile
+    const int tile_rows = kTileM / d.mw, tile_cols = kTileM - tile_rows * d.mw;   // advance per tile
 
     while (fit.valid || bit.valid) {
-      // ---------------- front: B tiles at the start of an item, A_lo for tile (fk, ft) ----------------
+      // ---------------- front ----------------
       if (fit.valid) {
-        if (ft == 0) {
+        if (ft == 0) {   // new item: per-frame B tiles (coefficients hi / lo) and scaled boxes
           const int par = fk & 1;
-          mbar_wait(&s.bars[BAR_B_EMPTY + par], ((fk >> 1) & 1) ^ 1);
+          bar_wait(BAR(BAR_B_EMPTY + par), ((fk >> 1) & 1) ^ 1);
           const int n = min(p.counts[fit.b], min(d.max_n, kMaxInstTc));
-          uint8_t* bh = s.bt + (size_t)(par * 2 + 0) * kNPad * 128;
-          uint8_t* bl = s.bt + (size_t)(par * 2 + 1) * kNPad * 128;
-          // row r (instance), 16 B chunk c: stored at chunk c ^ (r & 7)  (128B swizzle, K-major)
-          for (int q = st_tid; q < kNPad * 8; q += 128) {
-            const int r = q >> 3, c = q & 7;
+          const uint32_t bh = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
+          const uint32_t bl = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
+          {   // row r (instance), 16 B chunk c: stored at chunk c ^ (r & 7)  (128B swizzle, K-major); 128 threads = 16 x 8
+            const int r = st_tid >> 3, c = st_tid & 7;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)fit.b * d.max_n + r) * d.K + 4 * c));
             float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-            const int off = r * 128 + ((c ^ (r & 7)) << 4);
-            *reinterpret_cast<float4*>(bh + off) = h;
-            *reinterpret_cast<float4*>(bl + off) = l;
+            h.x = trunc_tf32(v.x); l.x = v.x - h.x;
+            h.y = trunc_tf32(v.y); l.y = v.y - h.y;
+            h.z = trunc_tf32(v.z); l.z = v.z - h.z;
+            h.w = trunc_tf32(v.w); l.w = v.w - h.w;
+            const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+            sts_v4(bh + off, h);
+            sts_v4(bl + off, l);
           }
-          for (int q = st_tid; q < kMaxInstTc * 4; q += 128) {
-            const int i = q >> 2, c = q & 3;
+          if (st_tid < kMaxInstTc * 4) {
+            const int i = st_tid >> 2, c = st_tid & 3;
             float v = 0.f;
             if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)fit.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
-            s.box[((fk & 3) * kMaxInstTc + i) * 4 + c] = v;
+            sts_f32(sbase + sm.box + (((fk & 3) * kMaxInstTc + i) * 4 + c) * 4, v);
           }
           fence_proxy_async();
           named_bar_sync(1, 32 * kWarpsSplit);
-          if (lane == 0) mbar_arrive(&s.bars[BAR_B_FULL + par]);
+          if (lane == 0) bar_arrive(BAR(BAR_B_FULL + par));
         }
         const int sh = fg % kStagesHi, sl = fg % kStagesLo;
-        mbar_wait(&s.bars[BAR_HI_FULL + sh], (fg / kStagesHi) & 1);
-        mbar_wait(&s.bars[BAR_LO_EMPTY + sl], ((fg / kStagesLo) & 1) ^ 1);
+        bar_wait(BAR(BAR_HI_FULL + sh), (fg / kStagesHi) & 1);
+        bar_wait(BAR(BAR_LO_EMPTY + sl), ((fg / kStagesLo) & 1) ^ 1);
         // transpose + split: thread = pixel row of the tile.  Reads of [k][px] are conflict-free across
         // the warp (consecutive px); each 16 B chunk c of the K-major row lands at chunk c ^ (px & 7).
-        const float* src = reinterpret_cast<const float*>(s.hi + (size_t)sh * kTileBytes) + st_tid;
-        uint8_t* dhi = s.lo + (size_t)sl * 2 * kTileBytes + (size_t)st_tid * 128;
-        uint8_t* dlo = dhi + kTileBytes;
+        const uint32_t src = sbase + sm.hi + sh * kTileBytes + st_tid * 4;
+        const uint32_t dhi = sbase + sm.op + sl * 2 * kTileBytes + st_tid * 128;
+        const uint32_t dlo = dhi + kTileBytes;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 v, h, l;
-          v.x = src[(4 * c + 0) * kTileM]; v.y = src[(4 * c + 1) * kTileM];
-          v.z = src[(4 * c + 2) * kTileM]; v.w = src[(4 * c + 3) * kTileM];
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-          const int off = (c ^ (st_tid & 7)) << 4;
-          *reinterpret_cast<float4*>(dhi + off) = h;
-          *reinterpret_cast<float4*>(dlo + off) = l;
+          v.x = lds_f32(src + (4 * c + 0) * kTileM * 4); v.y = lds_f32(src + (4 * c + 1) * kTileM * 4);
+          v.z = lds_f32(src + (4 * c + 2) * kTileM * 4); v.w = lds_f32(src + (4 * c + 3) * kTileM * 4);
+          h.x = trunc_tf32(v.x); l.x = v.x - h.x;
+          h.y = trunc_tf32(v.y); l.y = v.y - h.y;
+          h.z = trunc_tf32(v.z); l.z = v.z - h.z;
+          h.w = trunc_tf32(v.w); l.w = v.w - h.w;
+          const uint32_t off = (uint32_t)(c ^ (st_tid & 7)) << 4;
+          sts_v4(dhi + off, h);
+          sts_v4(dlo + off, l);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&s.bars[BAR_LO_FULL + sl]);
-          mbar_arrive(&s.bars[BAR_HI_EMPTY + sh]);
+          bar_arrive(BAR(BAR_LO_FULL + sl));
+          bar_arrive(BAR(BAR_HI_EMPTY + sh));
         }
         ++fg;
         if (++ft == fit.ntiles) { ft = 0; fit = get_item(p, ++fk); }
@@ -405,47 +470,50 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       if (lagged < kLag && fit.valid) { ++lagged; continue; }
       if (bit.valid) {
         const int ac = bg % kAcc;
-        mbar_wait(&s.bars[BAR_ACC_FULL + ac], (bg / kAcc) & 1);
+        bar_wait(BAR(BAR_ACC_FULL + ac), (bg / kAcc) & 1);
         __syncwarp();
         tc_fence_after();
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + ac * kNPad, r);
+        uint32_t r[kNI];
+        tmem_ld<kNI>(tmem_base + ((uint32_t)(quarter * 32) << 16) + ac * kNPad, r);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s.bars[BAR_ACC_EMPTY + ac]);
+        if (lane == 0) bar_arrive(BAR(BAR_ACC_EMPTY + ac));
 
-        const int n = min(p.counts[bit.b], min(d.max_n, kMaxInstTc));
-        const int px = bt * kTileM + quarter * 32 + lane;     // band-local pixel of this thread
-        const bool live = px < bit.npx;
-        const int row = px / d.mw, col = px - row * d.mw;     // band-local row
-        // chunks touched by this tile (warp-uniform bounds): rows [row_first, row_last]
+        const int n = min(p.counts[bit.b], min(d.max_n, kNI));
+        const bool live = (bt * kTileM + ep_px) < bit.npx;
+        // chunks touched by this tile (warp-uniform): acquire their buffers in order
         const int tile_last_px = min((bt + 1) * kTileM, bit.npx) - 1;
-        const int row_last = tile_last_px / d.mw;
-        const int c_hi = min(row_last / p.pr, bit.nchunks - 1);
-        while (acquired <= c_hi) {                            // acquire chunk buffers in order
+        const int c_hi = min((tile_last_px / d.mw) / p.pr, bit.nchunks - 1);
+        while (acquired <= c_hi) {
           const uint32_t gc = chunk_base + acquired;
-          mbar_wait(&s.bars[BAR_CH_EMPTY + gc % kChunkBufs], ((gc / kChunkBufs) & 1) ^ 1);
+          bar_wait(BAR(BAR_CH_EMPTY + gc % kChunkBufs), ((gc / kChunkBufs) & 1) ^ 1);
           ++acquired;
         }
         if (live) {
-          const float fx = (float)col, fy = (float)(bit.pa + row);
-          const int c1 = row / p.pr, rr = row - c1 * p.pr;
-          float* dst1 = (c1 < bit.nchunks)
-                            ? s.chunks + (size_t)((chunk_base + c1) % kChunkBufs) * p.chunk_floats + (size_t)rr * p.nst * d.mw + col
-                            : nullptr;
-          float* dst0 = (rr == 0 && c1 > 0)
-                            ? s.chunks + (size_t)((chunk_base + c1 - 1) % kChunkBufs) * p.chunk_floats + (size_t)p.pr * p.nst * d.mw + col
-                            : nullptr;
-          const float* bx = s.box + (bk & 3) * kMaxInstTc * 4;
+          const float fx = (float)bcol, fy = (float)(bit.pa + brow);
+          const int c1 = brow / p.pr, rr = brow - c1 * p.pr;
+          const uint32_t inst_stride = (uint32_t)d.mw * 4;
+          const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
+          const uint32_t chunks = sbase + sm.chunks;
+          const bool has1 = c1 < bit.nchunks, has0 = (rr == 0 && c1 > 0);
+          const uint32_t dst1 = chunks + ((chunk_base + c1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
+          const uint32_t dst0 = chunks + ((chunk_base + c1 + kChunkBufs - 1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
+          const uint32_t bx = sbase + sm.box + (bk & 3) * kMaxInstTc * 16;
 #pragma unroll
-          for (int i = 0; i < kMaxInstTc; ++i) {
+          for (int i = 0; i < kNI; ++i) {
             if (i < n) {
-              const bool keep = (fx >= bx[4 * i]) && (fx < bx[4 * i + 2]) && (fy >= bx[4 * i + 1]) && (fy < bx[4 * i + 3]);
+              const float4 q = lds_v4(bx + 16 * i);     // x1, y1, x2, y2 at proto resolution (ops.py:725-732)
+              const bool keep = (fx >= q.x) && (fx < q.z) && (fy >= q.y) && (fy < q.w);   // crop_mask, ops.py:688-704
               const float v = keep ? __uint_as_float(r[i]) : 0.f;
-              if (dst1) dst1[(size_t)i * d.mw] = v;
-              if (dst0) dst0[(size_t)i * d.mw] = v;
-              if (p.logits_dbg) p.logits_dbg[(((size_t)bit.b * d.max_n + i) * d.mh + bit.pa + row) * d.mw + col] = v;
+              r[i] = __float_as_uint(v);
+              if (has1) sts_f32(dst1 + i * inst_stride, v);
+              if (has0) sts_f32(dst0 + i * inst_stride, v);
             }
+          }
+          if (p.logits_dbg) {
+#pragma unroll
+            for (int i = 0; i < kNI; ++i)
+              if (i < n) p.logits_dbg[(((size_t)bit.b * d.max_n + i) * d.mh + bit.pa + brow) * d.mw + bcol] = __uint_as_float(r[i]);
           }
         }
         __syncwarp();
@@ -453,103 +521,116 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int rows_done = (bt + 1 == bit.ntiles) ? bit.nrows : ((bt + 1) * kTileM) / d.mw;   // complete rows so far
         while (completed < bit.nchunks && chunk_last_row(p, bit, completed) < rows_done) {
           const uint32_t gc = chunk_base + completed;
-          if (lane == 0) mbar_arrive(&s.bars[BAR_CH_FULL + gc % kChunkBufs]);
+          if (lane == 0) bar_arrive(BAR(BAR_CH_FULL + gc % kChunkBufs));
           ++completed;
         }
         ++bg;
+        // advance this thread's (row, col) by one tile
+        brow += tile_rows; bcol += tile_cols;
+        if (bcol >= d.mw) { bcol -= d.mw; ++brow; }
         if (++bt == bit.ntiles) {
           bt = 0;
           chunk_base += bit.nchunks;
           acquired = 0;
           completed = 0;
           bit = get_item(p, ++bk);
+          brow = ep_px / d.mw; bcol = ep_px - brow * d.mw;
         }
       }
     }
   } else {
     // =========================== upsample + threshold + store + reductions ===========================
-    const int ut = threadIdx.x - 32 * (2 + kWarpsSplit);     // 0..319
+    const int uw = warp - (2 + kWarpsSplit);                 // 0..kWarpsUp-1
+    const int ut = threadIdx.x - 32 * (2 + kWarpsSplit);
     const int NG = d.W >> 4, NG8 = ceil_div(NG, 8);
+    // lane -> (8 column groups) x (4 slots); slot -> (pair within the chunk, sub-block of 8 groups)
+    const int gl = lane & 7, slot = lane >> 3;
+    const int subs = 4 / p.pr;                               // pr = 4: 1, pr = 2: 2
+    const int pair = slot % p.pr, sub = slot / p.pr;
+    const int ng8w = ceil_div(NG8, subs);                    // warp tasks per instance
     const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
     const uint4 zeros = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t inst_stride = (uint32_t)d.mw * 4;
+    const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
+    const uint32_t latrow = sbase + sm.latrow;
     uint32_t gc = 0;
     for (int k = 0;; ++k) {
       const Item it = get_item(p, k);
       if (!it.valid) break;
-      const int n = min(p.counts[it.b], min(d.max_n, kMaxInstTc));
+      const int n = min(p.counts[it.b], min(d.max_n, kNI));
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
         const int buf = gc % kChunkBufs;
-        mbar_wait(&s.bars[BAR_CH_FULL + buf], (gc / kChunkBufs) & 1);
-        const float* cb = s.chunks + (size_t)buf * p.chunk_floats;
+        bar_wait(BAR(BAR_CH_FULL + buf), (gc / kChunkBufs) & 1);
+        const uint32_t cb = sbase + sm.chunks + buf * (uint32_t)p.chunk_floats * 4;
         const int r0 = it.pa + c * p.pr;                        // first pair of the chunk
         const int npairs = min(p.pr, it.pb - r0);
-        const int ntasks = n * NG8 * p.pr * 8;                  // gl (8) fastest, then pair, g8, instance
-        for (int q = ut; q < ntasks; q += kUpThreadsTc) {
-          const int gl = q & 7;
-          int rest = q >> 3;
-          const int pair = rest % p.pr; rest /= p.pr;
-          const int g8 = rest % NG8;
-          const int i = rest / NG8;
-          const int g = g8 * 8 + gl;
-          if (g >= NG || pair >= npairs) continue;
-          const int r = r0 + pair;
-          const bool last = (r == d.mh - 1);
-          const float* rowA = cb + ((size_t)pair * p.nst + i) * d.mw;
-          const float* rowB = last ? rowA : rowA + (size_t)p.nst * d.mw;
-          float sA[6], sB[6];
-          {
-            const float4 v = *reinterpret_cast<const float4*>(rowA + 4 * g);
-            sA[1] = v.x; sA[2] = v.y; sA[3] = v.z; sA[4] = v.w;
-            sA[0] = (g > 0) ? rowA[4 * g - 1] : v.x;
-            sA[5] = (4 * g + 4 < d.mw) ? rowA[4 * g + 4] : v.w;
-            const float4 u = *reinterpret_cast<const float4*>(rowB + 4 * g);
-            sB[1] = u.x; sB[2] = u.y; sB[3] = u.z; sB[4] = u.w;
-            sB[0] = (g > 0) ? rowB[4 * g - 1] : u.x;
-            sB[5] = (4 * g + 4 < d.mw) ? rowB[4 * g + 4] : u.w;
-          }
-          const float mnA = fminf(fminf(fminf(sA[0], sA[1]), fminf(sA[2], sA[3])), fminf(sA[4], sA[5]));
-          const float mxA = fmaxf(fmaxf(fmaxf(sA[0], sA[1]), fmaxf(sA[2], sA[3])), fmaxf(sA[4], sA[5]));
-          const float mnB = fminf(fminf(fminf(sB[0], sB[1]), fminf(sB[2], sB[3])), fminf(sB[4], sB[5]));
-          const float mxB = fmaxf(fmaxf(fmaxf(sB[0], sB[1]), fmaxf(sB[2], sB[3])), fmaxf(sB[4], sB[5]));
-          const size_t inst = (size_t)it.b * d.max_n + i;
-          uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
-          unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
+        const int r = r0 + pair;
+        const bool last = (r == d.mh - 1);
+        for (int wq = uw; wq < n * ng8w; wq += kWarpsUp) {
+          const int i = wq / ng8w;
+          const int g = ((wq - i * ng8w) * subs + sub) * 8 + gl;
+          const bool active = (g < NG) && (pair < npairs);
           ThreadStats ts;
-          auto emit = [&](const uint4& w, int Y) {
-            if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
-            ts.add_row(w, Y);
-            if ((w.x | w.y | w.z | w.w) && s.latrow[Y] >= 0) lattice_row(w, Y, 16 * g, d, lat);
-          };
-          const bool left = (g == 0);
-          const bool uni_pos = fminf(mnA, mnB) > kTiny, uni_neg = fmaxf(mxA, mxB) <= 0.f;
-          const int Y0 = 4 * r + 2;
-          float hA[16], hB[16];
-          const bool need_h = !(uni_pos || uni_neg);
-          if (need_h) { hinterp4(sA, hA, left); hinterp4(sB, hB, left); }
-          if (r == 0) {       // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
-            uint4 w;
-            if (mnA > kTiny) w = ones;
-            else if (mxA <= 0.f) w = zeros;
-            else { if (!need_h) hinterp4(sA, hA, left); w = hpack(hA); }
-            emit(w, 0);
-            emit(w, 1);
-          }
-          if (uni_pos) {
-            emit(ones, Y0); emit(ones, Y0 + 1);
-            if (!last) { emit(ones, Y0 + 2); emit(ones, Y0 + 3); }
-          } else if (uni_neg) {
-            emit(zeros, Y0); emit(zeros, Y0 + 1);
-            if (!last) { emit(zeros, Y0 + 2); emit(zeros, Y0 + 3); }
-          } else {
-            emit(vblend(hA, hB, 0.875f, 0.125f), Y0);
-            emit(vblend(hA, hB, 0.625f, 0.375f), Y0 + 1);
-            if (!last) {
-              emit(vblend(hA, hB, 0.375f, 0.625f), Y0 + 2);
-              emit(vblend(hA, hB, 0.125f, 0.875f), Y0 + 3);
+          if (active) {
+            const uint32_t rowA = cb + pair * row_stride + i * inst_stride + g * 16;
+            const uint32_t rowB = last ? rowA : rowA + row_stride;
+            float sA[6], sB[6];
+            {
+              const float4 v = lds_v4(rowA);
+              sA[1] = v.x; sA[2] = v.y; sA[3] = v.z; sA[4] = v.w;
+              sA[0] = (g > 0) ? lds_f32(rowA - 4) : v.x;
+              sA[5] = (4 * g + 4 < d.mw) ? lds_f32(rowA + 16) : v.w;
+              const float4 u = lds_v4(rowB);
+              sB[1] = u.x; sB[2] = u.y; sB[3] = u.z; sB[4] = u.w;
+              sB[0] = (g > 0) ? lds_f32(rowB - 4) : u.x;
+              sB[5] = (4 * g + 4 < d.mw) ? lds_f32(rowB + 16) : u.w;
             }
+            const float mnA = fminf(fminf(fminf(sA[0], sA[1]), fminf(sA[2], sA[3])), fminf(sA[4], sA[5]));
+            const float mxA = fmaxf(fmaxf(fmaxf(sA[0], sA[1]), fmaxf(sA[2], sA[3])), fmaxf(sA[4], sA[5]));
+            const float mnB = fminf(fminf(fminf(sB[0], sB[1]), fminf(sB[2], sB[3])), fminf(sB[4], sB[5]));
+            const float mxB = fmaxf(fmaxf(fmaxf(sB[0], sB[1]), fmaxf(sB[2], sB[3])), fmaxf(sB[4], sB[5]));
+            const size_t inst = (size_t)it.b * d.max_n + i;
+            uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
+            unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
+            auto emit = [&](const uint4& w, int Y) {
+              if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
+              ts.add_row(w, Y);
+              if ((w.x | w.y | w.z | w.w) && lds_s16(latrow + 2 * Y) >= 0) lattice_row(w, Y, 16 * g, d, lat);
+            };
+            const bool left = (g == 0);
+            const bool uni_pos = fminf(mnA, mnB) > kTiny, uni_neg = fmaxf(mxA, mxB) <= 0.f;
+            const int Y0 = 4 * r + 2;
+            float hA[16], hB[16];
+            const bool need_h = !(uni_pos || uni_neg);
+            if (need_h) { hinterp4(sA, hA, left); hinterp4(sB, hB, left); }
+            if (r == 0) {       // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
+              uint4 w;
+              if (mnA > kTiny) w = ones;
+              else if (mxA <= 0.f) w = zeros;
+              else { if (!need_h) hinterp4(sA, hA, left); w = hpack(hA); }
+              emit(w, 0);
+              emit(w, 1);
+            }
+            if (uni_pos) {
+              emit(ones, Y0); emit(ones, Y0 + 1);
+              if (!last) { emit(ones, Y0 + 2); emit(ones, Y0 + 3); }
+            } else if (uni_neg) {
+              emit(zeros, Y0); emit(zeros, Y0 + 1);
+              if (!last) { emit(zeros, Y0 + 2); emit(zeros, Y0 + 3); }
+            } else {
+              emit(vblend(hA, hB, 0.875f, 0.125f), Y0);
+              emit(vblend(hA, hB, 0.625f, 0.375f), Y0 + 1);
+              if (!last) {
+                emit(vblend(hA, hB, 0.375f, 0.625f), Y0 + 2);
+                emit(vblend(hA, hB, 0.125f, 0.875f), Y0 + 3);
+              }
+            }
+            ts.flush();
           }
-          ts.flush();
-          if (ts.area) {
+          // warp-level reduction (all lanes of a warp task share the instance), one set of smem atomics per warp
+          __syncwarp();
+          const unsigned area = __reduce_add_sync(0xffffffffu, ts.area);
+          if (area) {
             int minx = INT_MAX, maxx = -1;
 #pragma unroll
             for (int w4 = 0; w4 < 4; ++w4) {
@@ -558,30 +639,37 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                 maxx = max(maxx, 16 * g + 4 * w4 + ((31 - __clz(ts.orw[w4])) >> 3));
               }
             }
-            int* st = s.stat + i * 8;
-            atomicAdd(&st[0], (int)ts.area);
-            atomicMin(&st[1], minx);
-            atomicMin(&st[2], ts.miny);
-            atomicMax(&st[3], maxx);
-            atomicMax(&st[4], ts.maxy);
+            minx = __reduce_min_sync(0xffffffffu, minx);
+            maxx = __reduce_max_sync(0xffffffffu, maxx);
+            const int miny = __reduce_min_sync(0xffffffffu, ts.miny);
+            const int maxy = __reduce_max_sync(0xffffffffu, ts.maxy);
+            if (lane == 0) {
+              const uint32_t st = sbase + sm.stat + i * 32;
+              atoms_add(st, (int)area);
+              atoms_min(st + 4, minx);
+              atoms_min(st + 8, miny);
+              atoms_max(st + 12, maxx);
+              atoms_max(st + 16, maxy);
+            }
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s.bars[BAR_CH_EMPTY + buf]);
+        if (lane == 0) bar_arrive(BAR(BAR_CH_EMPTY + buf));
       }
       // ---- item done: publish the band's reductions for frame it.b ----
       named_bar_sync(2, kUpThreadsTc);
       if (ut < n) {
-        int* st = s.stat + ut * 8;
-        if (st[0]) {
+        const uint32_t st = sbase + sm.stat + ut * 32;
+        const int area = lds_s32(st);
+        if (area) {
           InstStats* dst = p.stats + (size_t)it.b * d.max_n + ut;
-          atomicAdd(&dst->area, (unsigned)st[0]);
-          atomicMin(&dst->minx, st[1]);
-          atomicMin(&dst->miny, st[2]);
-          atomicMax(&dst->maxx, st[3]);
-          atomicMax(&dst->maxy, st[4]);
+          atomicAdd(&dst->area, (unsigned)area);
+          atomicMin(&dst->minx, lds_s32(st + 4));
+          atomicMin(&dst->miny, lds_s32(st + 8));
+          atomicMax(&dst->maxx, lds_s32(st + 12));
+          atomicMax(&dst->maxy, lds_s32(st + 16));
         }
-        st[0] = 0; st[1] = INT_MAX; st[2] = INT_MAX; st[3] = -1; st[4] = -1;
+        sts_s32(st, 0); sts_s32(st + 4, INT_MAX); sts_s32(st + 8, INT_MAX); sts_s32(st + 12, -1); sts_s32(st + 16, -1);
       }
       named_bar_sync(2, kUpThreadsTc);
     }
@@ -608,6 +696,7 @@ struct FusedPlan {
   PFN_encodeTiled encode;
   int num_sms;
   int pr;
+  int ni;            // accumulator columns read back per tile (8 or 16)
   int chunk_floats;
   size_t smem_bytes;
   // cached tensor map
@@ -640,14 +729,18 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   int pr = 0;
   for (int cand : {4, 2}) {
     const int cf = (cand + 1) * d.max_n * d.mw;
-    if (fused_smem_layout(cf, d.H, nullptr, nullptr) + 1024 <= limit) { pr = cand; break; }
+    if ((size_t)fused_smem_map(cf, d.H).total + 1024 <= limit) { pr = cand; break; }
   }
   if (!pr) { delete pl; snprintf(err, errlen, "chunk buffers do not fit in shared memory (max_n=%d, mw=%d)", d.max_n, d.mw); return nullptr; }
   pl->pr = pr;
   pl->chunk_floats = (pr + 1) * d.max_n * d.mw;
-  pl->smem_bytes = fused_smem_layout(pl->chunk_floats, d.H, nullptr, nullptr) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
+  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, d.H).total + 1024;
+  pl->ni = d.max_n <= 8 ? 8 : 16;
+  cudaError_t e = cudaSuccess;
+  const void* fns[4] = {(const void*)fused_tc_kernel<true, 8>, (const void*)fused_tc_kernel<false, 8>,
+                        (const void*)fused_tc_kernel<true, 16>, (const void*)fused_tc_kernel<false, 16>};
+  for (const void* f : fns)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(%zu B): %s", pl->smem_bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
   return pl;
 }
@@ -691,8 +784,13 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.nbands = ceil_div(d.mh, p.ppb);
   p.n_items = B * p.nbands;
   const int grid = p.n_items < pl->num_sms ? p.n_items : pl->num_sms;
-  if (masks) fused_tc_kernel<true><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
-  else fused_tc_kernel<false><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+  if (pl->ni == 8) {
+    if (masks) fused_tc_kernel<true, 8><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+    else fused_tc_kernel<false, 8><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+  } else {
+    if (masks) fused_tc_kernel<true, 16><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+    else fused_tc_kernel<false, 16><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+  }
   return cudaGetLastError();
 }
 
