@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "va_up_common.cuh"
@@ -37,11 +38,13 @@ constexpr int kStagesHi = 3;                // TMA staging ring ([32 k][128 px] 
 constexpr int kStagesLo = 2;                // operand ring: one A_hi + one A_lo K-major tile per stage
 constexpr int kAcc = 4;                     // TMEM accumulator ring
 constexpr int kNPad = 16;                   // UMMA N (instances padded)
-constexpr int kLag = 2;                     // epilogue runs kLag tiles behind the split front
 constexpr int kChunkBufs = 3;
-constexpr int kWarpsSplit = 4;
-constexpr int kWarpsUp = 10;
-constexpr int kThreads = 32 * (2 + kWarpsSplit + kWarpsUp);   // 512
+constexpr int kWarpsSplit = 2;              // transpose + 3xTF32 split (two pixel rows per thread)
+constexpr int kWarpsEpi = 4;                // TMEM -> crop -> chunk buffers (one warp per TMEM lane quarter)
+constexpr int kWarpsUp = 8;
+constexpr int kFirstEpiWarp = 2 + kWarpsSplit;
+constexpr int kFirstUpWarp = kFirstEpiWarp + kWarpsEpi;
+constexpr int kThreads = 32 * (kFirstUpWarp + kWarpsUp);   // 512
 constexpr int kUpThreadsTc = 32 * kWarpsUp;
 constexpr int kMaxInstTc = 16;              // instances this kernel handles (N = 16)
 constexpr int kTmemCols = kAcc * kNPad;     // 64: power of two >= 32
@@ -58,10 +61,12 @@ struct FusedParams {
   int B;
   int nbands;        // bands per frame
   int ppb;           // row pairs per band
-  int pr;            // row pairs per chunk
+  int pr;            // row pairs per chunk (2 or 4)
+  int pr_shift;      // log2(pr)
   int n_items;
   int nst;           // instance stride of the chunk buffers (= max_n)
   int chunk_floats;  // floats per chunk buffer = (pr+1) * nst * mw
+  unsigned long long* timing;   // developer diagnostic (VA_FUSED_TIMING=1): [grid][5 roles][8] cycle counters, or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -193,7 +198,7 @@ struct SmemMap {
   uint32_t op;        // [kStagesLo][A_hi 16 KB | A_lo 16 KB]   K-major SW128 operand tiles
   uint32_t bt;        // [2 parity][hi, lo][kNPad * 128 B]
   uint32_t chunks;    // [kChunkBufs][chunk_floats] f32
-  uint32_t box;       // [4 items ring][kMaxInstTc][4] f32
+  uint32_t box;       // [2 item parity][kMaxInstTc][4] f32 (epilogue warps only)
   uint32_t stat;      // [kMaxInstTc][8] i32: area, minx, miny, maxx, maxy
   uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
   uint32_t bars;      // [BAR_COUNT] u64
@@ -290,6 +295,24 @@ __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&r)[8]) {
 template <>
 __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
+// cycle accounting of the mbarrier waits (only when p.timing != nullptr)
+struct RoleTimer {
+  unsigned long long* out;
+  long long t_start, wait[6];
+  __device__ __forceinline__ void begin(unsigned long long* o) { out = o; if (out) { t_start = clock64(); for (int i = 0; i < 6; ++i) wait[i] = 0; } }
+  __device__ __forceinline__ void end() { if (out) { out[0] = (unsigned long long)(clock64() - t_start); for (int i = 0; i < 6; ++i) out[1 + i] = (unsigned long long)wait[i]; } }
+};
+#define TIMED_WAIT(tm, slot, bar, parity)            \
+  do {                                                \
+    if ((tm).out) {                                   \
+      const long long t0__ = clock64();               \
+      bar_wait((bar), (parity));                      \
+      (tm).wait[(slot)] += clock64() - t0__;          \
+    } else {                                          \
+      bar_wait((bar), (parity));                      \
+    }                                                 \
+  } while (0)
+
 __device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,9 +334,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStagesHi; ++i) { bar_init(BAR(BAR_HI_FULL + i), 1); bar_init(BAR(BAR_HI_EMPTY + i), kWarpsSplit); }
     for (int i = 0; i < kStagesLo; ++i) { bar_init(BAR(BAR_LO_FULL + i), kWarpsSplit); bar_init(BAR(BAR_LO_EMPTY + i), 1); }
-    for (int i = 0; i < kAcc; ++i) { bar_init(BAR(BAR_ACC_FULL + i), 1); bar_init(BAR(BAR_ACC_EMPTY + i), kWarpsSplit); }
+    for (int i = 0; i < kAcc; ++i) { bar_init(BAR(BAR_ACC_FULL + i), 1); bar_init(BAR(BAR_ACC_EMPTY + i), kWarpsEpi); }
     for (int i = 0; i < 2; ++i) { bar_init(BAR(BAR_B_FULL + i), kWarpsSplit); bar_init(BAR(BAR_B_EMPTY + i), 1); }
-    for (int i = 0; i < kChunkBufs; ++i) { bar_init(BAR(BAR_CH_FULL + i), kWarpsSplit); bar_init(BAR(BAR_CH_EMPTY + i), kWarpsUp); }
+    for (int i = 0; i < kChunkBufs; ++i) { bar_init(BAR(BAR_CH_FULL + i), kWarpsEpi); bar_init(BAR(BAR_CH_EMPTY + i), kWarpsUp); }
     fence_barrier_init();
   }
   for (int y = threadIdx.x; y < d.H; y += kThreads) {
@@ -336,6 +359,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
+      RoleTimer tm; tm.begin(p.timing ? p.timing + ((size_t)blockIdx.x * 5 + 0) * 8 : nullptr);
       uint32_t g = 0;   // global tile counter of this CTA
       for (int k = 0;; ++k) {
         const Item it = get_item(p, k);
@@ -343,28 +367,30 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int px0 = it.pa * d.mw;
         for (int t = 0; t < it.ntiles; ++t, ++g) {
           const int st = g % kStagesHi;
-          bar_wait(BAR(BAR_HI_EMPTY + st), ((g / kStagesHi) & 1) ^ 1);
+          TIMED_WAIT(tm, 0, BAR(BAR_HI_EMPTY + st), ((g / kStagesHi) & 1) ^ 1);
           bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
           tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), px0 + t * kTileM, 0, it.b);
         }
       }
+      tm.end();
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kTileM, kNPad);
+      RoleTimer tm; tm.begin(p.timing ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
       uint32_t g = 0;
       for (int k = 0;; ++k) {
         const Item it = get_item(p, k);
         if (!it.valid) break;
         const int par = k & 1;
-        bar_wait(BAR(BAR_B_FULL + par), (k >> 1) & 1);
+        TIMED_WAIT(tm, 0, BAR(BAR_B_FULL + par), (k >> 1) & 1);
         const uint32_t b_hi = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
         const uint32_t b_lo = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
         for (int t = 0; t < it.ntiles; ++t, ++g) {
           const int sl = g % kStagesLo, ac = g % kAcc;
-          bar_wait(BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
-          bar_wait(BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);
+          TIMED_WAIT(tm, 1, BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
+          TIMED_WAIT(tm, 2, BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);
           tc_fence_after();
           const uint32_t a_hi = sbase + sm.op + sl * 2 * kTileBytes;
           const uint32_t a_lo = a_hi + kTileBytes;
@@ -385,77 +411,64 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         }
         bar_commit(BAR(BAR_B_EMPTY + par));
       }
+      tm.end();
     }
-  } else if (warp < 2 + kWarpsSplit) {
-    // =========================== split (front) + epilogue (back) ===========================
-    const int sw = warp - 2;                 // 0..3
-    const int st_tid = sw * 32 + lane;       // 0..127 = pixel row of the tile this thread transposes
-    const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are accessible to this warp
-    const int ep_px = quarter * 32 + lane;   // tile pixel this thread reads back from TMEM
-    int fk = 0, ft = 0;                      // front iterator (item, tile)
-    Item fit = get_item(p, 0);
-    uint32_t fg = 0;
-    int bk = 0, bt = 0;                      // back iterator
-    Item bit = get_item(p, 0);
-    uint32_t bg = 0;
-    uint32_t chunk_base = 0;                 // global chunk index of chunk 0 of the back item
-    int acquired = 0, completed = 0;         // chunks of the back item acquired for writing / signalled full
-    int lagged = 0;
-    int brow = ep_px / d.mw, bcol = ep_px - brow * d.mw;   // band-local (row, col) of this thread's pixel in the back tile
-    const int tile_rows = kTileM / d.mw, tile_cols = kTileM - tile_rows * d.mw;   // advance per tile
-
-    while (fit.valid || bit.valid) {
-      // ---------------- front ----------------
-      if (fit.valid) {
-        if (ft == 0) {   // new item: per-frame B tiles (coefficients hi / lo) and scaled boxes
-          const int par = fk & 1;
-          bar_wait(BAR(BAR_B_EMPTY + par), ((fk >> 1) & 1) ^ 1);
-          const int n = min(p.counts[fit.b], min(d.max_n, kMaxInstTc));
-          const uint32_t bh = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
-          const uint32_t bl = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
-          {   // row r (instance), 16 B chunk c: stored at chunk c ^ (r & 7)  (128B swizzle, K-major); 128 threads = 16 x 8
-            const int r = st_tid >> 3, c = st_tid & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)fit.b * d.max_n + r) * d.K + 4 * c));
-            float4 h, l;
-            h.x = trunc_tf32(v.x); l.x = v.x - h.x;
-            h.y = trunc_tf32(v.y); l.y = v.y - h.y;
-            h.z = trunc_tf32(v.z); l.z = v.z - h.z;
-            h.w = trunc_tf32(v.w); l.w = v.w - h.w;
-            const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-            sts_v4(bh + off, h);
-            sts_v4(bl + off, l);
-          }
-          if (st_tid < kMaxInstTc * 4) {
-            const int i = st_tid >> 2, c = st_tid & 3;
-            float v = 0.f;
-            if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)fit.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
-            sts_f32(sbase + sm.box + (((fk & 3) * kMaxInstTc + i) * 4 + c) * 4, v);
-          }
-          fence_proxy_async();
-          named_bar_sync(1, 32 * kWarpsSplit);
-          if (lane == 0) bar_arrive(BAR(BAR_B_FULL + par));
-        }
-        const int sh = fg % kStagesHi, sl = fg % kStagesLo;
-        bar_wait(BAR(BAR_HI_FULL + sh), (fg / kStagesHi) & 1);
-        bar_wait(BAR(BAR_LO_EMPTY + sl), ((fg / kStagesLo) & 1) ^ 1);
-        // transpose + split: thread = pixel row of the tile.  Reads of [k][px] are conflict-free across
-        // the warp (consecutive px); each 16 B chunk c of the K-major row lands at chunk c ^ (px & 7).
-        const uint32_t src = sbase + sm.hi + sh * kTileBytes + st_tid * 4;
-        const uint32_t dhi = sbase + sm.op + sl * 2 * kTileBytes + st_tid * 128;
-        const uint32_t dlo = dhi + kTileBytes;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 v, h, l;
-          v.x = lds_f32(src + (4 * c + 0) * kTileM * 4); v.y = lds_f32(src + (4 * c + 1) * kTileM * 4);
-          v.z = lds_f32(src + (4 * c + 2) * kTileM * 4); v.w = lds_f32(src + (4 * c + 3) * kTileM * 4);
+  } else if (warp < kFirstEpiWarp) {
+    // =========================== transpose + 3xTF32 split ===========================
+    const int st_tid = (warp - 2) * 32 + lane;       // 0 .. 32*kWarpsSplit-1
+    RoleTimer tm; tm.begin((p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
+    uint32_t g = 0;
+    for (int k = 0;; ++k) {
+      const Item it = get_item(p, k);
+      if (!it.valid) break;
+      {   // per-frame B tiles: coefficients hi / lo, K-major, 16 B chunk c of row r stored at chunk c ^ (r & 7)
+        const int par = k & 1;
+        TIMED_WAIT(tm, 0, BAR(BAR_B_EMPTY + par), ((k >> 1) & 1) ^ 1);
+        const int n = min(p.counts[it.b], min(d.max_n, kMaxInstTc));
+        const uint32_t bh = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
+        const uint32_t bl = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
+        for (int q = st_tid; q < kNPad * 8; q += 32 * kWarpsSplit) {   // 16 rows x 8 chunks
+          const int r = q >> 3, c = q & 7;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)it.b * d.max_n + r) * d.K + 4 * c));
+          float4 h, l;
           h.x = trunc_tf32(v.x); l.x = v.x - h.x;
           h.y = trunc_tf32(v.y); l.y = v.y - h.y;
           h.z = trunc_tf32(v.z); l.z = v.z - h.z;
           h.w = trunc_tf32(v.w); l.w = v.w - h.w;
-          const uint32_t off = (uint32_t)(c ^ (st_tid & 7)) << 4;
-          sts_v4(dhi + off, h);
-          sts_v4(dlo + off, l);
+          const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+          sts_v4(bh + off, h);
+          sts_v4(bl + off, l);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) bar_arrive(BAR(BAR_B_FULL + par));
+      }
+      for (int t = 0; t < it.ntiles; ++t, ++g) {
+        const int sh = g % kStagesHi, sl = g % kStagesLo;
+        TIMED_WAIT(tm, 1, BAR(BAR_HI_FULL + sh), (g / kStagesHi) & 1);
+        TIMED_WAIT(tm, 2, BAR(BAR_LO_EMPTY + sl), ((g / kStagesLo) & 1) ^ 1);
+        // thread = pixel rows st_tid, st_tid + 64, ... of the tile.  Reads of [k][px] are conflict-free across
+        // the warp (consecutive px); each 16 B chunk c of the K-major row lands at chunk c ^ (px & 7).
+#pragma unroll 1
+        for (int px = st_tid; px < kTileM; px += 32 * kWarpsSplit) {
+          const uint32_t src = sbase + sm.hi + sh * kTileBytes + px * 4;
+          const uint32_t dhi = sbase + sm.op + sl * 2 * kTileBytes + px * 128;
+          const uint32_t dlo = dhi + kTileBytes;
+          float v[kProtoK];
+#pragma unroll
+          for (int q = 0; q < kProtoK; ++q) v[q] = lds_f32(src + q * kTileM * 4);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 h, l;
+            h.x = trunc_tf32(v[4 * c + 0]); l.x = v[4 * c + 0] - h.x;
+            h.y = trunc_tf32(v[4 * c + 1]); l.y = v[4 * c + 1] - h.y;
+            h.z = trunc_tf32(v[4 * c + 2]); l.z = v[4 * c + 2] - h.z;
+            h.w = trunc_tf32(v[4 * c + 3]); l.w = v[4 * c + 3] - h.w;
+            const uint32_t off = (uint32_t)(c ^ (px & 7)) << 4;
+            sts_v4(dhi + off, h);
+            sts_v4(dlo + off, l);
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -463,14 +476,42 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           bar_arrive(BAR(BAR_LO_FULL + sl));
           bar_arrive(BAR(BAR_HI_EMPTY + sh));
         }
-        ++fg;
-        if (++ft == fit.ntiles) { ft = 0; fit = get_item(p, ++fk); }
       }
-      // ---------------- back: epilogue of the tile kLag steps behind ----------------
-      if (lagged < kLag && fit.valid) { ++lagged; continue; }
-      if (bit.valid) {
-        const int ac = bg % kAcc;
-        bar_wait(BAR(BAR_ACC_FULL + ac), (bg / kAcc) & 1);
+    }
+    tm.end();
+  } else if (warp < kFirstUpWarp) {
+    // =========================== epilogue: TMEM -> crop -> chunk buffers ===========================
+    const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are accessible to this warp
+    const int ep_px = quarter * 32 + lane;   // tile pixel this thread reads back
+    const int ep_tid = (warp - kFirstEpiWarp) * 32 + lane;
+    const int tile_rows = kTileM / d.mw, tile_cols = kTileM - tile_rows * d.mw;   // (row, col) advance per tile
+    const uint32_t inst_stride = (uint32_t)d.mw * 4;
+    const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
+    const uint32_t chunks = sbase + sm.chunks;
+    RoleTimer tm; tm.begin((p.timing && ep_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 3) * 8 : nullptr);
+    uint32_t g = 0, chunk_base = 0;
+    for (int k = 0;; ++k) {
+      const Item it = get_item(p, k);
+      if (!it.valid) break;
+      const int n = min(p.counts[it.b], min(d.max_n, kNI));
+      // scaled boxes of this frame (double-buffered by item parity; the 4 epilogue warps stay within one item)
+      const uint32_t bx = sbase + sm.box + (k & 1) * kMaxInstTc * 16;
+      if (ep_tid < kMaxInstTc * 4) {
+        const int i = ep_tid >> 2, c = ep_tid & 3;
+        float v = 0.f;
+        if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
+        sts_f32(bx + (i * 4 + c) * 4, v);
+      }
+      named_bar_sync(1, 32 * kWarpsEpi);
+      float4 box[kNI];                                         // x1, y1, x2, y2 at proto resolution (ops.py:725-732)
+#pragma unroll
+      for (int i = 0; i < kNI; ++i) box[i] = lds_v4(bx + 16 * i);
+      int brow = ep_px / d.mw, bcol = ep_px - brow * d.mw;   // band-local (row, col) of this thread's pixel
+      int done_rows = 0, done_cols = 0;                        // complete rows / extra pixels after the current tile
+      int acquired = 0, completed = 0;
+      for (int t = 0; t < it.ntiles; ++t, ++g) {
+        const int ac = g % kAcc;
+        TIMED_WAIT(tm, 0, BAR(BAR_ACC_FULL + ac), (g / kAcc) & 1);
         __syncwarp();
         tc_fence_after();
         uint32_t r[kNI];
@@ -479,30 +520,27 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_ACC_EMPTY + ac));
 
-        const int n = min(p.counts[bit.b], min(d.max_n, kNI));
-        const bool live = (bt * kTileM + ep_px) < bit.npx;
-        // chunks touched by this tile (warp-uniform): acquire their buffers in order
-        const int tile_last_px = min((bt + 1) * kTileM, bit.npx) - 1;
-        const int c_hi = min((tile_last_px / d.mw) / p.pr, bit.nchunks - 1);
-        while (acquired <= c_hi) {
+        done_rows += tile_rows; done_cols += tile_cols;
+        if (done_cols >= d.mw) { done_cols -= d.mw; ++done_rows; }
+        const bool last_tile = (t + 1 == it.ntiles);
+        const int rows_done = last_tile ? it.nrows : done_rows;
+        const int row_last = last_tile ? it.nrows - 1 : (done_cols == 0 ? done_rows - 1 : done_rows);
+        const int c_hi = min(row_last >> p.pr_shift, it.nchunks - 1);
+        while (acquired <= c_hi) {            // acquire the chunk buffers this tile writes, in order
           const uint32_t gc = chunk_base + acquired;
-          bar_wait(BAR(BAR_CH_EMPTY + gc % kChunkBufs), ((gc / kChunkBufs) & 1) ^ 1);
+          TIMED_WAIT(tm, 1, BAR(BAR_CH_EMPTY + gc % kChunkBufs), ((gc / kChunkBufs) & 1) ^ 1);
           ++acquired;
         }
-        if (live) {
-          const float fx = (float)bcol, fy = (float)(bit.pa + brow);
-          const int c1 = brow / p.pr, rr = brow - c1 * p.pr;
-          const uint32_t inst_stride = (uint32_t)d.mw * 4;
-          const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
-          const uint32_t chunks = sbase + sm.chunks;
-          const bool has1 = c1 < bit.nchunks, has0 = (rr == 0 && c1 > 0);
+        if (brow < it.nrows) {
+          const float fx = (float)bcol, fy = (float)(it.pa + brow);
+          const int c1 = brow >> p.pr_shift, rr = brow - (c1 << p.pr_shift);
+          const bool has1 = c1 < it.nchunks, has0 = (rr == 0 && c1 > 0);
           const uint32_t dst1 = chunks + ((chunk_base + c1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
           const uint32_t dst0 = chunks + ((chunk_base + c1 + kChunkBufs - 1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
-          const uint32_t bx = sbase + sm.box + (bk & 3) * kMaxInstTc * 16;
 #pragma unroll
           for (int i = 0; i < kNI; ++i) {
             if (i < n) {
-              const float4 q = lds_v4(bx + 16 * i);     // x1, y1, x2, y2 at proto resolution (ops.py:725-732)
+              const float4 q = box[i];
               const bool keep = (fx >= q.x) && (fx < q.z) && (fy >= q.y) && (fy < q.w);   // crop_mask, ops.py:688-704
               const float v = keep ? __uint_as_float(r[i]) : 0.f;
               r[i] = __float_as_uint(v);
@@ -513,46 +551,37 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           if (p.logits_dbg) {
 #pragma unroll
             for (int i = 0; i < kNI; ++i)
-              if (i < n) p.logits_dbg[(((size_t)bit.b * d.max_n + i) * d.mh + bit.pa + brow) * d.mw + bcol] = __uint_as_float(r[i]);
+              if (i < n) p.logits_dbg[(((size_t)it.b * d.max_n + i) * d.mh + it.pa + brow) * d.mw + bcol] = __uint_as_float(r[i]);
           }
         }
         __syncwarp();
-        // chunks completed by this tile
-        const int rows_done = (bt + 1 == bit.ntiles) ? bit.nrows : ((bt + 1) * kTileM) / d.mw;   // complete rows so far
-        while (completed < bit.nchunks && chunk_last_row(p, bit, completed) < rows_done) {
+        while (completed < it.nchunks && chunk_last_row(p, it, completed) < rows_done) {   // chunks completed by this tile
           const uint32_t gc = chunk_base + completed;
           if (lane == 0) bar_arrive(BAR(BAR_CH_FULL + gc % kChunkBufs));
           ++completed;
         }
-        ++bg;
-        // advance this thread's (row, col) by one tile
         brow += tile_rows; bcol += tile_cols;
         if (bcol >= d.mw) { bcol -= d.mw; ++brow; }
-        if (++bt == bit.ntiles) {
-          bt = 0;
-          chunk_base += bit.nchunks;
-          acquired = 0;
-          completed = 0;
-          bit = get_item(p, ++bk);
-          brow = ep_px / d.mw; bcol = ep_px - brow * d.mw;
-        }
       }
+      chunk_base += it.nchunks;
     }
+    tm.end();
   } else {
     // =========================== upsample + threshold + store + reductions ===========================
-    const int uw = warp - (2 + kWarpsSplit);                 // 0..kWarpsUp-1
-    const int ut = threadIdx.x - 32 * (2 + kWarpsSplit);
+    const int uw = warp - kFirstUpWarp;                      // 0..kWarpsUp-1
+    const int ut = threadIdx.x - 32 * kFirstUpWarp;
     const int NG = d.W >> 4, NG8 = ceil_div(NG, 8);
     // lane -> (8 column groups) x (4 slots); slot -> (pair within the chunk, sub-block of 8 groups)
     const int gl = lane & 7, slot = lane >> 3;
-    const int subs = 4 / p.pr;                               // pr = 4: 1, pr = 2: 2
-    const int pair = slot % p.pr, sub = slot / p.pr;
+    const int subs = 4 >> p.pr_shift;                        // pr = 4: 1, pr = 2: 2
+    const int pair = slot & (p.pr - 1), sub = slot >> p.pr_shift;
     const int ng8w = ceil_div(NG8, subs);                    // warp tasks per instance
     const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
     const uint4 zeros = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t inst_stride = (uint32_t)d.mw * 4;
     const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
     const uint32_t latrow = sbase + sm.latrow;
+    RoleTimer tm; tm.begin((p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
     uint32_t gc = 0;
     for (int k = 0;; ++k) {
       const Item it = get_item(p, k);
@@ -560,7 +589,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       const int n = min(p.counts[it.b], min(d.max_n, kNI));
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
         const int buf = gc % kChunkBufs;
-        bar_wait(BAR(BAR_CH_FULL + buf), (gc / kChunkBufs) & 1);
+        TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kChunkBufs) & 1);
         const uint32_t cb = sbase + sm.chunks + buf * (uint32_t)p.chunk_floats * 4;
         const int r0 = it.pa + c * p.pr;                        // first pair of the chunk
         const int npairs = min(p.pr, it.pb - r0);
@@ -592,38 +621,35 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             const size_t inst = (size_t)it.b * d.max_n + i;
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
             unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
-            auto emit = [&](const uint4& w, int Y) {
+            const bool left = (g == 0);
+            const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
+            const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
+            const bool blend = !(uni_pos || uni_neg);
+            float hA[16], hB[16];
+            if (blend || (r == 0 && !(uniA_pos || uniA_neg))) hinterp4(sA, hA, left);
+            if (blend) hinterp4(sB, hB, left);
+            // dst rows: [two top rows when r == 0] + 4 (2 at the bottom edge) rows of this pair.  One compact,
+            // rolled loop (code size matters: five roles share the instruction cache).
+            const int nrows_out = last ? 2 : 4;
+            const int jbeg = (r == 0) ? -2 : 0;
+            for (int j = jbeg; j < nrows_out; ++j) {
+              uint4 w;
+              int Y;
+              if (j < 0) {         // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
+                Y = j + 2;
+                w = uniA_pos ? ones : uniA_neg ? zeros : hpack(hA);
+              } else {
+                Y = 4 * r + 2 + j;
+                if (uni_pos) w = ones;
+                else if (uni_neg) w = zeros;
+                else {
+                  const float l1 = 0.125f + 0.25f * (float)j;     // .125 .375 .625 .875 (exact)
+                  w = vblend(hA, hB, 1.0f - l1, l1);
+                }
+              }
               if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
               ts.add_row(w, Y);
               if ((w.x | w.y | w.z | w.w) && lds_s16(latrow + 2 * Y) >= 0) lattice_row(w, Y, 16 * g, d, lat);
-            };
-            const bool left = (g == 0);
-            const bool uni_pos = fminf(mnA, mnB) > kTiny, uni_neg = fmaxf(mxA, mxB) <= 0.f;
-            const int Y0 = 4 * r + 2;
-            float hA[16], hB[16];
-            const bool need_h = !(uni_pos || uni_neg);
-            if (need_h) { hinterp4(sA, hA, left); hinterp4(sB, hB, left); }
-            if (r == 0) {       // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
-              uint4 w;
-              if (mnA > kTiny) w = ones;
-              else if (mxA <= 0.f) w = zeros;
-              else { if (!need_h) hinterp4(sA, hA, left); w = hpack(hA); }
-              emit(w, 0);
-              emit(w, 1);
-            }
-            if (uni_pos) {
-              emit(ones, Y0); emit(ones, Y0 + 1);
-              if (!last) { emit(ones, Y0 + 2); emit(ones, Y0 + 3); }
-            } else if (uni_neg) {
-              emit(zeros, Y0); emit(zeros, Y0 + 1);
-              if (!last) { emit(zeros, Y0 + 2); emit(zeros, Y0 + 3); }
-            } else {
-              emit(vblend(hA, hB, 0.875f, 0.125f), Y0);
-              emit(vblend(hA, hB, 0.625f, 0.375f), Y0 + 1);
-              if (!last) {
-                emit(vblend(hA, hB, 0.375f, 0.625f), Y0 + 2);
-                emit(vblend(hA, hB, 0.125f, 0.875f), Y0 + 3);
-              }
             }
             ts.flush();
           }
@@ -673,6 +699,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       }
       named_bar_sync(2, kUpThreadsTc);
     }
+    tm.end();
   }
 
   // ---- teardown ----
@@ -699,6 +726,7 @@ struct FusedPlan {
   int ni;            // accumulator columns read back per tile (8 or 16)
   int chunk_floats;
   size_t smem_bytes;
+  unsigned long long* timing;   // device buffer when VA_FUSED_TIMING=1
   // cached tensor map
   const float* map_ptr;
   int map_B;
@@ -742,10 +770,15 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   for (const void* f : fns)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(%zu B): %s", pl->smem_bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
+  const char* tenv = getenv("VA_FUSED_TIMING");
+  if (tenv && tenv[0] == '1') cudaMalloc(&pl->timing, (size_t)pl->num_sms * 5 * 8 * sizeof(unsigned long long));
   return pl;
 }
 
-void fused_plan_destroy(FusedPlan* p) { delete p; }
+void fused_plan_destroy(FusedPlan* p) {
+  if (p && p->timing) cudaFree(p->timing);
+  delete p;
+}
 
 cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, const float* coefs, const float* boxes,
                          const int* counts, int B, uint8_t* masks, float* logits_dbg, InstStats* stats, unsigned* lattice,
@@ -767,7 +800,8 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   FusedParams p;
   p.d = d; p.coefs = coefs; p.boxes = boxes; p.counts = counts; p.masks = masks; p.logits_dbg = logits_dbg;
   p.stats = stats; p.lattice = lattice; p.B = B;
-  p.pr = pl->pr; p.nst = d.max_n; p.chunk_floats = pl->chunk_floats;
+  p.timing = pl->timing;
+  p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = d.max_n; p.chunk_floats = pl->chunk_floats;
   // bands per frame: balance the persistent grid against the one-row halo each band recomputes
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int best_nb = 1;
@@ -790,6 +824,25 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   } else {
     if (masks) fused_tc_kernel<true, 16><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
     else fused_tc_kernel<false, 16><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+  }
+  if (pl->timing) {   // developer diagnostic: blocking read-back, per-role wait / busy cycles averaged over CTAs
+    cudaStreamSynchronize(st);
+    static unsigned long long h[256 * 5 * 8];
+    cudaMemcpy(h, pl->timing, (size_t)grid * 5 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    const char* roles[5] = {"tma", "mma", "split", "epilogue", "upsample"};
+    const char* waits[5][3] = {{"hi_empty", "", ""}, {"b_full", "acc_empty", "lo_full"}, {"b_empty", "hi_full", "lo_empty"},
+                               {"acc_full", "ch_empty", ""}, {"ch_full", "", ""}};
+    fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr);
+    for (int r = 0; r < 5; ++r) {
+      double tot = 0, w[3] = {0, 0, 0};
+      for (int c = 0; c < grid; ++c) {
+        tot += (double)h[(c * 5 + r) * 8];
+        for (int j = 0; j < 3; ++j) w[j] += (double)h[(c * 5 + r) * 8 + 1 + j];
+      }
+      fprintf(stderr, "[va timing] %-9s total %9.0f cyc  wait %s %5.1f%%  %s %5.1f%%  %s %5.1f%%  busy %5.1f%%\n", roles[r], tot / grid,
+              waits[r][0], 100 * w[0] / tot, waits[r][1], 100 * w[1] / tot, waits[r][2], 100 * w[2] / tot,
+              100 * (tot - w[0] - w[1] - w[2]) / tot);
+    }
   }
   return cudaGetLastError();
 }

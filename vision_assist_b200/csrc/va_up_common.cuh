@@ -67,18 +67,23 @@ __device__ __forceinline__ void publish_stats(const ThreadStats& t, int xbase, I
   }
 }
 
-// Sample the cell-centre lattice points that fall into this thread's 16 pixels of row Y.
-__device__ __forceinline__ void lattice_row(const uint4& w, int Y, int xbase, const Dims& d, unsigned* lat) {
-  const int half = d.gs >> 1;
-  const int ly = (Y - half) / d.gs;
-  const unsigned ww[4] = {w.x, w.y, w.z, w.w};
-  int lx = (xbase - half + d.gs - 1) / d.gs;
+// Sample the cell-centre lattice points that fall into this thread's 16 pixels of row Y (rare path:
+// one dst row in gs is a lattice row).  Scalars by value so that the out-of-line copy needs no stack.
+static __device__ __noinline__ void lattice_row_impl(unsigned w0, unsigned w1, unsigned w2, unsigned w3, int Y, int xbase, int gs,
+                                                     int lat_cols, int lat_words, unsigned* lat) {
+  const int half = gs >> 1;
+  const int ly = (Y - half) / gs;
+  int lx = (xbase - half + gs - 1) / gs;
   if (lx < 0) lx = 0;
-  for (; lx < d.lat_cols; ++lx) {
-    const int pos = d.gs * lx + half - xbase;
+  for (; lx < lat_cols; ++lx) {
+    const int pos = gs * lx + half - xbase;
     if (pos > 15) break;
-    if ((ww[pos >> 2] >> (8 * (pos & 3))) & 1u) atomicOr(&lat[ly * d.lat_words + (lx >> 5)], 1u << (lx & 31));
+    const unsigned ww = (pos < 4) ? w0 : (pos < 8) ? w1 : (pos < 12) ? w2 : w3;
+    if ((ww >> (8 * (pos & 3))) & 1u) atomicOr(&lat[ly * lat_words + (lx >> 5)], 1u << (lx & 31));
   }
+}
+__device__ __forceinline__ void lattice_row(const uint4& w, int Y, int xbase, const Dims& d, unsigned* lat) {
+  lattice_row_impl(w.x, w.y, w.z, w.w, Y, xbase, d.gs, d.lat_cols, d.lat_words, lat);
 }
 
 // ---------------------------------------------------------------------------------------------
