@@ -34,20 +34,23 @@ namespace va {
 
 constexpr int kTileM = 128;                 // pixels per MMA tile (TMEM lanes)
 constexpr int kTileBytes = kTileM * kProtoK * 4;   // 16 KB
-constexpr int kStagesHi = 3;                // TMA staging ring ([32 k][128 px] boxes, no swizzle)
-constexpr int kStagesLo = 2;                // operand ring: one A_hi + one A_lo K-major tile per stage
+constexpr int kStagesHi = 6;                // TMA staging ring ([32 k][128 px] boxes, no swizzle)
+constexpr int kStagesLo = 2;                // A-operand ring in TENSOR MEMORY: A_hi (32 cols) + A_lo (32 cols) per stage
 constexpr int kAcc = 4;                     // TMEM accumulator ring
 constexpr int kNPad = 16;                   // UMMA N (instances padded)
 constexpr int kChunkBufs = 3;
-constexpr int kWarpsSplit = 2;              // transpose + 3xTF32 split (two pixel rows per thread)
-constexpr int kWarpsEpi = 4;                // TMEM -> crop -> chunk buffers (one warp per TMEM lane quarter)
-constexpr int kWarpsUp = 8;
-constexpr int kFirstEpiWarp = 2 + kWarpsSplit;
+constexpr int kWarpsSplit = 4;              // one warp per TMEM lane quarter: staged box -> registers -> tcgen05.st
+constexpr int kWarpsEpi = 4;                // one warp per TMEM lane quarter: TMEM -> crop -> chunk buffers
+constexpr int kWarpsUp = 7;
+constexpr int kFirstSplitWarp = 1;          // warp 0: TMA producer + MMA issuer (one thread)
+constexpr int kFirstEpiWarp = kFirstSplitWarp + kWarpsSplit;
 constexpr int kFirstUpWarp = kFirstEpiWarp + kWarpsEpi;
 constexpr int kThreads = 32 * (kFirstUpWarp + kWarpsUp);   // 512
 constexpr int kUpThreadsTc = 32 * kWarpsUp;
 constexpr int kMaxInstTc = 16;              // instances this kernel handles (N = 16)
-constexpr int kTmemCols = kAcc * kNPad;     // 64: power of two >= 32
+constexpr int kTmemAOff = 0;                // TMEM columns [0, 128): A ring
+constexpr int kTmemAccOff = kStagesLo * 64; // TMEM columns [128, 192): accumulators
+constexpr int kTmemCols = 256;              // power of two >= 192
 
 struct FusedParams {
   Dims d;
@@ -195,10 +198,11 @@ __device__ __forceinline__ int chunk_last_row(const FusedParams& p, const Item& 
 // explicit ld.shared / st.shared on 32-bit shared addresses (no generic-space LD/ST).
 struct SmemMap {
   uint32_t hi;        // [kStagesHi][16 KB]   TMA staging, [32 k][128 px]
-  uint32_t op;        // [kStagesLo][A_hi 16 KB | A_lo 16 KB]   K-major SW128 operand tiles
   uint32_t bt;        // [2 parity][hi, lo][kNPad * 128 B]
   uint32_t chunks;    // [kChunkBufs][chunk_floats] f32
-  uint32_t box;       // [2 item parity][kMaxInstTc][4] f32 (epilogue warps only)
+  uint32_t box;       // [2 item parity][kMaxInstTc][4] f32 (epilogue warps)
+  uint32_t ubox;      // [kMaxInstTc][4] f32 (upsample warps)
+  uint32_t latpair;   // [mh] i16: the lattice dst row inside rows 4r+2..4r+5 of pair r, -1 if none
   uint32_t stat;      // [kMaxInstTc][8] i32: area, minx, miny, maxx, maxy
   uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
   uint32_t bars;      // [BAR_COUNT] u64
@@ -224,10 +228,11 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H) {
   uint32_t o = 0;
   auto take = [&](uint32_t bytes, uint32_t align) { o = (o + align - 1) / align * align; uint32_t r = o; o += bytes; return r; };
   m.hi = take(kStagesHi * kTileBytes, 1024);
-  m.op = take(kStagesLo * 2 * kTileBytes, 1024);
   m.bt = take(2 * 2 * kNPad * 128, 1024);
   m.chunks = take((uint32_t)kChunkBufs * chunk_floats * 4, 16);
-  m.box = take(4 * kMaxInstTc * 4 * 4, 16);
+  m.box = take(2 * kMaxInstTc * 4 * 4, 16);
+  m.ubox = take(kMaxInstTc * 4 * 4, 16);
+  m.latpair = take((uint32_t)(H / 4 + 8) * 2, 16);
   m.stat = take(kMaxInstTc * 8 * 4, 16);
   m.latrow = take((uint32_t)H * 2, 16);
   m.bars = take(BAR_COUNT * 8, 8);
@@ -318,6 +323,27 @@ __device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__
 // ---------------------------------------------------------------------------------------------
 // the kernel.  kNI = instances handled per accumulator read (8 or 16 TMEM columns)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: A operand read from tensor memory (one tf32 per 32-bit column)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <bool kWriteMasks, int kNI>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
@@ -339,15 +365,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     for (int i = 0; i < kChunkBufs; ++i) { bar_init(BAR(BAR_CH_FULL + i), kWarpsEpi); bar_init(BAR(BAR_CH_EMPTY + i), kWarpsUp); }
     fence_barrier_init();
   }
-  for (int y = threadIdx.x; y < d.H; y += kThreads) {
-    const int t = y - (d.gs >> 1);
-    sts_s16(sbase + sm.latrow + 2 * y, (t >= 0 && t % d.gs == 0) ? (short)(t / d.gs) : (short)-1);
+  for (int r = threadIdx.x; r < d.mh; r += kThreads) {   // lattice (cell-centre) dst row inside rows 4r+2 .. 4r+5
+    const int half = d.gs >> 1;
+    int ly = -1;
+    for (int j = 0; j < 4; ++j) {
+      const int t = 4 * r + 2 + j - half;
+      if (t >= 0 && t % d.gs == 0 && 4 * r + 2 + j < d.H) ly = 4 * r + 2 + j;
+    }
+    sts_s16(sbase + sm.latpair + 2 * r, (short)ly);
   }
   for (int t = threadIdx.x; t < kMaxInstTc * 8; t += kThreads) {
     const int f = t & 7;
     sts_s32(sbase + sm.stat + 4 * t, (f == 1 || f == 2) ? INT_MAX : (f == 3 || f == 4) ? -1 : 0);
   }
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + sm.tmem_slot), "r"((uint32_t)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -357,55 +388,46 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   const uint32_t tmem_base = lds_u32(sbase + sm.tmem_slot);
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer + MMA issuer (one thread) ===========================
     if (lane == 0) {
-      RoleTimer tm; tm.begin(p.timing ? p.timing + ((size_t)blockIdx.x * 5 + 0) * 8 : nullptr);
-      uint32_t g = 0;   // global tile counter of this CTA
-      for (int k = 0;; ++k) {
-        const Item it = get_item(p, k);
-        if (!it.valid) break;
-        const int px0 = it.pa * d.mw;
-        for (int t = 0; t < it.ntiles; ++t, ++g) {
-          const int st = g % kStagesHi;
-          TIMED_WAIT(tm, 0, BAR(BAR_HI_EMPTY + st), ((g / kStagesHi) & 1) ^ 1);
-          bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
-          tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), px0 + t * kTileM, 0, it.b);
-        }
-      }
-      tm.end();
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kTileM, kNPad);
       RoleTimer tm; tm.begin(p.timing ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
+      const uint32_t idesc = make_idesc(kTileM, kNPad);
+      // load iterator: runs kStagesHi tiles ahead of the MMA iterator
+      int lk = 0, lt = 0;
+      Item lit = get_item(p, 0);
+      uint32_t lg = 0;
       uint32_t g = 0;
       for (int k = 0;; ++k) {
         const Item it = get_item(p, k);
         if (!it.valid) break;
         const int par = k & 1;
-        TIMED_WAIT(tm, 0, BAR(BAR_B_FULL + par), (k >> 1) & 1);
         const uint32_t b_hi = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
         const uint32_t b_lo = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
         for (int t = 0; t < it.ntiles; ++t, ++g) {
+          while (lit.valid && lg < g + kStagesHi) {     // keep the staging ring full
+            const int st = lg % kStagesHi;
+            TIMED_WAIT(tm, 3, BAR(BAR_HI_EMPTY + st), ((lg / kStagesHi) & 1) ^ 1);
+            bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
+            tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), lit.pa * d.mw + lt * kTileM, 0, lit.b);
+            ++lg;
+            if (++lt == lit.ntiles) { lt = 0; lit = get_item(p, ++lk); }
+          }
+          if (t == 0) TIMED_WAIT(tm, 0, BAR(BAR_B_FULL + par), (k >> 1) & 1);
           const int sl = g % kStagesLo, ac = g % kAcc;
           TIMED_WAIT(tm, 1, BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
           TIMED_WAIT(tm, 2, BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);
           tc_fence_after();
-          const uint32_t a_hi = sbase + sm.op + sl * 2 * kTileBytes;
-          const uint32_t a_lo = a_hi + kTileBytes;
-          const uint32_t dcol = tmem_base + ac * kNPad;
-          // K-major SW128 operands: rows (pixels / instances) are 128 B, 8-row groups 1024 B apart (SBO),
-          // one k-step (8 tf32) = 32 B along the row.
+          const uint32_t a_hi = tmem_base + kTmemAOff + sl * 64;       // A in tensor memory: lane = pixel, column = k
+          const uint32_t a_lo = a_hi + 32;
+          const uint32_t dcol = tmem_base + kTmemAccOff + ac * kNPad;
+          // B (coefficients) K-major SW128 in shared memory: rows are 128 B, 8-row groups 1024 B apart (SBO),
+          // one k-step (8 tf32) = 32 B along the row = 8 TMEM columns of A.
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(dcol, make_smem_desc(a_hi + ks * 32, 16, 1024), make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(dcol, make_smem_desc(a_hi + ks * 32, 16, 1024), make_smem_desc(b_lo + ks * 32, 16, 1024), idesc, 1);
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(b_lo + ks * 32, 16, 1024), idesc, 1);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(dcol, make_smem_desc(a_lo + ks * 32, 16, 1024), make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, 1);
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_lo + ks * 8, make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, 1);
           bar_commit(BAR(BAR_LO_EMPTY + sl));
           bar_commit(BAR(BAR_ACC_FULL + ac));
         }
@@ -414,8 +436,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       tm.end();
     }
   } else if (warp < kFirstEpiWarp) {
-    // =========================== transpose + 3xTF32 split ===========================
-    const int st_tid = (warp - 2) * 32 + lane;       // 0 .. 32*kWarpsSplit-1
+    // =========================== 3xTF32 split: staged [k][px] box -> registers -> tensor memory ===========================
+    const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32) belong to this warp
+    const int st_tid = (warp - kFirstSplitWarp) * 32 + lane;
+    const int px = quarter * 32 + lane;              // tile pixel (= TMEM lane) of this thread
     RoleTimer tm; tm.begin((p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
     uint32_t g = 0;
     for (int k = 0;; ++k) {
@@ -427,19 +451,17 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int n = min(p.counts[it.b], min(d.max_n, kMaxInstTc));
         const uint32_t bh = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
         const uint32_t bl = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
-        for (int q = st_tid; q < kNPad * 8; q += 32 * kWarpsSplit) {   // 16 rows x 8 chunks
-          const int r = q >> 3, c = q & 7;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)it.b * d.max_n + r) * d.K + 4 * c));
-          float4 h, l;
-          h.x = trunc_tf32(v.x); l.x = v.x - h.x;
-          h.y = trunc_tf32(v.y); l.y = v.y - h.y;
-          h.z = trunc_tf32(v.z); l.z = v.z - h.z;
-          h.w = trunc_tf32(v.w); l.w = v.w - h.w;
-          const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-          sts_v4(bh + off, h);
-          sts_v4(bl + off, l);
-        }
+        const int r = st_tid >> 3, c = st_tid & 7;   // 128 threads = 16 rows x 8 chunks
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)it.b * d.max_n + r) * d.K + 4 * c));
+        float4 h, l;
+        h.x = trunc_tf32(v.x); l.x = v.x - h.x;
+        h.y = trunc_tf32(v.y); l.y = v.y - h.y;
+        h.z = trunc_tf32(v.z); l.z = v.z - h.z;
+        h.w = trunc_tf32(v.w); l.w = v.w - h.w;
+        const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+        sts_v4(bh + off, h);
+        sts_v4(bl + off, l);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_B_FULL + par));
@@ -447,35 +469,25 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       for (int t = 0; t < it.ntiles; ++t, ++g) {
         const int sh = g % kStagesHi, sl = g % kStagesLo;
         TIMED_WAIT(tm, 1, BAR(BAR_HI_FULL + sh), (g / kStagesHi) & 1);
-        TIMED_WAIT(tm, 2, BAR(BAR_LO_EMPTY + sl), ((g / kStagesLo) & 1) ^ 1);
-        // thread = pixel rows st_tid, st_tid + 64, ... of the tile.  Reads of [k][px] are conflict-free across
-        // the warp (consecutive px); each 16 B chunk c of the K-major row lands at chunk c ^ (px & 7).
-#pragma unroll 1
-        for (int px = st_tid; px < kTileM; px += 32 * kWarpsSplit) {
-          const uint32_t src = sbase + sm.hi + sh * kTileBytes + px * 4;
-          const uint32_t dhi = sbase + sm.op + sl * 2 * kTileBytes + px * 128;
-          const uint32_t dlo = dhi + kTileBytes;
-          float v[kProtoK];
+        const uint32_t src = sbase + sm.hi + sh * kTileBytes + px * 4;
+        uint32_t hi[kProtoK], lo[kProtoK];
 #pragma unroll
-          for (int q = 0; q < kProtoK; ++q) v[q] = lds_f32(src + q * kTileM * 4);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 h, l;
-            h.x = trunc_tf32(v[4 * c + 0]); l.x = v[4 * c + 0] - h.x;
-            h.y = trunc_tf32(v[4 * c + 1]); l.y = v[4 * c + 1] - h.y;
-            h.z = trunc_tf32(v[4 * c + 2]); l.z = v[4 * c + 2] - h.z;
-            h.w = trunc_tf32(v[4 * c + 3]); l.w = v[4 * c + 3] - h.w;
-            const uint32_t off = (uint32_t)(c ^ (px & 7)) << 4;
-            sts_v4(dhi + off, h);
-            sts_v4(dlo + off, l);
-          }
-        }
-        fence_proxy_async();
+        for (int q = 0; q < kProtoK; ++q) hi[q] = __float_as_uint(lds_f32(src + q * kTileM * 4));   // conflict-free: consecutive px
         __syncwarp();
-        if (lane == 0) {
-          bar_arrive(BAR(BAR_LO_FULL + sl));
-          bar_arrive(BAR(BAR_HI_EMPTY + sh));
-        }
+        if (lane == 0) bar_arrive(BAR(BAR_HI_EMPTY + sh));      // staging slot can be refilled
+        // the tensor core reads the top 19 bits of each word (truncation, measured): the raw value IS the hi
+        // operand; lo = x - trunc(x) is exact in fp32.
+#pragma unroll
+        for (int q = 0; q < kProtoK; ++q) lo[q] = __float_as_uint(__uint_as_float(hi[q]) - __uint_as_float(hi[q] & 0xffffe000u));
+        TIMED_WAIT(tm, 2, BAR(BAR_LO_EMPTY + sl), ((g / kStagesLo) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemAOff + sl * 64;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(BAR(BAR_LO_FULL + sl));
       }
     }
     tm.end();
@@ -515,7 +527,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         __syncwarp();
         tc_fence_after();
         uint32_t r[kNI];
-        tmem_ld<kNI>(tmem_base + ((uint32_t)(quarter * 32) << 16) + ac * kNPad, r);
+        tmem_ld<kNI>(tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemAccOff + ac * kNPad, r);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_ACC_EMPTY + ac));
@@ -580,13 +592,19 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const uint4 zeros = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t inst_stride = (uint32_t)d.mw * 4;
     const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
-    const uint32_t latrow = sbase + sm.latrow;
     RoleTimer tm; tm.begin((p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
     uint32_t gc = 0;
     for (int k = 0;; ++k) {
       const Item it = get_item(p, k);
       if (!it.valid) break;
       const int n = min(p.counts[it.b], min(d.max_n, kNI));
+      if (ut < kMaxInstTc * 4) {     // scaled boxes of this frame for the outside-the-box test
+        const int i = ut >> 2, c = ut & 3;
+        float v = 0.f;
+        if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
+        sts_f32(sbase + sm.ubox + (i * 4 + c) * 4, v);
+      }
+      named_bar_sync(2, kUpThreadsTc);
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
         const int buf = gc % kChunkBufs;
         TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kChunkBufs) & 1);
@@ -595,63 +613,93 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int npairs = min(p.pr, it.pb - r0);
         const int r = r0 + pair;
         const bool last = (r == d.mh - 1);
+        const int nrows_out = last ? 2 : 4;
+        const int jbeg = (r == 0) ? -2 : 0;                     // pair 0 also owns dst rows 0,1
+        const int laty = (pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
         for (int wq = uw; wq < n * ng8w; wq += kWarpsUp) {
           const int i = wq / ng8w;
           const int g = ((wq - i * ng8w) * subs + sub) * 8 + gl;
           const bool active = (g < NG) && (pair < npairs);
           ThreadStats ts;
           if (active) {
-            const uint32_t rowA = cb + pair * row_stride + i * inst_stride + g * 16;
-            const uint32_t rowB = last ? rowA : rowA + row_stride;
-            float sA[6], sB[6];
-            {
-              const float4 v = lds_v4(rowA);
-              sA[1] = v.x; sA[2] = v.y; sA[3] = v.z; sA[4] = v.w;
-              sA[0] = (g > 0) ? lds_f32(rowA - 4) : v.x;
-              sA[5] = (4 * g + 4 < d.mw) ? lds_f32(rowA + 16) : v.w;
-              const float4 u = lds_v4(rowB);
-              sB[1] = u.x; sB[2] = u.y; sB[3] = u.z; sB[4] = u.w;
-              sB[0] = (g > 0) ? lds_f32(rowB - 4) : u.x;
-              sB[5] = (4 * g + 4 < d.mw) ? lds_f32(rowB + 16) : u.w;
-            }
-            const float mnA = fminf(fminf(fminf(sA[0], sA[1]), fminf(sA[2], sA[3])), fminf(sA[4], sA[5]));
-            const float mxA = fmaxf(fmaxf(fmaxf(sA[0], sA[1]), fmaxf(sA[2], sA[3])), fmaxf(sA[4], sA[5]));
-            const float mnB = fminf(fminf(fminf(sB[0], sB[1]), fminf(sB[2], sB[3])), fminf(sB[4], sB[5]));
-            const float mxB = fmaxf(fmaxf(fmaxf(sB[0], sB[1]), fmaxf(sB[2], sB[3])), fmaxf(sB[4], sB[5]));
             const size_t inst = (size_t)it.b * d.max_n + i;
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
-            unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
-            const bool left = (g == 0);
-            const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
-            const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
-            const bool blend = !(uni_pos || uni_neg);
-            float hA[16], hB[16];
-            if (blend || (r == 0 && !(uniA_pos || uniA_neg))) hinterp4(sA, hA, left);
-            if (blend) hinterp4(sB, hB, left);
-            // dst rows: [two top rows when r == 0] + 4 (2 at the bottom edge) rows of this pair.  One compact,
-            // rolled loop (code size matters: five roles share the instruction cache).
-            const int nrows_out = last ? 2 : 4;
-            const int jbeg = (r == 0) ? -2 : 0;
-            for (int j = jbeg; j < nrows_out; ++j) {
-              uint4 w;
-              int Y;
-              if (j < 0) {         // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
-                Y = j + 2;
-                w = uniA_pos ? ones : uniA_neg ? zeros : hpack(hA);
-              } else {
-                Y = 4 * r + 2 + j;
-                if (uni_pos) w = ones;
-                else if (uni_neg) w = zeros;
-                else {
-                  const float l1 = 0.125f + 0.25f * (float)j;     // .125 .375 .625 .875 (exact)
-                  w = vblend(hA, hB, 1.0f - l1, l1);
+            const float4 q = lds_v4(sbase + sm.ubox + 16 * i);
+            // every proto pixel this task reads (rows r, r+1, cols 4g-1 .. 4g+4) is outside the instance's box:
+            // crop_mask zeroed them, the masks are 0 - store and skip everything else
+            const bool outside = ((float)(r + 1) < q.y) || ((float)r >= q.w) || ((float)(4 * g + 4) < q.x) || ((float)(4 * g - 1) >= q.z);
+            if (outside) {
+              if (kWriteMasks) {
+                for (int j = jbeg; j < nrows_out; ++j) {
+                  const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
+                  *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = zeros;
                 }
               }
-              if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
-              ts.add_row(w, Y);
-              if ((w.x | w.y | w.z | w.w) && lds_s16(latrow + 2 * Y) >= 0) lattice_row(w, Y, 16 * g, d, lat);
+            } else {
+              const uint32_t rowA = cb + pair * row_stride + i * inst_stride + g * 16;
+              const uint32_t rowB = last ? rowA : rowA + row_stride;
+              float sA[6], sB[6];
+              {
+                const float4 v = lds_v4(rowA);
+                sA[1] = v.x; sA[2] = v.y; sA[3] = v.z; sA[4] = v.w;
+                sA[0] = (g > 0) ? lds_f32(rowA - 4) : v.x;
+                sA[5] = (4 * g + 4 < d.mw) ? lds_f32(rowA + 16) : v.w;
+                const float4 u = lds_v4(rowB);
+                sB[1] = u.x; sB[2] = u.y; sB[3] = u.z; sB[4] = u.w;
+                sB[0] = (g > 0) ? lds_f32(rowB - 4) : u.x;
+                sB[5] = (4 * g + 4 < d.mw) ? lds_f32(rowB + 16) : u.w;
+              }
+              const float mnA = fminf(fminf(fminf(sA[0], sA[1]), fminf(sA[2], sA[3])), fminf(sA[4], sA[5]));
+              const float mxA = fmaxf(fmaxf(fmaxf(sA[0], sA[1]), fmaxf(sA[2], sA[3])), fmaxf(sA[4], sA[5]));
+              const float mnB = fminf(fminf(fminf(sB[0], sB[1]), fminf(sB[2], sB[3])), fminf(sB[4], sB[5]));
+              const float mxB = fmaxf(fmaxf(fmaxf(sB[0], sB[1]), fmaxf(sB[2], sB[3])), fmaxf(sB[4], sB[5]));
+              unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
+              const bool left = (g == 0);
+              const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
+              const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
+              if (uni_neg) {
+                if (kWriteMasks) {
+                  for (int j = jbeg; j < nrows_out; ++j) {
+                    const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
+                    *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = zeros;
+                  }
+                }
+              } else if (uni_pos) {
+                const int Yfirst = (jbeg < 0) ? 0 : 4 * r + 2, Ylast = 4 * r + 1 + nrows_out;
+                if (kWriteMasks) {
+                  for (int j = jbeg; j < nrows_out; ++j) {
+                    const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
+                    *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = ones;
+                  }
+                }
+                ts.area = 16u * (unsigned)(nrows_out - jbeg);
+                ts.orw[0] = ts.orw[1] = ts.orw[2] = ts.orw[3] = 0x01010101u;
+                ts.miny = Yfirst; ts.maxy = Ylast;
+                if (laty >= 0 && laty <= Ylast) lattice_row(ones, laty, 16 * g, d, lat);
+              } else {
+                // mixed signs: the exact 4-tap blend.  One compact, rolled loop (code size matters: the roles
+                // share the instruction cache).
+                float hA[16], hB[16];
+                hinterp4(sA, hA, left);
+                hinterp4(sB, hB, left);
+                for (int j = jbeg; j < nrows_out; ++j) {
+                  uint4 w;
+                  int Y;
+                  if (j < 0) {         // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
+                    Y = j + 2;
+                    w = hpack(hA);
+                  } else {
+                    Y = 4 * r + 2 + j;
+                    const float l1 = 0.125f + 0.25f * (float)j;     // .125 .375 .625 .875 (exact)
+                    w = vblend(hA, hB, 1.0f - l1, l1);
+                  }
+                  if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
+                  ts.add_row(w, Y);
+                  if (Y == laty && (w.x | w.y | w.z | w.w)) lattice_row(w, Y, 16 * g, d, lat);
+                }
+                ts.flush();
+              }
             }
-            ts.flush();
           }
           // warp-level reduction (all lanes of a warp task share the instance), one set of smem atomics per warp
           __syncwarp();
@@ -697,7 +745,6 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         }
         sts_s32(st, 0); sts_s32(st + 4, INT_MAX); sts_s32(st + 8, INT_MAX); sts_s32(st + 12, -1); sts_s32(st + 16, -1);
       }
-      named_bar_sync(2, kUpThreadsTc);
     }
     tm.end();
   }
@@ -705,7 +752,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -830,7 +877,7 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
     static unsigned long long h[256 * 5 * 8];
     cudaMemcpy(h, pl->timing, (size_t)grid * 5 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     const char* roles[5] = {"tma", "mma", "split", "epilogue", "upsample"};
-    const char* waits[5][3] = {{"hi_empty", "", ""}, {"b_full", "acc_empty", "lo_full"}, {"b_empty", "hi_full", "lo_empty"},
+    const char* waits[5][3] = {{"(merged)", "", ""}, {"b_full", "acc_empty", "lo_full"}, {"b_empty", "hi_full", "lo_empty"},
                                {"acc_full", "ch_empty", ""}, {"ch_full", "", ""}};
     fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr);
     for (int r = 0; r < 5; ++r) {

@@ -36,6 +36,7 @@ struct TailSmem {
   int* ecol_first;   // [cmax]   easy_cols[c]: first / last LIST index
   int* ecol_last;    // [cmax]
   int* orphan_ids;   // [rmax]
+  int* oflag;        // [T]      orphan marks
   int* sc;           // scalars, see enum
 };
 enum { S_FLAGS, S_SEL, S_X0, S_Y0, S_C, S_R, S_NORPH, S_NPEAKS, S_AREA, S_RM, S_MINX, S_MINY, S_MAXX, S_MAXY,
@@ -52,14 +53,14 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   const size_t o_l = take(sizeof(int) * d.rmax), o_p = take(sizeof(int) * PL);
   const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * d.rmax);
   const size_t o_cf = take(sizeof(int) * d.cmax), o_cl = take(sizeof(int) * d.cmax);
-  const size_t o_or = take(sizeof(int) * d.rmax), o_sc = take(sizeof(int) * S_COUNT);
+  const size_t o_or = take(sizeof(int) * d.rmax), o_of = take(sizeof(int) * T), o_sc = take(sizeof(int) * S_COUNT);
   if (s) {
     s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a);
     s->occ = (unsigned*)(base + o_occ); s->art = (unsigned*)(base + o_art);
     s->list_ids = (int*)(base + o_l); s->plane_owner = (int*)(base + o_p);
     s->erow_first = (int*)(base + o_ef); s->erow_last = (int*)(base + o_el);
     s->ecol_first = (int*)(base + o_cf); s->ecol_last = (int*)(base + o_cl);
-    s->orphan_ids = (int*)(base + o_or); s->sc = (int*)(base + o_sc);
+    s->orphan_ids = (int*)(base + o_or); s->oflag = (int*)(base + o_of); s->sc = (int*)(base + o_sc);
   }
   return o;
 }
@@ -217,33 +218,38 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   for (int t = d.off_occ + d.rmax * d.cmax + threadIdx.x; t < d.record_bytes; t += kTailThreads) rec[t] = 0;
 }
 
-// ProtrusionDetector closed form; one thread (C <= a few hundred bits).
+// ProtrusionDetector closed form; one thread: union of the top rows as bit words, then run extraction
+// with ffs (a handful of iterations for the <= cmax/2 runs).
 __device__ void find_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
   int* peaks = reinterpret_cast<int*>(rec + d.off_peaks);
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
   int ytop = INT_MAX;
   for (int k = 0; k < R; ++k) {
     const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
-    bool any = false;
-    for (int w = 0; w < cw; ++w) any |= (row[w] != 0);
+    unsigned any = 0;
+    for (int w = 0; w < cw; ++w) any |= row[w];
     if (any) ytop = min(ytop, s.row_y[s.list_ids[k]]);
   }
   int np = 0;
   if (ytop != INT_MAX) {
+    // union of the list rows painted on pixel row ytop (duplicate rows share a y); reuse erow_first as scratch
+    unsigned* uni = reinterpret_cast<unsigned*>(s.orphan_ids) + d.rmax - cw;   // tail of the orphan array is free
+    for (int w = 0; w < cw; ++w) uni[w] = 0;
+    for (int k = 0; k < R; ++k) {
+      if (s.row_y[s.list_ids[k]] != ytop) continue;
+      const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
+      for (int w = 0; w < cw; ++w) uni[w] |= row[w];
+    }
     int c = 0;
     while (c < C) {
-      bool on = false;
-      for (int k = 0; k < R && !on; ++k)
-        if (s.row_y[s.list_ids[k]] == ytop) on = bit_at(s.occ + (size_t)s.list_ids[k] * cw, c);
-      if (!on) { ++c; continue; }
-      int c1 = c;
-      while (c1 + 1 < C) {
-        bool on1 = false;
-        for (int k = 0; k < R && !on1; ++k)
-          if (s.row_y[s.list_ids[k]] == ytop) on1 = bit_at(s.occ + (size_t)s.list_ids[k] * cw, c1 + 1);
-        if (!on1) break;
-        ++c1;
-      }
+      // next set bit at or after c
+      int w = c >> 5;
+      unsigned v = uni[w] & (0xffffffffu << (c & 31));
+      while (!v && ++w < cw) v = uni[w];
+      if (!v) break;
+      c = (w << 5) + __ffs(v) - 1;
+      if (c >= C) break;
+      const int c1 = run_right(uni, c, C);
       const int xa = x0 + c * gs;
       const int xb = min(x0 + c1 * gs + gs, d.W - 1);
       if (np < d.pmax) {
@@ -269,18 +275,28 @@ __device__ void write_header(const TailSmem& s, uint8_t* rec) {
   *reinterpret_cast<va_frame_header*>(rec) = h;
 }
 
-// list rows no longer in the list but still owning their grid_lookup row
+// list rows no longer in the list but still owning their grid_lookup row, ordered by y.
+// All threads mark, thread 0 gathers (a handful of rows at most).
 __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], n = s.sc[S_NCREATED];
-  int no = 0;
-  for (int id = 0; id < n; ++id) {
+  int* s_flags = s.oflag;
+  for (int id = threadIdx.x; id < n; id += kTailThreads) {
     bool in_list = false;
     for (int k = 0; k < R && !in_list; ++k) in_list = (s.list_ids[k] == id);
-    if (in_list) continue;
     const int ly = s.row_y[id] / d.gs;
-    if (ly >= 0 && ly < plane_cap(d) && s.plane_owner[ly] == id && R + no < d.rmax) s.orphan_ids[no++] = id;
+    s_flags[id] = (!in_list && ly >= 0 && ly < plane_cap(d) && s.plane_owner[ly] == id) ? 1 : 0;
   }
-  s.sc[S_NORPH] = no;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int no = 0;
+    for (int id = 0; id < n; ++id) {
+      if (!s_flags[id] || R + no >= d.rmax) continue;
+      int pos = no++;
+      while (pos > 0 && s.row_y[s.orphan_ids[pos - 1]] > s.row_y[id]) { s.orphan_ids[pos] = s.orphan_ids[pos - 1]; --pos; }
+      s.orphan_ids[pos] = id;
+    }
+    s.sc[S_NORPH] = no;
+  }
 }
 
 __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
@@ -290,7 +306,7 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
     if (threadIdx.x == 0) { s.sc[S_R] = 0; s.sc[S_C] = 0; s.sc[S_NORPH] = 0; s.sc[S_NPEAKS] = 0; s.sc[S_FLAGS] |= VA_FLAG_EMPTY; }
     __syncthreads();
   } else {
-    if (threadIdx.x == 0) collect_orphans(d, s);
+    collect_orphans(d, s);
     easy_segments(d, s);
     __syncthreads();
   }
@@ -418,6 +434,18 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
         // ---- artificial band (FrameProcessor.py:126-165), replayed literally ----
         int list_len = Rm, ncreated = Rm;
         const int base = d.W / 2 - 8 * gs;
+        // artificial columns (FrameProcessor.py:60-65) as a bit mask over this frame's columns: the same for every band row
+        unsigned* am = reinterpret_cast<unsigned*>(s.erow_last);      // scratch until easy_segments runs
+        for (int w = 0; w < cw; ++w) {
+          unsigned m = 0;
+          for (int q = 0; q < 32; ++q) {
+            const int c = 32 * w + q;
+            if (c >= C) break;
+            const int delta = s.sc[S_X0] + c * gs - base;
+            if (delta >= 0 && delta % gs == 0 && delta / gs <= 16) m |= 1u << q;
+          }
+          am[w] = m;
+        }
         for (int i = d.band_start; i < d.H; i += gs) {
           const int ly = i / gs;
           const int row_idx = floor_div(i - s.sc[S_Y0], gs);
@@ -425,16 +453,9 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
           const int id = ncreated++;
           const int prev = s.plane_owner[ly];
           for (int w = 0; w < cw; ++w) {
-            unsigned am = 0;
-            for (int q = 0; q < 32; ++q) {
-              const int c = 32 * w + q;
-              if (c >= C) break;
-              const int delta = s.sc[S_X0] + c * gs - base;
-              if (delta >= 0 && delta % gs == 0 && delta / gs <= 16) am |= 1u << q;
-            }
             const unsigned pv = (prev >= 0) ? s.occ[(size_t)prev * cw + w] : 0u;
-            s.occ[(size_t)id * cw + w] = pv | am;
-            s.art[(size_t)id * cw + w] = ~pv & am;
+            s.occ[(size_t)id * cw + w] = pv | am[w];
+            s.art[(size_t)id * cw + w] = ~pv & am[w];
           }
           s.row_y[id] = i;
           s.row_attr[id] = row_idx;
