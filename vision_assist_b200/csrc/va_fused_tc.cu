@@ -37,7 +37,8 @@ constexpr int kTileBytes = kTileM * kProtoK * 4;   // 16 KB
 constexpr int kStagesHi = 6;                // TMA staging ring ([32 k][128 px] boxes, no swizzle)
 constexpr int kStagesLo = 2;                // A-operand ring in TENSOR MEMORY: A_hi (32 cols) + A_lo (32 cols) per stage
 constexpr int kAcc = 4;                     // TMEM accumulator ring
-constexpr int kNPad = 16;                   // UMMA N (instances padded)
+constexpr int kNPad = 16;                   // instances padded
+constexpr int kNMma = 2 * kNPad;            // UMMA N: [B_hi ; B_lo] stacked along N - the cost of a small MMA does not depend on N
 constexpr int kChunkBufs = 3;
 constexpr int kWarpsSplit = 4;              // one warp per TMEM lane quarter: staged box -> registers -> tcgen05.st
 constexpr int kWarpsEpi = 4;                // one warp per TMEM lane quarter: TMEM -> crop -> chunk buffers
@@ -49,8 +50,8 @@ constexpr int kThreads = 32 * (kFirstUpWarp + kWarpsUp);   // 512
 constexpr int kUpThreadsTc = 32 * kWarpsUp;
 constexpr int kMaxInstTc = 16;              // instances this kernel handles (N = 16)
 constexpr int kTmemAOff = 0;                // TMEM columns [0, 128): A ring
-constexpr int kTmemAccOff = kStagesLo * 64; // TMEM columns [128, 192): accumulators
-constexpr int kTmemCols = 256;              // power of two >= 192
+constexpr int kTmemAccOff = kStagesLo * 64; // TMEM columns [128, 256): accumulators (kAcc x kNMma)
+constexpr int kTmemCols = 256;
 
 struct FusedParams {
   Dims d;
@@ -174,11 +175,17 @@ struct Item {
   int nchunks;  // ceil((pb - pa) / pr)
 };
 
-__device__ __forceinline__ Item get_item(const FusedParams& p, int k) {
+// out of line on purpose: called once per item per role, and five inlined copies of its divisions would
+// compete with the hot loops for the instruction cache
+__device__ __noinline__ Item get_item(const FusedParams& p, int k) {
   Item it;
   const int item = blockIdx.x + k * gridDim.x;
   it.valid = item < p.n_items;
-  const int b = item / p.nbands, j = item - b * p.nbands;
+  const int b = item / p.nbands;
+  // rotate the band index with the frame: a persistent CTA strides the item list by gridDim.x, and when
+  // gridDim.x is a multiple of nbands a plain (frame, band) order would pin each CTA to ONE band - the bottom
+  // bands (where the sidewalk blob lives) cost more than the top ones
+  const int j = (item - b * p.nbands + b) % p.nbands;
   it.b = b;
   it.pa = j * p.ppb;
   it.pb = min(it.pa + p.ppb, p.d.mh);
@@ -198,7 +205,7 @@ __device__ __forceinline__ int chunk_last_row(const FusedParams& p, const Item& 
 // explicit ld.shared / st.shared on 32-bit shared addresses (no generic-space LD/ST).
 struct SmemMap {
   uint32_t hi;        // [kStagesHi][16 KB]   TMA staging, [32 k][128 px]
-  uint32_t bt;        // [2 parity][hi, lo][kNPad * 128 B]
+  uint32_t bt;        // [2 parity][kNMma rows x 128 B]: rows [0,16) = coefficients hi, rows [16,32) = lo
   uint32_t chunks;    // [kChunkBufs][chunk_floats] f32
   uint32_t box;       // [2 item parity][kMaxInstTc][4] f32 (epilogue warps)
   uint32_t ubox;      // [kMaxInstTc][4] f32 (upsample warps)
@@ -228,7 +235,7 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H) {
   uint32_t o = 0;
   auto take = [&](uint32_t bytes, uint32_t align) { o = (o + align - 1) / align * align; uint32_t r = o; o += bytes; return r; };
   m.hi = take(kStagesHi * kTileBytes, 1024);
-  m.bt = take(2 * 2 * kNPad * 128, 1024);
+  m.bt = take(2 * kNMma * 128, 1024);
   m.chunks = take((uint32_t)kChunkBufs * chunk_floats * 4, 16);
   m.box = take(2 * kMaxInstTc * 4 * 4, 16);
   m.ubox = take(kMaxInstTc * 4 * 4, 16);
@@ -307,16 +314,31 @@ struct RoleTimer {
   __device__ __forceinline__ void begin(unsigned long long* o) { out = o; if (out) { t_start = clock64(); for (int i = 0; i < 6; ++i) wait[i] = 0; } }
   __device__ __forceinline__ void end() { if (out) { out[0] = (unsigned long long)(clock64() - t_start); for (int i = 0; i < 6; ++i) out[1 + i] = (unsigned long long)wait[i]; } }
 };
-#define TIMED_WAIT(tm, slot, bar, parity)            \
-  do {                                                \
-    if ((tm).out) {                                   \
-      const long long t0__ = clock64();               \
-      bar_wait((bar), (parity));                      \
-      (tm).wait[(slot)] += clock64() - t0__;          \
-    } else {                                          \
-      bar_wait((bar), (parity));                      \
-    }                                                 \
+#define TIMED_WAIT(tm, slot, bar, parity)                           \
+  do {                                                               \
+    const long long t0__ = (kDiag && (tm).out) ? clock64() : 0;      \
+    bar_wait((bar), (parity));                                       \
+    if (kDiag && (tm).out) (tm).wait[(slot)] += clock64() - t0__;    \
   } while (0)
+
+template <int kN>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t (&r)[kN]);
+template <>
+__device__ __forceinline__ void tmem_ld_nowait<8>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_nowait<16>(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 
 __device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
@@ -344,7 +366,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
-template <bool kWriteMasks, int kNI>
+template <bool kWriteMasks, int kNI, bool kDiag>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -390,8 +412,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   if (warp == 0) {
     // =========================== TMA producer + MMA issuer (one thread) ===========================
     if (lane == 0) {
-      RoleTimer tm; tm.begin(p.timing ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
-      const uint32_t idesc = make_idesc(kTileM, kNPad);
+      RoleTimer tm; tm.begin((kDiag && p.timing) ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
+      const uint32_t idesc = make_idesc(kTileM, kNMma);
       // load iterator: runs kStagesHi tiles ahead of the MMA iterator
       int lk = 0, lt = 0;
       Item lit = get_item(p, 0);
@@ -401,9 +423,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const Item it = get_item(p, k);
         if (!it.valid) break;
         const int par = k & 1;
-        const uint32_t b_hi = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
-        const uint32_t b_lo = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
+        const uint32_t b_all = sbase + sm.bt + par * kNMma * 128;
         for (int t = 0; t < it.ntiles; ++t, ++g) {
+#pragma unroll 1
           while (lit.valid && lg < g + kStagesHi) {     // keep the staging ring full
             const int st = lg % kStagesHi;
             TIMED_WAIT(tm, 3, BAR(BAR_HI_EMPTY + st), ((lg / kStagesHi) & 1) ^ 1);
@@ -419,15 +441,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           tc_fence_after();
           const uint32_t a_hi = tmem_base + kTmemAOff + sl * 64;       // A in tensor memory: lane = pixel, column = k
           const uint32_t a_lo = a_hi + 32;
-          const uint32_t dcol = tmem_base + kTmemAccOff + ac * kNPad;
-          // B (coefficients) K-major SW128 in shared memory: rows are 128 B, 8-row groups 1024 B apart (SBO),
-          // one k-step (8 tf32) = 32 B along the row = 8 TMEM columns of A.
+          const uint32_t dcol = tmem_base + kTmemAccOff + ac * kNMma;
+          // D[:, 0:16] = (A_hi + A_lo) * B_hi^T, D[:, 16:32] = (A_hi + A_lo) * B_lo^T: 8 instructions of N = 32 instead
+          // of 12 of N = 16 (a small tcgen05.mma costs the same ~70 cycles for any N <= 128, measured).
+          // B K-major SW128 in shared memory: rows are 128 B, 8-row groups 1024 B apart (SBO), one k-step
+          // (8 tf32) = 32 B along the row = 8 TMEM columns of A.
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(b_all + ks * 32, 16, 1024), idesc, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(b_lo + ks * 32, 16, 1024), idesc, 1);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_lo + ks * 8, make_smem_desc(b_hi + ks * 32, 16, 1024), idesc, 1);
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_lo + ks * 8, make_smem_desc(b_all + ks * 32, 16, 1024), idesc, 1);
           bar_commit(BAR(BAR_LO_EMPTY + sl));
           bar_commit(BAR(BAR_ACC_FULL + ac));
         }
@@ -440,7 +462,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32) belong to this warp
     const int st_tid = (warp - kFirstSplitWarp) * 32 + lane;
     const int px = quarter * 32 + lane;              // tile pixel (= TMEM lane) of this thread
-    RoleTimer tm; tm.begin((p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
+    RoleTimer tm; tm.begin((kDiag && p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
     uint32_t g = 0;
     for (int k = 0;; ++k) {
       const Item it = get_item(p, k);
@@ -449,8 +471,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int par = k & 1;
         TIMED_WAIT(tm, 0, BAR(BAR_B_EMPTY + par), ((k >> 1) & 1) ^ 1);
         const int n = min(p.counts[it.b], min(d.max_n, kMaxInstTc));
-        const uint32_t bh = sbase + sm.bt + (par * 2 + 0) * kNPad * 128;
-        const uint32_t bl = sbase + sm.bt + (par * 2 + 1) * kNPad * 128;
+        const uint32_t bh = sbase + sm.bt + par * kNMma * 128;   // rows [0,16): hi
+        const uint32_t bl = bh + kNPad * 128;                      // rows [16,32): lo (16 = 2 swizzle periods: same XOR pattern)
         const int r = st_tid >> 3, c = st_tid & 7;   // 128 threads = 16 rows x 8 chunks
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)it.b * d.max_n + r) * d.K + 4 * c));
@@ -500,7 +522,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const uint32_t inst_stride = (uint32_t)d.mw * 4;
     const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
     const uint32_t chunks = sbase + sm.chunks;
-    RoleTimer tm; tm.begin((p.timing && ep_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 3) * 8 : nullptr);
+    RoleTimer tm; tm.begin((kDiag && p.timing && ep_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 3) * 8 : nullptr);
     uint32_t g = 0, chunk_base = 0;
     for (int k = 0;; ++k) {
       const Item it = get_item(p, k);
@@ -526,11 +548,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         TIMED_WAIT(tm, 0, BAR(BAR_ACC_FULL + ac), (g / kAcc) & 1);
         __syncwarp();
         tc_fence_after();
-        uint32_t r[kNI];
-        tmem_ld<kNI>(tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemAccOff + ac * kNPad, r);
+        uint32_t r[kNI], r2[kNI];
+        const long long t_ld0 = (kDiag && tm.out) ? clock64() : 0;
+        {
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemAccOff + ac * kNMma;
+          tmem_ld_nowait<kNI>(ta, r);               // (A_hi + A_lo) * B_hi
+          tmem_ld_nowait<kNI>(ta + kNPad, r2);      // (A_hi + A_lo) * B_lo
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < kNI; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_ACC_EMPTY + ac));
+        if (kDiag && tm.out) tm.wait[2] += clock64() - t_ld0;
 
         done_rows += tile_rows; done_cols += tile_cols;
         if (done_cols >= d.mw) { done_cols -= d.mw; ++done_rows; }
@@ -538,6 +569,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int rows_done = last_tile ? it.nrows : done_rows;
         const int row_last = last_tile ? it.nrows - 1 : (done_cols == 0 ? done_rows - 1 : done_rows);
         const int c_hi = min(row_last >> p.pr_shift, it.nchunks - 1);
+#pragma unroll 1
         while (acquired <= c_hi) {            // acquire the chunk buffers this tile writes, in order
           const uint32_t gc = chunk_base + acquired;
           TIMED_WAIT(tm, 1, BAR(BAR_CH_EMPTY + gc % kChunkBufs), ((gc / kChunkBufs) & 1) ^ 1);
@@ -549,24 +581,22 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           const bool has1 = c1 < it.nchunks, has0 = (rr == 0 && c1 > 0);
           const uint32_t dst1 = chunks + ((chunk_base + c1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
           const uint32_t dst0 = chunks + ((chunk_base + c1 + kChunkBufs - 1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
+          float* dbg = (kDiag && p.logits_dbg) ? p.logits_dbg + (((size_t)it.b * d.max_n) * d.mh + it.pa + brow) * d.mw + bcol : nullptr;
+          const size_t dbg_stride = (size_t)d.mh * d.mw;
 #pragma unroll
           for (int i = 0; i < kNI; ++i) {
             if (i < n) {
               const float4 q = box[i];
               const bool keep = (fx >= q.x) && (fx < q.z) && (fy >= q.y) && (fy < q.w);   // crop_mask, ops.py:688-704
               const float v = keep ? __uint_as_float(r[i]) : 0.f;
-              r[i] = __float_as_uint(v);
               if (has1) sts_f32(dst1 + i * inst_stride, v);
               if (has0) sts_f32(dst0 + i * inst_stride, v);
+              if (kDiag && dbg) dbg[i * dbg_stride] = v;
             }
-          }
-          if (p.logits_dbg) {
-#pragma unroll
-            for (int i = 0; i < kNI; ++i)
-              if (i < n) p.logits_dbg[(((size_t)it.b * d.max_n + i) * d.mh + it.pa + brow) * d.mw + bcol] = __uint_as_float(r[i]);
           }
         }
         __syncwarp();
+#pragma unroll 1
         while (completed < it.nchunks && chunk_last_row(p, it, completed) < rows_done) {   // chunks completed by this tile
           const uint32_t gc = chunk_base + completed;
           if (lane == 0) bar_arrive(BAR(BAR_CH_FULL + gc % kChunkBufs));
@@ -592,7 +622,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const uint4 zeros = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t inst_stride = (uint32_t)d.mw * 4;
     const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
-    RoleTimer tm; tm.begin((p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
+    RoleTimer tm; tm.begin((kDiag && p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
     uint32_t gc = 0;
     for (int k = 0;; ++k) {
       const Item it = get_item(p, k);
@@ -616,6 +646,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int nrows_out = last ? 2 : 4;
         const int jbeg = (r == 0) ? -2 : 0;                     // pair 0 also owns dst rows 0,1
         const int laty = (pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
+#pragma unroll 1
         for (int wq = uw; wq < n * ng8w; wq += kWarpsUp) {
           const int i = wq / ng8w;
           const int g = ((wq - i * ng8w) * subs + sub) * 8 + gl;
@@ -630,6 +661,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             const bool outside = ((float)(r + 1) < q.y) || ((float)r >= q.w) || ((float)(4 * g + 4) < q.x) || ((float)(4 * g - 1) >= q.z);
             if (outside) {
               if (kWriteMasks) {
+#pragma unroll 1
                 for (int j = jbeg; j < nrows_out; ++j) {
                   const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
                   *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = zeros;
@@ -657,31 +689,29 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
               const bool left = (g == 0);
               const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
               const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
-              if (uni_neg) {
-                if (kWriteMasks) {
-                  for (int j = jbeg; j < nrows_out; ++j) {
-                    const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
-                    *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = zeros;
-                  }
-                }
-              } else if (uni_pos) {
+              if (uni_neg || uni_pos) {
                 const int Yfirst = (jbeg < 0) ? 0 : 4 * r + 2, Ylast = 4 * r + 1 + nrows_out;
                 if (kWriteMasks) {
+                  const uint4 w = uni_pos ? ones : zeros;
+#pragma unroll 1
                   for (int j = jbeg; j < nrows_out; ++j) {
                     const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
-                    *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = ones;
+                    *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
                   }
                 }
-                ts.area = 16u * (unsigned)(nrows_out - jbeg);
-                ts.orw[0] = ts.orw[1] = ts.orw[2] = ts.orw[3] = 0x01010101u;
-                ts.miny = Yfirst; ts.maxy = Ylast;
-                if (laty >= 0 && laty <= Ylast) lattice_row(ones, laty, 16 * g, d, lat);
+                if (uni_pos) {
+                  ts.area = 16u * (unsigned)(nrows_out - jbeg);
+                  ts.orw[0] = ts.orw[1] = ts.orw[2] = ts.orw[3] = 0x01010101u;
+                  ts.miny = Yfirst; ts.maxy = Ylast;
+                  if (laty >= 0 && laty <= Ylast) lattice_row(ones, laty, 16 * g, d, lat);
+                }
               } else {
                 // mixed signs: the exact 4-tap blend.  One compact, rolled loop (code size matters: the roles
                 // share the instruction cache).
                 float hA[16], hB[16];
                 hinterp4(sA, hA, left);
                 hinterp4(sB, hB, left);
+#pragma unroll 1
                 for (int j = jbeg; j < nrows_out; ++j) {
                   uint4 w;
                   int Y;
@@ -812,8 +842,10 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, d.H).total + 1024;
   pl->ni = d.max_n <= 8 ? 8 : 16;
   cudaError_t e = cudaSuccess;
-  const void* fns[4] = {(const void*)fused_tc_kernel<true, 8>, (const void*)fused_tc_kernel<false, 8>,
-                        (const void*)fused_tc_kernel<true, 16>, (const void*)fused_tc_kernel<false, 16>};
+  const void* fns[8] = {(const void*)fused_tc_kernel<true, 8, false>,  (const void*)fused_tc_kernel<false, 8, false>,
+                        (const void*)fused_tc_kernel<true, 16, false>, (const void*)fused_tc_kernel<false, 16, false>,
+                        (const void*)fused_tc_kernel<true, 8, true>,   (const void*)fused_tc_kernel<false, 8, true>,
+                        (const void*)fused_tc_kernel<true, 16, true>,  (const void*)fused_tc_kernel<false, 16, true>};
   for (const void* f : fns)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(%zu B): %s", pl->smem_bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
@@ -865,20 +897,23 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.nbands = ceil_div(d.mh, p.ppb);
   p.n_items = B * p.nbands;
   const int grid = p.n_items < pl->num_sms ? p.n_items : pl->num_sms;
+  const bool diag = (logits_dbg != nullptr) || (pl->timing != nullptr);   // debug logits / role timing: separate instantiation
+#define VA_LAUNCH(WM, NI, DG) fused_tc_kernel<WM, NI, DG><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p)
   if (pl->ni == 8) {
-    if (masks) fused_tc_kernel<true, 8><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
-    else fused_tc_kernel<false, 8><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+    if (diag) { if (masks) VA_LAUNCH(true, 8, true); else VA_LAUNCH(false, 8, true); }
+    else      { if (masks) VA_LAUNCH(true, 8, false); else VA_LAUNCH(false, 8, false); }
   } else {
-    if (masks) fused_tc_kernel<true, 16><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
-    else fused_tc_kernel<false, 16><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p);
+    if (diag) { if (masks) VA_LAUNCH(true, 16, true); else VA_LAUNCH(false, 16, true); }
+    else      { if (masks) VA_LAUNCH(true, 16, false); else VA_LAUNCH(false, 16, false); }
   }
+#undef VA_LAUNCH
   if (pl->timing) {   // developer diagnostic: blocking read-back, per-role wait / busy cycles averaged over CTAs
     cudaStreamSynchronize(st);
     static unsigned long long h[256 * 5 * 8];
     cudaMemcpy(h, pl->timing, (size_t)grid * 5 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     const char* roles[5] = {"tma", "mma", "split", "epilogue", "upsample"};
     const char* waits[5][3] = {{"(merged)", "", ""}, {"b_full", "acc_empty", "lo_full"}, {"b_empty", "hi_full", "lo_empty"},
-                               {"acc_full", "ch_empty", ""}, {"ch_full", "", ""}};
+                               {"acc_full", "ch_empty", "tmem_ld"}, {"ch_full", "", ""}};
     fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr);
     for (int r = 0; r < 5; ++r) {
       double tot = 0, w[3] = {0, 0, 0};
