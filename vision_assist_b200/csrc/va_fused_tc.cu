@@ -50,8 +50,10 @@ constexpr int kThreads = 32 * (kFirstUpWarp + kWarpsUp);   // 512
 constexpr int kUpThreadsTc = 32 * kWarpsUp;
 constexpr int kMaxInstTc = 16;              // instances this kernel handles (N = 16)
 constexpr int kTmemAOff = 0;                // TMEM columns [0, 128): A ring
-constexpr int kTmemAccOff = kStagesLo * 64; // TMEM columns [128, 256): accumulators (kAcc x kNMma)
-constexpr int kTmemCols = 256;
+constexpr int kIssuers = 2;                 // MMA-issuing threads (lane 0 of split warps 0 and 1): tcgen05.mma from different warps overlap
+constexpr int kAccCols = kIssuers * kNMma;  // accumulator columns per tile: [hi pass | lo pass], each [B_hi | B_lo]
+constexpr int kTmemAccOff = kStagesLo * 64; // TMEM columns [128, 384): accumulators (kAcc x kAccCols)
+constexpr int kTmemCols = 512;
 
 struct FusedParams {
   Dims d;
@@ -210,6 +212,8 @@ struct SmemMap {
   uint32_t box;       // [2 item parity][kMaxInstTc][4] f32 (epilogue warps)
   uint32_t ubox;      // [kMaxInstTc][4] f32 (upsample warps)
   uint32_t latpair;   // [mh] i16: the lattice dst row inside rows 4r+2..4r+5 of pair r, -1 if none
+  uint32_t zeros;     // [(4*pr+2) * W] bytes of 0: source of the bulk zero-fill stores
+  uint32_t zero_bytes;
   uint32_t stat;      // [kMaxInstTc][8] i32: area, minx, miny, maxx, maxy
   uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
   uint32_t bars;      // [BAR_COUNT] u64
@@ -230,7 +234,7 @@ enum {
   BAR_COUNT = BAR_CH_EMPTY + kChunkBufs
 };
 
-__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H) {
+__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H, int zero_bytes) {
   SmemMap m;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes, uint32_t align) { o = (o + align - 1) / align * align; uint32_t r = o; o += bytes; return r; };
@@ -240,6 +244,8 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H) {
   m.box = take(2 * kMaxInstTc * 4 * 4, 16);
   m.ubox = take(kMaxInstTc * 4 * 4, 16);
   m.latpair = take((uint32_t)(H / 4 + 8) * 2, 16);
+  m.zero_bytes = (uint32_t)zero_bytes;
+  m.zeros = take((uint32_t)zero_bytes, 128);
   m.stat = take(kMaxInstTc * 8 * 4, 16);
   m.latrow = take((uint32_t)H * 2, 16);
   m.bars = take(BAR_COUNT * 8, 8);
@@ -372,7 +378,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   // dynamic shared memory is only guaranteed 16 B aligned: round the shared address up to 1024
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const SmemMap sm = fused_smem_map(p.chunk_floats, p.d.H);
+  const SmemMap sm = fused_smem_map(p.chunk_floats, p.d.H, (4 * p.pr + 2) * p.d.W);
   const Dims& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bars = sbase + sm.bars;
@@ -381,9 +387,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStagesHi; ++i) { bar_init(BAR(BAR_HI_FULL + i), 1); bar_init(BAR(BAR_HI_EMPTY + i), kWarpsSplit); }
-    for (int i = 0; i < kStagesLo; ++i) { bar_init(BAR(BAR_LO_FULL + i), kWarpsSplit); bar_init(BAR(BAR_LO_EMPTY + i), 1); }
-    for (int i = 0; i < kAcc; ++i) { bar_init(BAR(BAR_ACC_FULL + i), 1); bar_init(BAR(BAR_ACC_EMPTY + i), kWarpsEpi); }
-    for (int i = 0; i < 2; ++i) { bar_init(BAR(BAR_B_FULL + i), kWarpsSplit); bar_init(BAR(BAR_B_EMPTY + i), 1); }
+    for (int i = 0; i < kStagesLo; ++i) { bar_init(BAR(BAR_LO_FULL + i), kWarpsSplit); bar_init(BAR(BAR_LO_EMPTY + i), kIssuers); }
+    for (int i = 0; i < kAcc; ++i) { bar_init(BAR(BAR_ACC_FULL + i), kIssuers); bar_init(BAR(BAR_ACC_EMPTY + i), kWarpsEpi); }
+    for (int i = 0; i < 2; ++i) { bar_init(BAR(BAR_B_FULL + i), kWarpsSplit); bar_init(BAR(BAR_B_EMPTY + i), kIssuers); }
     for (int i = 0; i < kChunkBufs; ++i) { bar_init(BAR(BAR_CH_FULL + i), kWarpsEpi); bar_init(BAR(BAR_CH_EMPTY + i), kWarpsUp); }
     fence_barrier_init();
   }
@@ -396,6 +402,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     }
     sts_s16(sbase + sm.latpair + 2 * r, (short)ly);
   }
+  for (uint32_t t = threadIdx.x * 16u; t < sm.zero_bytes; t += kThreads * 16u) sts_v4(sbase + sm.zeros + t, make_float4(0.f, 0.f, 0.f, 0.f));
+  fence_proxy_async();
   for (int t = threadIdx.x; t < kMaxInstTc * 8; t += kThreads) {
     const int f = t & 7;
     sts_s32(sbase + sm.stat + 4 * t, (f == 1 || f == 2) ? INT_MAX : (f == 3 || f == 4) ? -1 : 0);
@@ -410,50 +418,21 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   const uint32_t tmem_base = lds_u32(sbase + sm.tmem_slot);
 
   if (warp == 0) {
-    // =========================== TMA producer + MMA issuer (one thread) ===========================
+    // =========================== TMA producer ===========================
     if (lane == 0) {
       RoleTimer tm; tm.begin((kDiag && p.timing) ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
-      const uint32_t idesc = make_idesc(kTileM, kNMma);
-      // load iterator: runs kStagesHi tiles ahead of the MMA iterator
-      int lk = 0, lt = 0;
-      Item lit = get_item(p, 0);
-      uint32_t lg = 0;
       uint32_t g = 0;
       for (int k = 0;; ++k) {
         const Item it = get_item(p, k);
         if (!it.valid) break;
-        const int par = k & 1;
-        const uint32_t b_all = sbase + sm.bt + par * kNMma * 128;
-        for (int t = 0; t < it.ntiles; ++t, ++g) {
+        const int px0 = it.pa * d.mw;
 #pragma unroll 1
-          while (lit.valid && lg < g + kStagesHi) {     // keep the staging ring full
-            const int st = lg % kStagesHi;
-            TIMED_WAIT(tm, 3, BAR(BAR_HI_EMPTY + st), ((lg / kStagesHi) & 1) ^ 1);
-            bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
-            tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), lit.pa * d.mw + lt * kTileM, 0, lit.b);
-            ++lg;
-            if (++lt == lit.ntiles) { lt = 0; lit = get_item(p, ++lk); }
-          }
-          if (t == 0) TIMED_WAIT(tm, 0, BAR(BAR_B_FULL + par), (k >> 1) & 1);
-          const int sl = g % kStagesLo, ac = g % kAcc;
-          TIMED_WAIT(tm, 1, BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
-          TIMED_WAIT(tm, 2, BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = tmem_base + kTmemAOff + sl * 64;       // A in tensor memory: lane = pixel, column = k
-          const uint32_t a_lo = a_hi + 32;
-          const uint32_t dcol = tmem_base + kTmemAccOff + ac * kNMma;
-          // D[:, 0:16] = (A_hi + A_lo) * B_hi^T, D[:, 16:32] = (A_hi + A_lo) * B_lo^T: 8 instructions of N = 32 instead
-          // of 12 of N = 16 (a small tcgen05.mma costs the same ~70 cycles for any N <= 128, measured).
-          // B K-major SW128 in shared memory: rows are 128 B, 8-row groups 1024 B apart (SBO), one k-step
-          // (8 tf32) = 32 B along the row = 8 TMEM columns of A.
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_hi + ks * 8, make_smem_desc(b_all + ks * 32, 16, 1024), idesc, ks > 0);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_lo + ks * 8, make_smem_desc(b_all + ks * 32, 16, 1024), idesc, 1);
-          bar_commit(BAR(BAR_LO_EMPTY + sl));
-          bar_commit(BAR(BAR_ACC_FULL + ac));
+        for (int t = 0; t < it.ntiles; ++t, ++g) {
+          const int st = g % kStagesHi;
+          TIMED_WAIT(tm, 0, BAR(BAR_HI_EMPTY + st), ((g / kStagesHi) & 1) ^ 1);
+          bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
+          tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), px0 + t * kTileM, 0, it.b);
         }
-        bar_commit(BAR(BAR_B_EMPTY + par));
       }
       tm.end();
     }
@@ -462,6 +441,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32) belong to this warp
     const int st_tid = (warp - kFirstSplitWarp) * 32 + lane;
     const int px = quarter * 32 + lane;              // tile pixel (= TMEM lane) of this thread
+    const int issuer = (warp - kFirstSplitWarp) < kIssuers ? (warp - kFirstSplitWarp) : -1;
+    const uint32_t idesc = make_idesc(kTileM, kNMma);
     RoleTimer tm; tm.begin((kDiag && p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
     uint32_t g = 0;
     for (int k = 0;; ++k) {
@@ -510,6 +491,29 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_LO_FULL + sl));
+        // ---- MMA issue.  tcgen05.mma instructions issued by DIFFERENT warps overlap (measured: ~70 cycles per
+        // small MMA per issuing thread, 2 issuers -> 2x the rate), so the two passes of a tile are issued by
+        // lane 0 of split warps 0 and 1 into separate accumulators; the epilogue adds them.
+        //   issuer 0: D0[:, 0:16 | 16:32] = A_hi * [B_hi | B_lo]^T      issuer 1: D1 = A_lo * [B_hi | B_lo]^T
+        if (issuer >= 0 && lane == 0) {
+          const int par = k & 1;
+          if (t == 0) TIMED_WAIT(tm, 3, BAR(BAR_B_FULL + par), (k >> 1) & 1);
+          const int ac = g % kAcc;
+          TIMED_WAIT(tm, 4, BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);       // all four lane quarters of A are in TMEM
+          TIMED_WAIT(tm, 5, BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t b_all = sbase + sm.bt + par * kNMma * 128;
+          const uint32_t a_op = tmem_base + kTmemAOff + sl * 64 + issuer * 32;     // A in tensor memory: lane = pixel, column = k
+          const uint32_t dcol = tmem_base + kTmemAccOff + ac * kAccCols + issuer * kNMma;
+          // B K-major SW128 in shared memory: rows are 128 B, 8-row groups 1024 B apart (SBO), one k-step
+          // (8 tf32) = 32 B along the row = 8 TMEM columns of A.
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(dcol, a_op + ks * 8, make_smem_desc(b_all + ks * 32, 16, 1024), idesc, ks > 0);
+          bar_commit(BAR(BAR_LO_EMPTY + sl));
+          bar_commit(BAR(BAR_ACC_FULL + ac));
+          if (t + 1 == it.ntiles) bar_commit(BAR(BAR_B_EMPTY + par));
+        }
+        __syncwarp();
       }
     }
     tm.end();
@@ -551,12 +555,16 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         uint32_t r[kNI], r2[kNI];
         const long long t_ld0 = (kDiag && tm.out) ? clock64() : 0;
         {
-          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemAccOff + ac * kNMma;
-          tmem_ld_nowait<kNI>(ta, r);               // (A_hi + A_lo) * B_hi
-          tmem_ld_nowait<kNI>(ta + kNPad, r2);      // (A_hi + A_lo) * B_lo
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemAccOff + ac * kAccCols;
+          uint32_t r3[kNI], r4[kNI];
+          tmem_ld_nowait<kNI>(ta, r);                       // A_hi * B_hi
+          tmem_ld_nowait<kNI>(ta + kNPad, r2);              // A_hi * B_lo
+          tmem_ld_nowait<kNI>(ta + kNMma, r3);              // A_lo * B_hi
+          tmem_ld_nowait<kNI>(ta + kNMma + kNPad, r4);      // A_lo * B_lo
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < kNI; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+          for (int i = 0; i < kNI; ++i)
+            r[i] = __float_as_uint((__uint_as_float(r[i]) + __uint_as_float(r3[i])) + (__uint_as_float(r2[i]) + __uint_as_float(r4[i])));
         }
         tc_fence_before();
         __syncwarp();
@@ -649,13 +657,30 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 #pragma unroll 1
         for (int wq = uw; wq < n * ng8w; wq += kWarpsUp) {
           const int i = wq / ng8w;
-          const int g = ((wq - i * ng8w) * subs + sub) * 8 + gl;
+          const int g8w = wq - i * ng8w;
+          const int g = (g8w * subs + sub) * 8 + gl;
+          const float4 q = lds_v4(sbase + sm.ubox + 16 * i);     // x1, y1, x2, y2 at proto resolution
+          // Every proto row this chunk reads (r0 .. r0+npairs) lies outside the instance's box: crop_mask zeroed
+          // them, so the chunk's dst rows of this instance are one contiguous block of zeros.  One bulk
+          // shared->global copy from the zero buffer (issued by the warp that owns column block 0) replaces
+          // the whole column sweep.
+          if (((float)(r0 + npairs) < q.y) || ((float)r0 >= q.w)) {
+            if (kWriteMasks && g8w == 0 && lane == 0) {
+              const int Ya = (r0 == 0) ? 0 : 4 * r0 + 2;
+              const int Yb = min(4 * (r0 + npairs - 1) + 5, d.H - 1);
+              uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + i) * d.H + Ya) * (size_t)d.W;
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sbase + sm.zeros),
+                           "r"((uint32_t)((Yb - Ya + 1) * d.W))
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
           const bool active = (g < NG) && (pair < npairs);
           ThreadStats ts;
           if (active) {
             const size_t inst = (size_t)it.b * d.max_n + i;
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
-            const float4 q = lds_v4(sbase + sm.ubox + 16 * i);
             // every proto pixel this task reads (rows r, r+1, cols 4g-1 .. 4g+4) is outside the instance's box:
             // crop_mask zeroed them, the masks are 0 - store and skip everything else
             const bool outside = ((float)(r + 1) < q.y) || ((float)r >= q.w) || ((float)(4 * g + 4) < q.x) || ((float)(4 * g - 1) >= q.z);
@@ -776,6 +801,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         sts_s32(st, 0); sts_s32(st + 4, INT_MAX); sts_s32(st + 8, INT_MAX); sts_s32(st + 12, -1); sts_s32(st + 16, -1);
       }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tm.end();
   }
 
@@ -834,12 +860,12 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   int pr = 0;
   for (int cand : {4, 2}) {
     const int cf = (cand + 1) * d.max_n * d.mw;
-    if ((size_t)fused_smem_map(cf, d.H).total + 1024 <= limit) { pr = cand; break; }
+    if ((size_t)fused_smem_map(cf, d.H, (4 * cand + 2) * d.W).total + 1024 <= limit) { pr = cand; break; }
   }
   if (!pr) { delete pl; snprintf(err, errlen, "chunk buffers do not fit in shared memory (max_n=%d, mw=%d)", d.max_n, d.mw); return nullptr; }
   pl->pr = pr;
   pl->chunk_floats = (pr + 1) * d.max_n * d.mw;
-  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, d.H).total + 1024;
+  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, d.H, (4 * pr + 2) * d.W).total + 1024;
   pl->ni = d.max_n <= 8 ? 8 : 16;
   cudaError_t e = cudaSuccess;
   const void* fns[8] = {(const void*)fused_tc_kernel<true, 8, false>,  (const void*)fused_tc_kernel<false, 8, false>,
@@ -912,7 +938,7 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
     static unsigned long long h[256 * 5 * 8];
     cudaMemcpy(h, pl->timing, (size_t)grid * 5 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     const char* roles[5] = {"tma", "mma", "split", "epilogue", "upsample"};
-    const char* waits[5][3] = {{"(merged)", "", ""}, {"b_full", "acc_empty", "lo_full"}, {"b_empty", "hi_full", "lo_empty"},
+    const char* waits[5][3] = {{"(unused)", "", ""}, {"hi_empty", "", ""}, {"b_empty", "hi_full", "lo_empty"},
                                {"acc_full", "ch_empty", "tmem_ld"}, {"ch_full", "", ""}};
     fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr);
     for (int r = 0; r < 5; ++r) {
