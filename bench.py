@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -128,7 +128,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     vals = []
-    fpc = 24
+    fpc = 48
     for _ in range(max(1, args.warmup) - 1):
         pass
     base = None
@@ -279,7 +279,7 @@ def run_ours(args, wl):
         "grid_only_frames_per_s": grid_only,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=16)
+        line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=48)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -288,7 +288,7 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
