@@ -67,16 +67,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = 1e30) -> dict:
+        """Summarise the samples taken inside [t_begin, t_end] (host clock); all samples if none fall inside."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        inside = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.05]
+        rows = inside if inside else [r for (_, r) in self.rows]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -86,7 +89,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -183,22 +186,24 @@ def run_ours(args, wl):
             return gather_records(records, B * world, dst=0)
         return records
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     eng.profile(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = eng.last_launch_count * args.steps
     asm_ms, tail_ms, calls = eng.profile_read()
@@ -208,7 +213,7 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
         ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = B * world * args.steps / (ms / 1000.0)
 
     # grid-only mode (masks never written), reported separately

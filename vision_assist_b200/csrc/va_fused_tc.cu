@@ -40,6 +40,9 @@ constexpr int kAcc = 4;                     // TMEM accumulator ring
 constexpr int kNPad = 16;                   // instances padded
 constexpr int kNMma = 2 * kNPad;            // UMMA N: [B_hi ; B_lo] stacked along N - the cost of a small MMA does not depend on N
 constexpr int kChunkBufs = 3;
+constexpr int kItemRing = 16;               // published item indices.  The TMA thread leads the slowest role by at most
+                                            // kStagesHi + kStagesLo + kAcc + kChunkBufs chunks < 32 tiles and every item has >= 2 tiles
+                                            // (checked at plan creation), so a slot is never republished before it was read
 constexpr int kWarpsSplit = 4;              // one warp per TMEM lane quarter: staged box -> registers -> tcgen05.st
 constexpr int kWarpsEpi = 4;                // one warp per TMEM lane quarter: TMEM -> crop -> chunk buffers
 constexpr int kWarpsUp = 7;
@@ -72,6 +75,7 @@ struct FusedParams {
   int n_items;
   int nst;           // instance stride of the chunk buffers (= max_n)
   int chunk_floats;  // floats per chunk buffer = (pr+1) * nst * mw
+  int* work_counter;            // global work-stealing counter (reset before every launch)
   unsigned long long* timing;   // developer diagnostic (VA_FUSED_TIMING=1): [grid][5 roles][8] cycle counters, or nullptr
 };
 
@@ -177,17 +181,16 @@ struct Item {
   int nchunks;  // ceil((pb - pa) / pr)
 };
 
-// out of line on purpose: called once per item per role, and five inlined copies of its divisions would
-// compete with the hot loops for the instruction cache
-__device__ __noinline__ Item get_item(const FusedParams& p, int k) {
+// Work item index -> (frame, band).  Items are handed out dynamically (work stealing through a global counter) in
+// bottom-band-first order: the bands that contain the sidewalk blob cost more, so the light top bands form the
+// tail of the schedule.  Out of line on purpose: called once per item per role, and inlined copies of its
+// divisions would compete with the hot loops for the instruction cache.
+__device__ __noinline__ Item decode_item(const FusedParams& p, int item) {
   Item it;
-  const int item = blockIdx.x + k * gridDim.x;
   it.valid = item < p.n_items;
-  const int b = item / p.nbands;
-  // rotate the band index with the frame: a persistent CTA strides the item list by gridDim.x, and when
-  // gridDim.x is a multiple of nbands a plain (frame, band) order would pin each CTA to ONE band - the bottom
-  // bands (where the sidewalk blob lives) cost more than the top ones
-  const int j = (item - b * p.nbands + b) % p.nbands;
+  const int jb = item / p.B;
+  const int b = item - jb * p.B;
+  const int j = p.nbands - 1 - jb;
   it.b = b;
   it.pa = j * p.ppb;
   it.pb = min(it.pa + p.ppb, p.d.mh);
@@ -218,6 +221,7 @@ struct SmemMap {
   uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
   uint32_t bars;      // [BAR_COUNT] u64
   uint32_t tmem_slot;
+  uint32_t items;     // [kItemRing] i32
   uint32_t total;
 };
 enum {
@@ -231,7 +235,8 @@ enum {
   BAR_B_EMPTY = BAR_B_FULL + 2,
   BAR_CH_FULL = BAR_B_EMPTY + 2,
   BAR_CH_EMPTY = BAR_CH_FULL + kChunkBufs,
-  BAR_COUNT = BAR_CH_EMPTY + kChunkBufs
+  BAR_ITEM = BAR_CH_EMPTY + kChunkBufs,      // item ring: the TMA thread publishes the stolen item indices
+  BAR_COUNT = BAR_ITEM + kItemRing
 };
 
 __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H, int zero_bytes) {
@@ -250,6 +255,7 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H, int z
   m.latrow = take((uint32_t)H * 2, 16);
   m.bars = take(BAR_COUNT * 8, 8);
   m.tmem_slot = take(16, 16);
+  m.items = take(kItemRing * 4, 16);
   m.total = o;
   return m;
 }
@@ -383,6 +389,11 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bars = sbase + sm.bars;
   auto BAR = [&](int idx) { return bars + 8u * (uint32_t)idx; };
+  // k-th item of this CTA as published by the TMA thread
+  auto next_item = [&](int k) -> Item {
+    bar_wait(BAR(BAR_ITEM + (k % kItemRing)), (k / kItemRing) & 1);
+    return decode_item(p, lds_s32(sbase + sm.items + 4 * (k % kItemRing)));
+  };
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
@@ -391,6 +402,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     for (int i = 0; i < kAcc; ++i) { bar_init(BAR(BAR_ACC_FULL + i), kIssuers); bar_init(BAR(BAR_ACC_EMPTY + i), kWarpsEpi); }
     for (int i = 0; i < 2; ++i) { bar_init(BAR(BAR_B_FULL + i), kWarpsSplit); bar_init(BAR(BAR_B_EMPTY + i), kIssuers); }
     for (int i = 0; i < kChunkBufs; ++i) { bar_init(BAR(BAR_CH_FULL + i), kWarpsEpi); bar_init(BAR(BAR_CH_EMPTY + i), kWarpsUp); }
+    for (int i = 0; i < kItemRing; ++i) bar_init(BAR(BAR_ITEM + i), 1);
     fence_barrier_init();
   }
   for (int r = threadIdx.x; r < d.mh; r += kThreads) {   // lattice (cell-centre) dst row inside rows 4r+2 .. 4r+5
@@ -423,7 +435,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       RoleTimer tm; tm.begin((kDiag && p.timing) ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
       uint32_t g = 0;
       for (int k = 0;; ++k) {
-        const Item it = get_item(p, k);
+        const int item = atomicAdd(p.work_counter, 1);
+        sts_s32(sbase + sm.items + 4 * (k % kItemRing), item);
+        bar_arrive(BAR(BAR_ITEM + (k % kItemRing)));          // release: the index is visible to the waiting roles
+        const Item it = decode_item(p, item);
         if (!it.valid) break;
         const int px0 = it.pa * d.mw;
 #pragma unroll 1
@@ -446,7 +461,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     RoleTimer tm; tm.begin((kDiag && p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
     uint32_t g = 0;
     for (int k = 0;; ++k) {
-      const Item it = get_item(p, k);
+      const Item it = next_item(k);
       if (!it.valid) break;
       {   // per-frame B tiles: coefficients hi / lo, K-major, 16 B chunk c of row r stored at chunk c ^ (r & 7)
         const int par = k & 1;
@@ -529,7 +544,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     RoleTimer tm; tm.begin((kDiag && p.timing && ep_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 3) * 8 : nullptr);
     uint32_t g = 0, chunk_base = 0;
     for (int k = 0;; ++k) {
-      const Item it = get_item(p, k);
+      const Item it = next_item(k);
       if (!it.valid) break;
       const int n = min(p.counts[it.b], min(d.max_n, kNI));
       // scaled boxes of this frame (double-buffered by item parity; the 4 epilogue warps stay within one item)
@@ -541,9 +556,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         sts_f32(bx + (i * 4 + c) * 4, v);
       }
       named_bar_sync(1, 32 * kWarpsEpi);
-      float4 box[kNI];                                         // x1, y1, x2, y2 at proto resolution (ops.py:725-732)
+      // crop_mask (ops.py:688-704) keeps proto pixel (col,row) iff col >= x1 && col < x2 && row >= y1 && row < y2 with
+      // FLOAT box bounds (x1.. scaled as ops.py:725-732).  col/row are integers, so this is exactly
+      // col in [ceil(x1), ceil(x2)) and row in [ceil(y1), ceil(y2)): integer bounds per instance, kept in
+      // registers for the whole item; one unsigned compare per axis.  Instances >= n have an empty box.
+      int cl[kNI], rl[kNI];
+      unsigned cwid[kNI], rwid[kNI];
 #pragma unroll
-      for (int i = 0; i < kNI; ++i) box[i] = lds_v4(bx + 16 * i);
+      for (int i = 0; i < kNI; ++i) {
+        const float4 q = lds_v4(bx + 16 * i);
+        const int x1 = (int)ceilf(fminf(fmaxf(q.x, -1e6f), 1e6f)), x2 = (int)ceilf(fminf(fmaxf(q.z, -1e6f), 1e6f));
+        const int y1 = (int)ceilf(fminf(fmaxf(q.y, -1e6f), 1e6f)), y2 = (int)ceilf(fminf(fmaxf(q.w, -1e6f), 1e6f));
+        cl[i] = x1; cwid[i] = (unsigned)max(x2 - x1, 0);
+        rl[i] = y1; rwid[i] = (i < n) ? (unsigned)max(y2 - y1, 0) : 0u;
+      }
       int brow = ep_px / d.mw, bcol = ep_px - brow * d.mw;   // band-local (row, col) of this thread's pixel
       int done_rows = 0, done_cols = 0;                        // complete rows / extra pixels after the current tile
       int acquired = 0, completed = 0;
@@ -584,23 +610,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           ++acquired;
         }
         if (brow < it.nrows) {
-          const float fx = (float)bcol, fy = (float)(it.pa + brow);
+          const int grow = it.pa + brow;
           const int c1 = brow >> p.pr_shift, rr = brow - (c1 << p.pr_shift);
           const bool has1 = c1 < it.nchunks, has0 = (rr == 0 && c1 > 0);
           const uint32_t dst1 = chunks + ((chunk_base + c1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
           const uint32_t dst0 = chunks + ((chunk_base + c1 + kChunkBufs - 1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
-          float* dbg = (kDiag && p.logits_dbg) ? p.logits_dbg + (((size_t)it.b * d.max_n) * d.mh + it.pa + brow) * d.mw + bcol : nullptr;
+          float* dbg = (kDiag && p.logits_dbg) ? p.logits_dbg + (((size_t)it.b * d.max_n) * d.mh + grow) * d.mw + bcol : nullptr;
           const size_t dbg_stride = (size_t)d.mh * d.mw;
 #pragma unroll
           for (int i = 0; i < kNI; ++i) {
-            if (i < n) {
-              const float4 q = box[i];
-              const bool keep = (fx >= q.x) && (fx < q.z) && (fy >= q.y) && (fy < q.w);   // crop_mask, ops.py:688-704
-              const float v = keep ? __uint_as_float(r[i]) : 0.f;
-              if (has1) sts_f32(dst1 + i * inst_stride, v);
-              if (has0) sts_f32(dst0 + i * inst_stride, v);
-              if (kDiag && dbg) dbg[i * dbg_stride] = v;
-            }
+            const bool keep = ((unsigned)(bcol - cl[i]) < cwid[i]) && ((unsigned)(grow - rl[i]) < rwid[i]);
+            const float v = keep ? __uint_as_float(r[i]) : 0.f;
+            if (has1) sts_f32(dst1 + i * inst_stride, v);
+            if (has0) sts_f32(dst0 + i * inst_stride, v);
+            if (kDiag && dbg && i < n) dbg[i * dbg_stride] = v;
           }
         }
         __syncwarp();
@@ -633,7 +656,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     RoleTimer tm; tm.begin((kDiag && p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
     uint32_t gc = 0;
     for (int k = 0;; ++k) {
-      const Item it = get_item(p, k);
+      const Item it = next_item(k);
       if (!it.valid) break;
       const int n = min(p.counts[it.b], min(d.max_n, kNI));
       if (ut < kMaxInstTc * 4) {     // scaled boxes of this frame for the outside-the-box test
@@ -830,6 +853,7 @@ struct FusedPlan {
   int chunk_floats;
   size_t smem_bytes;
   unsigned long long* timing;   // device buffer when VA_FUSED_TIMING=1
+  int* work_counter;
   // cached tensor map
   const float* map_ptr;
   int map_B;
@@ -841,6 +865,7 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   if (d.max_n > kMaxInstTc) { snprintf(err, errlen, "tcgen05 path handles max_n <= %d", kMaxInstTc); return nullptr; }
   if ((d.mw % 4) != 0 || (d.W % 16) != 0) { snprintf(err, errlen, "mw %% 4 / W %% 16"); return nullptr; }
   if (((size_t)d.mh * d.mw) % 4 != 0) { snprintf(err, errlen, "P %% 4"); return nullptr; }
+  if (d.mw * 5 < 2 * kTileM + 1) { snprintf(err, errlen, "tcgen05 path needs H=4*mh, W=4*mw with mw >= 52 (items of >= 2 tiles)"); return nullptr; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties failed"); return nullptr; }
   if (prop.major != 10) { snprintf(err, errlen, "device is sm_%d%d, tcgen05 needs sm_100", prop.major, prop.minor); return nullptr; }
@@ -875,6 +900,7 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   for (const void* f : fns)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(%zu B): %s", pl->smem_bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
+  if (cudaMalloc(&pl->work_counter, sizeof(int)) != cudaSuccess) { snprintf(err, errlen, "cudaMalloc(work counter) failed"); delete pl; return nullptr; }
   const char* tenv = getenv("VA_FUSED_TIMING");
   if (tenv && tenv[0] == '1') cudaMalloc(&pl->timing, (size_t)pl->num_sms * 5 * 8 * sizeof(unsigned long long));
   return pl;
@@ -882,6 +908,7 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
 
 void fused_plan_destroy(FusedPlan* p) {
   if (p && p->timing) cudaFree(p->timing);
+  if (p && p->work_counter) cudaFree(p->work_counter);
   delete p;
 }
 
@@ -906,23 +933,21 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.d = d; p.coefs = coefs; p.boxes = boxes; p.counts = counts; p.masks = masks; p.logits_dbg = logits_dbg;
   p.stats = stats; p.lattice = lattice; p.B = B;
   p.timing = pl->timing;
+  p.work_counter = pl->work_counter;
   p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = d.max_n; p.chunk_floats = pl->chunk_floats;
-  // bands per frame: balance the persistent grid against the one-row halo each band recomputes
+  // Bands per frame: items are stolen dynamically, so what matters is enough items per CTA for a short tail
+  // (>= ~12) against the one-row halo every band recomputes and re-reads (1/ppb).
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
-  int best_nb = 1;
-  double best_eff = 0.0;
-  for (int nb = 1; nb <= max_bands && nb <= 64; ++nb) {
-    int ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
-    const int nbands = ceil_div(d.mh, ppb);
-    const long items = (long)B * nbands;
-    const long rounds = (items + pl->num_sms - 1) / pl->num_sms;
-    const double eff = (double)items / (double)(rounds * pl->num_sms) * (double)ppb / (double)(ppb + 1.5);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_nb = nb; }
-  }
-  p.ppb = ceil_div(ceil_div(d.mh, best_nb), pl->pr) * pl->pr;
+  int nb = 1;
+  while (nb < max_bands && nb < 8 && (long)B * nb < 12L * pl->num_sms) ++nb;
+  p.ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
   p.nbands = ceil_div(d.mh, p.ppb);
   p.n_items = B * p.nbands;
   const int grid = p.n_items < pl->num_sms ? p.n_items : pl->num_sms;
+  {
+    cudaError_t e = cudaMemsetAsync(pl->work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
   const bool diag = (logits_dbg != nullptr) || (pl->timing != nullptr);   // debug logits / role timing: separate instantiation
 #define VA_LAUNCH(WM, NI, DG) fused_tc_kernel<WM, NI, DG><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p)
   if (pl->ni == 8) {
@@ -937,19 +962,28 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
     cudaStreamSynchronize(st);
     static unsigned long long h[256 * 5 * 8];
     cudaMemcpy(h, pl->timing, (size_t)grid * 5 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    const char* roles[5] = {"tma", "mma", "split", "epilogue", "upsample"};
-    const char* waits[5][3] = {{"(unused)", "", ""}, {"hi_empty", "", ""}, {"b_empty", "hi_full", "lo_empty"},
-                               {"acc_full", "ch_empty", "tmem_ld"}, {"ch_full", "", ""}};
+    const char* roles[5] = {"(unused)", "tma", "split+issue", "epilogue", "upsample"};
+    const char* waits[5][6] = {{"", "", "", "", "", ""},
+                               {"hi_empty", "", "", "", "", ""},
+                               {"b_empty", "hi_full", "lo_empty", "b_full", "lo_full", "acc_empty"},
+                               {"acc_full", "ch_empty", "tmem_ld", "", "", ""},
+                               {"ch_full", "", "", "", "", ""}};
     fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr);
-    for (int r = 0; r < 5; ++r) {
-      double tot = 0, w[3] = {0, 0, 0};
+    for (int r = 1; r < 5; ++r) {
+      double tot = 0, mx = 0, w[6] = {0, 0, 0, 0, 0, 0};
       for (int c = 0; c < grid; ++c) {
-        tot += (double)h[(c * 5 + r) * 8];
-        for (int j = 0; j < 3; ++j) w[j] += (double)h[(c * 5 + r) * 8 + 1 + j];
+        const double t = (double)h[(c * 5 + r) * 8];
+        tot += t;
+        if (t > mx) mx = t;
+        for (int j = 0; j < 6; ++j) w[j] += (double)h[(c * 5 + r) * 8 + 1 + j];
       }
-      fprintf(stderr, "[va timing] %-9s total %9.0f cyc  wait %s %5.1f%%  %s %5.1f%%  %s %5.1f%%  busy %5.1f%%\n", roles[r], tot / grid,
-              waits[r][0], 100 * w[0] / tot, waits[r][1], 100 * w[1] / tot, waits[r][2], 100 * w[2] / tot,
-              100 * (tot - w[0] - w[1] - w[2]) / tot);
+      double ws = 0;
+      fprintf(stderr, "[va timing] %-11s avg %8.0f max %8.0f cyc |", roles[r], tot / grid, mx);
+      for (int j = 0; j < 6; ++j) {
+        ws += w[j];
+        if (waits[r][j][0]) fprintf(stderr, " %s %4.1f%%", waits[r][j], 100 * w[j] / tot);
+      }
+      fprintf(stderr, " | busy %4.1f%%\n", 100 * (tot - ws) / tot);
     }
   }
   return cudaGetLastError();
