@@ -213,11 +213,11 @@ struct SmemMap {
   uint32_t bt;        // [2 parity][kNMma rows x 128 B]: rows [0,16) = coefficients hi, rows [16,32) = lo
   uint32_t chunks;    // [kChunkBufs][chunk_floats] f32
   uint32_t box;       // [2 item parity][kMaxInstTc][4] f32 (epilogue warps)
-  uint32_t ubox;      // [kMaxInstTc][4] f32 (upsample warps)
+  uint32_t ubox;      // [kWarpsUp][kMaxInstTc][4] f32 (one private copy per upsample warp: no cross-warp barrier)
   uint32_t latpair;   // [mh] i16: the lattice dst row inside rows 4r+2..4r+5 of pair r, -1 if none
   uint32_t zeros;     // [(4*pr+2) * W] bytes of 0: source of the bulk zero-fill stores
   uint32_t zero_bytes;
-  uint32_t stat;      // [kMaxInstTc][8] i32: area, minx, miny, maxx, maxy
+  uint32_t stat;      // [kWarpsUp][kMaxInstTc][8] i32: area, minx, miny, maxx, maxy (private per upsample warp)
   uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
   uint32_t bars;      // [BAR_COUNT] u64
   uint32_t tmem_slot;
@@ -247,11 +247,11 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H, int z
   m.bt = take(2 * kNMma * 128, 1024);
   m.chunks = take((uint32_t)kChunkBufs * chunk_floats * 4, 16);
   m.box = take(2 * kMaxInstTc * 4 * 4, 16);
-  m.ubox = take(kMaxInstTc * 4 * 4, 16);
+  m.ubox = take(kWarpsUp * kMaxInstTc * 4 * 4, 16);
   m.latpair = take((uint32_t)(H / 4 + 8) * 2, 16);
   m.zero_bytes = (uint32_t)zero_bytes;
   m.zeros = take((uint32_t)zero_bytes, 128);
-  m.stat = take(kMaxInstTc * 8 * 4, 16);
+  m.stat = take(kWarpsUp * kMaxInstTc * 8 * 4, 16);
   m.latrow = take((uint32_t)H * 2, 16);
   m.bars = take(BAR_COUNT * 8, 8);
   m.tmem_slot = take(16, 16);
@@ -416,7 +416,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   }
   for (uint32_t t = threadIdx.x * 16u; t < sm.zero_bytes; t += kThreads * 16u) sts_v4(sbase + sm.zeros + t, make_float4(0.f, 0.f, 0.f, 0.f));
   fence_proxy_async();
-  for (int t = threadIdx.x; t < kMaxInstTc * 8; t += kThreads) {
+  for (int t = threadIdx.x; t < kWarpsUp * kMaxInstTc * 8; t += kThreads) {
     const int f = t & 7;
     sts_s32(sbase + sm.stat + 4 * t, (f == 1 || f == 2) ? INT_MAX : (f == 3 || f == 4) ? -1 : 0);
   }
@@ -659,13 +659,17 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       const Item it = next_item(k);
       if (!it.valid) break;
       const int n = min(p.counts[it.b], min(d.max_n, kNI));
-      if (ut < kMaxInstTc * 4) {     // scaled boxes of this frame for the outside-the-box test
-        const int i = ut >> 2, c = ut & 3;
+      // scaled boxes of this frame for the outside-the-box tests: a private copy per warp, so the upsample warps
+      // never wait for each other
+      const uint32_t ubox = sbase + sm.ubox + uw * kMaxInstTc * 16;
+      const uint32_t wstat = sbase + sm.stat + uw * kMaxInstTc * 32;
+      for (int q4 = lane; q4 < kMaxInstTc * 4; q4 += 32) {
+        const int i = q4 >> 2, c = q4 & 3;
         float v = 0.f;
         if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
-        sts_f32(sbase + sm.ubox + (i * 4 + c) * 4, v);
+        sts_f32(ubox + q4 * 4, v);
       }
-      named_bar_sync(2, kUpThreadsTc);
+      __syncwarp();
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
         const int buf = gc % kChunkBufs;
         TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kChunkBufs) & 1);
@@ -677,12 +681,14 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int nrows_out = last ? 2 : 4;
         const int jbeg = (r == 0) ? -2 : 0;                     // pair 0 also owns dst rows 0,1
         const int laty = (pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
+        int i = 0, g8w = uw;                 // warp task index wq = uw, uw + kWarpsUp, ... decoded incrementally as (i, g8w)
+        while (g8w >= ng8w) { g8w -= ng8w; ++i; }
 #pragma unroll 1
-        for (int wq = uw; wq < n * ng8w; wq += kWarpsUp) {
-          const int i = wq / ng8w;
-          const int g8w = wq - i * ng8w;
+        for (; i < n; g8w += kWarpsUp) {
+          while (g8w >= ng8w) { g8w -= ng8w; ++i; }
+          if (i >= n) break;
           const int g = (g8w * subs + sub) * 8 + gl;
-          const float4 q = lds_v4(sbase + sm.ubox + 16 * i);     // x1, y1, x2, y2 at proto resolution
+          const float4 q = lds_v4(ubox + 16 * i);     // x1, y1, x2, y2 at proto resolution
           // Every proto row this chunk reads (r0 .. r0+npairs) lies outside the instance's box: crop_mask zeroed
           // them, so the chunk's dst rows of this instance are one contiguous block of zeros.  One bulk
           // shared->global copy from the zero buffer (issued by the warp that owns column block 0) replaces
@@ -796,7 +802,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             const int miny = __reduce_min_sync(0xffffffffu, ts.miny);
             const int maxy = __reduce_max_sync(0xffffffffu, ts.maxy);
             if (lane == 0) {
-              const uint32_t st = sbase + sm.stat + i * 32;
+              const uint32_t st = wstat + i * 32;
               atoms_add(st, (int)area);
               atoms_min(st + 4, minx);
               atoms_min(st + 8, miny);
@@ -808,21 +814,22 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_CH_EMPTY + buf));
       }
-      // ---- item done: publish the band's reductions for frame it.b ----
-      named_bar_sync(2, kUpThreadsTc);
-      if (ut < n) {
-        const uint32_t st = sbase + sm.stat + ut * 32;
+      // ---- item done: publish this warp's reductions for frame it.b ----
+      __syncwarp();
+      if (lane < n) {
+        const uint32_t st = wstat + lane * 32;
         const int area = lds_s32(st);
         if (area) {
-          InstStats* dst = p.stats + (size_t)it.b * d.max_n + ut;
+          InstStats* dst = p.stats + (size_t)it.b * d.max_n + lane;
           atomicAdd(&dst->area, (unsigned)area);
           atomicMin(&dst->minx, lds_s32(st + 4));
           atomicMin(&dst->miny, lds_s32(st + 8));
           atomicMax(&dst->maxx, lds_s32(st + 12));
           atomicMax(&dst->maxy, lds_s32(st + 16));
+          sts_s32(st, 0); sts_s32(st + 4, INT_MAX); sts_s32(st + 8, INT_MAX); sts_s32(st + 12, -1); sts_s32(st + 16, -1);
         }
-        sts_s32(st, 0); sts_s32(st + 4, INT_MAX); sts_s32(st + 8, INT_MAX); sts_s32(st + 12, -1); sts_s32(st + 16, -1);
       }
+      __syncwarp();
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tm.end();
