@@ -21,7 +21,7 @@
 
 namespace va {
 
-constexpr int kTailThreads = 128;
+constexpr int kTailThreads = 256;
 
 struct TailSmem {
   // "created rows" table: ids [0, 2*rmax)
@@ -358,20 +358,31 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   const int gs = d.gs, cw = d.cwords;
   const int T = 2 * d.rmax, PL = plane_cap(d);
 
+  __shared__ unsigned s_area[kMaxInst];
+  __shared__ int s_bbox[kMaxInst][4];
   for (int t = threadIdx.x; t < PL; t += kTailThreads) s.plane_owner[t] = -1;
   for (int t = threadIdx.x; t < T * cw; t += kTailThreads) { s.occ[t] = 0; s.art[t] = 0; }
+  if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
+    const int i = threadIdx.x;
+    InstStats v;
+    v.area = 0; v.minx = 0; v.miny = 0; v.maxx = -1; v.maxy = -1;
+    if (i < n) v = st[i];
+    s_area[i] = v.area;
+    s_bbox[i][0] = v.minx; s_bbox[i][1] = v.miny; s_bbox[i][2] = v.maxx; s_bbox[i][3] = v.maxy;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
     s.sc[S_USE_EASY] = 1;
     // ---- instance selection: largest pixel area, first maximum (FrameProcessor.py:71-73 uses
-    //      cv2.contourArea of the polygon; see DESIGN.md "selection") ----
+    //      cv2.contourArea of the polygon; see DESIGN.md "selection").  Areas were pre-loaded in parallel. ----
     int sel = -1;
     unsigned best = 0;
     if (sel_in) {
       sel = sel_in[b];
-      if (sel < 0 || sel >= n) sel = -1; else best = st[sel].area;
+      if (sel < 0 || sel >= n) sel = -1; else best = s_area[sel];
     } else {
-      for (int i = 0; i < n; ++i) if (st[i].area > best) { best = st[i].area; sel = i; }
+      for (int i = 0; i < n; ++i) if (s_area[i] > best) { best = s_area[i]; sel = i; }
       if (sel < 0 && n > 0) sel = 0;
     }
     s.sc[S_SEL] = sel;
@@ -382,7 +393,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     } else {
       int x, y, w, h;
       if (rects) { x = rects[4 * b]; y = rects[4 * b + 1]; w = rects[4 * b + 2]; h = rects[4 * b + 3]; }
-      else { x = st[sel].minx; y = st[sel].miny; w = st[sel].maxx - x + 1; h = st[sel].maxy - y + 1; }
+      else { x = s_bbox[sel][0]; y = s_bbox[sel][1]; w = s_bbox[sel][2] - x + 1; h = s_bbox[sel][3] - y + 1; }
       s.sc[S_MINX] = x; s.sc[S_MINY] = y; s.sc[S_MAXX] = x + w - 1; s.sc[S_MAXY] = y + h - 1;
       x -= x % gs;                                   // FrameProcessor.py:79
       y -= y % gs;                                   // :80
