@@ -250,6 +250,7 @@ def run_ours(args, wl):
         if world > 1:
             dist.destroy_process_group()
         return
+    latency = measure_latency(wl, local) if world == 1 else None
     peak, peak_src = load_peaks()
     alg_kernel = B * (4 * 32 * mh * mw + 4 * n * 32 + 16 * n + n * H * W)       # dominant kernel: assembly
     alg_step = B * eng.algorithmic_bytes_per_frame(n, True)
@@ -282,12 +283,65 @@ def run_ours(args, wl):
                      "tail_ms": tail_ms / max(calls, 1), "peak_source": peak_src,
                      "step_frac": (alg_step / (ms / args.steps / 1000.0) / 1e9) / peak},
         "grid_only_frames_per_s": grid_only,
+        "latency_b1": latency,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=48)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_latency(wl, device, iters: int = 300):
+    """p50 / p99 single-frame latency (B = 1): launch -> record visible on the host (pinned D2H included),
+    grid-only mode (the reference's FrameProcessor consumes only the grid), with and without a CUDA graph."""
+    import torch
+    from vision_assist_b200 import synth
+    from vision_assist_b200.engine import MaskGridEngine
+    H, W, mh, mw, n, gs = (wl[k] for k in ("H", "W", "mh", "mw", "n", "gs"))
+    eng = MaskGridEngine(H=H, W=W, mh=mh, mw=mw, max_n=n, gs=gs, max_batch=1, device=device)
+    hp, hc, hb, hn = synth.make_batch(424242, 1, n, H, W, mh, mw, max_n=n)
+    protos, coefs, boxes, counts = hp.cuda(), hc.cuda(), hb.cuda(), hn.cuda()
+    rec = torch.empty((1, eng.record_bytes), dtype=torch.uint8, device="cuda")
+    hrec = torch.empty((1, eng.record_bytes), dtype=torch.uint8, pin_memory=True)
+    out = {}
+
+    def once():
+        eng.run(protos, coefs, boxes, counts, records_out=rec, write_masks=False)
+        hrec.copy_(rec, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def stats(fn):
+        for _ in range(20):
+            fn()
+        ts = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e6)
+        ts.sort()
+        return {"p50_us": ts[len(ts) // 2], "p99_us": ts[int(len(ts) * 0.99) - 1]}
+
+    out["eager"] = stats(once)
+    try:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                eng.run(protos, coefs, boxes, counts, records_out=rec, write_masks=False)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            eng.run(protos, coefs, boxes, counts, records_out=rec, write_masks=False)
+            hrec.copy_(rec, non_blocking=True)
+
+        def replay():
+            graph.replay()
+            torch.cuda.synchronize()
+        out["cuda_graph"] = stats(replay)
+    except Exception as e:  # graph capture is an optimisation of the measurement, not of the path
+        out["cuda_graph"] = {"error": str(e)[:120]}
+    out["what"] = "B=1, grid-only, launch -> record in pinned host memory (perf_counter around run + D2H + sync)"
+    return out
 
 
 def main():
