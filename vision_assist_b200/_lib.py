@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libva_sm100.so")
+LIB_PATH = os.environ.get("VA_LIB_PATH") or os.path.join(_HERE, "libva_sm100.so")   # VA_LIB_PATH: tuning builds
 
 VA_OK, VA_ERR_INVALID, VA_ERR_CUDA, VA_ERR_CAPACITY, VA_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 VA_CFG_CHECK_SIMPLE, VA_CFG_NO_TENSOR_CORE = 1, 2

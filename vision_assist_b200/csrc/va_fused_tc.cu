@@ -34,19 +34,19 @@ namespace va {
 
 constexpr int kTileM = 128;                 // pixels per MMA tile (TMEM lanes)
 constexpr int kTileBytes = kTileM * kProtoK * 4;   // 16 KB
-constexpr int kStagesHi = 6;                // TMA staging ring ([32 k][128 px] boxes, no swizzle)
+constexpr int kStagesHi = 5;                // TMA staging ring ([32 k][128 px] boxes, no swizzle)
 constexpr int kStagesLo = 2;                // A-operand ring in TENSOR MEMORY: A_hi (32 cols) + A_lo (32 cols) per stage
 constexpr int kAcc = 4;                     // TMEM accumulator ring
 constexpr int kNPad = 16;                   // instances padded
 constexpr int kNMma = 2 * kNPad;            // UMMA N: [B_hi ; B_lo] stacked along N - the cost of a small MMA does not depend on N
-constexpr int kChunkBufs = 3;
-constexpr int kItemRing = 16;               // published item indices.  The TMA thread leads the slowest role by at most
-                                            // kStagesHi + kStagesLo + kAcc + kChunkBufs chunks < 32 tiles and every item has >= 2 tiles
+constexpr int kChunkBufs = 4;                // maximum; the plan uses 4 when they fit in shared memory, else 3 (FusedParams::nbuf)
+constexpr int kItemRing = 32;               // published item indices.  The TMA thread leads the slowest role by at most
+                                            // kStagesHi + kStagesLo + kAcc tiles + kChunkBufs chunks < 64 tiles and every item has >= 2 tiles
                                             // (checked at plan creation), so a slot is never republished before it was read
 constexpr int kWarpsSplit = 4;              // one warp per TMEM lane quarter: staged box -> registers -> tcgen05.st
 constexpr int kWarpsEpi = 4;                // one warp per TMEM lane quarter: TMEM -> crop -> chunk buffers
 constexpr int kWarpsUp = 7;
-constexpr int kFirstSplitWarp = 1;          // warp 0: TMA producer + MMA issuer (one thread)
+constexpr int kFirstSplitWarp = 1;          // warp 0: TMA producer
 constexpr int kFirstEpiWarp = kFirstSplitWarp + kWarpsSplit;
 constexpr int kFirstUpWarp = kFirstEpiWarp + kWarpsEpi;
 constexpr int kThreads = 32 * (kFirstUpWarp + kWarpsUp);   // 512
@@ -75,6 +75,7 @@ struct FusedParams {
   int n_items;
   int nst;           // instance stride of the chunk buffers (= max_n)
   int chunk_floats;  // floats per chunk buffer = (pr+1) * nst * mw
+  int nbuf;          // chunk buffers in the ring (3 or 4)
   int* work_counter;            // global work-stealing counter (reset before every launch)
   unsigned long long* timing;   // developer diagnostic (VA_FUSED_TIMING=1): [grid][5 roles][8] cycle counters, or nullptr
 };
@@ -239,13 +240,13 @@ enum {
   BAR_COUNT = BAR_ITEM + kItemRing
 };
 
-__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int H, int zero_bytes) {
+__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int nbuf, int H, int zero_bytes) {
   SmemMap m;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes, uint32_t align) { o = (o + align - 1) / align * align; uint32_t r = o; o += bytes; return r; };
   m.hi = take(kStagesHi * kTileBytes, 1024);
   m.bt = take(2 * kNMma * 128, 1024);
-  m.chunks = take((uint32_t)kChunkBufs * chunk_floats * 4, 16);
+  m.chunks = take((uint32_t)nbuf * chunk_floats * 4, 16);
   m.box = take(2 * kMaxInstTc * 4 * 4, 16);
   m.ubox = take(kWarpsUp * kMaxInstTc * 4 * 4, 16);
   m.latpair = take((uint32_t)(H / 4 + 8) * 2, 16);
@@ -378,13 +379,13 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
-template <bool kWriteMasks, int kNI, bool kDiag>
+template <bool kWriteMasks, int kNI, bool kDiag, int kNBuf>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   // dynamic shared memory is only guaranteed 16 B aligned: round the shared address up to 1024
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const SmemMap sm = fused_smem_map(p.chunk_floats, p.d.H, (4 * p.pr + 2) * p.d.W);
+  const SmemMap sm = fused_smem_map(p.chunk_floats, kNBuf, p.d.H, (4 * p.pr + 2) * p.d.W);
   const Dims& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bars = sbase + sm.bars;
@@ -606,15 +607,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 #pragma unroll 1
         while (acquired <= c_hi) {            // acquire the chunk buffers this tile writes, in order
           const uint32_t gc = chunk_base + acquired;
-          TIMED_WAIT(tm, 1, BAR(BAR_CH_EMPTY + gc % kChunkBufs), ((gc / kChunkBufs) & 1) ^ 1);
+          TIMED_WAIT(tm, 1, BAR(BAR_CH_EMPTY + gc % kNBuf), ((gc / kNBuf) & 1) ^ 1);
           ++acquired;
         }
         if (brow < it.nrows) {
           const int grow = it.pa + brow;
           const int c1 = brow >> p.pr_shift, rr = brow - (c1 << p.pr_shift);
           const bool has1 = c1 < it.nchunks, has0 = (rr == 0 && c1 > 0);
-          const uint32_t dst1 = chunks + ((chunk_base + c1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
-          const uint32_t dst0 = chunks + ((chunk_base + c1 + kChunkBufs - 1) % kChunkBufs) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
+          const uint32_t dst1 = chunks + ((chunk_base + c1) % kNBuf) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
+          const uint32_t dst0 = chunks + ((chunk_base + c1 + kNBuf - 1) % kNBuf) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
           float* dbg = (kDiag && p.logits_dbg) ? p.logits_dbg + (((size_t)it.b * d.max_n) * d.mh + grow) * d.mw + bcol : nullptr;
           const size_t dbg_stride = (size_t)d.mh * d.mw;
 #pragma unroll
@@ -630,7 +631,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 #pragma unroll 1
         while (completed < it.nchunks && chunk_last_row(p, it, completed) < rows_done) {   // chunks completed by this tile
           const uint32_t gc = chunk_base + completed;
-          if (lane == 0) bar_arrive(BAR(BAR_CH_FULL + gc % kChunkBufs));
+          if (lane == 0) bar_arrive(BAR(BAR_CH_FULL + gc % kNBuf));
           ++completed;
         }
         brow += tile_rows; bcol += tile_cols;
@@ -671,8 +672,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       }
       __syncwarp();
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
-        const int buf = gc % kChunkBufs;
-        TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kChunkBufs) & 1);
+        const int buf = gc % kNBuf;
+        TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kNBuf) & 1);
         const uint32_t cb = sbase + sm.chunks + buf * (uint32_t)p.chunk_floats * 4;
         const int r0 = it.pa + c * p.pr;                        // first pair of the chunk
         const int npairs = min(p.pr, it.pb - r0);
@@ -856,6 +857,7 @@ struct FusedPlan {
   PFN_encodeTiled encode;
   int num_sms;
   int pr;
+  int nbuf;
   int ni;            // accumulator columns read back per tile (8 or 16)
   int chunk_floats;
   size_t smem_bytes;
@@ -889,23 +891,28 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   pl->num_sms = prop.multiProcessorCount;
   // pairs per chunk: largest of {4, 2} whose three chunk buffers fit next to the tile rings
   const size_t limit = (size_t)prop.sharedMemPerBlockOptin - 1024;
-  int pr = 0;
+  int pr = 0, nbuf = 0;
   for (int cand : {4, 2}) {
-    const int cf = (cand + 1) * d.max_n * d.mw;
-    if ((size_t)fused_smem_map(cf, d.H, (4 * cand + 2) * d.W).total + 1024 <= limit) { pr = cand; break; }
+    for (int nb : {4, 3}) {
+      const int cf = (cand + 1) * d.max_n * d.mw;
+      if ((size_t)fused_smem_map(cf, nb, d.H, (4 * cand + 2) * d.W).total + 1024 <= limit) { pr = cand; nbuf = nb; break; }
+    }
+    if (pr) break;
   }
   if (!pr) { delete pl; snprintf(err, errlen, "chunk buffers do not fit in shared memory (max_n=%d, mw=%d)", d.max_n, d.mw); return nullptr; }
   pl->pr = pr;
+  pl->nbuf = nbuf;
   pl->chunk_floats = (pr + 1) * d.max_n * d.mw;
-  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, d.H, (4 * pr + 2) * d.W).total + 1024;
+  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, nbuf, d.H, (4 * pr + 2) * d.W).total + 1024;
   pl->ni = d.max_n <= 8 ? 8 : 16;
   cudaError_t e = cudaSuccess;
-  const void* fns[8] = {(const void*)fused_tc_kernel<true, 8, false>,  (const void*)fused_tc_kernel<false, 8, false>,
-                        (const void*)fused_tc_kernel<true, 16, false>, (const void*)fused_tc_kernel<false, 16, false>,
-                        (const void*)fused_tc_kernel<true, 8, true>,   (const void*)fused_tc_kernel<false, 8, true>,
-                        (const void*)fused_tc_kernel<true, 16, true>,  (const void*)fused_tc_kernel<false, 16, true>};
-  for (const void* f : fns)
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes);
+#define VA_ATTR(WM, NI, DG, NB) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)fused_tc_kernel<WM, NI, DG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes)
+#define VA_ATTR4(NI, NB) VA_ATTR(true, NI, false, NB); VA_ATTR(false, NI, false, NB); VA_ATTR(true, NI, true, NB); VA_ATTR(false, NI, true, NB)
+  if (pl->nbuf == 4) { if (pl->ni == 8) { VA_ATTR4(8, 4); } else { VA_ATTR4(16, 4); } }
+  else               { if (pl->ni == 8) { VA_ATTR4(8, 3); } else { VA_ATTR4(16, 3); } }
+#undef VA_ATTR4
+#undef VA_ATTR
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(%zu B): %s", pl->smem_bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
   if (cudaMalloc(&pl->work_counter, sizeof(int)) != cudaSuccess) { snprintf(err, errlen, "cudaMalloc(work counter) failed"); delete pl; return nullptr; }
   const char* tenv = getenv("VA_FUSED_TIMING");
@@ -941,12 +948,13 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.stats = stats; p.lattice = lattice; p.B = B;
   p.timing = pl->timing;
   p.work_counter = pl->work_counter;
-  p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = d.max_n; p.chunk_floats = pl->chunk_floats;
+  p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = d.max_n; p.chunk_floats = pl->chunk_floats; p.nbuf = pl->nbuf;
   // Bands per frame: items are stolen dynamically, so what matters is enough items per CTA for a short tail
   // (>= ~12) against the one-row halo every band recomputes and re-reads (1/ppb).
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int nb = 1;
   while (nb < max_bands && nb < 8 && (long)B * nb < 12L * pl->num_sms) ++nb;
+  if (const char* e = getenv("VA_FUSED_NBANDS")) { const int v = atoi(e); if (v >= 1 && v <= max_bands) nb = v; }   // tuning aid
   p.ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
   p.nbands = ceil_div(d.mh, p.ppb);
   p.n_items = B * p.nbands;
@@ -956,14 +964,16 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
     if (e != cudaSuccess) return e;
   }
   const bool diag = (logits_dbg != nullptr) || (pl->timing != nullptr);   // debug logits / role timing: separate instantiation
-#define VA_LAUNCH(WM, NI, DG) fused_tc_kernel<WM, NI, DG><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p)
+#define VA_LAUNCH(WM, NI, DG, NB) fused_tc_kernel<WM, NI, DG, NB><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p)
+#define VA_LAUNCH_NB(WM, NI, DG) do { if (pl->nbuf == 4) VA_LAUNCH(WM, NI, DG, 4); else VA_LAUNCH(WM, NI, DG, 3); } while (0)
   if (pl->ni == 8) {
-    if (diag) { if (masks) VA_LAUNCH(true, 8, true); else VA_LAUNCH(false, 8, true); }
-    else      { if (masks) VA_LAUNCH(true, 8, false); else VA_LAUNCH(false, 8, false); }
+    if (diag) { if (masks) VA_LAUNCH_NB(true, 8, true); else VA_LAUNCH_NB(false, 8, true); }
+    else      { if (masks) VA_LAUNCH_NB(true, 8, false); else VA_LAUNCH_NB(false, 8, false); }
   } else {
-    if (diag) { if (masks) VA_LAUNCH(true, 16, true); else VA_LAUNCH(false, 16, true); }
-    else      { if (masks) VA_LAUNCH(true, 16, false); else VA_LAUNCH(false, 16, false); }
+    if (diag) { if (masks) VA_LAUNCH_NB(true, 16, true); else VA_LAUNCH_NB(false, 16, true); }
+    else      { if (masks) VA_LAUNCH_NB(true, 16, false); else VA_LAUNCH_NB(false, 16, false); }
   }
+#undef VA_LAUNCH_NB
 #undef VA_LAUNCH
   if (pl->timing) {   // developer diagnostic: blocking read-back, per-role wait / busy cycles averaged over CTAs
     cudaStreamSynchronize(st);
