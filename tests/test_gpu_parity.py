@@ -158,6 +158,26 @@ def test_cfg1_full_batch_256(tc):
 
 
 @pytest.mark.parametrize("tc", PATHS)
+def test_sixteen_instance_accumulator_path(tc):
+    """max_n in (8, 16]: the tcgen05 kernel reads 16 accumulator columns per pass."""
+    H = W = 640
+    B, n = 6, 12
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=16, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(6000, B, n, H, W, 160, 160, max_n=16)
+    counts[1] = 16 if False else 12
+    counts[2] = 9
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    for b in range(B):
+        nb = int(counts[b])
+        up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
+        nd, nout = band_mismatch_report(masks[b, :nb], up)
+        assert nout == 0, (nd, nout)
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "direct"), f"n=12 frame {b}")
+
+
+@pytest.mark.parametrize("tc", PATHS)
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
     eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)

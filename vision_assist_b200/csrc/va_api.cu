@@ -252,7 +252,7 @@ static int assemble(va_ctx* c, const float* protos, const float* coefs, const fl
     const int nb = (B - b0 < step) ? B - b0 : step;
     float* lg = logits_out ? logits_out + b0 * fr_logits : c->scratch.logits;
     VA_CUDA(c, launch_logits(d, protos + b0 * fr_protos, coefs + b0 * fr_coefs, boxes + b0 * fr_boxes, counts + b0, nb, lg, st));
-    VA_CUDA(c, launch_upsample(d, lg, counts + b0, nb, masks ? masks + b0 * fr_masks : nullptr,
+    VA_CUDA(c, launch_upsample(d, lg, boxes + b0 * fr_boxes, counts + b0, nb, masks ? masks + b0 * fr_masks : nullptr,
                                c->scratch.stats + (size_t)b0 * d.max_n,
                                c->scratch.lattice + (size_t)b0 * d.max_n * d.lat_rows * d.lat_words, st));
     c->last_launches += 2;

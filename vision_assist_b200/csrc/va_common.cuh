@@ -56,7 +56,7 @@ __host__ __device__ inline int floor_div(int a, int b) {
 cudaError_t launch_logits(const Dims& d, const float* protos, const float* coefs, const float* boxes,
                           const int* counts, int B, float* logits, cudaStream_t st);
 // bilinear upsample + threshold (+ stats / lattice) from proto-resolution logits (ops.py:736-737)
-cudaError_t launch_upsample(const Dims& d, const float* logits, const int* counts, int B, uint8_t* masks,
+cudaError_t launch_upsample(const Dims& d, const float* logits, const float* boxes, const int* counts, int B, uint8_t* masks,
                             InstStats* stats, unsigned int* lattice, cudaStream_t st);
 // stats / lattice from caller-provided binary masks
 cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, InstStats* stats,

@@ -143,10 +143,32 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 
 template <bool kWriteMasks>
 __global__ void __launch_bounds__(kUpThreads)
-upsample_generic_kernel(Dims d, const float* __restrict__ logits, const int* __restrict__ counts,
-                        uint8_t* __restrict__ masks, InstStats* __restrict__ stats, unsigned* __restrict__ lattice) {
+upsample_generic_kernel(Dims d, const float* __restrict__ logits, const float* __restrict__ boxes,
+                        const int* __restrict__ counts, uint8_t* __restrict__ masks, InstStats* __restrict__ stats,
+                        unsigned* __restrict__ lattice) {
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= min(counts[b], d.max_n)) return;
+  const size_t inst = (size_t)b * d.max_n + i;
+  // Conservative dst-space rectangle outside of which no source tap can lie inside the instance's box
+  // (crop_mask, ops.py:688-704, zeroed everything else): threads outside it only store zeros.
+  __shared__ int s_rect[4];
+  if (threadIdx.x == 0) {
+    int Xa = 0, Ya = 0, Xb = d.W - 1, Yb = d.H - 1;
+    if (boxes) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(boxes + inst * 4));
+      const float bx1 = __fmul_rn(q.x, d.wr), by1 = __fmul_rn(q.y, d.hr), bx2 = __fmul_rn(q.z, d.wr), by2 = __fmul_rn(q.w, d.hr);
+      // kept proto cols [ceil(bx1), ceil(bx2)-1]; a dst pixel X reads cols x0(X), x0(X)+1 with x0 = floor(sx*(X+.5)-.5)
+      const float cA = ceilf(fminf(fmaxf(bx1, -4.f), 1e6f)), cB = ceilf(fminf(fmaxf(bx2, -4.f), 1e6f)) - 1.f;
+      const float rA = ceilf(fminf(fmaxf(by1, -4.f), 1e6f)), rB = ceilf(fminf(fmaxf(by2, -4.f), 1e6f)) - 1.f;
+      // X touches cols [cA,cB] iff x0(X)+1 >= cA and x0(X) <= cB  <=>  (cA-.5)/sx-.5 <= X < (cB+1.5)/sx-.5 ; widen by >= 1
+      Xa = max(0, (int)floorf((cA - 1.5f) / d.sx) - 1);
+      Xb = min(d.W - 1, (int)ceilf((cB + 1.5f) / d.sx) + 1);
+      Ya = max(0, (int)floorf((rA - 1.5f) / d.sy) - 1);
+      Yb = min(d.H - 1, (int)ceilf((rB + 1.5f) / d.sy) + 1);
+    }
+    s_rect[0] = Xa; s_rect[1] = Ya; s_rect[2] = Xb; s_rect[3] = Yb;
+  }
+  __syncthreads();
   const int NG = ceil_div(d.W, 16);
   const int NG8 = ceil_div(NG, 8);
   const int NY4 = ceil_div(d.H, 4);
@@ -155,39 +177,41 @@ upsample_generic_kernel(Dims d, const float* __restrict__ logits, const int* __r
   const int lane = threadIdx.x & 31;
   const int g = (wt % NG8) * 8 + (lane & 7);
   const int Y = (wt / NG8) * 4 + (lane >> 3);
-  const size_t inst = (size_t)b * d.max_n + i;
   const float* L = logits + inst * d.mh * d.mw;
   unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
   ThreadStats ts;
   if (g < NG && Y < d.H) {
-    int y0, y1;
-    float ly0, ly1;
-    src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
-    const float* r0 = L + (size_t)y0 * d.mw;
-    const float* r1 = L + (size_t)y1 * d.mw;
     const int X0 = 16 * g, X1 = min(X0 + 15, d.W - 1);
-    int xa, xb, t0;
-    float f0, f1;
-    src_index(d.sx, X0, d.mw, xa, t0, f0, f1);
-    src_index(d.sx, X1, d.mw, t0, xb, f0, f1);
-    float mn = INFINITY, mx = -INFINITY;
-    for (int x = xa; x <= xb; ++x) {
-      const float u = __ldg(r0 + x), v = __ldg(r1 + x);
-      mn = fminf(mn, fminf(u, v));
-      mx = fmaxf(mx, fmaxf(u, v));
-    }
     unsigned ww[4] = {0, 0, 0, 0};
-    if (mn > kTiny) {
-      for (int px = 0; px <= X1 - X0; ++px) ww[px >> 2] |= 1u << (8 * (px & 3));
-    } else if (mx > 0.f) {
-      for (int px = 0; px <= X1 - X0; ++px) {
-        int x0, x1;
-        float lx0, lx1;
-        src_index(d.sx, X0 + px, d.mw, x0, x1, lx0, lx1);
-        const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
-        const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
-        const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
-        if (o > 0.f) ww[px >> 2] |= 1u << (8 * (px & 3));
+    const bool in_rect = !(Y < s_rect[1] || Y > s_rect[3] || X1 < s_rect[0] || X0 > s_rect[2]);
+    if (in_rect) {
+      int y0, y1;
+      float ly0, ly1;
+      src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
+      const float* r0 = L + (size_t)y0 * d.mw;
+      const float* r1 = L + (size_t)y1 * d.mw;
+      int xa, xb, t0;
+      float f0, f1;
+      src_index(d.sx, X0, d.mw, xa, t0, f0, f1);
+      src_index(d.sx, X1, d.mw, t0, xb, f0, f1);
+      float mn = INFINITY, mx = -INFINITY;
+      for (int x = xa; x <= xb; ++x) {
+        const float u = __ldg(r0 + x), v = __ldg(r1 + x);
+        mn = fminf(mn, fminf(u, v));
+        mx = fmaxf(mx, fmaxf(u, v));
+      }
+      if (mn > kTiny) {
+        for (int px = 0; px <= X1 - X0; ++px) ww[px >> 2] |= 1u << (8 * (px & 3));
+      } else if (mx > 0.f) {
+        for (int px = 0; px <= X1 - X0; ++px) {
+          int x0, x1;
+          float lx0, lx1;
+          src_index(d.sx, X0 + px, d.mw, x0, x1, lx0, lx1);
+          const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
+          const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
+          const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
+          if (o > 0.f) ww[px >> 2] |= 1u << (8 * (px & 3));
+        }
       }
     }
     const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
@@ -196,11 +220,13 @@ upsample_generic_kernel(Dims d, const float* __restrict__ logits, const int* __r
       if (X0 + 15 < d.W && (d.W & 15) == 0) *reinterpret_cast<uint4*>(M) = w;
       else for (int px = 0; px <= X1 - X0; ++px) M[px] = (ww[px >> 2] >> (8 * (px & 3))) & 1u;
     }
-    ts.add_row(w, Y);
-    const int t = Y - (d.gs >> 1);
-    if (t >= 0 && t % d.gs == 0 && (ww[0] | ww[1] | ww[2] | ww[3])) lattice_row(w, Y, X0, d, lat);
+    if (ww[0] | ww[1] | ww[2] | ww[3]) {
+      ts.add_row(w, Y);
+      const int t = Y - (d.gs >> 1);
+      if (t >= 0 && t % d.gs == 0) lattice_row(w, Y, X0, d, lat);
+    }
   }
-  publish_stats(ts, 16 * g, stats + inst);
+  if (__any_sync(0xffffffffu, ts.acc != 0)) publish_stats(ts, 16 * g, stats + inst);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -258,7 +284,7 @@ __global__ void init_scratch_kernel(InstStats* stats, size_t n_stats, unsigned* 
 }
 
 // ---------------------------------------------------------------------------------------------
-cudaError_t launch_upsample(const Dims& d, const float* logits, const int* counts, int B, uint8_t* masks,
+cudaError_t launch_upsample(const Dims& d, const float* logits, const float* boxes, const int* counts, int B, uint8_t* masks,
                             InstStats* stats, unsigned* lattice, cudaStream_t st) {
   const bool x4 = (d.H == 4 * d.mh) && (d.W == 4 * d.mw) && (d.mw % 4 == 0);
   if (x4) {
@@ -269,8 +295,8 @@ cudaError_t launch_upsample(const Dims& d, const float* logits, const int* count
   } else {
     const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4);
     dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
-    if (masks) upsample_generic_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
-    else upsample_generic_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
+    if (masks) upsample_generic_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, stats, lattice);
+    else upsample_generic_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, stats, lattice);
   }
   return cudaGetLastError();
 }
