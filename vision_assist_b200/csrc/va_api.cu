@@ -80,6 +80,7 @@ static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, s
   d.rmax = ceil_div(c.H, c.gs) + nband + 2;
   d.cmax = ceil_div(c.W, c.gs);
   d.cwords = ceil_div(d.cmax, 32);
+  if (d.cwords > 64) { snprintf(why, n, "W / gs must not exceed 2048 columns"); return false; }
   d.pmax = (d.cmax + 1) / 2 + 1;
   int o = 0;
   L.off_header = o; o += 64;

@@ -51,7 +51,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   const size_t o_y = take(sizeof(int) * T), o_a = take(sizeof(int) * T);
   const size_t o_occ = take(sizeof(unsigned) * T * d.cwords), o_art = take(sizeof(unsigned) * T * d.cwords);
   const size_t o_l = take(sizeof(int) * d.rmax), o_p = take(sizeof(int) * PL);
-  const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * d.rmax);
+  const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * max(d.rmax, d.cwords));
   const size_t o_cf = take(sizeof(int) * d.cmax), o_cl = take(sizeof(int) * d.cmax);
   const size_t o_or = take(sizeof(int) * d.rmax), o_of = take(sizeof(int) * T), o_sc = take(sizeof(int) * S_COUNT);
   if (s) {
@@ -66,6 +66,8 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
 }
 
 size_t tail_smem_bytes(const Dims& d) { return tail_smem_layout(d, nullptr, nullptr); }
+
+constexpr int kMaxColWords = 64;   // va_create rejects ceil(W/gs) > 2048
 
 __device__ __forceinline__ bool bit_at(const unsigned* row, int c) { return (row[c >> 5] >> (c & 31)) & 1u; }
 
@@ -218,32 +220,37 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   for (int t = d.off_occ + d.rmax * d.cmax + threadIdx.x; t < d.record_bytes; t += kTailThreads) rec[t] = 0;
 }
 
-// ProtrusionDetector closed form; one thread: union of the top rows as bit words, then run extraction
-// with ffs (a handful of iterations for the <= cmax/2 runs).
+// ProtrusionDetector closed form; executed by warp 0: one lane per list row finds the top-most occupied
+// pixel row, the union of the rows painted on it is OR-reduced per 32-column word, lane 0 extracts the runs.
 __device__ void find_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
   int* peaks = reinterpret_cast<int*>(rec + d.off_peaks);
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
+  const int lane = threadIdx.x & 31;
   int ytop = INT_MAX;
-  for (int k = 0; k < R; ++k) {
+  for (int k = lane; k < R; k += 32) {
     const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
     unsigned any = 0;
     for (int w = 0; w < cw; ++w) any |= row[w];
     if (any) ytop = min(ytop, s.row_y[s.list_ids[k]]);
   }
+  ytop = __reduce_min_sync(0xffffffffu, ytop);
+  __shared__ unsigned uni[kMaxColWords];
+  if (ytop != INT_MAX) {
+    for (int w = 0; w < cw; ++w) {
+      unsigned v = 0;
+      for (int k = lane; k < R; k += 32)
+        if (s.row_y[s.list_ids[k]] == ytop) v |= s.occ[(size_t)s.list_ids[k] * cw + w];
+      v = __reduce_or_sync(0xffffffffu, v);
+      if (lane == 0) uni[w] = v;
+    }
+  }
+  __syncwarp();
+  if (lane != 0) return;
   int np = 0;
   if (ytop != INT_MAX) {
-    // union of the list rows painted on pixel row ytop (duplicate rows share a y); reuse erow_first as scratch
-    unsigned* uni = reinterpret_cast<unsigned*>(s.orphan_ids) + d.rmax - cw;   // tail of the orphan array is free
-    for (int w = 0; w < cw; ++w) uni[w] = 0;
-    for (int k = 0; k < R; ++k) {
-      if (s.row_y[s.list_ids[k]] != ytop) continue;
-      const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
-      for (int w = 0; w < cw; ++w) uni[w] |= row[w];
-    }
     int c = 0;
     while (c < C) {
-      // next set bit at or after c
-      int w = c >> 5;
+      int w = c >> 5;                                   // next set bit at or after c
       unsigned v = uni[w] & (0xffffffffu << (c & 31));
       while (!v && ++w < cw) v = uni[w];
       if (!v) break;
@@ -310,11 +317,11 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
     easy_segments(d, s);
     __syncthreads();
   }
-  penalties_and_record(d, s, rec);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {          // warp 0: peaks + header, concurrently with the other warps' penalty cells
     find_peaks(d, s, rec);
-    write_header(s, rec);
+    if (threadIdx.x == 0) write_header(s, rec);
   }
+  penalties_and_record(d, s, rec);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,6 +444,19 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       s.list_ids[r] = r;
       s.plane_owner[ly0 + r] = r;
     }
+    {
+      // artificial columns (FrameProcessor.py:60-65) as a bit mask over this frame's columns, the same for every
+      // band row: one column per thread, one ballot per 32 columns (erow_last is scratch until easy_segments runs)
+      unsigned* am = reinterpret_cast<unsigned*>(s.erow_last);
+      const int base = d.W / 2 - 8 * gs;
+      for (int c0 = threadIdx.x & ~31; c0 < 32 * cw; c0 += kTailThreads) {
+        const int c = c0 + (threadIdx.x & 31);
+        const int delta = s.sc[S_X0] + c * gs - base;
+        const bool bit = c < C && delta >= 0 && delta % gs == 0 && delta / gs <= 16;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        if ((threadIdx.x & 31) == 0) am[c0 >> 5] = m;
+      }
+    }
     any = __syncthreads_or(any);
     if (threadIdx.x == 0) {
       if (!any) {
@@ -444,19 +464,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       } else {
         // ---- artificial band (FrameProcessor.py:126-165), replayed literally ----
         int list_len = Rm, ncreated = Rm;
-        const int base = d.W / 2 - 8 * gs;
-        // artificial columns (FrameProcessor.py:60-65) as a bit mask over this frame's columns: the same for every band row
-        unsigned* am = reinterpret_cast<unsigned*>(s.erow_last);      // scratch until easy_segments runs
-        for (int w = 0; w < cw; ++w) {
-          unsigned m = 0;
-          for (int q = 0; q < 32; ++q) {
-            const int c = 32 * w + q;
-            if (c >= C) break;
-            const int delta = s.sc[S_X0] + c * gs - base;
-            if (delta >= 0 && delta % gs == 0 && delta / gs <= 16) m |= 1u << q;
-          }
-          am[w] = m;
-        }
+        const unsigned* am = reinterpret_cast<const unsigned*>(s.erow_last);   // built by all warps above
         for (int i = d.band_start; i < d.H; i += gs) {
           const int ly = i / gs;
           const int row_idx = floor_div(i - s.sc[S_Y0], gs);
