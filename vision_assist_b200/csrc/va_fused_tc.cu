@@ -73,7 +73,9 @@ struct FusedParams {
   int pr;            // row pairs per chunk (2 or 4)
   int pr_shift;      // log2(pr)
   int n_items;
-  int nst;           // instance stride of the chunk buffers (= max_n)
+  int groups;        // instance groups per frame: group q covers instances [q*gsize, (q+1)*gsize)
+  int gsize;         // instances per group (= kNI of the instantiation: 8 or 16)
+  int nst;           // instance stride of the chunk buffers (= gsize)
   int chunk_floats;  // floats per chunk buffer = (pr+1) * nst * mw
   int nbuf;          // chunk buffers in the ring (3 or 4)
   int* work_counter;            // global work-stealing counter (reset before every launch)
@@ -175,6 +177,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 struct Item {
   int valid;
   int b;        // frame
+  int i0;       // first instance of the item's group
+  int n;        // instances of the group that exist in this frame (0 .. gsize)
   int pa, pb;   // row pairs [pa, pb): pair r blends proto rows r and min(r+1, mh-1) into dst rows 4r+2..4r+5
   int nrows;    // proto rows pa .. min(pb, mh-1)
   int npx;      // nrows * mw
@@ -182,17 +186,23 @@ struct Item {
   int nchunks;  // ceil((pb - pa) / pr)
 };
 
-// Work item index -> (frame, band).  Items are handed out dynamically (work stealing through a global counter) in
+// Work item index -> (band, frame, instance group), group fastest: the groups of one (frame, band) read the same
+// prototype rows and are stolen by different CTAs at nearly the same time, so all but the first read hit L2.
+// Items are handed out dynamically (work stealing through a global counter) in
 // bottom-band-first order: the bands that contain the sidewalk blob cost more, so the light top bands form the
 // tail of the schedule.  Out of line on purpose: called once per item per role, and inlined copies of its
 // divisions would compete with the hot loops for the instruction cache.
 __device__ __noinline__ Item decode_item(const FusedParams& p, int item) {
   Item it;
   it.valid = item < p.n_items;
-  const int jb = item / p.B;
-  const int b = item - jb * p.B;
+  const int fb = item / p.groups;
+  const int q = item - fb * p.groups;
+  const int jb = fb / p.B;
+  const int b = fb - jb * p.B;
   const int j = p.nbands - 1 - jb;
   it.b = b;
+  it.i0 = q * p.gsize;
+  it.n = it.valid ? max(min(min(p.counts[b], p.d.max_n) - it.i0, p.gsize), 0) : 0;
   it.pa = j * p.ppb;
   it.pb = min(it.pa + p.ppb, p.d.mh);
   it.nrows = min(it.pb, p.d.mh - 1) - it.pa + 1;
@@ -436,10 +446,14 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       RoleTimer tm; tm.begin((kDiag && p.timing) ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
       uint32_t g = 0;
       for (int k = 0;; ++k) {
-        const int item = atomicAdd(p.work_counter, 1);
+        Item it;
+        int item;
+        do {                                                   // instance groups with no instance in this frame are dropped here
+          item = atomicAdd(p.work_counter, 1);
+          it = decode_item(p, item);
+        } while (it.valid && it.n == 0);
         sts_s32(sbase + sm.items + 4 * (k % kItemRing), item);
         bar_arrive(BAR(BAR_ITEM + (k % kItemRing)));          // release: the index is visible to the waiting roles
-        const Item it = decode_item(p, item);
         if (!it.valid) break;
         const int px0 = it.pa * d.mw;
 #pragma unroll 1
@@ -467,12 +481,12 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       {   // per-frame B tiles: coefficients hi / lo, K-major, 16 B chunk c of row r stored at chunk c ^ (r & 7)
         const int par = k & 1;
         TIMED_WAIT(tm, 0, BAR(BAR_B_EMPTY + par), ((k >> 1) & 1) ^ 1);
-        const int n = min(p.counts[it.b], min(d.max_n, kMaxInstTc));
+        const int n = it.n;
         const uint32_t bh = sbase + sm.bt + par * kNMma * 128;   // rows [0,16): hi
         const uint32_t bl = bh + kNPad * 128;                      // rows [16,32): lo (16 = 2 swizzle periods: same XOR pattern)
         const int r = st_tid >> 3, c = st_tid & 7;   // 128 threads = 16 rows x 8 chunks
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)it.b * d.max_n + r) * d.K + 4 * c));
+        if (r < n) v = __ldg(reinterpret_cast<const float4*>(p.coefs + ((size_t)it.b * d.max_n + it.i0 + r) * d.K + 4 * c));
         float4 h, l;
         h.x = trunc_tf32(v.x); l.x = v.x - h.x;
         h.y = trunc_tf32(v.y); l.y = v.y - h.y;
@@ -547,13 +561,13 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     for (int k = 0;; ++k) {
       const Item it = next_item(k);
       if (!it.valid) break;
-      const int n = min(p.counts[it.b], min(d.max_n, kNI));
+      const int n = it.n;
       // scaled boxes of this frame (double-buffered by item parity; the 4 epilogue warps stay within one item)
       const uint32_t bx = sbase + sm.box + (k & 1) * kMaxInstTc * 16;
       if (ep_tid < kMaxInstTc * 4) {
         const int i = ep_tid >> 2, c = ep_tid & 3;
         float v = 0.f;
-        if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
+        if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + it.i0 + i) * 4 + c), (c & 1) ? d.hr : d.wr);
         sts_f32(bx + (i * 4 + c) * 4, v);
       }
       named_bar_sync(1, 32 * kWarpsEpi);
@@ -569,7 +583,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int x1 = (int)ceilf(fminf(fmaxf(q.x, -1e6f), 1e6f)), x2 = (int)ceilf(fminf(fmaxf(q.z, -1e6f), 1e6f));
         const int y1 = (int)ceilf(fminf(fmaxf(q.y, -1e6f), 1e6f)), y2 = (int)ceilf(fminf(fmaxf(q.w, -1e6f), 1e6f));
         cl[i] = x1; cwid[i] = (unsigned)max(x2 - x1, 0);
-        rl[i] = y1; rwid[i] = (i < n) ? (unsigned)max(y2 - y1, 0) : 0u;
+        rl[i] = (i < n) ? y1 : (INT_MAX >> 1); rwid[i] = (i < n) ? (unsigned)max(y2 - y1, 0) : 0u;
       }
       int brow = ep_px / d.mw, bcol = ep_px - brow * d.mw;   // band-local (row, col) of this thread's pixel
       int done_rows = 0, done_cols = 0;                        // complete rows / extra pixels after the current tile
@@ -598,12 +612,14 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         if (lane == 0) bar_arrive(BAR(BAR_ACC_EMPTY + ac));
         if (kDiag && tm.out) tm.wait[2] += clock64() - t_ld0;
 
+        const int tile_ra = it.pa + done_rows;                 // first proto row this tile touches
         done_rows += tile_rows; done_cols += tile_cols;
         if (done_cols >= d.mw) { done_cols -= d.mw; ++done_rows; }
         const bool last_tile = (t + 1 == it.ntiles);
         const int rows_done = last_tile ? it.nrows : done_rows;
         const int row_last = last_tile ? it.nrows - 1 : (done_cols == 0 ? done_rows - 1 : done_rows);
         const int c_hi = min(row_last >> p.pr_shift, it.nchunks - 1);
+        const int tile_rb = it.pa + row_last;                  // last proto row this tile touches
 #pragma unroll 1
         while (acquired <= c_hi) {            // acquire the chunk buffers this tile writes, in order
           const uint32_t gc = chunk_base + acquired;
@@ -616,10 +632,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           const bool has1 = c1 < it.nchunks, has0 = (rr == 0 && c1 > 0);
           const uint32_t dst1 = chunks + ((chunk_base + c1) % kNBuf) * (uint32_t)p.chunk_floats * 4 + rr * row_stride + bcol * 4;
           const uint32_t dst0 = chunks + ((chunk_base + c1 + kNBuf - 1) % kNBuf) * (uint32_t)p.chunk_floats * 4 + p.pr * row_stride + bcol * 4;
-          float* dbg = (kDiag && p.logits_dbg) ? p.logits_dbg + (((size_t)it.b * d.max_n) * d.mh + grow) * d.mw + bcol : nullptr;
+          float* dbg = (kDiag && p.logits_dbg) ? p.logits_dbg + (((size_t)it.b * d.max_n + it.i0) * d.mh + grow) * d.mw + bcol : nullptr;
           const size_t dbg_stride = (size_t)d.mh * d.mw;
 #pragma unroll
           for (int i = 0; i < kNI; ++i) {
+            // A stored row rho is read by the upsample tasks of pairs rho-1 and rho, and a task whose two rows are
+            // outside the instance's box rows (r+1 < y1 or r >= y2) never reads its chunk rows.  So when every row of
+            // this tile is at least 2 above or 1 below the box (or the instance does not exist), nothing will read
+            // what would be stored here: skip the instance (warp-uniform).
+            if (!kDiag && (tile_rb + 2 <= rl[i] || tile_ra - 1 >= rl[i] + (int)rwid[i])) continue;
             const bool keep = ((unsigned)(bcol - cl[i]) < cwid[i]) && ((unsigned)(grow - rl[i]) < rwid[i]);
             const float v = keep ? __uint_as_float(r[i]) : 0.f;
             if (has1) sts_f32(dst1 + i * inst_stride, v);
@@ -650,16 +671,19 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const int subs = 4 >> p.pr_shift;                        // pr = 4: 1, pr = 2: 2
     const int pair = slot & (p.pr - 1), sub = slot >> p.pr_shift;
     const int ng8w = ceil_div(NG8, subs);                    // warp tasks per instance
+    const int ng8w_mod = ng8w % kWarpsUp;
     const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
     const uint4 zeros = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t inst_stride = (uint32_t)d.mw * 4;
     const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
     RoleTimer tm; tm.begin((kDiag && p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
     uint32_t gc = 0;
+    int base = 0;                        // (live task count) % kWarpsUp
+    int zw = 0;                          // warp that issues the next bulk zero-fill
     for (int k = 0;; ++k) {
       const Item it = next_item(k);
       if (!it.valid) break;
-      const int n = min(p.counts[it.b], min(d.max_n, kNI));
+      const int n = it.n;
       // scaled boxes of this frame for the outside-the-box tests: a private copy per warp, so the upsample warps
       // never wait for each other
       const uint32_t ubox = sbase + sm.ubox + uw * kMaxInstTc * 16;
@@ -667,7 +691,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       for (int q4 = lane; q4 < kMaxInstTc * 4; q4 += 32) {
         const int i = q4 >> 2, c = q4 & 3;
         float v = 0.f;
-        if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + i) * 4 + c), (c & 1) ? d.hr : d.wr);
+        if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + it.i0 + i) * 4 + c), (c & 1) ? d.hr : d.wr);
         sts_f32(ubox + q4 * 4, v);
       }
       __syncwarp();
@@ -682,34 +706,41 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int nrows_out = last ? 2 : 4;
         const int jbeg = (r == 0) ? -2 : 0;                     // pair 0 also owns dst rows 0,1
         const int laty = (pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
-        int i = 0, g8w = uw;                 // warp task index wq = uw, uw + kWarpsUp, ... decoded incrementally as (i, g8w)
-        while (g8w >= ng8w) { g8w -= ng8w; ++i; }
+        // Warp tasks: (instance, block of 8*subs column groups).  Instances whose box rows miss the chunk are settled
+        // per instance (one bulk zero-fill, issued by the upsample warps in turn); the tasks of the remaining
+        // ("live") instances are numbered consecutively and dealt round-robin: task wq = live_ordinal * ng8w + g8w
+        // belongs to warp wq % kWarpsUp.  The numbering runs on across chunks and items, so the warps that get one task
+        // more than the others rotate.
 #pragma unroll 1
-        for (; i < n; g8w += kWarpsUp) {
-          while (g8w >= ng8w) { g8w -= ng8w; ++i; }
-          if (i >= n) break;
-          const int g = (g8w * subs + sub) * 8 + gl;
+        for (int i = 0; i < n; ++i) {
           const float4 q = lds_v4(ubox + 16 * i);     // x1, y1, x2, y2 at proto resolution
           // Every proto row this chunk reads (r0 .. r0+npairs) lies outside the instance's box: crop_mask zeroed
           // them, so the chunk's dst rows of this instance are one contiguous block of zeros.  One bulk
-          // shared->global copy from the zero buffer (issued by the warp that owns column block 0) replaces
-          // the whole column sweep.
+          // shared->global copy from the zero buffer replaces the whole column sweep.
           if (((float)(r0 + npairs) < q.y) || ((float)r0 >= q.w)) {
-            if (kWriteMasks && g8w == 0 && lane == 0) {
+            if (kWriteMasks && zw == uw && lane == 0) {
               const int Ya = (r0 == 0) ? 0 : 4 * r0 + 2;
               const int Yb = min(4 * (r0 + npairs - 1) + 5, d.H - 1);
-              uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + i) * d.H + Ya) * (size_t)d.W;
+              uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + it.i0 + i) * d.H + Ya) * (size_t)d.W;
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sbase + sm.zeros),
                            "r"((uint32_t)((Yb - Ya + 1) * d.W))
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            zw = (zw + 1 == kWarpsUp) ? 0 : zw + 1;
             continue;
           }
+          int g8w = uw - base;
+          if (g8w < 0) g8w += kWarpsUp;
+          base += ng8w_mod;
+          if (base >= kWarpsUp) base -= kWarpsUp;
+#pragma unroll 1
+          for (; g8w < ng8w; g8w += kWarpsUp) {
+          const int g = (g8w * subs + sub) * 8 + gl;
           const bool active = (g < NG) && (pair < npairs);
           ThreadStats ts;
           if (active) {
-            const size_t inst = (size_t)it.b * d.max_n + i;
+            const size_t inst = (size_t)it.b * d.max_n + it.i0 + i;
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
             // every proto pixel this task reads (rows r, r+1, cols 4g-1 .. 4g+4) is outside the instance's box:
             // crop_mask zeroed them, the masks are 0 - store and skip everything else
@@ -811,7 +842,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
               atoms_max(st + 16, maxy);
             }
           }
-        }
+          }   // tasks of instance i
+        }     // instances
         __syncwarp();
         if (lane == 0) bar_arrive(BAR(BAR_CH_EMPTY + buf));
       }
@@ -821,7 +853,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const uint32_t st = wstat + lane * 32;
         const int area = lds_s32(st);
         if (area) {
-          InstStats* dst = p.stats + (size_t)it.b * d.max_n + lane;
+          InstStats* dst = p.stats + (size_t)it.b * d.max_n + it.i0 + lane;
           atomicAdd(&dst->area, (unsigned)area);
           atomicMin(&dst->minx, lds_s32(st + 4));
           atomicMin(&dst->miny, lds_s32(st + 8));
@@ -858,7 +890,8 @@ struct FusedPlan {
   int num_sms;
   int pr;
   int nbuf;
-  int ni;            // accumulator columns read back per tile (8 or 16)
+  int ni;            // instances per group = accumulator columns read back per tile (8 or 16)
+  int groups;        // instance groups per frame = ceil(max_n / ni)
   int chunk_floats;
   size_t smem_bytes;
   unsigned long long* timing;   // device buffer when VA_FUSED_TIMING=1
@@ -871,7 +904,7 @@ struct FusedPlan {
 
 FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen) {
   if (!(d.H == 4 * d.mh && d.W == 4 * d.mw)) { snprintf(err, errlen, "tcgen05 path needs H=4*mh, W=4*mw"); return nullptr; }
-  if (d.max_n > kMaxInstTc) { snprintf(err, errlen, "tcgen05 path handles max_n <= %d", kMaxInstTc); return nullptr; }
+  if (d.max_n > kMaxInst) { snprintf(err, errlen, "tcgen05 path handles max_n <= %d", kMaxInst); return nullptr; }
   if ((d.mw % 4) != 0 || (d.W % 16) != 0) { snprintf(err, errlen, "mw %% 4 / W %% 16"); return nullptr; }
   if (((size_t)d.mh * d.mw) % 4 != 0) { snprintf(err, errlen, "P %% 4"); return nullptr; }
   if (d.mw * 5 < 2 * kTileM + 1) { snprintf(err, errlen, "tcgen05 path needs H=4*mh, W=4*mw with mw >= 52 (items of >= 2 tiles)"); return nullptr; }
@@ -889,22 +922,33 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   memset(pl, 0, sizeof(*pl));
   pl->encode = (PFN_encodeTiled)fn;
   pl->num_sms = prop.multiProcessorCount;
-  // pairs per chunk: largest of {4, 2} whose three chunk buffers fit next to the tile rings
+  // Instances are processed in groups of `ni` (8 or 16 accumulator columns); a frame with more instances becomes
+  // several work items per band that re-read the same prototype rows (from L2).  Pick the group size, the row pairs
+  // per chunk and the number of chunk buffers that fit next to the tile rings; measured: groups of 16 beat groups of 8
+  // whenever they fit (half the prototype re-reads and splits per mask byte).
   const size_t limit = (size_t)prop.sharedMemPerBlockOptin - 1024;
-  int pr = 0, nbuf = 0;
-  for (int cand : {4, 2}) {
-    for (int nb : {4, 3}) {
-      const int cf = (cand + 1) * d.max_n * d.mw;
-      if ((size_t)fused_smem_map(cf, nb, d.H, (4 * cand + 2) * d.W).total + 1024 <= limit) { pr = cand; nbuf = nb; break; }
+  int pr = 0, nbuf = 0, ni = 0;
+  int force_ni = 0;
+  if (const char* e = getenv("VA_FUSED_GSIZE")) force_ni = atoi(e);   // tuning aid: 8 or 16
+  for (int g : {16, 8}) {
+    if (g == 16 && d.max_n <= 8) continue;
+    if (force_ni && g != force_ni && d.max_n > 8) continue;
+    for (int cand : {4, 2}) {
+      for (int nb : {4, 3}) {
+        const int cf = (cand + 1) * g * d.mw;
+        if ((size_t)fused_smem_map(cf, nb, d.H, (4 * cand + 2) * d.W).total + 1024 <= limit) { pr = cand; nbuf = nb; ni = g; break; }
+      }
+      if (pr) break;
     }
     if (pr) break;
   }
   if (!pr) { delete pl; snprintf(err, errlen, "chunk buffers do not fit in shared memory (max_n=%d, mw=%d)", d.max_n, d.mw); return nullptr; }
   pl->pr = pr;
   pl->nbuf = nbuf;
-  pl->chunk_floats = (pr + 1) * d.max_n * d.mw;
+  pl->ni = ni;
+  pl->groups = ceil_div(d.max_n, ni);
+  pl->chunk_floats = (pr + 1) * ni * d.mw;
   pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, nbuf, d.H, (4 * pr + 2) * d.W).total + 1024;
-  pl->ni = d.max_n <= 8 ? 8 : 16;
   cudaError_t e = cudaSuccess;
 #define VA_ATTR(WM, NI, DG, NB) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)fused_tc_kernel<WM, NI, DG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes)
@@ -948,16 +992,16 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.stats = stats; p.lattice = lattice; p.B = B;
   p.timing = pl->timing;
   p.work_counter = pl->work_counter;
-  p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = d.max_n; p.chunk_floats = pl->chunk_floats; p.nbuf = pl->nbuf;
+  p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = pl->ni; p.gsize = pl->ni; p.groups = pl->groups; p.chunk_floats = pl->chunk_floats; p.nbuf = pl->nbuf;
   // Bands per frame: items are stolen dynamically, so what matters is enough items per CTA for a short tail
   // (>= ~12) against the one-row halo every band recomputes and re-reads (1/ppb).
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int nb = 1;
-  while (nb < max_bands && nb < 8 && (long)B * nb < 12L * pl->num_sms) ++nb;
+  while (nb < max_bands && nb < 8 && (long)B * nb * pl->groups < 12L * pl->num_sms) ++nb;
   if (const char* e = getenv("VA_FUSED_NBANDS")) { const int v = atoi(e); if (v >= 1 && v <= max_bands) nb = v; }   // tuning aid
   p.ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
   p.nbands = ceil_div(d.mh, p.ppb);
-  p.n_items = B * p.nbands;
+  p.n_items = B * p.nbands * p.groups;
   const int grid = p.n_items < pl->num_sms ? p.n_items : pl->num_sms;
   {
     cudaError_t e = cudaMemsetAsync(pl->work_counter, 0, sizeof(int), st);
@@ -985,7 +1029,7 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
                                {"b_empty", "hi_full", "lo_empty", "b_full", "lo_full", "acc_empty"},
                                {"acc_full", "ch_empty", "tmem_ld", "", "", ""},
                                {"ch_full", "", "", "", "", ""}};
-    fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr);
+    fprintf(stderr, "[va timing] grid=%d items=%d nbands=%d ppb=%d pr=%d nbuf=%d gsize=%d groups=%d\n", grid, p.n_items, p.nbands, p.ppb, p.pr, p.nbuf, p.gsize, p.groups);
     for (int r = 1; r < 5; ++r) {
       double tot = 0, mx = 0, w[6] = {0, 0, 0, 0, 0, 0};
       for (int c = 0; c < grid; ++c) {
