@@ -21,7 +21,8 @@
 
 namespace va {
 
-constexpr int kTailThreads = 256;
+constexpr int kTailThreads = 256;       // default CTA size; large grids (small gs) use up to kTailMaxThreads
+constexpr int kTailMaxThreads = 512;
 
 struct TailSmem {
   // "created rows" table: ids [0, 2*rmax)
@@ -120,7 +121,7 @@ __device__ __forceinline__ double blend_penalty(double rp, double cp) {
 __device__ void easy_segments(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords;
   const bool use = s.sc[S_USE_EASY] != 0;
-  for (int k = threadIdx.x; k < d.rmax; k += kTailThreads) {
+  for (int k = threadIdx.x; k < d.rmax; k += (int)blockDim.x) {
     int first = -1, last = -1, cnt = 0;
     if (use && k < R) {
       const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
@@ -137,7 +138,7 @@ __device__ void easy_segments(const Dims& d, const TailSmem& s) {
     s.erow_first[k] = first;
     s.erow_last[k] = last;
   }
-  for (int c = threadIdx.x; c < d.cmax; c += kTailThreads) {
+  for (int c = threadIdx.x; c < d.cmax; c += (int)blockDim.x) {
     int first = -1, last = -1, cnt = 0;
     if (use && c < C) {
       for (int k = 0; k < R; ++k) {
@@ -162,7 +163,7 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   uint8_t* occ_out = rec + d.off_occ;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const int cells = d.rmax * d.cmax;
-  for (int t = threadIdx.x; t < cells; t += kTailThreads) {
+  for (int t = threadIdx.x; t < cells; t += (int)blockDim.x) {
     const int k = t / d.cmax, c = t - k * d.cmax;
     double p = qnan;
     uint8_t ob = 0;
@@ -205,7 +206,7 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   }
   int* ry = reinterpret_cast<int*>(rec + d.off_row_y);
   int* ra = reinterpret_cast<int*>(rec + d.off_row_attr);
-  for (int k = threadIdx.x; k < d.rmax; k += kTailThreads) {
+  for (int k = threadIdx.x; k < d.rmax; k += (int)blockDim.x) {
     int y = 0, a = 0;
     if (k < R + norph) {
       const int id = (k < R) ? s.list_ids[k] : s.orphan_ids[k - R];
@@ -216,8 +217,8 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
     ra[k] = a;
   }
   // alignment padding: keep every byte of the record deterministic
-  for (int t = d.off_row_attr + 4 * d.rmax + threadIdx.x; t < d.off_penalty; t += kTailThreads) rec[t] = 0;
-  for (int t = d.off_occ + d.rmax * d.cmax + threadIdx.x; t < d.record_bytes; t += kTailThreads) rec[t] = 0;
+  for (int t = d.off_row_attr + 4 * d.rmax + threadIdx.x; t < d.off_penalty; t += (int)blockDim.x) rec[t] = 0;
+  for (int t = d.off_occ + d.rmax * d.cmax + threadIdx.x; t < d.record_bytes; t += (int)blockDim.x) rec[t] = 0;
 }
 
 // ProtrusionDetector closed form; executed by warp 0: one lane per list row finds the top-most occupied
@@ -287,7 +288,7 @@ __device__ void write_header(const TailSmem& s, uint8_t* rec) {
 __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], n = s.sc[S_NCREATED];
   int* s_flags = s.oflag;
-  for (int id = threadIdx.x; id < n; id += kTailThreads) {
+  for (int id = threadIdx.x; id < n; id += (int)blockDim.x) {
     bool in_list = false;
     for (int k = 0; k < R && !in_list; ++k) in_list = (s.list_ids[k] == id);
     const int ly = s.row_y[id] / d.gs;
@@ -332,7 +333,7 @@ __device__ int euler_number(const Dims& d, const uint8_t* m) {
   // zero-padded image.
   int acc = 0;
   const int total = (d.H + 1) * (d.W + 1);
-  for (int t = threadIdx.x; t < total; t += kTailThreads) {
+  for (int t = threadIdx.x; t < total; t += (int)blockDim.x) {
     const int y = t / (d.W + 1) - 1, x = t % (d.W + 1) - 1;
     const int a = (y >= 0 && x >= 0) ? (m[(size_t)y * d.W + x] != 0) : 0;
     const int b = (y >= 0 && x + 1 < d.W) ? (m[(size_t)y * d.W + x + 1] != 0) : 0;
@@ -351,7 +352,7 @@ __device__ int euler_number(const Dims& d, const uint8_t* m) {
   return s_red / 4;
 }
 
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailMaxThreads)
 tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stats, unsigned* __restrict__ lattice,
             const uint8_t* __restrict__ masks, const int* __restrict__ rects, const int* __restrict__ sel_in,
             uint8_t* __restrict__ records) {
@@ -367,8 +368,8 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
 
   __shared__ unsigned s_area[kMaxInst];
   __shared__ int s_bbox[kMaxInst][4];
-  for (int t = threadIdx.x; t < PL; t += kTailThreads) s.plane_owner[t] = -1;
-  for (int t = threadIdx.x; t < T * cw; t += kTailThreads) { s.occ[t] = 0; s.art[t] = 0; }
+  for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
+  for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
   if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
     const int i = threadIdx.x;
     InstStats v;
@@ -425,7 +426,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     const int lx0 = s.sc[S_X0] / gs, ly0 = s.sc[S_Y0] / gs;
     const unsigned* lat = lattice + ((size_t)b * d.max_n + sel) * d.lat_rows * d.lat_words;
     int any = 0;
-    for (int t = threadIdx.x; t < Rm * cw; t += kTailThreads) {
+    for (int t = threadIdx.x; t < Rm * cw; t += (int)blockDim.x) {
       const int r = t / cw, w = t - r * cw;
       const unsigned* lrow = lat + (size_t)(ly0 + r) * d.lat_words;
       const int bitpos = lx0 + 32 * w;
@@ -438,7 +439,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       s.occ[(size_t)r * cw + w] = v;
       any |= (v != 0);
     }
-    for (int r = threadIdx.x; r < Rm; r += kTailThreads) {
+    for (int r = threadIdx.x; r < Rm; r += (int)blockDim.x) {
       s.row_y[r] = s.sc[S_Y0] + r * gs;
       s.row_attr[r] = r;
       s.list_ids[r] = r;
@@ -449,7 +450,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       // band row: one column per thread, one ballot per 32 columns (erow_last is scratch until easy_segments runs)
       unsigned* am = reinterpret_cast<unsigned*>(s.erow_last);
       const int base = d.W / 2 - 8 * gs;
-      for (int c0 = threadIdx.x & ~31; c0 < 32 * cw; c0 += kTailThreads) {
+      for (int c0 = threadIdx.x & ~31; c0 < 32 * cw; c0 += (int)blockDim.x) {
         const int c = c0 + (threadIdx.x & 31);
         const int delta = s.sc[S_X0] + c * gs - base;
         const bool bit = c < C && delta >= 0 && delta % gs == 0 && delta / gs <= 16;
@@ -506,19 +507,19 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
 
   // ---- reset the reduction scratch for the next call ----
   __syncthreads();
-  for (int i = threadIdx.x; i < d.max_n; i += kTailThreads) {
+  for (int i = threadIdx.x; i < d.max_n; i += (int)blockDim.x) {
     InstStats z;
     z.area = 0; z.minx = INT_MAX; z.miny = INT_MAX; z.maxx = -1; z.maxy = -1; z.euler4 = 0; z.pad0 = 0; z.pad1 = 0;
     st[i] = z;
   }
   unsigned* latb = lattice + (size_t)b * d.max_n * d.lat_rows * d.lat_words;
-  for (int t = threadIdx.x; t < d.max_n * d.lat_rows * d.lat_words; t += kTailThreads) latb[t] = 0u;
+  for (int t = threadIdx.x; t < d.max_n * d.lat_rows * d.lat_words; t += (int)blockDim.x) latb[t] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
 // grid mode: list rows (+ optional lookup rows) given by the caller
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailMaxThreads)
 grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __restrict__ row_y,
                  const int* __restrict__ row_attr, const uint8_t* __restrict__ occ, const int* __restrict__ plane_y,
                  const uint8_t* __restrict__ plane_occ, uint8_t* __restrict__ records) {
@@ -532,8 +533,8 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
   const int R = min(max(h.n_rows, 0), d.rmax), C = min(max(h.n_cols, 0), d.cmax);
   const int NP = (plane_y && plane_occ) ? min(max(h.n_plane, 0), d.rmax) : 0;
 
-  for (int t = threadIdx.x; t < PL; t += kTailThreads) s.plane_owner[t] = -1;
-  for (int t = threadIdx.x; t < T * cw; t += kTailThreads) { s.occ[t] = 0; s.art[t] = 0; }
+  for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
+  for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
   if (threadIdx.x == 0) {
     for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
     s.sc[S_USE_EASY] = h.use_easy;
@@ -546,7 +547,7 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
   }
   __syncthreads();
   // bit-pack rows: one thread per (row, word)
-  for (int t = threadIdx.x; t < (R + NP) * cw; t += kTailThreads) {
+  for (int t = threadIdx.x; t < (R + NP) * cw; t += (int)blockDim.x) {
     const int id = t / cw, w = t - id * cw;
     const uint8_t* src = (id < R) ? occ + ((size_t)b * d.rmax + id) * d.cmax
                                   : plane_occ + ((size_t)b * d.rmax + (id - R)) * d.cmax;
@@ -561,7 +562,7 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
     s.occ[t] = vo;
     s.art[t] = va_;
   }
-  for (int id = threadIdx.x; id < R + NP; id += kTailThreads) {
+  for (int id = threadIdx.x; id < R + NP; id += (int)blockDim.x) {
     s.row_y[id] = (id < R) ? row_y[(size_t)b * d.rmax + id] : plane_y[(size_t)b * d.rmax + (id - R)];
     s.row_attr[id] = (id < R) ? row_attr[(size_t)b * d.rmax + id] : -1;
     if (id < R) s.list_ids[id] = id;
@@ -584,6 +585,12 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// 512 threads once the record has more than 2048 cells (gs <= 8 at 640^2, 1080p at gs = 20)
+static int tail_threads(const Dims& d) {
+  const int cells = d.rmax * d.cmax;
+  return cells > 2048 ? kTailMaxThreads : kTailThreads;
+}
+
 cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice,
                         const uint8_t* masks, const int* rects, const int* sel, uint8_t* records, cudaStream_t st) {
   const size_t smem = tail_smem_bytes(d);
@@ -591,7 +598,7 @@ cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stat
     cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  tail_kernel<<<B, kTailThreads, smem, st>>>(d, counts, stats, lattice, masks, rects, sel, records);
+  tail_kernel<<<B, tail_threads(d), smem, st>>>(d, counts, stats, lattice, masks, rects, sel, records);
   return cudaGetLastError();
 }
 
@@ -603,7 +610,7 @@ cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int*
     cudaError_t e = cudaFuncSetAttribute(grid_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  grid_mode_kernel<<<B, kTailThreads, smem, st>>>(d, hdr, row_y, row_attr, occ, plane_y, plane_occ, records);
+  grid_mode_kernel<<<B, tail_threads(d), smem, st>>>(d, hdr, row_y, row_attr, occ, plane_y, plane_occ, records);
   return cudaGetLastError();
 }
 

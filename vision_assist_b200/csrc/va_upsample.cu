@@ -141,89 +141,132 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
   l0 = 1.0f - l1;
 }
 
+constexpr int kGenRows = 8;   // dst rows per thread (same 16 columns): the column span and its sign range are reused
+
 template <bool kWriteMasks>
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, 8)
 upsample_generic_kernel(Dims d, const float* __restrict__ logits, const float* __restrict__ boxes,
                         const int* __restrict__ counts, uint8_t* __restrict__ masks, InstStats* __restrict__ stats,
                         unsigned* __restrict__ lattice) {
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= min(counts[b], d.max_n)) return;
   const size_t inst = (size_t)b * d.max_n + i;
-  // Conservative dst-space rectangle outside of which no source tap can lie inside the instance's box
-  // (crop_mask, ops.py:688-704, zeroed everything else): threads outside it only store zeros.
-  __shared__ int s_rect[4];
-  if (threadIdx.x == 0) {
-    int Xa = 0, Ya = 0, Xb = d.W - 1, Yb = d.H - 1;
-    if (boxes) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(boxes + inst * 4));
-      const float bx1 = __fmul_rn(q.x, d.wr), by1 = __fmul_rn(q.y, d.hr), bx2 = __fmul_rn(q.z, d.wr), by2 = __fmul_rn(q.w, d.hr);
-      // kept proto cols [ceil(bx1), ceil(bx2)-1]; a dst pixel X reads cols x0(X), x0(X)+1 with x0 = floor(sx*(X+.5)-.5)
-      const float cA = ceilf(fminf(fmaxf(bx1, -4.f), 1e6f)), cB = ceilf(fminf(fmaxf(bx2, -4.f), 1e6f)) - 1.f;
-      const float rA = ceilf(fminf(fmaxf(by1, -4.f), 1e6f)), rB = ceilf(fminf(fmaxf(by2, -4.f), 1e6f)) - 1.f;
-      // X touches cols [cA,cB] iff x0(X)+1 >= cA and x0(X) <= cB  <=>  (cA-.5)/sx-.5 <= X < (cB+1.5)/sx-.5 ; widen by >= 1
-      Xa = max(0, (int)floorf((cA - 1.5f) / d.sx) - 1);
-      Xb = min(d.W - 1, (int)ceilf((cB + 1.5f) / d.sx) + 1);
-      Ya = max(0, (int)floorf((rA - 1.5f) / d.sy) - 1);
-      Yb = min(d.H - 1, (int)ceilf((rB + 1.5f) / d.sy) + 1);
-    }
-    s_rect[0] = Xa; s_rect[1] = Ya; s_rect[2] = Xb; s_rect[3] = Yb;
-  }
-  __syncthreads();
+  // warp tile: 8 column groups (128 px) x 4 row blocks of kGenRows rows; a store instruction writes four 128 B row pieces
   const int NG = ceil_div(d.W, 16);
   const int NG8 = ceil_div(NG, 8);
-  const int NY4 = ceil_div(d.H, 4);
+  const int NYB = ceil_div(d.H, 4 * kGenRows);
   const int wt = blockIdx.x * (kUpThreads / 32) + (threadIdx.x >> 5);
-  if (wt >= NG8 * NY4) return;
+  if (wt >= NG8 * NYB) return;
   const int lane = threadIdx.x & 31;
+  // Conservative dst-space rectangle outside of which no source tap can lie inside the instance's box
+  // (crop_mask, ops.py:688-704, zeroed everything else): threads outside it only store zeros.  Lanes 0..3 compute one
+  // bound each (no shared memory, no block barrier: the warps of a CTA are independent).
+  int rXa = 0, rYa = 0, rXb = d.W - 1, rYb = d.H - 1;
+  if (boxes) {
+    const int c = lane & 3;                                       // 0: x1, 1: y1, 2: x2, 3: y2
+    const float scaled = __fmul_rn(__ldg(boxes + inst * 4 + c), (c & 1) ? d.hr : d.wr);
+    // kept proto cols [ceil(bx1), ceil(bx2)-1]; a dst pixel X reads cols x0(X), x0(X)+1 with x0 = floor(sx*(X+.5)-.5):
+    // X touches cols [cA,cB] iff (cA-.5)/sx-.5 <= X < (cB+1.5)/sx-.5 ; widened by >= 1 on both sides
+    const float e = ceilf(fminf(fmaxf(scaled, -4.f), 1e6f)) - ((c & 2) ? 1.f : 0.f);
+    const float sc = (c & 1) ? d.sy : d.sx;
+    const int lim = (c & 1) ? d.H - 1 : d.W - 1;
+    const int v = (c & 2) ? min(lim, (int)ceilf((e + 1.5f) / sc) + 1) : max(0, (int)floorf((e - 1.5f) / sc) - 1);
+    rXa = __shfl_sync(0xffffffffu, v, 0);
+    rYa = __shfl_sync(0xffffffffu, v, 1);
+    rXb = __shfl_sync(0xffffffffu, v, 2);
+    rYb = __shfl_sync(0xffffffffu, v, 3);
+  }
   const int g = (wt % NG8) * 8 + (lane & 7);
-  const int Y = (wt / NG8) * 4 + (lane >> 3);
+  const int Ybeg = ((wt / NG8) * 4 + (lane >> 3)) * kGenRows;
+  const int Yend = min(Ybeg + kGenRows, d.H);
   const float* L = logits + inst * d.mh * d.mw;
   unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
   ThreadStats ts;
-  if (g < NG && Y < d.H) {
+  if (g < NG && Ybeg < d.H) {
     const int X0 = 16 * g, X1 = min(X0 + 15, d.W - 1);
-    unsigned ww[4] = {0, 0, 0, 0};
-    const bool in_rect = !(Y < s_rect[1] || Y > s_rect[3] || X1 < s_rect[0] || X0 > s_rect[2]);
-    if (in_rect) {
-      int y0, y1;
-      float ly0, ly1;
-      src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
-      const float* r0 = L + (size_t)y0 * d.mw;
-      const float* r1 = L + (size_t)y1 * d.mw;
-      int xa, xb, t0;
+    const int npx = X1 - X0 + 1;
+    const bool col_in = !(X1 < rXa || X0 > rXb);
+    int xa = 0, xb = 0;                        // proto columns the 16 pixels can read
+    if (col_in) {
+      int t;
       float f0, f1;
-      src_index(d.sx, X0, d.mw, xa, t0, f0, f1);
-      src_index(d.sx, X1, d.mw, t0, xb, f0, f1);
-      float mn = INFINITY, mx = -INFINITY;
-      for (int x = xa; x <= xb; ++x) {
-        const float u = __ldg(r0 + x), v = __ldg(r1 + x);
-        mn = fminf(mn, fminf(u, v));
-        mx = fmaxf(mx, fmaxf(u, v));
-      }
-      if (mn > kTiny) {
-        for (int px = 0; px <= X1 - X0; ++px) ww[px >> 2] |= 1u << (8 * (px & 3));
-      } else if (mx > 0.f) {
-        for (int px = 0; px <= X1 - X0; ++px) {
-          int x0, x1;
-          float lx0, lx1;
-          src_index(d.sx, X0 + px, d.mw, x0, x1, lx0, lx1);
-          const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
-          const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
-          const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
-          if (o > 0.f) ww[px >> 2] |= 1u << (8 * (px & 3));
+      src_index(d.sx, X0, d.mw, xa, t, f0, f1);
+      src_index(d.sx, X1, d.mw, t, xb, f0, f1);
+    }
+    uint8_t* M = kWriteMasks ? masks + inst * (size_t)d.H * d.W + X0 : nullptr;
+    const bool vec = (npx == 16) && ((d.W & 15) == 0);
+    if (!col_in || Yend <= rYa || Ybeg > rYb) {
+      // whole thread tile outside the rectangle (the common case with many small instances): zeros, nothing else
+      if (kWriteMasks) {
+        uint8_t* Mr = M + (size_t)Ybeg * d.W;
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < kGenRows; ++j)
+            if (Ybeg + j < Yend) *reinterpret_cast<uint4*>(Mr + (size_t)j * d.W) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          for (int Y = Ybeg; Y < Yend; ++Y, Mr += d.W)
+            for (int px = 0; px < npx; ++px) Mr[px] = 0;
         }
       }
-    }
-    const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
-    if (kWriteMasks) {
-      uint8_t* M = masks + inst * (size_t)d.H * d.W + (size_t)Y * d.W + X0;
-      if (X0 + 15 < d.W && (d.W & 15) == 0) *reinterpret_cast<uint4*>(M) = w;
-      else for (int px = 0; px <= X1 - X0; ++px) M[px] = (ww[px >> 2] >> (8 * (px & 3))) & 1u;
-    }
-    if (ww[0] | ww[1] | ww[2] | ww[3]) {
+    } else {
+    int py0 = -1, py1 = -1;
+    float mn = 0.f, mx = 0.f;
+    // next lattice (cell-centre) row at or after Ybeg: rows gs/2, gs/2 + gs, ...
+    int Ylat = (d.gs >> 1) + ceil_div(max(Ybeg - (d.gs >> 1), 0), d.gs) * d.gs;
+#pragma unroll 1
+    for (int Y = Ybeg; Y < Yend; ++Y) {
+      unsigned ww[4] = {0u, 0u, 0u, 0u};
+      if (Y >= rYa && Y <= rYb) {
+        int y0, y1;
+        float ly0, ly1;
+        src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
+        const float* r0 = L + (size_t)y0 * d.mw;
+        const float* r1 = L + (size_t)y1 * d.mw;
+        if (y0 != py0 || y1 != py1) {            // sign range of every tap these 16 pixels can read in rows y0, y1
+          mn = INFINITY; mx = -INFINITY;
+          for (int x = xa; x <= xb; ++x) {
+            const float u = __ldg(r0 + x), v = __ldg(r1 + x);
+            mn = fminf(mn, fminf(u, v));
+            mx = fmaxf(mx, fmaxf(u, v));
+          }
+          py0 = y0; py1 = y1;
+        }
+        if (mn > kTiny) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int left = npx - 4 * q;        // pixels of this word that exist
+            ww[q] = left >= 4 ? 0x01010101u : left <= 0 ? 0u : (0x01010101u >> (8 * (4 - left)));
+          }
+        } else if (mx > 0.f) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            unsigned acc = 0;
+#pragma unroll 1
+            for (int k = 0; k < 4 && 4 * q + k < npx; ++k) {
+              int x0, x1;
+              float lx0, lx1;
+              src_index(d.sx, X0 + 4 * q + k, d.mw, x0, x1, lx0, lx1);
+              const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
+              const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
+              const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
+              if (o > 0.f) acc |= 1u << (8 * k);
+            }
+            ww[q] = acc;
+          }
+        }
+      }
+      const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+      if (kWriteMasks) {
+        uint8_t* Mr = M + (size_t)Y * d.W;
+        if (vec) *reinterpret_cast<uint4*>(Mr) = w;
+        else for (int px = 0; px < npx; ++px) Mr[px] = (uint8_t)(((px < 4 ? w.x : px < 8 ? w.y : px < 12 ? w.z : w.w) >> (8 * (px & 3))) & 1u);
+      }
+      if (Y == Ylat) {
+        Ylat += d.gs;
+        if (ww[0] | ww[1] | ww[2] | ww[3]) lattice_row(w, Y, X0, d, lat);
+      }
       ts.add_row(w, Y);
-      const int t = Y - (d.gs >> 1);
-      if (t >= 0 && t % d.gs == 0) lattice_row(w, Y, X0, d, lat);
+    }
     }
   }
   if (__any_sync(0xffffffffu, ts.acc != 0)) publish_stats(ts, 16 * g, stats + inst);
@@ -293,7 +336,7 @@ cudaError_t launch_upsample(const Dims& d, const float* logits, const float* box
     if (masks) upsample4x_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
     else upsample4x_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
   } else {
-    const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4);
+    const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4 * kGenRows);
     dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
     if (masks) upsample_generic_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, stats, lattice);
     else upsample_generic_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, stats, lattice);
