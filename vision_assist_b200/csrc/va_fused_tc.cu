@@ -184,6 +184,7 @@ struct Item {
   int npx;      // nrows * mw
   int ntiles;   // ceil(npx / 128)
   int nchunks;  // ceil((pb - pa) / pr)
+  int band_pa, band_pb;   // the whole band; [pa, pb) is its live part (chunks that intersect the hull of the group's boxes)
 };
 
 // Work item index -> (band, frame, instance group), group fastest: the groups of one (frame, band) read the same
@@ -192,7 +193,7 @@ struct Item {
 // bottom-band-first order: the bands that contain the sidewalk blob cost more, so the light top bands form the
 // tail of the schedule.  Out of line on purpose: called once per item per role, and inlined copies of its
 // divisions would compete with the hot loops for the instruction cache.
-__device__ __noinline__ Item decode_item(const FusedParams& p, int item) {
+__device__ __noinline__ Item decode_item(const FusedParams& p, int item, int c_lo, int c_hi) {
   Item it;
   it.valid = item < p.n_items;
   const int fb = item / p.groups;
@@ -203,12 +204,19 @@ __device__ __noinline__ Item decode_item(const FusedParams& p, int item) {
   it.b = b;
   it.i0 = q * p.gsize;
   it.n = it.valid ? max(min(min(p.counts[b], p.d.max_n) - it.i0, p.gsize), 0) : 0;
-  it.pa = j * p.ppb;
-  it.pb = min(it.pa + p.ppb, p.d.mh);
-  it.nrows = min(it.pb, p.d.mh - 1) - it.pa + 1;
-  it.npx = it.nrows * p.d.mw;
-  it.ntiles = ceil_div(it.npx, kTileM);
-  it.nchunks = ceil_div(it.pb - it.pa, p.pr);
+  it.band_pa = j * p.ppb;
+  it.band_pb = min(it.band_pa + p.ppb, p.d.mh);
+  // live chunks [c_lo, c_hi) of the band (the TMA warp computes them from the boxes; (0, INT_MAX) = whole band)
+  it.pa = min(it.band_pa + c_lo * p.pr, it.band_pb);
+  it.pb = (c_hi >= p.ppb) ? it.band_pb : max(min(it.band_pa + c_hi * p.pr, it.band_pb), it.pa);
+  if (it.pb > it.pa) {
+    it.nrows = min(it.pb, p.d.mh - 1) - it.pa + 1;
+    it.npx = it.nrows * p.d.mw;
+    it.ntiles = ceil_div(it.npx, kTileM);
+    it.nchunks = ceil_div(it.pb - it.pa, p.pr);
+  } else {
+    it.nrows = it.npx = it.ntiles = it.nchunks = 0;
+  }
   return it;
 }
 
@@ -232,7 +240,7 @@ struct SmemMap {
   uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
   uint32_t bars;      // [BAR_COUNT] u64
   uint32_t tmem_slot;
-  uint32_t items;     // [kItemRing] i32
+  uint32_t items;     // [kItemRing][4] i32
   uint32_t total;
 };
 enum {
@@ -266,7 +274,7 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int nbuf, in
   m.latrow = take((uint32_t)H * 2, 16);
   m.bars = take(BAR_COUNT * 8, 8);
   m.tmem_slot = take(16, 16);
-  m.items = take(kItemRing * 4, 16);
+  m.items = take(kItemRing * 16, 16);   // {item index, first live chunk, end of live chunks, -}
   m.total = o;
   return m;
 }
@@ -403,7 +411,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   // k-th item of this CTA as published by the TMA thread
   auto next_item = [&](int k) -> Item {
     bar_wait(BAR(BAR_ITEM + (k % kItemRing)), (k / kItemRing) & 1);
-    return decode_item(p, lds_s32(sbase + sm.items + 4 * (k % kItemRing)));
+    const uint32_t e = sbase + sm.items + 16 * (k % kItemRing);
+    return decode_item(p, lds_s32(e), lds_s32(e + 4), lds_s32(e + 8));
   };
 
   // ---- one-time setup ----
@@ -441,31 +450,62 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   const uint32_t tmem_base = lds_u32(sbase + sm.tmem_slot);
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      RoleTimer tm; tm.begin((kDiag && p.timing) ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
-      uint32_t g = 0;
-      for (int k = 0;; ++k) {
-        Item it;
-        int item;
-        do {                                                   // instance groups with no instance in this frame are dropped here
-          item = atomicAdd(p.work_counter, 1);
-          it = decode_item(p, item);
-        } while (it.valid && it.n == 0);
-        sts_s32(sbase + sm.items + 4 * (k % kItemRing), item);
-        bar_arrive(BAR(BAR_ITEM + (k % kItemRing)));          // release: the index is visible to the waiting roles
-        if (!it.valid) break;
+    // =========================== work stealing + TMA producer ===========================
+    // The whole warp fetches and sizes the next item; lane 0 then issues its tile loads.  (Fetching item k+1 while
+    // the tiles of item k are being issued was measured slower: a CTA then holds a reserved item while others idle
+    // at the end of the launch.)
+    RoleTimer tm; tm.begin((kDiag && p.timing && lane == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 1) * 8 : nullptr);
+    uint32_t g = 0;
+    for (int k = 0;; ++k) {
+      Item it;
+      int item = 0;
+      do {                                                   // instance groups with no instance in this frame are dropped here
+        if (lane == 0) item = atomicAdd(p.work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        it = decode_item(p, item, 0, INT_MAX);
+      } while (it.valid && it.n == 0);
+      // Hull of the group's boxes in proto rows: chunks of the band that lie above / below every box produce only
+      // zeros (crop_mask) - they are neither loaded nor multiplied; the upsample warps zero-fill their rows.
+      int c_lo = 0, c_hi = it.nchunks;
+      if (it.valid && !(kDiag && p.logits_dbg)) {
+        float y1 = INFINITY, y2 = -INFINITY;
+        if (lane < it.n) {
+          const float* bx = p.boxes + ((size_t)it.b * d.max_n + it.i0 + lane) * 4;
+          y1 = __fmul_rn(__ldg(bx + 1), d.hr);
+          y2 = __fmul_rn(__ldg(bx + 3), d.hr);
+          if (!(y1 == y1)) y1 = -INFINITY;                    // NaN never passes the "outside" tests: keep everything
+          if (!(y2 == y2)) y2 = INFINITY;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+          y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+        }
+        // same test as the upsample warps' per-instance chunk test, against the hull
+        while (c_lo < c_hi && (float)min(it.pa + (c_lo + 1) * p.pr, it.pb) < y1) ++c_lo;
+        while (c_hi > c_lo && (float)(it.pa + (c_hi - 1) * p.pr) >= y2) --c_hi;
+        it = decode_item(p, item, c_lo, c_hi);
+      }
+      if (lane == 0) {
+        const uint32_t e = sbase + sm.items + 16 * (k % kItemRing);
+        sts_s32(e, item); sts_s32(e + 4, c_lo); sts_s32(e + 8, c_hi);
+        bar_arrive(BAR(BAR_ITEM + (k % kItemRing)));          // release: the entry is visible to the waiting roles
+      }
+      if (!it.valid) break;
+      if (lane == 0) {
         const int px0 = it.pa * d.mw;
 #pragma unroll 1
-        for (int t = 0; t < it.ntiles; ++t, ++g) {
-          const int st = g % kStagesHi;
-          TIMED_WAIT(tm, 0, BAR(BAR_HI_EMPTY + st), ((g / kStagesHi) & 1) ^ 1);
+        for (int t = 0; t < it.ntiles; ++t) {
+          const int st = (g + t) % kStagesHi;
+          TIMED_WAIT(tm, 0, BAR(BAR_HI_EMPTY + st), (((g + t) / kStagesHi) & 1) ^ 1);
           bar_expect_tx(BAR(BAR_HI_FULL + st), kTileBytes);
           tma_load_3d_a(sbase + sm.hi + st * kTileBytes, &tmap, BAR(BAR_HI_FULL + st), px0 + t * kTileM, 0, it.b);
         }
       }
-      tm.end();
+      g += it.ntiles;
+      __syncwarp();
     }
+    tm.end();
   } else if (warp < kFirstEpiWarp) {
     // =========================== 3xTF32 split: staged [k][px] box -> registers -> tensor memory ===========================
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32) belong to this warp
@@ -475,12 +515,14 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const uint32_t idesc = make_idesc(kTileM, kNMma);
     RoleTimer tm; tm.begin((kDiag && p.timing && st_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 2) * 8 : nullptr);
     uint32_t g = 0;
+    int kk = 0;                                      // items that have tiles (parity of the B tile / box double buffers)
     for (int k = 0;; ++k) {
       const Item it = next_item(k);
       if (!it.valid) break;
+      if (it.ntiles == 0) continue;                  // no live chunk: only the upsample warps act (zero fill)
       {   // per-frame B tiles: coefficients hi / lo, K-major, 16 B chunk c of row r stored at chunk c ^ (r & 7)
-        const int par = k & 1;
-        TIMED_WAIT(tm, 0, BAR(BAR_B_EMPTY + par), ((k >> 1) & 1) ^ 1);
+        const int par = kk & 1;
+        TIMED_WAIT(tm, 0, BAR(BAR_B_EMPTY + par), ((kk >> 1) & 1) ^ 1);
         const int n = it.n;
         const uint32_t bh = sbase + sm.bt + par * kNMma * 128;   // rows [0,16): hi
         const uint32_t bl = bh + kNPad * 128;                      // rows [16,32): lo (16 = 2 swizzle periods: same XOR pattern)
@@ -526,8 +568,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         // lane 0 of split warps 0 and 1 into separate accumulators; the epilogue adds them.
         //   issuer 0: D0[:, 0:16 | 16:32] = A_hi * [B_hi | B_lo]^T      issuer 1: D1 = A_lo * [B_hi | B_lo]^T
         if (issuer >= 0 && lane == 0) {
-          const int par = k & 1;
-          if (t == 0) TIMED_WAIT(tm, 3, BAR(BAR_B_FULL + par), (k >> 1) & 1);
+          const int par = kk & 1;
+          if (t == 0) TIMED_WAIT(tm, 3, BAR(BAR_B_FULL + par), (kk >> 1) & 1);
           const int ac = g % kAcc;
           TIMED_WAIT(tm, 4, BAR(BAR_LO_FULL + sl), (g / kStagesLo) & 1);       // all four lane quarters of A are in TMEM
           TIMED_WAIT(tm, 5, BAR(BAR_ACC_EMPTY + ac), ((g / kAcc) & 1) ^ 1);
@@ -545,6 +587,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         }
         __syncwarp();
       }
+      ++kk;
     }
     tm.end();
   } else if (warp < kFirstUpWarp) {
@@ -558,12 +601,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const uint32_t chunks = sbase + sm.chunks;
     RoleTimer tm; tm.begin((kDiag && p.timing && ep_tid == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 3) * 8 : nullptr);
     uint32_t g = 0, chunk_base = 0;
+    int kk = 0;
     for (int k = 0;; ++k) {
       const Item it = next_item(k);
       if (!it.valid) break;
+      if (it.ntiles == 0) continue;
       const int n = it.n;
       // scaled boxes of this frame (double-buffered by item parity; the 4 epilogue warps stay within one item)
-      const uint32_t bx = sbase + sm.box + (k & 1) * kMaxInstTc * 16;
+      const uint32_t bx = sbase + sm.box + (kk & 1) * kMaxInstTc * 16;
+      ++kk;
       if (ep_tid < kMaxInstTc * 4) {
         const int i = ep_tid >> 2, c = ep_tid & 3;
         float v = 0.f;
@@ -695,6 +741,34 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         sts_f32(ubox + q4 * 4, v);
       }
       __syncwarp();
+      // Dead parts of the band (above / below the hull of the boxes): the masks are zero there.  Bulk copies from the
+      // zero buffer in pieces of <= zero_bytes; piece q belongs to upsample thread q % (32 * kWarpsUp).
+      const int rows_per = 4 * p.pr + 2;
+      const int YaA = (it.band_pa == 0) ? 0 : 4 * it.band_pa + 2;                 // part A: pairs [band_pa, pa)
+      const int rowsA = (it.pa > it.band_pa) ? min(4 * (it.pa - 1) + 5, d.H - 1) - YaA + 1 : 0;
+      const int YaB = 4 * it.pb + 2;                                               // part B: pairs [pb, band_pb)
+      const int rowsB = (it.band_pb > it.pb) ? min(4 * (it.band_pb - 1) + 5, d.H - 1) - ((it.pb == 0) ? 0 : YaB) + 1 : 0;
+      const int piecesA = ceil_div(rowsA, rows_per), PP = piecesA + ceil_div(rowsB, rows_per);
+      const int D = kWriteMasks ? n * PP : 0;
+      int zprev = 0;
+      auto zero_fill = [&](int upto) {
+#pragma unroll 1
+        for (int q = ut; q < upto; q += 32 * kWarpsUp) {
+          if (q < zprev) continue;
+          const int i = q / PP, rest = q - i * PP;
+          const bool partB = rest >= piecesA;
+          const int pc = partB ? rest - piecesA : rest;
+          const int y0 = partB ? ((it.pb == 0) ? 0 : YaB) : YaA, rows = partB ? rowsB : rowsA;
+          const int y = y0 + pc * rows_per;
+          uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + it.i0 + i) * d.H + y) * (size_t)d.W;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sbase + sm.zeros),
+                       "r"((uint32_t)(min(rows_per, y0 + rows - y) * d.W))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        zprev = upto;
+      };
+      if (D) zero_fill(D);            // all at once: measured faster than releasing a share per live chunk
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
         const int buf = gc % kNBuf;
         TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kNBuf) & 1);
@@ -994,10 +1068,10 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.work_counter = pl->work_counter;
   p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = pl->ni; p.gsize = pl->ni; p.groups = pl->groups; p.chunk_floats = pl->chunk_floats; p.nbuf = pl->nbuf;
   // Bands per frame: items are stolen dynamically, so what matters is enough items per CTA for a short tail
-  // (>= ~12) against the one-row halo every band recomputes and re-reads (1/ppb).
+  // (>= ~8) against the one-row halo every band recomputes and re-reads (1/ppb).
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int nb = 1;
-  while (nb < max_bands && nb < 8 && (long)B * nb * pl->groups < 12L * pl->num_sms) ++nb;
+  while (nb < max_bands && nb < 8 && (long)B * nb * pl->groups < 8L * pl->num_sms) ++nb;
   if (const char* e = getenv("VA_FUSED_NBANDS")) { const int v = atoi(e); if (v >= 1 && v <= max_bands) nb = v; }   // tuning aid
   p.ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
   p.nbands = ceil_div(d.mh, p.ppb);
