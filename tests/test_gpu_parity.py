@@ -178,6 +178,41 @@ def test_sixteen_instance_accumulator_path(tc):
 
 
 @pytest.mark.parametrize("tc", PATHS)
+def test_instance_groups_ragged_counts_and_dead_bands(tc):
+    """max_n = 32 (two instance groups of 16 on the tcgen05 path), ragged counts that leave a group empty or
+    partly filled, and boxes chosen so that whole bands lie outside the hull of a group's boxes: thin boxes at the
+    top / bottom edge, boxes outside the frame, empty and inverted boxes."""
+    H = W = 640
+    B, n = 8, 32
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(7000, B, n, H, W, 160, 160, max_n=32)
+    for b, c in enumerate([32, 17, 16, 5, 1, 0, 24, 32]):
+        counts[b] = c
+    g = torch.Generator().manual_seed(7)
+    boxes[0, 16:] = torch.tensor([40., 600., 600., 639.])            # group 1 lives in the bottom band only
+    boxes[1, 16] = torch.tensor([100., 0., 500., 9.])                # one thin instance at the very top
+    boxes[2, :16, 1] = 300.; boxes[2, :16, 3] = 340.                 # all boxes inside one band
+    boxes[3, 0] = torch.tensor([-50., -80., -10., -5.])              # outside the frame (negative)
+    boxes[3, 1] = torch.tensor([700., 700., 900., 900.])             # outside the frame (beyond)
+    boxes[3, 2] = torch.tensor([200., 300., 200., 300.])             # empty
+    boxes[3, 3] = torch.tensor([400., 500., 300., 100.])             # inverted
+    boxes[6, :24] = torch.rand(24, 4, generator=g) * 640             # arbitrary, mostly inverted / degenerate
+    boxes[7, :, 1] = 0.; boxes[7, :, 3] = 640.                       # full height: nothing is dead
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    for b in range(B):
+        nb = int(counts[b])
+        if nb:
+            up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
+            nd, nout = band_mismatch_report(masks[b, :nb], up)
+            assert nout == 0, (b, nd, nout)
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "direct"), f"groups frame {b}")
+    r_nomask, _ = eng.run(*to_dev(protos, coefs, boxes, counts), write_masks=False)
+    assert torch.equal(r_nomask, records)
+
+
+@pytest.mark.parametrize("tc", PATHS)
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
     eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)
