@@ -16,6 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import graph as ograph
 from . import grid as ogrid
 from . import mask_assembly as oma
 from . import penalty as open_
@@ -34,7 +35,8 @@ def state_to_result(st: ogrid.GridState | None, flags: int = 0, sel: int = -1) -
                     rows_y=np.zeros(0, np.int32), rows_attr=np.zeros(0, np.int32),
                     occ=np.zeros((0, 0), np.uint8), penalty=np.zeros((0, 0), np.float64),
                     peaks=np.zeros((0, 2), np.int32), orphan_y=np.zeros(0, np.int32),
-                    orphan_occ=np.zeros((0, 0), np.uint8))
+                    orphan_occ=np.zeros((0, 0), np.uint8), start=(-1, -1), goals=np.zeros((0, 2), np.int32),
+                    nbr=np.zeros((0, 0), np.uint8), lookup_row=np.zeros(0, np.int32))
     pen = open_.calculate_penalties(st)
     R, C = len(st.grids), len(st.grids[0])
     rows_y = np.array([row[0].y for row in st.grids], np.int32)
@@ -53,9 +55,14 @@ def state_to_result(st: ogrid.GridState | None, flags: int = 0, sel: int = -1) -
     for k, y in enumerate(oy):
         for g in orphan_rows[y]:
             oocc[k, (g.x - st.x0) // st.gs] = (0 if g.empty else 1) | (2 if g.artificial else 0)
+    # start / goal cells of _find_paths and the _create_graph neighbourhood
+    start, goals = ograph.start_and_goals(st, peaks)
     return dict(flags=flags, sel=sel, x0=st.x0, y0=st.y0, C=C, R=R, rows_y=rows_y, rows_attr=rows_attr,
                 occ=occ, penalty=pen, peaks=np.array(peaks, np.int32).reshape(-1, 2),
-                orphan_y=np.array(oy, np.int32), orphan_occ=oocc)
+                orphan_y=np.array(oy, np.int32), orphan_occ=oocc,
+                start=start if start is not None else (-1, -1),
+                goals=np.array([g if g is not None else (-1, -1) for g in goals], np.int32).reshape(-1, 2),
+                nbr=ograph.neighbour_mask(st), lookup_row=ograph.lookup_rows(st, oy))
 
 
 def euler_number_8(mask: np.ndarray) -> int:

@@ -67,7 +67,41 @@ def ref_state_arrays(fp, ref, H, W):
         npk = len(pk)
         for k, p in enumerate(pk):
             peaks[k] = (p.x, p.y)
-    return dict(R=R, C=C, x0=x0, rows_y=rows_y, rows_attr=rows_attr, occ=occ, pen=pen, peaks=peaks, npk=npk)
+    # the reference's own start / goal cell choice (utils.get_closest_grid_to_point as used by
+    # FrameProcessor._find_paths :236-239) and _create_graph (:184-207) as a neighbour bit mask per list cell
+    start = np.full(2, -1, np.int32)
+    goals = np.full((PMAX, 2), -1, np.int32)
+    nbr = np.zeros((RMAX, CMAX), np.uint8)
+    if R:
+        gs = ref.FrameProcessor.grid_size
+
+        def where(obj):
+            for k, row in enumerate(fp.grids):
+                for c, g in enumerate(row):
+                    if g is obj:
+                        return k, c
+            return -1, -1
+
+        Coordinate = ref.models.Coordinate
+        sg = ref.utils.get_closest_grid_to_point(Coordinate(x=W // 2, y=H), fp.grids)
+        if sg is not None:
+            start[:] = where(sg)
+        for k in range(npk):
+            eg = ref.utils.get_closest_grid_to_point(Coordinate(x=int(peaks[k, 0]), y=int(peaks[k, 1])), fp.grids)
+            if eg is not None:
+                goals[k] = where(eg)
+        graph = fp._create_graph()
+        for r, row in enumerate(fp.grids):
+            for c, g in enumerate(row):
+                if g.empty:
+                    continue
+                x, y = g.coords.x, g.coords.y
+                have = {pos for pos, _ in graph.get((x, y), [])}
+                for bit, pos in enumerate(((x + gs, y), (x - gs, y), (x, y + gs), (x, y - gs))):
+                    if pos in have:
+                        nbr[r, c] |= 1 << bit
+    return dict(R=R, C=C, x0=x0, rows_y=rows_y, rows_attr=rows_attr, occ=occ, pen=pen, peaks=peaks, npk=npk,
+                start=start, goals=goals, nbr=nbr)
 
 
 def gen_fixtures(ref):
@@ -98,6 +132,9 @@ def gen_fixtures(ref):
         out[f"{nm}/rows_y"] = a["rows_y"][:a["R"]]
         out[f"{nm}/rows_attr"] = a["rows_attr"][:a["R"]]
         out[f"{nm}/peaks"] = a["peaks"][:a["npk"]]
+        out[f"{nm}/start"] = a["start"]
+        out[f"{nm}/goals"] = a["goals"][:a["npk"]]
+        out[f"{nm}/nbr"] = a["nbr"][:a["R"], :a["C"]]
         # also with easy segments (what FrameProcessor.__call__ would do with np_grids set)
         fp2 = refharness.new_frame_processor(ref)
         fp2.frame = fp.frame
@@ -131,7 +168,7 @@ def gen_polygons(ref, n_cases=172):
            [(640, 640, 32)] * 10 + [(384, 640, 8)] * 10 + [(650, 650, 20)] * 12
     out = {}
     keep = dict(H=[], W=[], gs=[], err=[], R=[], C=[], x0=[], npk=[])
-    arrs = dict(rows_y=[], rows_attr=[], occ=[], pen=[], peaks=[])
+    arrs = dict(rows_y=[], rows_attr=[], occ=[], pen=[], peaks=[], start=[], goals=[], nbr=[])
     polys_all, poly_off = [], [0]
     case_poly = []
     for H, W, gs in cfgs[:n_cases]:
@@ -204,7 +241,8 @@ def gen_frames(ref):
     out = {"cases": np.array([c[:6] + c[7:] for c in FRAME_CASES], np.int32),
            "families": np.array([c[6] for c in FRAME_CASES])}
     for ci, (H, W, mh, mw, n, gs, fam, first, count) in enumerate(FRAME_CASES):
-        acc = dict(R=[], C=[], x0=[], npk=[], rows_y=[], rows_attr=[], occ=[], pen=[], peaks=[], areas=[])
+        acc = dict(R=[], C=[], x0=[], npk=[], rows_y=[], rows_attr=[], occ=[], pen=[], peaks=[], start=[], goals=[],
+                   nbr=[], areas=[])
         for f in range(first, first + count):
             p, c, b = synth.make_frame(f, n, H, W, mh, mw, 32, fam)
             masks = ref.ops.process_mask(p, c, b, (H, W), upsample=True)
@@ -214,7 +252,7 @@ def gen_frames(ref):
             fp.frame = np.zeros((H, W, 3), np.uint8)
             fp._extract_grid_information([refharness.FakeResult(xy)])
             a = ref_state_arrays(fp, ref, H, W)
-            for k in ("R", "C", "x0", "npk", "rows_y", "rows_attr", "occ", "pen", "peaks"):
+            for k in ("R", "C", "x0", "npk", "rows_y", "rows_attr", "occ", "pen", "peaks", "start", "goals", "nbr"):
                 acc[k].append(a[k])
             acc["areas"].append(masks.reshape(n, -1).sum(1).numpy().astype(np.int64))
         for k, v in acc.items():

@@ -24,7 +24,8 @@ def polygon_cases():
         yield dict(idx=i, H=int(z["H"][i]), W=int(z["W"][i]), gs=int(z["gs"][i]), err=int(z["err"][i]),
                    R=R, C=C, x0=int(z["x0"][i]), polys=polys,
                    rows_y=z["rows_y"][i][:R], rows_attr=z["rows_attr"][i][:R], occ=z["occ"][i][:R, :C],
-                   pen=z["pen"][i][:R, :C], peaks=z["peaks"][i][:int(z["npk"][i])])
+                   pen=z["pen"][i][:R, :C], peaks=z["peaks"][i][:int(z["npk"][i])],
+                   start=z["start"][i], goals=z["goals"][i][:int(z["npk"][i])], nbr=z["nbr"][i][:R, :C])
 
 
 def assert_result_matches(res: dict, case: dict, what=""):
@@ -43,3 +44,8 @@ def assert_result_matches(res: dict, case: dict, what=""):
         (what, np.nanmax(np.abs(a - b)))
     assert np.array_equal(np.asarray(res["peaks"]).reshape(-1, 2), case["peaks"].reshape(-1, 2)), \
         (what, res["peaks"], case["peaks"])
+    if "start" in case and "start" in res:      # start / goal cells, graph neighbourhood
+        assert tuple(int(v) for v in res["start"]) == tuple(int(v) for v in case["start"]), (what, res["start"], case["start"])
+        assert np.array_equal(np.asarray(res["goals"]).reshape(-1, 2), case["goals"].reshape(-1, 2)), what
+        if "nbr" in res:
+            assert np.array_equal(res["nbr"], case["nbr"]), what

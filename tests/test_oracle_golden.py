@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import goldenio
+from oracle import graph as ograph
 from oracle import grid as og
 from oracle import mask_assembly as oma
 from oracle import penalty as open_
@@ -48,6 +49,11 @@ def test_reference_fixtures_penalties_and_peaks():
         pk = oprot.peaks_closed_form(rows_y, (occ & 1).astype(bool), 0, st.W, 20)
         assert pk == [tuple(p) for p in z[f"{nm}/peaks"].tolist()], nm
         assert oprot.peaks_raster(st.grids, st.H, st.W, 20) == pk
+        # start / goal cells and graph neighbourhood as the reference's own functions give them
+        start, goals = ograph.start_and_goals(st, pk)
+        assert tuple(start) == tuple(int(v) for v in z[f"{nm}/start"]), nm
+        assert [tuple(g) for g in goals] == [tuple(g) for g in z[f"{nm}/goals"].tolist()], nm
+        assert np.array_equal(ograph.neighbour_mask(st), z[f"{nm}/nbr"]), nm
 
 
 def test_reference_png_known_answers():
@@ -99,7 +105,9 @@ def test_frames_golden_contour_and_direct_routes():
             R, C = int(z[f"{ci}/R"][k]), int(z[f"{ci}/C"][k])
             case = dict(R=R, C=C, x0=int(z[f"{ci}/x0"][k]), rows_y=z[f"{ci}/rows_y"][k][:R],
                         rows_attr=z[f"{ci}/rows_attr"][k][:R], occ=z[f"{ci}/occ"][k][:R, :C],
-                        pen=z[f"{ci}/pen"][k][:R, :C], peaks=z[f"{ci}/peaks"][k][:int(z[f"{ci}/npk"][k])])
+                        pen=z[f"{ci}/pen"][k][:R, :C], peaks=z[f"{ci}/peaks"][k][:int(z[f"{ci}/npk"][k])],
+                        start=z[f"{ci}/start"][k], goals=z[f"{ci}/goals"][k][:int(z[f"{ci}/npk"][k])],
+                        nbr=z[f"{ci}/nbr"][k][:R, :C])
             goldenio.assert_result_matches(res, case, f"frame case {ci}/{k}")
             assert np.array_equal(res["masks"].reshape(n, -1).sum(1), z[f"{ci}/areas"][k])
             rd = opl.frame_from_masks(res["masks"], gs, "direct")

@@ -6,6 +6,7 @@ import torch
 
 import polygen
 import refharness
+from oracle import graph as ograph
 from oracle import grid as og
 from oracle import mask_assembly as oma
 from oracle import penalty as open_
@@ -71,6 +72,26 @@ def test_grid_penalty_peaks_match_reference(ref, H, W, gs, n):
             want = [(p.x, p.y) for p in fp.protrusion_detector(fp.frame, fp.grids, fp.grid_lookup)]
             res = opl.state_to_result(st)
             assert want == oprot.peaks_raster(st.grids, H, W, gs) == [tuple(p) for p in res["peaks"].tolist()]
+            # start / goal cells (utils.py:6-32 as called at FrameProcessor.py:236-239) and _create_graph (:184-207)
+            Coordinate = ref.models.Coordinate
+
+            def where(obj):
+                return next(((k, c) for k, rr in enumerate(fp.grids) for c, g in enumerate(rr) if g is obj), (-1, -1))
+
+            sg = ref.utils.get_closest_grid_to_point(Coordinate(x=W // 2, y=H), fp.grids)
+            assert (where(sg) if sg is not None else (-1, -1)) == tuple(res["start"])
+            for (px, py), goal in zip(want, res["goals"].tolist()):
+                eg = ref.utils.get_closest_grid_to_point(Coordinate(x=px, y=py), fp.grids)
+                assert where(eg) == tuple(goal)
+            graph = fp._create_graph()
+            nbr = ograph.neighbour_mask(st)
+            for r, rr in enumerate(fp.grids):
+                for c, g in enumerate(rr):
+                    x, y = g.coords.x, g.coords.y
+                    have = {pos for pos, _ in graph.get((x, y), [])} if not g.empty else set()
+                    bits = sum(1 << b for b, pos in enumerate(((x + gs, y), (x - gs, y), (x, y + gs), (x, y - gs)))
+                               if pos in have)
+                    assert bits == nbr[r, c]
     finally:
         _set_gs(ref, 20)
 
