@@ -85,6 +85,12 @@ typedef struct va_config {
  *   penalty  : double[rmax][cmax]  Grid.penalty, NaN where the cell is empty (None in the reference)
  *   peaks    : int32 [pmax][2]     (x, y) of ProtrusionDetector's returned Coordinates
  *   occ      : uint8 [rmax][cmax]  bit0 = not Grid.empty, bit1 = Grid.artificial
+ *   goals    : int32 [pmax][2]     (list row, column) of the path end cell of every peak: the non-empty list
+ *                                  cell closest to it (utils.py:6-32 as called at FrameProcessor.py:238-239)
+ *   lookup   : int32 [lookup_rows] for y = ly*gs: record row that owns grid_lookup at y, -1 if none.  This is the
+ *                                  A* graph of FrameProcessor._create_graph (:184-207) in implicit form: a non-empty
+ *                                  list cell (x, y) has the edge to (x +- gs, y) iff that column exists, and to
+ *                                  (x, y +- gs) iff lookup[(y +- gs) / gs] >= 0 (also towards empty cells, :203)
  * Rows [0, n_rows) are FrameProcessor.grids in list order (np_grids = occ & 1); rows
  * [n_rows, n_rows + n_orphans) are rows that are only reachable through grid_lookup.
  * Cell (k, c) has Grid.coords = (x0 + c*gs, row_y[k]) and Grid.col = c. */
@@ -100,7 +106,8 @@ typedef struct va_frame_header {
   int32_t n_mask_rows;
   int32_t minx, miny, maxx, maxy; /* pixel bbox of the selected mask */
   int32_t euler;      /* Euler number when VA_CFG_CHECK_SIMPLE, else 0 */
-  int32_t reserved;
+  int32_t start_cell; /* (list row << 16) | column of the path start cell, -1 if none: the non-empty list cell
+                         closest to (W/2, H) - utils.get_closest_grid_to_point as called at FrameProcessor.py:236 */
 } va_frame_header;
 
 typedef struct va_layout {
@@ -109,7 +116,7 @@ typedef struct va_layout {
   int32_t off_header, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ;
   int32_t lat_rows, lat_cols; /* cell-centre lattice sampled from the masks */
   int32_t algorithmic_bytes_per_frame_n1; /* SURVEY 8(d) with n = 1 masks written; informational */
-  int32_t reserved[3];
+  int32_t off_goals, off_lookup, lookup_rows;
 } va_layout;
 
 /* Grid-mode input header for va_grid_to_penalty_peaks (PenaltyCalculator / ProtrusionDetector

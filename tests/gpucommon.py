@@ -26,6 +26,13 @@ def assert_record_equals_oracle(rec, res: dict, what=""):
     assert np.array_equal(rec.peaks, res["peaks"].reshape(-1, 2)), (what, rec.peaks, res["peaks"])
     assert np.array_equal(rec.orphan_y, res["orphan_y"]), what
     assert np.array_equal(rec.orphan_occ, res["orphan_occ"]), what
+    # path start / end cells, grid_lookup row table, implicit _create_graph neighbourhood
+    assert tuple(rec.start) == tuple(int(v) for v in res["start"]), (what, rec.start, res["start"])
+    assert np.array_equal(rec.goals, np.asarray(res["goals"]).reshape(-1, 2)), (what, rec.goals, res["goals"])
+    n = len(res["lookup_row"])
+    assert np.array_equal(rec.lookup_row[:n], res["lookup_row"]) and (rec.lookup_row[n:] == -1).all(), \
+        (what, rec.lookup_row, res["lookup_row"])
+    assert np.array_equal(rec.neighbour_mask(), res["nbr"]), what
 
 
 def to_dev(*ts):

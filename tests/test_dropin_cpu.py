@@ -15,6 +15,7 @@ from oracle import pipeline as opl
 from vision_assist_b200 import config as vconfig
 from vision_assist_b200 import models as vmodels
 from vision_assist_b200.engine import FrameRecord
+from vision_assist_b200.FrameProcessor import FrameProcessor as VFP
 from vision_assist_b200.materialise import objects_to_grid_input, record_to_objects
 
 
@@ -23,7 +24,8 @@ def record_from_oracle(res: dict) -> FrameRecord:
     return FrameRecord(flags=res["flags"], sel=res["sel"], x0=res["x0"], y0=res["y0"], C=res["C"], R=R,
                        n_orphans=len(res["orphan_y"]), area=0, bbox=(0, 0, 0, 0), euler=0,
                        rows_y=res["rows_y"], rows_attr=res["rows_attr"], occ=res["occ"], penalty=res["penalty"],
-                       peaks=res["peaks"], orphan_y=res["orphan_y"], orphan_occ=res["orphan_occ"])
+                       peaks=res["peaks"], orphan_y=res["orphan_y"], orphan_occ=res["orphan_occ"],
+                       start=tuple(res["start"]), goals=res["goals"], lookup_row=res["lookup_row"])
 
 
 def test_record_to_objects_roundtrip():
@@ -106,7 +108,9 @@ def test_reference_host_stages_on_materialised_objects():
             want_cost = [p.total_cost for p in paths_ref]
 
             st = og.extract_grid_from_polygons(polys, H, W, 20)
-            rec = record_from_oracle(opl.state_to_result(st))
+            res_full = opl.state_to_result(st)
+            res_nbr = res_full["nbr"]
+            rec = record_from_oracle(res_full)
             fp2 = refharness.new_frame_processor(ref)
             fp2.frame = fp.frame
             fp2.grids, fp2.grid_lookup, fp2.np_grids = record_to_objects(rec, 20)
@@ -118,7 +122,20 @@ def test_reference_host_stages_on_materialised_objects():
             paths2 = fp2._find_paths(peaks2, graph2)
             assert [[(g.coords.x, g.coords.y) for g in p.grids] for p in paths2] == want
             assert [p.total_cost for p in paths2] == want_cost
+            # the drop-in FrameProcessor._find_paths with the start / end cells taken from the record
+            # instead of utils.get_closest_grid_to_point; A* itself is the reference's
+            VFP._instance, VFP._initialized = None, False
+            vfp = VFP(model=None)
+            vfp.bind_host_stages(path_finder=ref.PathFinder.path_finder, Path=ref.models.Path)
+            vfp.frame, vfp.frame_record = fp.frame, rec
+            vfp.grids, vfp.grid_lookup, vfp.np_grids = fp2.grids, fp2.grid_lookup, fp2.np_grids
+            ref.PathFinder.path_finder.angle_cache.clear()
+            paths3 = vfp._find_paths(peaks2, fp2._create_graph())
+            assert [[(g.coords.x, g.coords.y) for g in p.grids] for p in paths3] == want
+            assert [p.total_cost for p in paths3] == want_cost
+            assert np.array_equal(rec.neighbour_mask(), res_nbr)
             done += 1
         assert done >= 20
     finally:
         vmodels.bind_models(vmodels)
+        VFP._instance, VFP._initialized = None, False

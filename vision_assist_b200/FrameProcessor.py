@@ -176,16 +176,29 @@ class FrameProcessor:
 
     # -- FrameProcessor.py:230-271 (host; needs the reference's path_finder / Path) ---------------
     def _find_paths(self, protrusion_peaks, graph):
-        if self.path_finder is None or self.get_closest_grid_to_point is None or self.Path is None:
-            raise RuntimeError("bind_host_stages(path_finder=..., get_closest_grid_to_point=..., Path=...) first: "
+        if self.path_finder is None or self.Path is None:
+            raise RuntimeError("bind_host_stages(path_finder=..., Path=...) first: "
                                "A* stays host code from the reference (PathFinder.py)")
         Coordinate, _, _ = models.classes()
         all_paths = []
         if not self.grids:
             return all_paths
-        start = self.get_closest_grid_to_point(Coordinate(x=self.frame.shape[1] // 2, y=self.frame.shape[0]), self.grids)
-        for peak in protrusion_peaks:
-            end = self.get_closest_grid_to_point(peak, self.grids)
+        # start / end cells (utils.get_closest_grid_to_point, FrameProcessor.py:236-239): chosen on the GPU with the
+        # record when the peaks are the record's own; otherwise the bound host function
+        rec = self.frame_record
+        device_cells = (rec is not None and rec.goals is not None and rec.start[0] >= 0
+                        and len(rec.goals) == len(protrusion_peaks)
+                        and all((p.x, p.y) == (int(q[0]), int(q[1])) for p, q in zip(protrusion_peaks, rec.peaks)))
+        if device_cells:
+            start = self.grids[rec.start[0]][rec.start[1]]
+            ends = [self.grids[int(k)][int(c)] for k, c in rec.goals]
+        else:
+            if self.get_closest_grid_to_point is None:
+                raise RuntimeError("bind_host_stages(get_closest_grid_to_point=...) is needed for peaks that did not "
+                                   "come from the GPU record")
+            start = self.get_closest_grid_to_point(Coordinate(x=self.frame.shape[1] // 2, y=self.frame.shape[0]), self.grids)
+            ends = [self.get_closest_grid_to_point(peak, self.grids) for peak in protrusion_peaks]
+        for end in ends:
             grid_path, total_cost = self.path_finder.find_path(graph, start, end, self.grid_lookup)
             if grid_path:
                 all_paths.append(self.Path(grids=grid_path, total_cost=total_cost, path_type="path"))

@@ -28,7 +28,8 @@ class VaConfig(C.Structure):
 class VaLayout(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("record_bytes", "rmax", "cmax", "pmax", "off_header", "off_row_y",
                                          "off_row_attr", "off_penalty", "off_peaks", "off_occ", "lat_rows",
-                                         "lat_cols", "algorithmic_bytes_per_frame_n1")] + [("reserved", C.c_int32 * 3)]
+                                         "lat_cols", "algorithmic_bytes_per_frame_n1", "off_goals", "off_lookup",
+                                         "lookup_rows")]
 
 
 class VaGridInput(C.Structure):

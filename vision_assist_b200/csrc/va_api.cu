@@ -90,6 +90,9 @@ static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, s
   d.off_penalty = o; o += 8 * d.rmax * d.cmax;
   d.off_peaks = o; o += 8 * d.pmax;
   d.off_occ = o; o += d.rmax * d.cmax;
+  o = align_up(o, 4);
+  d.off_goals = o; o += 8 * d.pmax;
+  d.off_lookup = o; o += 4 * 2 * d.rmax;
   d.record_bytes = align_up(o, 16);
   d.wr = (float)((double)c.mw / (double)c.W);              // python float ratio cast to fp32 by torch
   d.hr = (float)((double)c.mh / (double)c.H);
@@ -99,6 +102,7 @@ static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, s
   L.record_bytes = d.record_bytes; L.rmax = d.rmax; L.cmax = d.cmax; L.pmax = d.pmax;
   L.off_header = 0; L.off_row_y = d.off_row_y; L.off_row_attr = d.off_row_attr; L.off_penalty = d.off_penalty;
   L.off_peaks = d.off_peaks; L.off_occ = d.off_occ; L.lat_rows = d.lat_rows; L.lat_cols = d.lat_cols;
+  L.off_goals = d.off_goals; L.off_lookup = d.off_lookup; L.lookup_rows = 2 * d.rmax;
   L.algorithmic_bytes_per_frame_n1 = 4 * c.K * c.mh * c.mw + 4 * c.K + 16 + c.H * c.W + d.rmax * d.cmax * 9 + 64;
   return true;
 }

@@ -28,7 +28,7 @@ struct Dims {
   int lat_rows, lat_cols, lat_words;   // cell-centre lattice: point (gs*lx+gs/2, gs*ly+gs/2)
   int plane_rows;                      // ceil(H/gs): rows of the grid_lookup plane
   int rmax, cmax, pmax, cwords;        // record capacity; cwords = ceil(cmax/32)
-  int record_bytes, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ;
+  int record_bytes, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ, off_goals, off_lookup;
   int band_start;                      // FrameProcessor.py:126-127 starting_y
   int flags;                           // VA_CFG_*
   float wr, hr;                        // fl32(mw/W), fl32(mh/H): box scale, ops.py:725-732

@@ -37,11 +37,11 @@ struct TailSmem {
   int* ecol_first;   // [cmax]   easy_cols[c]: first / last LIST index
   int* ecol_last;    // [cmax]
   int* orphan_ids;   // [rmax]
-  int* oflag;        // [T]      orphan marks
+  int* oflag;        // [T]      orphan marks; later: created id -> record row
   int* sc;           // scalars, see enum
 };
 enum { S_FLAGS, S_SEL, S_X0, S_Y0, S_C, S_R, S_NORPH, S_NPEAKS, S_AREA, S_RM, S_MINX, S_MINY, S_MAXX, S_MAXY,
-       S_EULER, S_NCREATED, S_USE_EASY, S_COUNT };
+       S_EULER, S_NCREATED, S_USE_EASY, S_START, S_COUNT };
 
 __host__ __device__ inline int plane_cap(const Dims& d) { return 2 * d.rmax; }
 
@@ -155,7 +155,7 @@ __device__ void easy_segments(const Dims& d, const TailSmem& s) {
   }
 }
 
-__device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
+__device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* rec, int tid, int nt) {
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
   const int norph = s.sc[S_NORPH];
   const int PL = plane_cap(d);
@@ -163,7 +163,7 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   uint8_t* occ_out = rec + d.off_occ;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const int cells = d.rmax * d.cmax;
-  for (int t = threadIdx.x; t < cells; t += (int)blockDim.x) {
+  for (int t = tid; t < cells; t += nt) {
     const int k = t / d.cmax, c = t - k * d.cmax;
     double p = qnan;
     uint8_t ob = 0;
@@ -206,7 +206,7 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   }
   int* ry = reinterpret_cast<int*>(rec + d.off_row_y);
   int* ra = reinterpret_cast<int*>(rec + d.off_row_attr);
-  for (int k = threadIdx.x; k < d.rmax; k += (int)blockDim.x) {
+  for (int k = tid; k < d.rmax; k += nt) {
     int y = 0, a = 0;
     if (k < R + norph) {
       const int id = (k < R) ? s.list_ids[k] : s.orphan_ids[k - R];
@@ -217,8 +217,9 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
     ra[k] = a;
   }
   // alignment padding: keep every byte of the record deterministic
-  for (int t = d.off_row_attr + 4 * d.rmax + threadIdx.x; t < d.off_penalty; t += (int)blockDim.x) rec[t] = 0;
-  for (int t = d.off_occ + d.rmax * d.cmax + threadIdx.x; t < d.record_bytes; t += (int)blockDim.x) rec[t] = 0;
+  for (int t = d.off_row_attr + 4 * d.rmax + tid; t < d.off_penalty; t += nt) rec[t] = 0;
+  for (int t = d.off_occ + d.rmax * d.cmax + tid; t < d.off_goals; t += nt) rec[t] = 0;
+  for (int t = d.off_lookup + 8 * d.rmax + tid; t < d.record_bytes; t += nt) rec[t] = 0;
 }
 
 // ProtrusionDetector closed form; executed by warp 0: one lane per list row finds the top-most occupied
@@ -279,7 +280,7 @@ __device__ void write_header(const TailSmem& s, uint8_t* rec) {
   h.n_cols = s.sc[S_C]; h.n_rows = s.sc[S_R]; h.n_orphans = s.sc[S_NORPH]; h.n_peaks = s.sc[S_NPEAKS];
   h.area = s.sc[S_AREA]; h.n_mask_rows = s.sc[S_RM];
   h.minx = s.sc[S_MINX]; h.miny = s.sc[S_MINY]; h.maxx = s.sc[S_MAXX]; h.maxy = s.sc[S_MAXY];
-  h.euler = s.sc[S_EULER]; h.reserved = 0;
+  h.euler = s.sc[S_EULER]; h.start_cell = s.sc[S_START];
   *reinterpret_cast<va_frame_header*>(rec) = h;
 }
 
@@ -307,6 +308,59 @@ __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   }
 }
 
+// SURVEY 8(f1), executed by warp 0 right after find_peaks (while the other warps compute penalty cells).
+// Path start / end cells: utils.get_closest_grid_to_point (utils.py:6-32) as _find_paths calls it
+// (FrameProcessor.py:236-239) - the non-empty LIST cell whose centre is closest to the point, first minimum in list
+// order.  The reference compares np.sqrt of exact integers; the squared integer distances order the same way.
+// One 64-bit key per candidate, (distance^2 << 32) | (k * cmax + c), minimised per lane and then over the warp.
+// Also the grid_lookup row table that makes the _create_graph neighbourhood (:184-207) implicit in the record.
+__device__ void start_goals_lookup(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();                                                           // lane 0's peaks / S_NPEAKS are visible
+  const int R = s.sc[S_R], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0], half = gs >> 1;
+  const int npk = s.sc[S_NPEAKS], norph = s.sc[S_NORPH], T = 2 * d.rmax, PL = plane_cap(d);
+  const int* peaks = reinterpret_cast<const int*>(rec + d.off_peaks);     // written by lane 0 in find_peaks
+  int* goals = reinterpret_cast<int*>(rec + d.off_goals);
+  for (int pt = 0; pt <= npk; ++pt) {
+    const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
+    unsigned long long best = ~0ull;
+    for (int t = lane; t < R * cw; t += 32) {
+      const int k = t / cw, w = t - k * cw;
+      const int id = s.list_ids[k];
+      unsigned v = s.occ[(size_t)id * cw + w];
+      const long long dy = py - (s.row_y[id] + half);
+      while (v) {
+        const int c = 32 * w + __ffs(v) - 1;
+        v &= v - 1;
+        const long long dx = px - (x0 + c * gs + half);
+        best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * d.cmax + c));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+      const unsigned cell = (unsigned)best;
+      const int gk = (best == ~0ull) ? -1 : (int)(cell / d.cmax), gc = (best == ~0ull) ? -1 : (int)(cell % d.cmax);
+      if (pt == 0) s.sc[S_START] = (gk < 0) ? -1 : ((gk << 16) | gc);
+      else { goals[2 * (pt - 1)] = gk; goals[2 * (pt - 1) + 1] = gc; }
+    }
+  }
+  for (int q = npk + lane; q < d.pmax; q += 32) { goals[2 * q] = 0; goals[2 * q + 1] = 0; }
+  // created id -> record row (first list position, or R + j for the j-th orphan)
+  for (int t = lane; t < T; t += 32) s.oflag[t] = INT_MAX;
+  __syncwarp();
+  for (int k = lane; k < R; k += 32) atomicMin(&s.oflag[s.list_ids[k]], k);
+  for (int j = lane; j < norph; j += 32) s.oflag[s.orphan_ids[j]] = R + j;
+  __syncwarp();
+  int* lookup = reinterpret_cast<int*>(rec + d.off_lookup);
+  for (int ly = lane; ly < PL; ly += 32) {
+    const int owner = (R > 0) ? s.plane_owner[ly] : -1;
+    const int v = (owner >= 0) ? s.oflag[owner] : -1;
+    lookup[ly] = (v == INT_MAX) ? -1 : v;
+  }
+  __syncwarp();
+}
+
 __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
   // common tail once list / plane / scalars are in shared memory
   __syncthreads();
@@ -318,11 +372,14 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
     easy_segments(d, s);
     __syncthreads();
   }
-  if (threadIdx.x < 32) {          // warp 0: peaks + header, concurrently with the other warps' penalty cells
+  if (threadIdx.x < 32) {
+    // warp 0: peaks, path start / end cells, lookup rows, header - concurrently with the other warps' penalty cells
     find_peaks(d, s, rec);
+    start_goals_lookup(d, s, rec);
     if (threadIdx.x == 0) write_header(s, rec);
+  } else {
+    penalties_and_record(d, s, rec, (int)threadIdx.x - 32, (int)blockDim.x - 32);
   }
-  penalties_and_record(d, s, rec);
 }
 
 // ---------------------------------------------------------------------------------------------

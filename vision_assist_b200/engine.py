@@ -34,6 +34,10 @@ class FrameRecord:
     peaks: np.ndarray       # int32 [n_peaks, 2]
     orphan_y: np.ndarray    # int32 [n_orphans]
     orphan_occ: np.ndarray  # uint8 [n_orphans, C]
+    _gs: int = 20
+    start: tuple = (-1, -1)             # (list row, column) of the path start cell (FrameProcessor.py:236), (-1, -1) if none
+    goals: np.ndarray | None = None     # int32 [n_peaks, 2]: (list row, column) of each peak's end cell (:238-239)
+    lookup_row: np.ndarray | None = None   # int32 [lookup_rows]: record row owning grid_lookup at y = ly * gs, -1 if none
 
     @property
     def np_grids(self) -> np.ndarray:
@@ -43,7 +47,27 @@ class FrameRecord:
     def as_dict(self) -> dict:
         return dict(flags=self.flags, sel=self.sel, x0=self.x0, y0=self.y0, C=self.C, R=self.R,
                     rows_y=self.rows_y, rows_attr=self.rows_attr, occ=self.occ, penalty=self.penalty,
-                    peaks=self.peaks, orphan_y=self.orphan_y, orphan_occ=self.orphan_occ)
+                    peaks=self.peaks, orphan_y=self.orphan_y, orphan_occ=self.orphan_occ, start=self.start,
+                    goals=self.goals, lookup_row=self.lookup_row)
+
+    def neighbour_mask(self) -> np.ndarray:
+        """FrameProcessor._create_graph (FrameProcessor.py:184-207) from the record's implicit form: uint8 [R, C],
+        bit0 right, bit1 left, bit2 down, bit3 up; 0 for empty cells (they are not graph nodes)."""
+        R, C = self.R, self.C
+        out = np.zeros((R, C), np.uint8)
+        if R == 0:
+            return out
+        node = (self.occ & 1).astype(bool)
+        ly = self.rows_y // self._gs
+        n = len(self.lookup_row)
+        down = np.array([(l + 1 < n) and self.lookup_row[l + 1] >= 0 for l in ly])
+        up = np.array([(l - 1 >= 0) and self.lookup_row[l - 1] >= 0 for l in ly])
+        cols = np.arange(C)
+        out |= (node & (cols + 1 < C)[None, :]).astype(np.uint8)
+        out |= (node & (cols - 1 >= 0)[None, :]).astype(np.uint8) << 1
+        out |= (node & down[:, None]).astype(np.uint8) << 2
+        out |= (node & up[:, None]).astype(np.uint8) << 3
+        return out
 
     def raise_reference_errors(self) -> None:
         """Re-raise what the reference raises for this frame."""
@@ -231,13 +255,13 @@ class MaskGridEngine:
         """records: u8 [B, record_bytes] torch (any device) or numpy -> list of FrameRecord."""
         if isinstance(records, torch.Tensor):
             records = records.cpu().numpy()
-        return [decode_record(records[i], self.layout) for i in range(records.shape[0])]
+        return [decode_record(records[i], self.layout, self.gs) for i in range(records.shape[0])]
 
 
-def decode_record(blob: np.ndarray, L) -> FrameRecord:
+def decode_record(blob: np.ndarray, L, gs: int = 20) -> FrameRecord:
     blob = np.ascontiguousarray(blob)
     h = blob[:64].view(np.int32)
-    flags, sel, x0, y0, Cc, R, norph, npk, area, rm, minx, miny, maxx, maxy, euler = (int(v) for v in h[:15])
+    flags, sel, x0, y0, Cc, R, norph, npk, area, rm, minx, miny, maxx, maxy, euler, start = (int(v) for v in h[:16])
     ry = blob[L.off_row_y:L.off_row_y + 4 * L.rmax].view(np.int32)
     ra = blob[L.off_row_attr:L.off_row_attr + 4 * L.rmax].view(np.int32)
     pen = blob[L.off_penalty:L.off_penalty + 8 * L.rmax * L.cmax].view(np.float64).reshape(L.rmax, L.cmax)
@@ -246,4 +270,7 @@ def decode_record(blob: np.ndarray, L) -> FrameRecord:
     return FrameRecord(flags=flags, sel=sel, x0=x0, y0=y0, C=Cc, R=R, n_orphans=norph, area=area,
                        bbox=(minx, miny, maxx, maxy), euler=euler, rows_y=ry[:R].copy(), rows_attr=ra[:R].copy(),
                        occ=occ[:R, :Cc].copy(), penalty=pen[:R, :Cc].copy(), peaks=pk[:npk].copy(),
-                       orphan_y=ry[R:R + norph].copy(), orphan_occ=occ[R:R + norph, :Cc].copy())
+                       orphan_y=ry[R:R + norph].copy(), orphan_occ=occ[R:R + norph, :Cc].copy(), _gs=gs,
+                       start=(start >> 16, start & 0xffff) if start >= 0 else (-1, -1),
+                       goals=blob[L.off_goals:L.off_goals + 8 * L.pmax].view(np.int32).reshape(L.pmax, 2)[:npk].copy(),
+                       lookup_row=blob[L.off_lookup:L.off_lookup + 4 * L.lookup_rows].view(np.int32).copy())
