@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vision_assist_b200.sharding import gather_records, shard_range
+from vision_assist_b200.sharding import RecordGatherer, gather_records, shard_range
 
 
 def test_shard_range_partitions():
@@ -45,6 +45,45 @@ def test_gather_records_world2_ragged():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, 7, 48, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
+
+
+def _pipelined_worker(rank, world, port, n_local, rb, steps, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = RecordGatherer(n_local, rb, "cpu", dst=0, depth=2)
+    ok, views = True, []
+    for step in range(steps):
+        buf = g.next_buffer()
+        buf.copy_(torch.full((n_local, rb), (7 * step + rank) % 256, dtype=torch.uint8))
+        views.append((step, g.gather()))
+        if rank == 0 and step >= 1:          # the previous step's slot is complete once it is waited for
+            pass
+    g.flush()
+    if rank == 0:
+        # the last `depth` steps are still resident in their slots
+        for step, v in views[-2:]:
+            want = np.concatenate([np.full((n_local, rb), (7 * step + r) % 256, np.uint8) for r in range(world)])
+            ok = ok and bool(np.array_equal(v.numpy(), want))
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_record_gatherer_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pipelined_worker, args=(r, 2, port, 5, 32, 6, q)) for r in range(2)]
     for p in procs:
         p.start()
     ok = q.get(timeout=120)
