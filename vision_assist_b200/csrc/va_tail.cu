@@ -38,6 +38,7 @@ struct TailSmem {
   int* ecol_last;    // [cmax]
   int* orphan_ids;   // [rmax]
   int* oflag;        // [T]      orphan marks; later: created id -> record row
+  unsigned long long* best;   // [pmax + 1] closest-cell keys (block-wide search of large grids): 0 = start, 1.. = peaks
   int* sc;           // scalars, see enum
 };
 enum { S_FLAGS, S_SEL, S_X0, S_Y0, S_C, S_R, S_NORPH, S_NPEAKS, S_AREA, S_RM, S_MINX, S_MINY, S_MAXX, S_MAXY,
@@ -55,6 +56,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * max(d.rmax, d.cwords));
   const size_t o_cf = take(sizeof(int) * d.cmax), o_cl = take(sizeof(int) * d.cmax);
   const size_t o_or = take(sizeof(int) * d.rmax), o_of = take(sizeof(int) * T), o_sc = take(sizeof(int) * S_COUNT);
+  const size_t o_best = take(sizeof(unsigned long long) * (d.pmax + 1));
   if (s) {
     s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a);
     s->occ = (unsigned*)(base + o_occ); s->art = (unsigned*)(base + o_art);
@@ -62,6 +64,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
     s->erow_first = (int*)(base + o_ef); s->erow_last = (int*)(base + o_el);
     s->ecol_first = (int*)(base + o_cf); s->ecol_last = (int*)(base + o_cl);
     s->orphan_ids = (int*)(base + o_or); s->oflag = (int*)(base + o_of); s->sc = (int*)(base + o_sc);
+    s->best = (unsigned long long*)(base + o_best);
   }
   return o;
 }
@@ -361,6 +364,61 @@ __device__ void start_goals_lookup(const Dims& d, const TailSmem& s, uint8_t* re
   __syncwarp();
 }
 
+// The same for large grids (small cells / large frames), by the whole block after the penalty phase: one work item
+// per (point, list row, 32-column word), keys minimised with shared-memory atomics.
+__device__ void start_goals_lookup_block(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  const int R = s.sc[S_R], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0], half = gs >> 1;
+  const int npk = s.sc[S_NPEAKS], P = 1 + npk, norph = s.sc[S_NORPH], T = 2 * d.rmax, PL = plane_cap(d);
+  const int* peaks = reinterpret_cast<const int*>(rec + d.off_peaks);     // written by warp 0 before the barrier
+  for (int t = threadIdx.x; t < d.pmax + 1; t += (int)blockDim.x) s.best[t] = ~0ull;
+  for (int t = threadIdx.x; t < T; t += (int)blockDim.x) s.oflag[t] = INT_MAX;
+  __syncthreads();
+  const int per_point = R * cw;
+  for (int t = threadIdx.x; t < P * per_point; t += (int)blockDim.x) {
+    const int pt = t / per_point, rest = t - pt * per_point;
+    const int k = rest / cw, w = rest - k * cw;
+    const int id = s.list_ids[k];
+    unsigned v = s.occ[(size_t)id * cw + w];
+    if (!v) continue;
+    const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
+    const long long dy = py - (s.row_y[id] + half);
+    unsigned long long best = ~0ull;
+    while (v) {
+      const int c = 32 * w + __ffs(v) - 1;
+      v &= v - 1;
+      const long long dx = px - (x0 + c * gs + half);
+      best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * d.cmax + c));
+    }
+    atomicMin(&s.best[pt], best);
+  }
+  for (int k = threadIdx.x; k < R; k += (int)blockDim.x) atomicMin(&s.oflag[s.list_ids[k]], k);
+  for (int j = threadIdx.x; j < norph; j += (int)blockDim.x) s.oflag[s.orphan_ids[j]] = R + j;
+  __syncthreads();
+  int* goals = reinterpret_cast<int*>(rec + d.off_goals);
+  for (int q = threadIdx.x; q < d.pmax; q += (int)blockDim.x) {
+    int gk = 0, gc = 0;
+    if (q < npk) {
+      const unsigned long long b = s.best[q + 1];
+      const unsigned cell = (unsigned)b;
+      gk = (b == ~0ull) ? -1 : (int)(cell / d.cmax);
+      gc = (b == ~0ull) ? -1 : (int)(cell % d.cmax);
+    }
+    goals[2 * q] = gk;
+    goals[2 * q + 1] = gc;
+  }
+  int* lookup = reinterpret_cast<int*>(rec + d.off_lookup);
+  for (int ly = threadIdx.x; ly < PL; ly += (int)blockDim.x) {
+    const int owner = (R > 0) ? s.plane_owner[ly] : -1;
+    const int v = (owner >= 0) ? s.oflag[owner] : -1;
+    lookup[ly] = (v == INT_MAX) ? -1 : v;
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long b = s.best[0];
+    const unsigned cell = (unsigned)b;
+    s.sc[S_START] = (R == 0 || b == ~0ull) ? -1 : (int)(((cell / d.cmax) << 16) | (cell % d.cmax));
+  }
+}
+
 __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
   // common tail once list / plane / scalars are in shared memory
   __syncthreads();
@@ -372,13 +430,23 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
     easy_segments(d, s);
     __syncthreads();
   }
-  if (threadIdx.x < 32) {
-    // warp 0: peaks, path start / end cells, lookup rows, header - concurrently with the other warps' penalty cells
-    find_peaks(d, s, rec);
-    start_goals_lookup(d, s, rec);
-    if (threadIdx.x == 0) write_header(s, rec);
+  if (d.rmax * d.cwords <= 128) {
+    if (threadIdx.x < 32) {
+      // warp 0: peaks, path start / end cells, lookup rows, header - concurrently with the other warps' penalty cells
+      find_peaks(d, s, rec);
+      start_goals_lookup(d, s, rec);
+      if (threadIdx.x == 0) write_header(s, rec);
+    } else {
+      penalties_and_record(d, s, rec, (int)threadIdx.x - 32, (int)blockDim.x - 32);
+    }
   } else {
-    penalties_and_record(d, s, rec, (int)threadIdx.x - 32, (int)blockDim.x - 32);
+    // large grids: the cell search is shared by the whole block
+    if (threadIdx.x < 32) find_peaks(d, s, rec);
+    penalties_and_record(d, s, rec, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    start_goals_lookup_block(d, s, rec);
+    __syncthreads();
+    if (threadIdx.x == 0) write_header(s, rec);
   }
 }
 
