@@ -193,7 +193,7 @@ struct Item {
 // bottom-band-first order: the bands that contain the sidewalk blob cost more, so the light top bands form the
 // tail of the schedule.  Out of line on purpose: called once per item per role, and inlined copies of its
 // divisions would compete with the hot loops for the instruction cache.
-__device__ __noinline__ Item decode_item(const FusedParams& p, int item, int c_lo, int c_hi) {
+__device__ __noinline__ Item decode_item(const FusedParams& p, int item, int c_lo, int c_hi, int n_known) {
   Item it;
   it.valid = item < p.n_items;
   const int fb = item / p.groups;
@@ -203,7 +203,8 @@ __device__ __noinline__ Item decode_item(const FusedParams& p, int item, int c_l
   const int j = p.nbands - 1 - jb;
   it.b = b;
   it.i0 = q * p.gsize;
-  it.n = it.valid ? max(min(min(p.counts[b], p.d.max_n) - it.i0, p.gsize), 0) : 0;
+  // instances of the group present in this frame: read once by the TMA warp, passed on through the item ring
+  it.n = !it.valid ? 0 : (n_known >= 0) ? n_known : max(min(min(p.counts[b], p.d.max_n) - it.i0, p.gsize), 0);
   it.band_pa = j * p.ppb;
   it.band_pb = min(it.band_pa + p.ppb, p.d.mh);
   // live chunks [c_lo, c_hi) of the band (the TMA warp computes them from the boxes; (0, INT_MAX) = whole band)
@@ -274,7 +275,7 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int nbuf, in
   m.latrow = take((uint32_t)H * 2, 16);
   m.bars = take(BAR_COUNT * 8, 8);
   m.tmem_slot = take(16, 16);
-  m.items = take(kItemRing * 16, 16);   // {item index, first live chunk, end of live chunks, -}
+  m.items = take(kItemRing * 16, 16);   // {item index, first live chunk, end of live chunks, instances}
   m.total = o;
   return m;
 }
@@ -412,7 +413,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   auto next_item = [&](int k) -> Item {
     bar_wait(BAR(BAR_ITEM + (k % kItemRing)), (k / kItemRing) & 1);
     const uint32_t e = sbase + sm.items + 16 * (k % kItemRing);
-    return decode_item(p, lds_s32(e), lds_s32(e + 4), lds_s32(e + 8));
+    return decode_item(p, lds_s32(e), lds_s32(e + 4), lds_s32(e + 8), lds_s32(e + 12));
   };
 
   // ---- one-time setup ----
@@ -462,7 +463,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       do {                                                   // instance groups with no instance in this frame are dropped here
         if (lane == 0) item = atomicAdd(p.work_counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
-        it = decode_item(p, item, 0, INT_MAX);
+        it = decode_item(p, item, 0, INT_MAX, -1);
       } while (it.valid && it.n == 0);
       // Hull of the group's boxes in proto rows: chunks of the band that lie above / below every box produce only
       // zeros (crop_mask) - they are neither loaded nor multiplied; the upsample warps zero-fill their rows.
@@ -484,11 +485,11 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         // same test as the upsample warps' per-instance chunk test, against the hull
         while (c_lo < c_hi && (float)min(it.pa + (c_lo + 1) * p.pr, it.pb) < y1) ++c_lo;
         while (c_hi > c_lo && (float)(it.pa + (c_hi - 1) * p.pr) >= y2) --c_hi;
-        it = decode_item(p, item, c_lo, c_hi);
+        it = decode_item(p, item, c_lo, c_hi, it.n);
       }
       if (lane == 0) {
         const uint32_t e = sbase + sm.items + 16 * (k % kItemRing);
-        sts_s32(e, item); sts_s32(e + 4, c_lo); sts_s32(e + 8, c_hi);
+        sts_s32(e, item); sts_s32(e + 4, c_lo); sts_s32(e + 8, c_hi); sts_s32(e + 12, it.n);
         bar_arrive(BAR(BAR_ITEM + (k % kItemRing)));          // release: the entry is visible to the waiting roles
       }
       if (!it.valid) break;
@@ -741,34 +742,43 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         sts_f32(ubox + q4 * 4, v);
       }
       __syncwarp();
-      // Dead parts of the band (above / below the hull of the boxes): the masks are zero there.  Bulk copies from the
-      // zero buffer in pieces of <= zero_bytes; piece q belongs to upsample thread q % (32 * kWarpsUp).
-      const int rows_per = 4 * p.pr + 2;
-      const int YaA = (it.band_pa == 0) ? 0 : 4 * it.band_pa + 2;                 // part A: pairs [band_pa, pa)
-      const int rowsA = (it.pa > it.band_pa) ? min(4 * (it.pa - 1) + 5, d.H - 1) - YaA + 1 : 0;
-      const int YaB = 4 * it.pb + 2;                                               // part B: pairs [pb, band_pb)
-      const int rowsB = (it.band_pb > it.pb) ? min(4 * (it.band_pb - 1) + 5, d.H - 1) - ((it.pb == 0) ? 0 : YaB) + 1 : 0;
-      const int piecesA = ceil_div(rowsA, rows_per), PP = piecesA + ceil_div(rowsB, rows_per);
-      const int D = kWriteMasks ? n * PP : 0;
-      int zprev = 0;
-      auto zero_fill = [&](int upto) {
+      // Live chunk range [ci_lo, ci_hi) of every instance (lane = instance): a chunk whose proto rows r0 .. r0+npairs
+      // all lie outside the instance's box rows was zeroed by crop_mask, and because the test is monotonic in r0
+      // the dead chunks are a prefix and a suffix of the item.  The chunk loop below only visits live (chunk,
+      // instance) pairs; dead ones get one bulk zero-fill of the chunk's dst rows (issued when the chunk comes up, so
+      // that the copies are spread over the item and do not queue up in front of the prototype loads).
+      int ci_lo = 0, ci_hi = 0;
+      if (lane < n) {
+        const float y1 = lds_f32(ubox + 16 * lane + 4), y2 = lds_f32(ubox + 16 * lane + 12);
+        ci_hi = it.nchunks;
+        while (ci_lo < ci_hi && (float)min(it.pa + (ci_lo + 1) * p.pr, it.pb) < y1) ++ci_lo;
+        while (ci_hi > ci_lo && (float)(it.pa + (ci_hi - 1) * p.pr) >= y2) --ci_hi;
+      }
+      if (kWriteMasks) {
+        // Parts of the band the hull of the boxes excluded (no chunk exists for them): zero for every instance.
+        // Pieces of <= zero_bytes, one per lane; the instances go round the upsample warps.
+        const int rows_per = 4 * p.pr + 2;
 #pragma unroll 1
-        for (int q = ut; q < upto; q += 32 * kWarpsUp) {
-          if (q < zprev) continue;
-          const int i = q / PP, rest = q - i * PP;
-          const bool partB = rest >= piecesA;
-          const int pc = partB ? rest - piecesA : rest;
-          const int y0 = partB ? ((it.pb == 0) ? 0 : YaB) : YaA, rows = partB ? rowsB : rowsA;
-          const int y = y0 + pc * rows_per;
-          uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + it.i0 + i) * d.H + y) * (size_t)d.W;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sbase + sm.zeros),
-                       "r"((uint32_t)(min(rows_per, y0 + rows - y) * d.W))
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        for (int part = 0; part < 2; ++part) {
+          const int A = part ? it.pb : it.band_pa, Bp = part ? it.band_pb : it.pa;
+          if (A >= Bp) continue;
+          const int Ya = (A == 0) ? 0 : 4 * A + 2;
+          const int Yb = min(4 * (Bp - 1) + 5, d.H - 1);
+#pragma unroll 1
+          for (int i = 0; i < n; ++i) {
+            if (zw == uw) {
+              uint8_t* base = p.masks + ((size_t)it.b * d.max_n + it.i0 + i) * (size_t)d.H * d.W;
+              for (int y = Ya + lane * rows_per; y <= Yb; y += 32 * rows_per) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t)y * d.W),
+                             "r"(sbase + sm.zeros), "r"((uint32_t)(min(rows_per, Yb + 1 - y) * d.W))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+            zw = (zw + 1 == kWarpsUp) ? 0 : zw + 1;
+          }
         }
-        zprev = upto;
-      };
-      if (D) zero_fill(D);            // all at once: measured faster than releasing a share per live chunk
+      }
       for (int c = 0; c < it.nchunks; ++c, ++gc) {
         const int buf = gc % kNBuf;
         TIMED_WAIT(tm, 0, BAR(BAR_CH_FULL + buf), (gc / kNBuf) & 1);
@@ -780,30 +790,35 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int nrows_out = last ? 2 : 4;
         const int jbeg = (r == 0) ? -2 : 0;                     // pair 0 also owns dst rows 0,1
         const int laty = (pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
-        // Warp tasks: (instance, block of 8*subs column groups).  Instances whose box rows miss the chunk are settled
-        // per instance (one bulk zero-fill, issued by the upsample warps in turn); the tasks of the remaining
-        // ("live") instances are numbered consecutively and dealt round-robin: task wq = live_ordinal * ng8w + g8w
-        // belongs to warp wq % kWarpsUp.  The numbering runs on across chunks and items, so the warps that get one task
-        // more than the others rotate.
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) {
-          const float4 q = lds_v4(ubox + 16 * i);     // x1, y1, x2, y2 at proto resolution
-          // Every proto row this chunk reads (r0 .. r0+npairs) lies outside the instance's box: crop_mask zeroed
-          // them, so the chunk's dst rows of this instance are one contiguous block of zeros.  One bulk
-          // shared->global copy from the zero buffer replaces the whole column sweep.
-          if (((float)(r0 + npairs) < q.y) || ((float)r0 >= q.w)) {
-            if (kWriteMasks && zw == uw && lane == 0) {
-              const int Ya = (r0 == 0) ? 0 : 4 * r0 + 2;
-              const int Yb = min(4 * (r0 + npairs - 1) + 5, d.H - 1);
+        // Warp tasks: (live instance, block of 8*subs column groups), numbered consecutively and dealt round-robin:
+        // task wq = live_ordinal * ng8w + g8w belongs to warp wq % kWarpsUp.  The numbering runs on across chunks
+        // and items, so the warps that get one task more than the others rotate.
+        unsigned live = __ballot_sync(0xffffffffu, lane < n && ci_lo <= c && c < ci_hi);
+        if (kWriteMasks) {
+          // dead instances of this chunk: instance i is zero-filled by warp (i + c) % kWarpsUp (bits i, i+7, ...)
+          int kq = (uw - c) % kWarpsUp;
+          if (kq < 0) kq += kWarpsUp;
+          unsigned dead = ~live & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u)) & (0x10204081u << kq);
+          if (lane == 0) {
+            const int Ya = (r0 == 0) ? 0 : 4 * r0 + 2;
+            const int Yb = min(4 * (r0 + npairs - 1) + 5, d.H - 1);
+            while (dead) {
+              const int i = __ffs(dead) - 1;
+              dead &= dead - 1;
               uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + it.i0 + i) * d.H + Ya) * (size_t)d.W;
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sbase + sm.zeros),
                            "r"((uint32_t)((Yb - Ya + 1) * d.W))
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            zw = (zw + 1 == kWarpsUp) ? 0 : zw + 1;
-            continue;
           }
+          __syncwarp();
+        }
+#pragma unroll 1
+        while (live) {
+          const int i = __ffs(live) - 1;
+          live &= live - 1;
+          const float4 q = lds_v4(ubox + 16 * i);     // x1, y1, x2, y2 at proto resolution
           int g8w = uw - base;
           if (g8w < 0) g8w += kWarpsUp;
           base += ng8w_mod;

@@ -166,8 +166,11 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   uint8_t* occ_out = rec + d.off_occ;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const int cells = d.rmax * d.cmax;
-  for (int t = tid; t < cells; t += nt) {
-    const int k = t / d.cmax, c = t - k * d.cmax;
+  for (int u = tid; u < cells; u += nt) {
+    // cell (k, c) with the columns rotated by the row: a thread stride that is a multiple of cmax (224 = 7 * 32,
+    // 480 = 5 * 96) would otherwise pin every thread to one column, and the cost of a cell depends on its column
+    const int k = u / d.cmax, c = (u - k * d.cmax + k) % d.cmax;
+    const int t = k * d.cmax + c;
     double p = qnan;
     uint8_t ob = 0;
     if (k < R + norph && c < C) {
@@ -373,23 +376,24 @@ __device__ void start_goals_lookup_block(const Dims& d, const TailSmem& s, uint8
   for (int t = threadIdx.x; t < d.pmax + 1; t += (int)blockDim.x) s.best[t] = ~0ull;
   for (int t = threadIdx.x; t < T; t += (int)blockDim.x) s.oflag[t] = INT_MAX;
   __syncthreads();
-  const int per_point = R * cw;
-  for (int t = threadIdx.x; t < P * per_point; t += (int)blockDim.x) {
-    const int pt = t / per_point, rest = t - pt * per_point;
-    const int k = rest / cw, w = rest - k * cw;
-    const int id = s.list_ids[k];
-    unsigned v = s.occ[(size_t)id * cw + w];
-    if (!v) continue;
+  for (int pt = 0; pt < P; ++pt) {           // per point: per-thread minimum, warp minimum, one shared atomic per warp
     const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
-    const long long dy = py - (s.row_y[id] + half);
     unsigned long long best = ~0ull;
-    while (v) {
-      const int c = 32 * w + __ffs(v) - 1;
-      v &= v - 1;
-      const long long dx = px - (x0 + c * gs + half);
-      best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * d.cmax + c));
+    for (int t = threadIdx.x; t < R * cw; t += (int)blockDim.x) {
+      const int k = t / cw, w = t - k * cw;
+      const int id = s.list_ids[k];
+      unsigned v = s.occ[(size_t)id * cw + w];
+      const long long dy = py - (s.row_y[id] + half);
+      while (v) {
+        const int c = 32 * w + __ffs(v) - 1;
+        v &= v - 1;
+        const long long dx = px - (x0 + c * gs + half);
+        best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * d.cmax + c));
+      }
     }
-    atomicMin(&s.best[pt], best);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&s.best[pt], best);
   }
   for (int k = threadIdx.x; k < R; k += (int)blockDim.x) atomicMin(&s.oflag[s.list_ids[k]], k);
   for (int j = threadIdx.x; j < norph; j += (int)blockDim.x) s.oflag[s.orphan_ids[j]] = R + j;
@@ -442,7 +446,7 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
   } else {
     // large grids: the cell search is shared by the whole block
     if (threadIdx.x < 32) find_peaks(d, s, rec);
-    penalties_and_record(d, s, rec, (int)threadIdx.x, (int)blockDim.x);
+    penalties_and_record(d, s, rec, (int)threadIdx.x, (int)blockDim.x);   // measured: better than leaving warp 0 out
     __syncthreads();
     start_goals_lookup_block(d, s, rec);
     __syncthreads();
