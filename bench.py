@@ -299,7 +299,7 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
-def measure_latency(wl, device, iters: int = 300):
+def measure_latency(wl, device, iters: int = 1000):
     """p50 / p99 single-frame latency (B = 1): launch -> record visible on the host (pinned D2H included),
     grid-only mode (the reference's FrameProcessor consumes only the grid), with and without a CUDA graph."""
     import torch

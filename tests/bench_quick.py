@@ -12,11 +12,11 @@ masks = torch.empty((B, n, 640, 640), dtype=torch.uint8, device="cuda")
 rec = torch.empty((B, eng.record_bytes), dtype=torch.uint8, device="cuda")
 for _ in range(5): eng.run(protos, coefs, boxes, counts, masks_out=masks, records_out=rec)
 torch.cuda.synchronize()
-eng.profile(True)
+if os.environ.get('VA_PROFILE', '1') == '1': eng.profile(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 K = 100
 for _ in range(K): eng.run(protos, coefs, boxes, counts, masks_out=masks, records_out=rec)
 e1.record(); torch.cuda.synchronize()
-a, t, c = eng.profile_read()
+a, t, c = eng.profile_read() if os.environ.get('VA_PROFILE', '1') == '1' else (0.0, 0.0, 1)
 print(f"{os.environ.get('TAG','')}: step {e0.elapsed_time(e1)/K:.4f} ms  fused {a/c:.4f} ms  tail {t/c:.4f} ms  -> {B*K/e0.elapsed_time(e1)*1000:.0f} fps")

@@ -449,6 +449,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds_u32(sbase + sm.tmem_slot);
+  // Programmatic dependent launch: the tail kernel (launched with programmatic stream serialization) may become
+  // resident on SMs whose CTA of this kernel has already exited; it waits in griddepcontrol.wait for the whole grid.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // =========================== work stealing + TMA producer ===========================
@@ -687,7 +690,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             // outside the instance's box rows (r+1 < y1 or r >= y2) never reads its chunk rows.  So when every row of
             // this tile is at least 2 above or 1 below the box (or the instance does not exist), nothing will read
             // what would be stored here: skip the instance (warp-uniform).
-            if (!kDiag && (tile_rb + 2 <= rl[i] || tile_ra - 1 >= rl[i] + (int)rwid[i])) continue;
+            if (!(kDiag && p.logits_dbg) && (tile_rb + 2 <= rl[i] || tile_ra - 1 >= rl[i] + (int)rwid[i])) continue;
             const bool keep = ((unsigned)(bcol - cl[i]) < cwid[i]) && ((unsigned)(grow - rl[i]) < rwid[i]);
             const float v = keep ? __uint_as_float(r[i]) : 0.f;
             if (has1) sts_f32(dst1 + i * inst_stride, v);
@@ -1087,6 +1090,8 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int nb = 1;
   while (nb < max_bands && nb < 8 && (long)B * nb * pl->groups < 8L * pl->num_sms) ++nb;
+  // tiny batches (single-frame latency): more, shorter bands until every SM has an item
+  while (nb < max_bands && (long)B * nb * pl->groups < (long)pl->num_sms) ++nb;
   if (const char* e = getenv("VA_FUSED_NBANDS")) { const int v = atoi(e); if (v >= 1 && v <= max_bands) nb = v; }   // tuning aid
   p.ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
   p.nbands = ceil_div(d.mh, p.ppb);

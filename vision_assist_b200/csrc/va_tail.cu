@@ -17,6 +17,8 @@
 #include <climits>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "va_common.cuh"
 
 namespace va {
@@ -499,6 +501,10 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   __shared__ int s_bbox[kMaxInst][4];
   for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
   for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
+  // Programmatic dependent launch: this kernel may become resident while the mask kernel is still draining (its
+  // CTAs finish at different times); everything above touched only shared memory and kernel inputs.  Wait here for
+  // the mask kernel's writes (statistics, lattice bits, masks).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
     const int i = threadIdx.x;
     InstStats v;
@@ -727,8 +733,19 @@ cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stat
     cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  tail_kernel<<<B, tail_threads(d), smem, st>>>(d, counts, stats, lattice, masks, rects, sel, records);
-  return cudaGetLastError();
+  // launched with programmatic stream serialization: see griddepcontrol.wait in the kernel
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B);
+  cfg.blockDim = dim3(tail_threads(d));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const bool no_pdl = getenv("VA_NO_PDL") != nullptr;   // tuning aid: plain stream-ordered launch
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, tail_kernel, d, counts, stats, lattice, masks, rects, sel, records);
 }
 
 cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,
