@@ -41,8 +41,9 @@ def to_dev(*ts):
 
 def band_mismatch_report(gpu_masks: np.ndarray, up_logits: np.ndarray, band: float = 1e-4):
     """Binary-mask parity rule of the north star: masks must be bit-exact except pixels whose
-    reference upsampled logit is within `band` of the threshold.  Returns (n_diff, n_diff_outside_band)."""
+    reference upsampled logit is within `band` of the threshold (and not exactly 0).  Returns (n_diff, n_diff_outside_band)."""
     ref = (up_logits > 0).astype(np.uint8)
     diff = gpu_masks != ref
-    outside = diff & (np.abs(up_logits) >= band)
+    # a reference logit of exactly 0 is a pixel crop_mask (or an all-zero blend) produced: no tolerance there
+    outside = diff & ((np.abs(up_logits) >= band) | (up_logits == 0))
     return int(diff.sum()), int(outside.sum())

@@ -213,6 +213,68 @@ def test_instance_groups_ragged_counts_and_dead_bands(tc):
 
 
 @pytest.mark.parametrize("tc", PATHS)
+@pytest.mark.parametrize("max_n,seed", [(8, 1), (16, 2), (32, 3)])
+def test_box_fuzz_masks_and_records(tc, max_n, seed):
+    """Adversarial boxes against every exactness shortcut of the mask kernels (hull of the group's boxes, live chunk
+    ranges, epilogue skips, zero fills): edges on / next to integer proto coordinates, sub-pixel and inverted boxes,
+    boxes outside the frame, +-inf and NaN coordinates, ragged counts.  Masks must equal the oracle's process_mask
+    except inside the 1e-4 logit band; records must be bit-exact for the masks produced."""
+    H = W = 640
+    B = 24
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=max_n, gs=20, max_batch=B)
+    g = torch.Generator().manual_seed(1000 + seed)
+    protos, coefs, boxes, counts = synth.make_batch(9000 + 100 * seed, B, max_n, H, W, 160, 160, family="noise", max_n=max_n)
+    protos[B // 2:] = synth.make_batch(9500 + 100 * seed, B - B // 2, max_n, H, W, 160, 160, family="sidewalk", max_n=max_n)[0]
+    counts[:] = torch.randint(0, max_n + 1, (B,), generator=g, dtype=torch.int32)
+    counts[0], counts[1] = max_n, 1
+    for b in range(B):
+        for i in range(max_n):
+            kind = int(torch.randint(0, 10, (1,), generator=g))
+            r = torch.rand(4, generator=g)
+            if kind == 0:      # edges exactly on proto pixel boundaries (multiples of 4 frame pixels)
+                x1, y1 = 4 * int(r[0] * 100), 4 * int(r[1] * 100)
+                bx = [x1, y1, x1 + 4 * int(1 + r[2] * 60), y1 + 4 * int(1 + r[3] * 60)]
+            elif kind == 1:    # just off the boundaries
+                x1, y1 = 4 * int(r[0] * 100) + 1e-3, 4 * int(r[1] * 100) - 1e-3
+                bx = [x1, y1, x1 + 4 * int(1 + r[2] * 60) - 2e-3, y1 + 4 * int(1 + r[3] * 60) + 2e-3]
+            elif kind == 2:    # thin horizontal strip (one or two proto rows)
+                y1 = float(r[1] * 630)
+                bx = [float(r[0] * 300), y1, float(300 + r[2] * 340), y1 + float(r[3] * 8)]
+            elif kind == 3:    # thin vertical strip
+                x1 = float(r[0] * 630)
+                bx = [x1, float(r[1] * 300), x1 + float(r[2] * 8), float(300 + r[3] * 340)]
+            elif kind == 4:    # inverted / empty
+                bx = [float(r[0] * 640), float(r[1] * 640), float(r[0] * 640 - r[2] * 50), float(r[1] * 640 - r[3] * 50)]
+            elif kind == 5:    # outside the frame
+                bx = [-200 + float(r[0] * 100), 700 + float(r[1] * 100), -50 + float(r[2] * 40), 900 + float(r[3] * 40)]
+            elif kind == 6:    # covers everything, infinite bounds
+                bx = [float("-inf"), -5.0, float("inf"), 1e9]
+            elif kind == 7:    # NaN coordinate: every comparison is false -> the mask is empty
+                bx = [float(r[0] * 300), float("nan"), float(300 + r[2] * 300), float(300 + r[3] * 300)]
+            else:              # ordinary random box
+                x1, y1 = float(r[0] * 500), float(r[1] * 500)
+                bx = [x1, y1, x1 + float(r[2] * 400), y1 + float(r[3] * 400)]
+            boxes[b, i] = torch.tensor(bx)
+    records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+    recs = eng.decode(records)
+    masks = masks.cpu().numpy()
+    n_band = 0
+    for b in range(B):
+        nb = int(counts[b])
+        if nb:
+            up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
+            nd, nout = band_mismatch_report(masks[b, :nb], np.nan_to_num(up, nan=0.0))
+            assert nout == 0, (b, nd, nout)
+            # a reference logit of exactly 0 comes from crop_mask: no tolerance there
+            assert int(masks[b, :nb][up == 0].sum()) == 0, (b, int(masks[b, :nb][up == 0].sum()))
+            n_band += nd
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "direct"), f"fuzz frame {b}")
+    r_nomask, _ = eng.run(*to_dev(protos, coefs, boxes, counts), write_masks=False)
+    assert torch.equal(r_nomask, records)
+    print(f"[parity] box fuzz max_n={max_n}: {n_band} mask pixels inside the 1e-4 band")
+
+
+@pytest.mark.parametrize("tc", PATHS)
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
     eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)

@@ -372,6 +372,16 @@ __device__ __forceinline__ void tmem_ld_nowait<16>(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+// A box with a NaN coordinate keeps no pixel in the reference (every comparison of crop_mask, ops.py:688-704, is
+// false).  All roles replace it by the empty box (+inf, +inf, -inf, -inf), for which every "outside" test of this
+// kernel is true.  `v` is coordinate c (0: x1, 1: y1, 2: x2, 3: y2) of an instance whose four coordinates are held by
+// four consecutive, 4-aligned lanes; all 32 lanes must call.
+__device__ __forceinline__ float sanitize_box_coord(float v, int c) {
+  const unsigned nan_lanes = __ballot_sync(0xffffffffu, v != v);
+  const bool any = (nan_lanes >> ((threadIdx.x & 31) & ~3)) & 0xfu;
+  return any ? ((c < 2) ? INFINITY : -INFINITY) : v;
+}
+
 __device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,10 +485,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         float y1 = INFINITY, y2 = -INFINITY;
         if (lane < it.n) {
           const float* bx = p.boxes + ((size_t)it.b * d.max_n + it.i0 + lane) * 4;
-          y1 = __fmul_rn(__ldg(bx + 1), d.hr);
-          y2 = __fmul_rn(__ldg(bx + 3), d.hr);
-          if (!(y1 == y1)) y1 = -INFINITY;                    // NaN never passes the "outside" tests: keep everything
-          if (!(y2 == y2)) y2 = INFINITY;
+          const float4 q = __ldg(reinterpret_cast<const float4*>(bx));
+          y1 = __fmul_rn(q.y, d.hr);
+          y2 = __fmul_rn(q.w, d.hr);
+          if (q.x != q.x || q.y != q.y || q.z != q.z || q.w != q.w) { y1 = INFINITY; y2 = -INFINITY; }   // NaN box = empty box
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -618,7 +628,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int i = ep_tid >> 2, c = ep_tid & 3;
         float v = 0.f;
         if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + it.i0 + i) * 4 + c), (c & 1) ? d.hr : d.wr);
-        sts_f32(bx + (i * 4 + c) * 4, v);
+        sts_f32(bx + (i * 4 + c) * 4, sanitize_box_coord(v, c));
       }
       named_bar_sync(1, 32 * kWarpsEpi);
       // crop_mask (ops.py:688-704) keeps proto pixel (col,row) iff col >= x1 && col < x2 && row >= y1 && row < y2 with
@@ -742,7 +752,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int i = q4 >> 2, c = q4 & 3;
         float v = 0.f;
         if (i < n) v = __fmul_rn(__ldg(p.boxes + ((size_t)it.b * d.max_n + it.i0 + i) * 4 + c), (c & 1) ? d.hr : d.wr);
-        sts_f32(ubox + q4 * 4, v);
+        sts_f32(ubox + q4 * 4, sanitize_box_coord(v, c));
       }
       __syncwarp();
       // Live chunk range [ci_lo, ci_hi) of every instance (lane = instance): a chunk whose proto rows r0 .. r0+npairs
