@@ -26,7 +26,7 @@ def make_engine(tc, **kw):
     e = MaskGridEngine(tensor_core=tc, **kw)
     if tc and not e.uses_tensor_core:
         why = e.lib.va_last_error(e._ctx).decode()
-        # documented limits of the tcgen05 kernel: exact-4x geometry, max_n <= 16;
+        # documented limit of the tcgen05 kernel: exact-4x geometry (H = 4*mh, W = 4*mw);
         # those configurations run on the CUDA-core contraction and are covered by the other id
         if "needs H=4*mh" in why or "max_n <=" in why:
             pytest.skip(why)
@@ -272,6 +272,33 @@ def test_box_fuzz_masks_and_records(tc, max_n, seed):
     r_nomask, _ = eng.run(*to_dev(protos, coefs, boxes, counts), write_masks=False)
     assert torch.equal(r_nomask, records)
     print(f"[parity] box fuzz max_n={max_n}: {n_band} mask pixels inside the 1e-4 band")
+
+
+def test_band_count_invariance():
+    """The tensor-core kernel cuts a frame into 1 .. 20 bands depending on the batch size (work items per SM);
+    masks and records must not depend on that.  The same 32 frames at B = 1, 3, 32, 96, 640 and 1280 (one band per
+    frame) against the B = 32 result, which test_cfg1_full_batch_256-style parity pins to the oracle."""
+    H = W = 640
+    n = 8
+    protos, coefs, boxes, counts = synth.make_batch(300, 32, n, H, W, 160, 160, max_n=n)
+    counts[5] = 0
+    counts[9] = 3
+    base = None
+    for B in (32, 1, 3, 96, 640, 1280):
+        eng = make_engine(True, H=H, W=W, mh=160, mw=160, max_n=n, gs=20, max_batch=B)
+        reps = (B + 31) // 32
+        dev = [t.repeat(reps, *([1] * (t.dim() - 1)))[:B].contiguous().cuda() for t in (protos, coefs, boxes, counts)]
+        records, masks = eng.run(*dev)
+        if base is None:
+            base = (records.clone(), masks.clone())
+            continue
+        idx = torch.arange(B, device="cuda") % 32
+        assert torch.equal(records, base[0][idx]), B
+        for b0 in range(0, B, 32):                       # masks block-wise to bound memory
+            hi = min(b0 + 32, B)
+            assert torch.equal(masks[b0:hi], base[1][: hi - b0]), (B, b0)
+        del eng, records, masks, dev
+        torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("tc", PATHS)
