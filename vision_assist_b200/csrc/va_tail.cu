@@ -17,14 +17,20 @@
 #include <climits>
 #include <cmath>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "va_common.cuh"
 
 namespace va {
 
-constexpr int kTailThreads = 256;       // default CTA size; large grids (small gs) use up to kTailMaxThreads
+constexpr int kTailThreads = 256;       // smallest CTA size (tuning aid VA_TAIL_THREADS); the launch uses kTailMaxThreads
 constexpr int kTailMaxThreads = 512;
+
+// developer diagnostic (VA_TAIL_TIMING=1): cycle stamps of block 0 at the phase boundaries, printed by the kernel
+constexpr int kTailDebugFlag = 1 << 30;
+__device__ long long g_tail_t[16];
+#define TT(k) do { if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 32))) g_tail_t[(k) % 100] = clock64(); } while (0)
 
 struct TailSmem {
   // "created rows" table: ids [0, 2*rmax)
@@ -433,17 +439,22 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
     __syncthreads();
   } else {
     collect_orphans(d, s);
+    TT(5);
     easy_segments(d, s);
     __syncthreads();
   }
+  TT(6);
   if (d.rmax * d.cwords <= 128) {
     if (threadIdx.x < 32) {
       // warp 0: peaks, path start / end cells, lookup rows, header - concurrently with the other warps' penalty cells
       find_peaks(d, s, rec);
+      TT(7);
       start_goals_lookup(d, s, rec);
+      TT(8);
       if (threadIdx.x == 0) write_header(s, rec);
     } else {
       penalties_and_record(d, s, rec, (int)threadIdx.x - 32, (int)blockDim.x - 32);
+      TT(110);
     }
   } else {
     // large grids: the cell search is shared by the whole block
@@ -496,6 +507,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   const int n = min(counts[b], d.max_n);
   const int gs = d.gs, cw = d.cwords;
   const int T = 2 * d.rmax, PL = plane_cap(d);
+  TT(0);
 
   __shared__ unsigned s_area[kMaxInst];
   __shared__ int s_bbox[kMaxInst][4];
@@ -505,6 +517,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   // CTAs finish at different times); everything above touched only shared memory and kernel inputs.  Wait here for
   // the mask kernel's writes (statistics, lattice bits, masks).
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  TT(1);
   if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
     const int i = threadIdx.x;
     InstStats v;
@@ -550,6 +563,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       else if (C > d.cmax || Rm > d.rmax) flags = VA_FLAG_OVERFLOW | VA_FLAG_EMPTY;
     }
     s.sc[S_FLAGS] = flags;
+    TT(2);
   }
   __syncthreads();
 
@@ -594,6 +608,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       }
     }
     any = __syncthreads_or(any);
+    TT(3);
     if (threadIdx.x == 0) {
       if (!any) {
         s.sc[S_FLAGS] |= VA_FLAG_EMPTY;              // FrameProcessor.py:99-101
@@ -638,17 +653,34 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       if (e != 1) s.sc[S_FLAGS] |= VA_FLAG_NON_SIMPLE;
     }
   }
+  TT(4);
   finish_record(d, s, rec);
+  TT(13);
+  TT(114);
 
   // ---- reset the reduction scratch for the next call ----
   __syncthreads();
+  TT(9);
+  TT(115);
   for (int i = threadIdx.x; i < d.max_n; i += (int)blockDim.x) {
     InstStats z;
     z.area = 0; z.minx = INT_MAX; z.miny = INT_MAX; z.maxx = -1; z.maxy = -1; z.euler4 = 0; z.pad0 = 0; z.pad1 = 0;
     st[i] = z;
   }
+  TT(11);
   unsigned* latb = lattice + (size_t)b * d.max_n * d.lat_rows * d.lat_words;
   for (int t = threadIdx.x; t < d.max_n * d.lat_rows * d.lat_words; t += (int)blockDim.x) latb[t] = 0u;
+  TT(12);
+  if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = g_tail_t[0], te = clock64();
+    printf("[va tail] reset: stats %lld lattice %lld rest %lld | t0 before barrier %lld t32 before %lld t32 after %lld (from t6)\n", g_tail_t[11] - g_tail_t[9], g_tail_t[12] - g_tail_t[11], te - g_tail_t[12],
+           g_tail_t[13] - g_tail_t[6], g_tail_t[14] - g_tail_t[6], g_tail_t[15] - g_tail_t[6]);
+    printf("[va tail] cycles: wait %lld select %lld sample %lld band %lld | orphans %lld easy %lld | warp0: peaks %lld cells %lld"
+           " | warp1 penalties %lld | end barrier %lld total %lld\n",
+           g_tail_t[1] - t0, g_tail_t[2] - g_tail_t[1], g_tail_t[3] - g_tail_t[2], g_tail_t[4] - g_tail_t[3],
+           g_tail_t[5] - g_tail_t[4], g_tail_t[6] - g_tail_t[5], g_tail_t[7] - g_tail_t[6], g_tail_t[8] - g_tail_t[7],
+           g_tail_t[10] - g_tail_t[6], g_tail_t[9] - g_tail_t[6], te - t0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,10 +752,12 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// 512 threads once the record has more than 2048 cells (gs <= 8 at 640^2, 1080p at gs = 20)
+// the penalty cells (fp64 divisions, dependent chains) are the long phase: as many threads as the register file allows
 static int tail_threads(const Dims& d) {
   const int cells = d.rmax * d.cmax;
-  return cells > 2048 ? kTailMaxThreads : kTailThreads;
+  if (const char* e = getenv("VA_TAIL_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512) return v; }   // tuning aid
+  (void)cells;
+  return kTailMaxThreads;   // measured: 512 threads beat 256 also at 640^2 / gs = 20 (31 -> 23 us per 256 frames); 1024 are slower
 }
 
 cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice,
