@@ -78,7 +78,7 @@ struct FusedParams {
   int nst;           // instance stride of the chunk buffers (= gsize)
   int chunk_floats;  // floats per chunk buffer = (pr+1) * nst * mw
   int nbuf;          // chunk buffers in the ring (3 or 4)
-  int* work_counter;            // global work-stealing counter (reset before every launch)
+  int* work_counter;            // [0] global work-stealing counter, [1] finished CTAs (the last one resets both)
   unsigned long long* timing;   // developer diagnostic (VA_FUSED_TIMING=1): [grid][5 roles][8] cycle counters, or nullptr
 };
 
@@ -973,6 +973,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  // The last CTA to finish re-arms the work counter for the next launch (every CTA has drawn its final, invalid
+  // item by now), so no memset node is needed between launches - also under CUDA-graph replay.
+  if (threadIdx.x == 32) {
+    __threadfence();
+    if (atomicAdd(p.work_counter + 1, 1) == (int)gridDim.x - 1) {
+      p.work_counter[0] = 0;
+      p.work_counter[1] = 0;
+    }
+  }
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
@@ -1060,7 +1069,11 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
 #undef VA_ATTR4
 #undef VA_ATTR
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(%zu B): %s", pl->smem_bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
-  if (cudaMalloc(&pl->work_counter, sizeof(int)) != cudaSuccess) { snprintf(err, errlen, "cudaMalloc(work counter) failed"); delete pl; return nullptr; }
+  if (cudaMalloc(&pl->work_counter, 2 * sizeof(int)) != cudaSuccess || cudaMemset(pl->work_counter, 0, 2 * sizeof(int)) != cudaSuccess) {
+    snprintf(err, errlen, "cudaMalloc(work counter) failed");
+    delete pl;
+    return nullptr;
+  }
   const char* tenv = getenv("VA_FUSED_TIMING");
   if (tenv && tenv[0] == '1') cudaMalloc(&pl->timing, (size_t)pl->num_sms * 5 * 8 * sizeof(unsigned long long));
   return pl;
@@ -1100,17 +1113,14 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int nb = 1;
   while (nb < max_bands && nb < 8 && (long)B * nb * pl->groups < 8L * pl->num_sms) ++nb;
-  // tiny batches (single-frame latency): more, shorter bands until every SM has an item
-  while (nb < max_bands && (long)B * nb * pl->groups < (long)pl->num_sms) ++nb;
-  if (const char* e = getenv("VA_FUSED_NBANDS")) { const int v = atoi(e); if (v >= 1 && v <= max_bands) nb = v; }   // tuning aid
+  // tiny batches (single-frame latency): more, shorter bands - down to one chunk of pr row pairs - until every SM has an item
+  const int max_bands_tiny = (d.mh / pl->pr) > 0 ? d.mh / pl->pr : 1;
+  while (nb < max_bands_tiny && (long)B * nb * pl->groups < (long)pl->num_sms) ++nb;
+  if (const char* e = getenv("VA_FUSED_NBANDS")) { const int v = atoi(e); if (v >= 1 && v <= max_bands_tiny) nb = v; }   // tuning aid
   p.ppb = ceil_div(ceil_div(d.mh, nb), pl->pr) * pl->pr;
   p.nbands = ceil_div(d.mh, p.ppb);
   p.n_items = B * p.nbands * p.groups;
   const int grid = p.n_items < pl->num_sms ? p.n_items : pl->num_sms;
-  {
-    cudaError_t e = cudaMemsetAsync(pl->work_counter, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
-  }
   const bool diag = (logits_dbg != nullptr) || (pl->timing != nullptr);   // debug logits / role timing: separate instantiation
 #define VA_LAUNCH(WM, NI, DG, NB) fused_tc_kernel<WM, NI, DG, NB><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p)
 #define VA_LAUNCH_NB(WM, NI, DG) do { if (pl->nbuf == 4) VA_LAUNCH(WM, NI, DG, 4); else VA_LAUNCH(WM, NI, DG, 3); } while (0)
