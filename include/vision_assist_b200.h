@@ -186,9 +186,10 @@ VA_API int va_grid_to_penalty_peaks(va_ctx* ctx, const va_grid_input* hdr, const
  * contraction path the context uses (1 = tcgen05/TMEM, 0 = CUDA-core FFMA). */
 VA_API int va_last_launch_count(const va_ctx* ctx);
 
-/* Optional device timing of va_run_fused: when enabled every call records CUDA events on the
- * caller's stream around the mask-assembly kernel(s) and the tail kernel (at most 512 calls between
- * reads).  va_profile_read synchronises on them, returns the summed milliseconds and resets. */
+/* Optional device timing of va_run_fused: with on = N > 0 every N-th call records CUDA events on the
+ * caller's stream around the mask-assembly kernel(s) and the tail kernel (at most 512 timed calls
+ * between reads; the events cost a few microseconds per timed call).  va_profile_read synchronises on
+ * them, returns the summed milliseconds and the number of timed calls, and resets. */
 VA_API int va_profile_enable(va_ctx* ctx, int32_t on);
 VA_API int va_profile_read(va_ctx* ctx, float* assemble_ms, float* tail_ms, int32_t* calls);
 VA_API int va_uses_tensor_core(const va_ctx* ctx);

@@ -20,7 +20,8 @@ struct va_ctx {
   int last_launches;
   char err[512];
   // optional per-call device timing (va_profile_enable): events on the caller's stream
-  int prof_on, prof_count;
+  int prof_on, prof_count;     // prof_on = sampling stride (0 = off): every prof_on-th call is timed
+  int prof_calls;
   cudaEvent_t prof_ev[kProfMax][3];
   // host-buffer pipeline (va_run_fused_host), created lazily
   bool host_ready;
@@ -204,8 +205,9 @@ extern "C" int va_profile_enable(va_ctx* c, int on) {
     for (int i = 0; i < kProfMax; ++i)
       for (int j = 0; j < 3; ++j) VA_CUDA(c, cudaEventCreate(&c->prof_ev[i][j]));
   }
-  c->prof_on = on ? 1 : 0;
+  c->prof_on = on > 0 ? on : 0;
   c->prof_count = 0;
+  c->prof_calls = 0;
   return VA_OK;
 }
 
@@ -291,7 +293,7 @@ extern "C" int va_run_fused(va_ctx* c, const float* protos, const float* coefs, 
   cudaStream_t st = (cudaStream_t)stream;
   VA_CUDA(c, cudaSetDevice(c->cfg.device));
   c->last_launches = 0;
-  const bool prof = c->prof_on && c->prof_count < kProfMax;
+  const bool prof = c->prof_on && (c->prof_calls++ % c->prof_on) == 0 && c->prof_count < kProfMax;
   cudaEvent_t* ev = prof ? c->prof_ev[c->prof_count] : nullptr;
   if (prof) VA_CUDA(c, cudaEventRecord(ev[0], st));
   rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, nullptr, st);

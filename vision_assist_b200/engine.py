@@ -126,9 +126,10 @@ class MaskGridEngine:
     def last_launch_count(self) -> int:
         return int(self.lib.va_last_launch_count(self._ctx))
 
-    def profile(self, on: bool = True) -> None:
-        """Record CUDA events around the assembly and tail kernels of every run() (C ABI va_profile_enable)."""
-        self._check(self.lib.va_profile_enable(self._ctx, 1 if on else 0))
+    def profile(self, on: bool | int = True) -> None:
+        """Record CUDA events around the assembly and tail kernels of every `on`-th run() (True = every call;
+        C ABI va_profile_enable)."""
+        self._check(self.lib.va_profile_enable(self._ctx, int(on)))
 
     def profile_read(self):
         """-> (assemble_ms_total, tail_ms_total, calls) since the last read; synchronises."""
