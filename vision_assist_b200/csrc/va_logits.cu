@@ -18,6 +18,7 @@ logits_kernel(Dims d, const float* __restrict__ protos, const float* __restrict_
               const float* __restrict__ boxes, const int* __restrict__ counts, float* __restrict__ logits) {
   __shared__ float s_coefT[kProtoK][kMaxInst];   // [k][i]: the n values for one k are contiguous
   __shared__ float s_box[kMaxInst][4];
+  __shared__ unsigned s_live;                    // instances whose box rows intersect the rows of this CTA's pixels
 
   const int b = blockIdx.y;
   const int n = min(counts[b], d.max_n);
@@ -33,7 +34,19 @@ logits_kernel(Dims d, const float* __restrict__ protos, const float* __restrict_
     const float v = boxes[((size_t)b * d.max_n + i) * 4 + c];
     s_box[i][c] = __fmul_rn(v, (c & 1) ? d.hr : d.wr);       // x1,x2 * wr ; y1,y2 * hr
   }
+  if (threadIdx.x == 0) s_live = 0u;
   __syncthreads();
+  if (threadIdx.x < kMaxInst) {
+    // crop_mask keeps row r iff r >= y1 && r < y2: an instance none of whose kept rows is among this CTA's rows
+    // gets zeros without the 32 multiply-adds per pixel (a NaN bound fails both comparisons -> not live: zeros)
+    const int i = threadIdx.x;
+    const int first_px = blockIdx.x * kLogitsThreads * kPxPerThread;
+    const int last_px = min(first_px + kLogitsThreads * kPxPerThread, P) - 1;
+    const float ra = (float)(first_px / d.mw), rb = (float)(last_px / d.mw);
+    if (i < n && rb >= s_box[i][1] && ra < s_box[i][3]) atomicOr(&s_live, 1u << i);
+  }
+  __syncthreads();
+  const unsigned live = s_live;
 
   const int p0 = (blockIdx.x * kLogitsThreads + threadIdx.x) * kPxPerThread;
   if (p0 >= P) return;
@@ -55,6 +68,7 @@ logits_kernel(Dims d, const float* __restrict__ protos, const float* __restrict_
     float a0[8], a1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+    if ((live >> i0) & 0xffu) {                      // block-uniform
 #pragma unroll
     for (int k = 0; k < kProtoK; ++k) {
       const float4 c0 = *reinterpret_cast<const float4*>(&s_coefT[k][i0]);
@@ -65,6 +79,7 @@ logits_kernel(Dims d, const float* __restrict__ protos, const float* __restrict_
         a0[j] = fmaf(cc[j], v[k].x, a0[j]);
         a1[j] = fmaf(cc[j], v[k].y, a1[j]);
       }
+    }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
