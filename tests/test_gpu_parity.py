@@ -302,6 +302,29 @@ def test_band_count_invariance():
         torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("H,W,mh,mw,gs", [(270, 480, 40, 40, 10), (333, 500, 48, 64, 20), (200, 304, 100, 152, 8),
+                                           (96, 128, 96, 128, 8), (80, 96, 160, 192, 4), (1000, 1000, 36, 52, 20),
+                                           (641, 643, 160, 160, 20)])
+def test_generic_geometry_fuzz(H, W, mh, mw, gs):
+    """Generic-scale path (CUDA-core contraction + generic upsample): non-integer, anisotropic, unit and
+    down-sampling scales, widths that are not a multiple of 16 (ragged right edge) or of the cell size."""
+    B, n = 4, 5
+    eng = MaskGridEngine(H=H, W=W, mh=mh, mw=mw, max_n=8, gs=gs, max_batch=B)
+    assert not eng.uses_tensor_core or (H == 4 * mh and W == 4 * mw)
+    for fam, first in (("sidewalk", 1200), ("noise", 1300)):
+        protos, coefs, boxes, counts = synth.make_batch(first, B, n, H, W, mh, mw, family=fam, max_n=8)
+        counts[1] = 2
+        records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
+        recs = eng.decode(records)
+        masks = masks.cpu().numpy()
+        for b in range(B):
+            nb = int(counts[b])
+            up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
+            nd, nout = band_mismatch_report(masks[b, :nb], up)
+            assert nout == 0, (fam, b, nd, nout)
+            assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], gs, "direct"), f"{fam} {H}x{W} frame {b}")
+
+
 @pytest.mark.parametrize("tc", PATHS)
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
