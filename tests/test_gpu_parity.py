@@ -326,6 +326,37 @@ def test_generic_geometry_fuzz(H, W, mh, mw, gs):
 
 
 @pytest.mark.parametrize("tc", PATHS)
+def test_mixed_call_sequence_keeps_scratch_clean(tc):
+    """The context's reduction scratch (areas, bounding boxes, lattice bits) is consumed and reset by whichever call
+    used it: any interleaving of the entry points must leave the next call's result unchanged."""
+    H = W = 640
+    B, n = 12, 8
+    eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=n, gs=20, max_batch=B)
+    protos, coefs, boxes, counts = synth.make_batch(8100, B, n, H, W, 160, 160, max_n=n)
+    counts[2] = 0
+    counts[7] = 5
+    dev = to_dev(protos, coefs, boxes, counts)
+    rec0, masks0 = eng.run(*dev)
+    masks_only = eng.assemble_masks(*dev)
+    live = (torch.arange(n)[None, :] < counts[:, None]).cuda()
+    assert torch.equal(masks_only[live], masks0[live])
+    m = torch.where(live[:, :, None, None], masks0, torch.zeros_like(masks0))
+    rec1 = eng.masks_to_records(m, dev[3])
+    assert torch.equal(rec1, rec0)                      # same masks through the mask-driven entry point
+    rec2, _ = eng.run(*dev, write_masks=False)
+    assert torch.equal(rec2, rec0)
+    half = [t[:5].contiguous() for t in dev]
+    eng.assemble_masks(*half)
+    rec3, masks3 = eng.run(*dev)
+    assert torch.equal(rec3, rec0) and torch.equal(masks3[live], masks0[live])
+    h = [t.cpu().pin_memory() for t in (protos, coefs, boxes, counts)]
+    rec4 = eng.run_host(*h)
+    assert torch.equal(rec4.cuda(), rec0)
+    rec5, _ = eng.run(*dev)
+    assert torch.equal(rec5, rec0)
+
+
+@pytest.mark.parametrize("tc", PATHS)
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
     eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)
