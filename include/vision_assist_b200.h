@@ -182,6 +182,26 @@ VA_API int va_grid_to_penalty_peaks(va_ctx* ctx, const va_grid_input* hdr, const
                              const int32_t* row_attr, const uint8_t* occ, const int32_t* plane_y,
                              const uint8_t* plane_occ, int32_t B, uint8_t* records_out, void* stream);
 
+/* Front of the path: confidence filter + NMS on the raw segmentation-head output.
+ * Replaces ops.non_max_suppression(pred, conf_thres, iou_thres, nc=nc, max_det=max_det) (vendored ultralytics,
+ * testing/old/segmenting_using_tflite/ops.py:214-363, with torchvision.ops.nms) as model.predict(frame, conf=0.5)
+ * runs it (FrameProcessor.py:322): best class only, class-offset boxes unless agnostic, stable descending scores.
+ *   pred [B][4 + nc + K][A] f32: rows cx, cy, w, h, nc class confidences, K mask coefficients; A anchors
+ *   outputs in the layout va_run_fused takes: coefs_out [B][max_n][K], boxes_out [B][max_n][4] (xyxy, input pixels),
+ *   counts_out [B]; conf_out [B][max_n] f32 and cls_out [B][max_n] i32 may be NULL.  Slots >= counts are zero.
+ *   max_det <= max_n survivors are kept (the reference's max_det is 300: choose max_n accordingly).
+ *   counts_out[b] = -(number of candidates) when more than 512 anchors pass conf_thres (capacity of the kernel). */
+typedef struct va_nms_params {
+  float conf_thres;   /* 0.5 in FrameProcessor.py:322 */
+  float iou_thres;    /* ultralytics predict default 0.7 */
+  int32_t nc;         /* number of classes */
+  int32_t max_det;    /* <= max_n */
+  int32_t agnostic;   /* 1 = no class offset */
+  int32_t max_wh;     /* class offset in pixels, ops.py default 7680 */
+} va_nms_params;
+VA_API int va_nms(va_ctx* ctx, const float* pred, int32_t A, const va_nms_params* prm, int32_t B, float* coefs_out,
+                  float* boxes_out, float* conf_out, int32_t* cls_out, int32_t* counts_out, void* stream);
+
 /* Introspection for benchmarks: number of kernels launched by the last call, and which
  * contraction path the context uses (1 = tcgen05/TMEM, 0 = CUDA-core FFMA). */
 VA_API int va_last_launch_count(const va_ctx* ctx);

@@ -17,6 +17,7 @@ Files:
                     (cropped logits + packed binary masks).
   frames.npz        seeded synthetic frames through the whole reference chain
                     process_mask -> masks2segments -> scale_coords -> FrameProcessor -> penalties -> peaks.
+  nms.npz           seeded synthetic raw head outputs through the vendored ops.non_max_suppression.
 """
 from __future__ import annotations
 
@@ -261,6 +262,30 @@ def gen_frames(ref):
     print("frames.npz:", sum(c[-1] for c in FRAME_CASES), "frames")
 
 
+NMS_CASES = [  # (first_idx, B, A, nc, n_objects, ties, conf_thres, iou_thres, max_det)
+    (0, 4, 8400, 1, 6, False, 0.5, 0.7, 300),
+    (10, 3, 8400, 1, 12, True, 0.5, 0.7, 300),
+    (20, 3, 2100, 3, 8, False, 0.5, 0.45, 300),
+    (30, 2, 8400, 2, 10, True, 0.5, 0.6, 8),
+    (40, 2, 300, 1, 0, False, 0.5, 0.7, 300),       # nothing above the threshold
+]
+
+
+def gen_nms(ref):
+    """the vendored ops.non_max_suppression (with torchvision.ops.nms) on synthetic head outputs."""
+    out = {"cases": np.array([[c[0], c[1], c[2], c[3], c[4], int(c[5]), c[8]] for c in NMS_CASES], np.int32),
+           "thres": np.array([[c[6], c[7]] for c in NMS_CASES], np.float32)}
+    total = 0
+    for ci, (first, B, A, nc, nobj, ties, ct, it, md) in enumerate(NMS_CASES):
+        pred = synth.make_head_output(first, B, A=A, nc=nc, n_objects=nobj, ties=ties)
+        res = ref.ops.non_max_suppression(pred.clone(), conf_thres=ct, iou_thres=it, nc=nc, max_det=md)
+        for b, r in enumerate(res):
+            out[f"{ci}/{b}"] = r.numpy().astype(np.float32)
+            total += r.shape[0]
+    np.savez_compressed(os.path.join(HERE, "nms.npz"), **out)
+    print("nms.npz:", len(NMS_CASES), "cases,", total, "kept rows")
+
+
 if __name__ == "__main__":
     ref = refharness.load()
     torch.set_num_threads(1)
@@ -268,6 +293,7 @@ if __name__ == "__main__":
     gen_polygons(ref)
     gen_mask_assembly(ref)
     gen_frames(ref)
+    gen_nms(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

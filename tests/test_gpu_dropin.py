@@ -54,6 +54,44 @@ def test_cfg0_single_frame_head_output_model():
         assert fp(frame) == []
 
 
+def test_raw_head_output_route():
+    """Raw head output -> va_nms -> fused path inside the drop-in FrameProcessor equals the route that starts
+    from the oracle's non_max_suppression rows."""
+    from oracle import nms as onms
+    from vision_assist_b200 import synth
+    FPmod, _, _ = _fresh()
+    H = W = 640
+    pred = synth.make_head_output(77, 1, A=8400, nc=1, n_objects=5)[0]
+    protos = synth.make_frame(5, 8, H, W, 160, 160)[0]
+    rows = onms.nms_image(pred.numpy(), conf_thres=0.5, iou_thres=0.7, nc=1, max_det=32)
+    assert rows.shape[0] >= 2
+
+    class RawModel:
+        def predict(self, frame, conf=0.5, verbose=False):
+            return [FPmod.RawHeadResult(protos.cuda(), pred.cuda(), nc=1, conf=conf)]
+
+    FPmod.FrameProcessor._instance = None
+    FPmod.FrameProcessor._initialized = False
+    fp = FPmod.FrameProcessor(RawModel(), verbose=False, debug=False)
+    frame = np.zeros((H, W, 3), np.uint8)
+    peaks = fp(frame)
+    rec_raw = fp.frame_record
+    import torch
+    model = FPmod.HeadOutputModel(lambda f: (protos.cuda(), torch.from_numpy(rows[:, 6:]).cuda(), torch.from_numpy(rows[:, :4]).cuda()))
+    FPmod.FrameProcessor._instance = None
+    FPmod.FrameProcessor._initialized = False
+    fp2 = FPmod.FrameProcessor(model, verbose=False, debug=False)
+    peaks2 = fp2(frame)
+    rec = fp2.frame_record
+    if rec is None:
+        assert rec_raw is None and peaks == [] and peaks2 == []
+        return
+    assert [(p.x, p.y) for p in peaks] == [(p.x, p.y) for p in peaks2]
+    assert np.array_equal(rec_raw.occ, rec.occ) and np.array_equal(rec_raw.rows_y, rec.rows_y)
+    assert np.array_equal(np.nan_to_num(rec_raw.penalty, nan=-1.0), np.nan_to_num(rec.penalty, nan=-1.0))
+    assert rec_raw.start == rec.start and np.array_equal(rec_raw.goals, rec.goals)
+
+
 def test_polygon_model_route_and_reference_errors():
     FPmod, _, _ = _fresh()
 

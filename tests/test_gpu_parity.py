@@ -10,6 +10,7 @@ import polygen
 from gpucommon import assert_record_equals_oracle, band_mismatch_report, to_dev
 from oracle import grid as og
 from oracle import mask_assembly as oma
+from oracle import nms as onms
 from oracle import penalty as open_
 from oracle import pipeline as opl
 from oracle import protrusion as oprot
@@ -354,6 +355,48 @@ def test_mixed_call_sequence_keeps_scratch_clean(tc):
     assert torch.equal(rec4.cuda(), rec0)
     rec5, _ = eng.run(*dev)
     assert torch.equal(rec5, rec0)
+
+
+def test_nms_golden_and_oracle():
+    """va_nms against the golden rows of the vendored non_max_suppression and against the oracle on
+    further seeds; then head output -> va_nms -> va_run_fused must equal va_run_fused on the oracle's rows."""
+    z = goldenio.load("nms.npz")
+    eng = MaskGridEngine(H=640, W=640, mh=160, mw=160, max_n=32, gs=20, max_batch=8)
+
+    def check(pred, want_rows, ct, it, nc, md):
+        coefs, boxes, conf, cls, counts = eng.nms(pred.cuda(), conf_thres=ct, iou_thres=it, nc=nc, max_det=min(md, 32))
+        for b, want in enumerate(want_rows):
+            k = int(counts[b])
+            assert k == min(want.shape[0], md, 32), (b, k, want.shape)
+            got = np.concatenate([boxes[b, :k].cpu().numpy(), conf[b, :k, None].cpu().numpy(),
+                                  cls[b, :k, None].cpu().numpy().astype(np.float32), coefs[b, :k].cpu().numpy()], 1)
+            assert np.array_equal(got.view(np.uint32), want[:k].view(np.uint32)), b
+            assert float(boxes[b, k:].abs().sum()) == 0.0 and float(coefs[b, k:].abs().sum()) == 0.0
+        return coefs, boxes, counts
+
+    for ci, (first, B, A, nc, nobj, ties, md) in enumerate(z["cases"].tolist()):
+        ct, it = (float(v) for v in z["thres"][ci])
+        pred = synth.make_head_output(first, B, A=A, nc=nc, n_objects=nobj, ties=bool(ties))
+        check(pred, [z[f"{ci}/{b}"] for b in range(B)], ct, it, nc, md)
+    for seed in range(6):                                   # more seeds against the oracle
+        nc = 1 + seed % 3
+        pred = synth.make_head_output(500 + 10 * seed, 4, A=8400, nc=nc, n_objects=4 + 2 * seed, ties=bool(seed % 2))
+        want = onms.nms_batch(pred.numpy(), conf_thres=0.5, iou_thres=0.7, nc=nc, max_det=32)
+        coefs, boxes, counts = check(pred, want, 0.5, 0.7, nc, 32)
+    # the front end feeds the hot path without a host round trip
+    protos = synth.make_batch(40, 4, 8, 640, 640, 160, 160, max_n=32)[0].cuda()
+    rec_a, masks_a = eng.run(protos, coefs, boxes, counts)
+    c2 = torch.zeros_like(coefs); b2 = torch.zeros_like(boxes)
+    for b, rows in enumerate(want):
+        k = rows.shape[0]
+        b2[b, :k] = torch.from_numpy(rows[:, :4]).cuda(); c2[b, :k] = torch.from_numpy(rows[:, 6:]).cuda()
+    rec_b, masks_b = eng.run(protos, c2, b2, torch.tensor([r.shape[0] for r in want], dtype=torch.int32).cuda())
+    assert torch.equal(rec_a, rec_b)
+    # more candidates than the kernel holds: reported, not guessed
+    dense = torch.rand(1, 37, 4000)
+    dense[:, 4] = 0.9
+    cnt = eng.nms(dense.cuda())[4]
+    assert int(cnt[0]) == -4000
 
 
 @pytest.mark.parametrize("tc", PATHS)

@@ -8,6 +8,7 @@ import goldenio
 from oracle import graph as ograph
 from oracle import grid as og
 from oracle import mask_assembly as oma
+from oracle import nms as onms
 from oracle import penalty as open_
 from oracle import pipeline as opl
 from oracle import protrusion as oprot
@@ -130,3 +131,19 @@ def test_euler_number():
     assert opl.euler_number_8(m) == 1      # 2 components, 1 hole
     m[9, 9] = 1                            # diagonal touch joins under 8-connectivity
     assert opl.euler_number_8(m) == 0
+
+
+def test_nms_golden():
+    """the oracle's non_max_suppression against the vendored ultralytics function (+ torchvision nms)."""
+    z = goldenio.load("nms.npz")
+    rows = 0
+    for ci, (first, B, A, nc, nobj, ties, md) in enumerate(z["cases"].tolist()):
+        ct, it = (float(v) for v in z["thres"][ci])
+        pred = synth.make_head_output(first, B, A=A, nc=nc, n_objects=nobj, ties=bool(ties)).numpy()
+        got = onms.nms_batch(pred, conf_thres=ct, iou_thres=it, nc=nc, max_det=md)
+        for b in range(B):
+            want = z[f"{ci}/{b}"]
+            assert got[b].shape == want.shape, (ci, b, got[b].shape, want.shape)
+            assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32)), (ci, b)
+            rows += want.shape[0]
+    assert rows > 100

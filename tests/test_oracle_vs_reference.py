@@ -9,6 +9,7 @@ import refharness
 from oracle import graph as ograph
 from oracle import grid as og
 from oracle import mask_assembly as oma
+from oracle import nms as onms
 from oracle import penalty as open_
 from oracle import pipeline as opl
 from oracle import protrusion as oprot
@@ -121,3 +122,23 @@ def test_process_mask_matches_vendored_ops(ref):
         for s in segs:
             a = ref.ops.scale_coords((ih, iw), s.copy(), (720, 1280))
             assert np.array_equal(a, oma.scale_coords((ih, iw), s, (720, 1280)))
+
+
+def test_nms_matches_vendored_ops(ref):
+    """oracle.nms against ops.non_max_suppression (vendored ultralytics) with torchvision.ops.nms: random head
+    outputs, 1 and 3 classes, score ties, sparse and dense overlaps - bit-exact rows."""
+    for seed in range(24):
+        g = torch.Generator().manual_seed(seed)
+        nc = 1 if seed % 3 else 3
+        A = [300, 2100, 8400][seed % 3]
+        pred = torch.rand(2, 4 + nc + 32, A, generator=g)
+        pred[:, :2] *= 600
+        pred[:, 2:4] = pred[:, 2:4] * (60 if seed % 2 else 300) + 5
+        pred[:, 4:4 + nc] = pred[:, 4:4 + nc] ** (3 if seed % 2 else 1)
+        if seed % 5 == 0:
+            pred[:, 4] = torch.round(pred[:, 4] * 20) / 20
+        want = ref.ops.non_max_suppression(pred.clone(), conf_thres=0.5, iou_thres=0.7, nc=nc, max_det=300)
+        got = onms.nms_batch(pred.numpy(), conf_thres=0.5, iou_thres=0.7, nc=nc, max_det=300)
+        for w, m in zip(want, got):
+            assert tuple(w.shape) == m.shape, seed
+            assert np.array_equal(w.numpy().view(np.uint32), m.view(np.uint32)), seed

@@ -11,6 +11,8 @@ Two model duck types are accepted by `model.predict(frame, conf=0.5, verbose=...
   * head tensors: a result with `.protos [K,mh,mw]`, `.coefs [n,K]`, `.boxes [n,4]` CUDA tensors
     (see `HeadOutputModel`) -> one `va_run_fused` launch sequence does mask assembly, grid,
     penalties and peaks;
+  * raw head output: a result with `.pred [4+nc+K, A]` and `.protos` (see `RawHeadResult`) -> `va_nms` (confidence
+    filter + NMS of ops.non_max_suppression) and the same fused path, still without a host round trip;
   * ultralytics-style `result.masks.xy` polygons (FrameProcessor.py:67-73) -> host cv2.fillPoly of
     the contourArea-largest polygon, then `va_mask_to_records`.
 A* path finding / path analysis stay host code: pass the reference's `path_finder`,
@@ -37,6 +39,16 @@ class HeadOutputResult:
 
     def __init__(self, protos: torch.Tensor, coefs: torch.Tensor, boxes: torch.Tensor):
         self.protos, self.coefs, self.boxes = protos, coefs, boxes
+        self.masks = None
+
+
+class RawHeadResult:
+    """One frame of RAW segmentation-head output: `pred` [4 + nc + K, A] (cx, cy, w, h, class confidences, mask
+    coefficients per anchor) and `protos` [K, mh, mw]; the confidence filter and NMS of
+    ops.non_max_suppression run on the GPU (va_nms) in front of the mask path."""
+
+    def __init__(self, protos: torch.Tensor, pred: torch.Tensor, nc: int = 1, conf: float = 0.5, iou: float = 0.7):
+        self.protos, self.pred, self.nc, self.conf, self.iou = protos, pred, nc, conf, iou
         self.masks = None
 
 
@@ -110,7 +122,20 @@ class FrameProcessor:
         gs = config.grid_size
         for result in results:
             rec = None
-            if getattr(result, "protos", None) is not None:
+            if getattr(result, "pred", None) is not None:
+                # raw head output: confidence filter + NMS (va_nms), then the fused mask -> grid path
+                K, mh, mw = result.protos.shape
+                eng = self._engine_for(H, W, mh, mw, 32)
+                coefs, boxes, _, _, counts = eng.nms(result.pred.contiguous()[None], conf_thres=result.conf,
+                                                     iou_thres=result.iou, nc=result.nc)
+                n = int(counts[0])
+                if n < 0:
+                    raise RuntimeError(f"va_nms: {-n} candidates above the confidence threshold exceed the kernel's capacity")
+                if n == 0:
+                    continue
+                records, _ = eng.run(result.protos.contiguous()[None], coefs, boxes, counts, write_masks=False)
+                rec = eng.decode(records)[0]
+            elif getattr(result, "protos", None) is not None:
                 n = int(result.coefs.shape[0])
                 if n == 0:
                     continue

@@ -17,7 +17,7 @@ VA_CFG_CHECK_SIMPLE, VA_CFG_NO_TENSOR_CORE = 1, 2
 VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG_OVERFLOW = 1, 2, 4, 8, 16
 
 EXPORTS = ["va_abi_version", "va_create", "va_destroy", "va_last_error", "va_get_layout", "va_assemble_masks",
-           "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks",
+           "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks", "va_nms",
            "va_last_launch_count", "va_uses_tensor_core", "va_profile_enable", "va_profile_read"]
 
 
@@ -30,6 +30,11 @@ class VaLayout(C.Structure):
                                          "off_row_attr", "off_penalty", "off_peaks", "off_occ", "lat_rows",
                                          "lat_cols", "algorithmic_bytes_per_frame_n1", "off_goals", "off_lookup",
                                          "lookup_rows")]
+
+
+class VaNmsParams(C.Structure):
+    _fields_ = [("conf_thres", C.c_float), ("iou_thres", C.c_float), ("nc", C.c_int32), ("max_det", C.c_int32),
+                ("agnostic", C.c_int32), ("max_wh", C.c_int32)]
 
 
 class VaGridInput(C.Structure):
@@ -68,6 +73,7 @@ def load() -> C.CDLL:
     lib.va_run_fused_host.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     lib.va_mask_to_records.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.va_grid_to_penalty_peaks.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.va_nms.argtypes = [vp, vp, i32, C.POINTER(VaNmsParams), i32, vp, vp, vp, vp, vp, vp]
     lib.va_last_launch_count.argtypes = [vp]
     lib.va_uses_tensor_core.argtypes = [vp]
     lib.va_profile_enable.argtypes = [vp, i32]

@@ -228,6 +228,24 @@ extern "C" int va_profile_read(va_ctx* c, float* assemble_ms, float* tail_ms, in
   return VA_OK;
 }
 
+extern "C" int va_nms(va_ctx* c, const float* pred, int32_t A, const va_nms_params* prm, int32_t B, float* coefs_out,
+                      float* boxes_out, float* conf_out, int32_t* cls_out, int32_t* counts_out, void* stream) {
+  if (!c) return VA_ERR_INVALID;
+  if (!pred || !prm || !coefs_out || !boxes_out || !counts_out) { set_err(c, "va_nms: null pointer"); return VA_ERR_INVALID; }
+  if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
+  if (A < 1 || prm->nc < 1 || prm->max_det < 1 || prm->max_det > c->cfg.max_n) {
+    set_err(c, "va_nms: need A >= 1, nc >= 1, 1 <= max_det <= max_n (%d)", c->cfg.max_n);
+    return VA_ERR_INVALID;
+  }
+  if (B == 0) return VA_OK;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  const float off = prm->agnostic ? 0.f : (float)prm->max_wh;
+  VA_CUDA(c, launch_nms(pred, A, prm->nc, c->cfg.K, prm->conf_thres, prm->iou_thres, off, prm->max_det, c->cfg.max_n, B,
+                        coefs_out, boxes_out, conf_out, cls_out, counts_out, (cudaStream_t)stream));
+  c->last_launches = 1;
+  return VA_OK;
+}
+
 extern "C" int va_last_launch_count(const va_ctx* c) { return c ? c->last_launches : 0; }
 extern "C" int va_uses_tensor_core(const va_ctx* c) { return (c && c->plan) ? 1 : 0; }
 

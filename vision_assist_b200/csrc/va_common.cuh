@@ -72,6 +72,11 @@ cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int*
                              uint8_t* records, cudaStream_t st);
 size_t tail_smem_bytes(const Dims& d);
 
+// candidate filter + NMS on raw head output (va_nms.cu); counts_out[b] < 0: more than the 512 candidates it holds
+cudaError_t launch_nms(const float* pred, int A, int nc, int nm, float conf_thres, float iou_thres, float class_offset,
+                       int max_det, int max_n, int B, float* coefs_out, float* boxes_out, float* conf_out, int* cls_out,
+                       int* counts_out, cudaStream_t st);
+
 // tcgen05 / TMA fused kernel (va_fused_tc.cu)
 struct FusedPlan;  // opaque, owned by the context
 FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen);

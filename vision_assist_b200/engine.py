@@ -171,6 +171,30 @@ class MaskGridEngine:
                                                C.c_void_p(logits.data_ptr()) if want_logits else None, self._stream()))
         return (masks, logits) if want_logits else masks
 
+    def nms(self, pred: torch.Tensor, conf_thres: float = 0.5, iou_thres: float = 0.7, nc: int = 1,
+            max_det: int | None = None, agnostic: bool = False, max_wh: int = 7680):
+        """ops.non_max_suppression (+ torchvision nms) on the raw head output `pred` [B, 4 + nc + K, A] ->
+        (coefs [B,max_n,K], boxes [B,max_n,4] xyxy, conf [B,max_n], cls [B,max_n] i32, counts [B] i32): the first
+        three in exactly the layout `run()` takes.  Raises if an image has more candidates than the kernel holds."""
+        if not (pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3):
+            raise ValueError("expected a contiguous float32 CUDA tensor [B, 4 + nc + K, A]")
+        B, Cc, A = pred.shape
+        if Cc != 4 + nc + self.K:
+            raise ValueError(f"expected {4 + nc + self.K} rows (4 + nc + K), got {Cc}")
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        dev = pred.device
+        coefs = torch.empty((B, self.max_n, self.K), dtype=torch.float32, device=dev)
+        boxes = torch.empty((B, self.max_n, 4), dtype=torch.float32, device=dev)
+        conf = torch.empty((B, self.max_n), dtype=torch.float32, device=dev)
+        cls = torch.empty((B, self.max_n), dtype=torch.int32, device=dev)
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        prm = _lib.VaNmsParams(conf_thres, iou_thres, nc, self.max_n if max_det is None else max_det, int(agnostic), max_wh)
+        self._check(self.lib.va_nms(self._ctx, C.c_void_p(pred.data_ptr()), A, C.byref(prm), B, C.c_void_p(coefs.data_ptr()),
+                                    C.c_void_p(boxes.data_ptr()), C.c_void_p(conf.data_ptr()), C.c_void_p(cls.data_ptr()),
+                                    C.c_void_p(counts.data_ptr()), self._stream()))
+        return coefs, boxes, conf, cls, counts
+
     def run(self, protos, coefs, boxes, counts, masks_out: torch.Tensor | None = None,
             records_out: torch.Tensor | None = None, write_masks: bool = True):
         """Whole path; returns (records u8 [B, record_bytes], masks or None), all on the device."""

@@ -109,3 +109,34 @@ def make_batch(first_idx: int, B: int, n: int, H: int, W: int, mh: int, mw: int,
         coefs[b, :n] = c
         boxes[b, :n] = bx
     return protos, coefs, boxes, counts
+
+
+def make_head_output(first_idx: int, B: int, A: int = 8400, nc: int = 1, K: int = 32, H: int = 640, W: int = 640,
+                     n_objects: int = 6, ties: bool = False):
+    """Synthetic raw segmentation-head output [B, 4 + nc + K, A] (cx, cy, w, h, class confidences, mask
+    coefficients): a few objects, each answered by a cluster of overlapping anchors with high confidence (what
+    NMS has to thin out), over a background of low-confidence anchors.  Seeded per image like make_frame."""
+    out = torch.empty(B, 4 + nc + K, A)
+    for b in range(B):
+        g = torch.Generator().manual_seed(0xB3000000 + first_idx + b)
+        p = torch.rand(4 + nc + K, A, generator=g)
+        p[0] *= W; p[1] *= H
+        p[2] = 8 + p[2] * 60; p[3] = 8 + p[3] * 60
+        p[4:4 + nc] *= 0.45                                   # background below conf = 0.5
+        p[4 + nc:] = (p[4 + nc:] - 0.5) * 2
+        for o in range(n_objects):
+            cx, cy = float(torch.rand(1, generator=g)) * W, float(torch.rand(1, generator=g)) * H
+            bw, bh = 40 + float(torch.rand(1, generator=g)) * 300, 40 + float(torch.rand(1, generator=g)) * 300
+            cls = int(torch.randint(0, nc, (1,), generator=g))
+            m = int(torch.randint(3, 40, (1,), generator=g))
+            idx = torch.randint(0, A, (m,), generator=g)
+            jit = torch.randn(4, m, generator=g)
+            p[0, idx] = cx + jit[0] * 6; p[1, idx] = cy + jit[1] * 6
+            p[2, idx] = bw * (1 + 0.08 * jit[2]); p[3, idx] = bh * (1 + 0.08 * jit[3])
+            conf = 0.5 + 0.5 * torch.rand(m, generator=g)
+            if ties:
+                conf = torch.round(conf * 16) / 16
+            p[4:4 + nc, idx] = 0.1
+            p[4 + cls, idx] = conf
+        out[b] = p
+    return out
