@@ -96,54 +96,62 @@ class ClockSampler:
 # CPU baseline: the oracle port of the reference path on the host cores
 # ---------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    first, count, wl = args
+    """One worker = one host core: synthesise `count` frames (untimed), run the reference route on them, return
+    the seconds spent in the route."""
+    first, count, wl, warm = args
     import torch
     torch.set_num_threads(1)
     from oracle import pipeline as opl
     from vision_assist_b200 import synth
     frames = [synth.make_frame(first + i, wl["n"], wl["H"], wl["W"], wl["mh"], wl["mw"]) for i in range(count)]
-    opl.frame_from_tensors(*frames[0], (wl["H"], wl["W"]), wl["gs"], "contour")     # warm-up
+    if warm:
+        opl.frame_from_tensors(*frames[0], (wl["H"], wl["W"]), wl["gs"], "contour")
     t0 = time.perf_counter()
     for p, c, b in frames:
         opl.frame_from_tensors(p, c, b, (wl["H"], wl["W"]), wl["gs"], "contour")
     return time.perf_counter() - t0
 
 
-def cpu_baseline(wl: dict, frames_per_core: int, cores: int | None = None) -> dict:
-    """process_mask -> masks2segments -> scale_coords -> grid -> penalties -> peaks (reference route)
-    on `cores` processes, one torch thread each, disjoint frame shards; wall clock over the pool."""
+def cpu_baseline(wl: dict, frames_per_core: int, cores: int | None = None, steps: int = 1, warmup: int = 0) -> dict:
+    """process_mask -> masks2segments -> scale_coords -> grid -> penalties -> peaks (reference route) on `cores`
+    processes, one torch thread each, disjoint frame shards.  A step = `frames_per_core` frames on every core, timed
+    as the slowest worker's time in the route (inputs are synthesised before the clock starts, as on the GPU side);
+    value = frames of the `steps` timed steps / the sum of their times."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(10_000 + 7 * r, 1, wl) for r in range(cores)])       # spawn + import warm-up
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(20_000 + r * frames_per_core, frames_per_core, wl) for r in range(cores)])
-        wall = time.perf_counter() - t0
-    total = frames_per_core * cores
-    return {"value": total / wall, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{total} frames of the workload ({frames_per_core} per core), oracle port of the reference "
-                      f"route (process_mask, findContours, fillPoly grid, penalties, peaks), wall {wall:.2f} s"}
+        pool.map(_cpu_worker, [(10_000 + 7 * r, 1, wl, True) for r in range(cores)])       # spawn + import warm-up
+        for w in range(warmup):
+            pool.map(_cpu_worker, [(15_000 + (w * cores + r) * frames_per_core, frames_per_core, wl, False) for r in range(cores)])
+        secs = 0.0
+        for k in range(steps):
+            secs += max(pool.map(_cpu_worker, [(20_000 + (k * cores + r) * frames_per_core, frames_per_core, wl, False)
+                                               for r in range(cores)]))
+    total = frames_per_core * cores * steps
+    return {"value": total / secs, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of {frames_per_core * cores} frames of the workload ({frames_per_core} per core), oracle "
+                      f"port of the reference route (process_mask, findContours, fillPoly grid, penalties, peaks), {secs:.2f} s"}
 
 
 def run_reference(args, wl):
+    """Reference arm: the reference algorithm's CPU implementation (oracle port) on every host core.  Exactly
+    --steps timed steps after --warmup untimed ones; the per-step sample is sized so that the run stays within
+    about two minutes (at most 48 frames per core per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    fpc = 48
-    for _ in range(max(1, args.warmup) - 1):
-        pass
-    base = None
-    for step in range(max(1, min(args.steps, 3))):
-        base = cpu_baseline(wl, fpc)
-        vals.append(base["value"])
-    v = statistics.median(vals)
-    base["value"] = v
+    cores = os.cpu_count() or 1
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget_s, sec_per_frame = 90.0, 0.025
+    fpc = int(budget_s / ((steps + warmup) * sec_per_frame))
+    fpc = max(1, min(48, fpc))
+    base = cpu_baseline(wl, fpc, cores, steps=steps, warmup=warmup)
+    v = base["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wl["B"] / v,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * fpc * cores / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": wl["desc"]},
+            "data": "synthetic", "config": {"workload": wl["desc"], "frames_per_step": fpc * cores},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
