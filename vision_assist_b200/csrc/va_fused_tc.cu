@@ -645,6 +645,11 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         cl[i] = x1; cwid[i] = (unsigned)max(x2 - x1, 0);
         rl[i] = (i < n) ? y1 : (INT_MAX >> 1); rwid[i] = (i < n) ? (unsigned)max(y2 - y1, 0) : 0u;
       }
+      // lane i also keeps the row range of instance i: one ballot per tile gives the instances worth storing
+      int my_rl = INT_MAX >> 1, my_rend = INT_MAX >> 1;
+#pragma unroll
+      for (int i = 0; i < kNI; ++i)
+        if (lane == i) { my_rl = rl[i]; my_rend = rl[i] + (int)rwid[i]; }
       int brow = ep_px / d.mw, bcol = ep_px - brow * d.mw;   // band-local (row, col) of this thread's pixel
       int done_rows = 0, done_cols = 0;                        // complete rows / extra pixels after the current tile
       int acquired = 0, completed = 0;
@@ -680,6 +685,12 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int row_last = last_tile ? it.nrows - 1 : (done_cols == 0 ? done_rows - 1 : done_rows);
         const int c_hi = min(row_last >> p.pr_shift, it.nchunks - 1);
         const int tile_rb = it.pa + row_last;                  // last proto row this tile touches
+        // A stored row rho is read by the upsample tasks of pairs rho-1 and rho, and a task whose two rows are
+        // outside the instance's box rows (r+1 < y1 or r >= y2) never reads its chunk rows.  So when every row of
+        // this tile is at least 2 above or 1 below the box (or the instance does not exist), nothing will read what
+        // would be stored: such instances are skipped (warp-uniform mask).
+        const unsigned store_mask = (kDiag && p.logits_dbg) ? 0xffffffffu
+                                    : __ballot_sync(0xffffffffu, !(tile_rb + 2 <= my_rl || tile_ra - 1 >= my_rend));
 #pragma unroll 1
         while (acquired <= c_hi) {            // acquire the chunk buffers this tile writes, in order
           const uint32_t gc = chunk_base + acquired;
@@ -696,11 +707,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           const size_t dbg_stride = (size_t)d.mh * d.mw;
 #pragma unroll
           for (int i = 0; i < kNI; ++i) {
-            // A stored row rho is read by the upsample tasks of pairs rho-1 and rho, and a task whose two rows are
-            // outside the instance's box rows (r+1 < y1 or r >= y2) never reads its chunk rows.  So when every row of
-            // this tile is at least 2 above or 1 below the box (or the instance does not exist), nothing will read
-            // what would be stored here: skip the instance (warp-uniform).
-            if (!(kDiag && p.logits_dbg) && (tile_rb + 2 <= rl[i] || tile_ra - 1 >= rl[i] + (int)rwid[i])) continue;
+            if (!((store_mask >> i) & 1u)) continue;
             const bool keep = ((unsigned)(bcol - cl[i]) < cwid[i]) && ((unsigned)(grow - rl[i]) < rwid[i]);
             const float v = keep ? __uint_as_float(r[i]) : 0.f;
             if (has1) sts_f32(dst1 + i * inst_stride, v);
