@@ -302,7 +302,7 @@ def run_ours(args, wl):
         "latency_b1": latency,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=48)
+        line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=96)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
