@@ -1,9 +1,10 @@
-"""Boundary constants of the reference (config.py:1-21)."""
+"""Boundary constants of the reference interface (reference config.py:1-21): the cell size every stage shares and
+the penalty colour look-up used by PenaltyCalculator.get_penalty_colour (nearest key, colours are BGR)."""
 grid_size = 20
 
-# BGR, nearest-key lookup in PenaltyCalculator.get_penalty_colour
-penalty_colour_gradient = {
-    1.0000: (0, 0, 255), 0.9166: (0, 60, 255), 0.8333: (0, 88, 255), 0.7500: (0, 109, 255),
-    0.6666: (0, 128, 255), 0.5833: (8, 145, 255), 0.5000: (0, 163, 249), 0.4166: (0, 183, 232),
-    0.3333: (0, 202, 208), 0.1666: (0, 221, 176), 0.0833: (0, 239, 129), 0.0000: (0, 255, 15),
-}
+# threshold keys in descending order and the green / red components of their colours (blue is 0 except one entry)
+_KEYS = (1.0, 0.9166, 0.8333, 0.75, 0.6666, 0.5833, 0.5, 0.4166, 0.3333, 0.1666, 0.0833, 0.0)
+_GREEN = (0, 60, 88, 109, 128, 145, 163, 183, 202, 221, 239, 255)
+_RED = (255, 255, 255, 255, 255, 255, 249, 232, 208, 176, 129, 15)
+_BLUE = (0, 0, 0, 0, 0, 8, 0, 0, 0, 0, 0, 0)
+penalty_colour_gradient = {k: (b, g, r) for k, b, g, r in zip(_KEYS, _BLUE, _GREEN, _RED)}
