@@ -7,12 +7,13 @@ from vision_assist_b200.engine import MaskGridEngine
 
 B = int(os.environ.get("VA_B", "256")); n = int(os.environ.get("VA_N", "8"))
 M = int(os.environ.get("VA_M", "160")); S = 4 * M
+HH, WW = (int(v) for v in os.environ.get("VA_HW", f"{S}x{S}").split("x"))
 tc = os.environ.get("VA_TC", "1") == "1"
-eng = MaskGridEngine(H=S, W=S, mh=M, mw=M, max_n=n, gs=20, max_batch=B, tensor_core=tc)
-hp, hc, hb, hn = synth.make_batch(0, 32, n, S, S, M, M, max_n=n)
+eng = MaskGridEngine(H=HH, W=WW, mh=M, mw=M, max_n=n, gs=20, max_batch=B, tensor_core=tc)
+hp, hc, hb, hn = synth.make_batch(0, 32, n, HH, WW, M, M, max_n=n)
 reps = B // 32
 protos = hp.repeat(reps, 1, 1, 1).cuda(); coefs = hc.repeat(reps, 1, 1).cuda(); boxes = hb.repeat(reps, 1, 1).cuda(); counts = hn.repeat(reps).cuda()
-masks = torch.empty((B, n, S, S), dtype=torch.uint8, device="cuda")
+masks = torch.empty((B, n, HH, WW), dtype=torch.uint8, device="cuda")
 rec = torch.empty((B, eng.record_bytes), dtype=torch.uint8, device="cuda")
 for _ in range(int(os.environ.get("VA_ITERS", "4"))):
     eng.run(protos, coefs, boxes, counts, masks_out=masks, records_out=rec)
