@@ -190,7 +190,8 @@ VA_API int va_grid_to_penalty_peaks(va_ctx* ctx, const va_grid_input* hdr, const
  *   outputs in the layout va_run_fused takes: coefs_out [B][max_n][K], boxes_out [B][max_n][4] (xyxy, input pixels),
  *   counts_out [B]; conf_out [B][max_n] f32 and cls_out [B][max_n] i32 may be NULL.  Slots >= counts are zero.
  *   max_det <= max_n survivors are kept (the reference's max_det is 300: choose max_n accordingly).
- *   counts_out[b] = -(number of candidates) when more than 512 anchors pass conf_thres (capacity of the kernel). */
+ *   The kernel holds 512 candidates per image.  When more anchors pass conf_thres it keeps the 512 best by (score,
+ *   anchor order) - exact whenever max_det of them survive; otherwise counts_out[b] = -(number of candidates). */
 typedef struct va_nms_params {
   float conf_thres;   /* 0.5 in FrameProcessor.py:322 */
   float iou_thres;    /* ultralytics predict default 0.7 */

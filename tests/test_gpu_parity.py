@@ -392,11 +392,21 @@ def test_nms_golden_and_oracle():
         b2[b, :k] = torch.from_numpy(rows[:, :4]).cuda(); c2[b, :k] = torch.from_numpy(rows[:, 6:]).cuda()
     rec_b, masks_b = eng.run(protos, c2, b2, torch.tensor([r.shape[0] for r in want], dtype=torch.int32).cuda())
     assert torch.equal(rec_a, rec_b)
-    # more candidates than the kernel holds: reported, not guessed
-    dense = torch.rand(1, 37, 4000)
-    dense[:, 4] = 0.9
-    cnt = eng.nms(dense.cuda())[4]
-    assert int(cnt[0]) == -4000
+    # more candidates than the kernel holds (512): the best 512 by (score, anchor order) are enough whenever max_det
+    # of them survive - exact; otherwise the overflow is reported, not guessed
+    g = torch.Generator().manual_seed(99)
+    dense = torch.rand(3, 37, 4000, generator=g)
+    dense[:, :2] *= 600
+    dense[:, 2:4] = 8 + dense[:, 2:4] * 60
+    dense[0, 4] = 0.9                                        # all tied: anchor order decides
+    dense[1, 4] = 0.5 + 0.5 * torch.rand(4000, generator=g)  # distinct scores
+    dense[2, 4] = torch.round((0.5 + 0.5 * torch.rand(4000, generator=g)) * 64) / 64   # many ties on the threshold key
+    want = onms.nms_batch(dense.numpy(), conf_thres=0.5, iou_thres=0.7, nc=1, max_det=32)
+    check(dense, want, 0.5, 0.7, 1, 32)
+    same = torch.rand(1, 37, 4000, generator=g)
+    same[:, :4] = torch.tensor([300., 300., 100., 100.])[None, :, None]        # every box identical: one survivor
+    same[:, 4] = 0.9
+    assert int(eng.nms(same.cuda())[4][0]) == -4000
 
 
 @pytest.mark.parametrize("tc", PATHS)

@@ -27,7 +27,9 @@ struct NmsSmem {
   unsigned mask[kNmsCap][kNmsWords];     // sorted position p: later positions q with IoU(p, q) > threshold
   int kept[kNmsCap];
   int warp_tot[kNmsThreads / 32];
-  int n, nkept;
+  unsigned hist[256];                    // radix select of the kNmsCap best scores when more anchors pass the filter
+  unsigned sel_prefix, sel_need;
+  int n, nkept, n_eq;
 };
 
 size_t nms_smem_bytes() { return sizeof(NmsSmem); }
@@ -41,19 +43,95 @@ nms_kernel(const float* __restrict__ pred, int A, int nc, int nm, float conf_thr
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* P = pred + (size_t)b * (4 + nc + nm) * A;
 
-  // ---- 1. confidence filter, ordered compaction (anchor order is the reference's tie-break) ----
-  int base = 0;
+  // best class confidence of an anchor (first maximum; NaN is sticky like torch.max and fails the filter)
+  auto anchor_conf = [&](int a, int& j) -> float {
+    float conf = -INFINITY;
+    j = 0;
+    for (int c = 0; c < nc; ++c) {
+      const float v = __ldg(P + (size_t)(4 + c) * A + a);
+      if (c == 0 || v > conf || v != v) { conf = v; j = c; }
+    }
+    return conf;
+  };
+  auto orderable = [](float f) -> unsigned {            // ascending in the float order
+    const unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+  };
+  // ---- 0. how many anchors pass the confidence filter ----
+  int total = 0;
+  {
+    int mine = 0;
+    for (int a = tid; a < A; a += kNmsThreads) { int j; mine += (anchor_conf(a, j) > conf_thres) ? 1 : 0; }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) s.warp_tot[warp] = mine;
+    __syncthreads();
+    for (int w = 0; w < kNmsThreads / 32; ++w) total += s.warp_tot[w];
+    __syncthreads();
+  }
+  // More candidates than the kernel holds: keep the kNmsCap best by (score descending, anchor ascending) - the
+  // order in which the greedy NMS visits them.  Suppression only flows from better to worse candidates, so the
+  // survivors among the best kNmsCap are exactly the reference's first survivors; the result is complete when
+  // max_det of them survive (checked below).  4-pass radix select on the orderable score bits.
+  unsigned thr_key = 0;     // candidates with key > thr_key are in; n_eq of those with key == thr_key (anchor order)
+  int n_eq = 0;
+  const bool overflow = total > kNmsCap;
+  if (overflow) {
+    unsigned prefix = 0;
+    int need = kNmsCap;                                  // still to be found among keys with the current prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int t = tid; t < 256; t += kNmsThreads) s.hist[t] = 0;
+      __syncthreads();
+      const unsigned himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+      for (int a = tid; a < A; a += kNmsThreads) {
+        int j;
+        const float conf = anchor_conf(a, j);
+        if (!(conf > conf_thres)) continue;
+        const unsigned key = orderable(conf);
+        if ((key & himask) == (prefix & himask)) atomicAdd(&s.hist[(key >> shift) & 0xffu], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int acc = 0, d = 255;
+        for (; d > 0; --d) {                            // largest digit first
+          if (acc + (int)s.hist[d] >= need) break;
+          acc += (int)s.hist[d];
+        }
+        s.sel_prefix = prefix | ((unsigned)d << shift);
+        s.sel_need = (unsigned)(need - acc);
+      }
+      __syncthreads();
+      prefix = s.sel_prefix;
+      need = (int)s.sel_need;
+      __syncthreads();
+    }
+    thr_key = prefix;
+    n_eq = need;
+  }
+  // ---- 1. ordered compaction of the selected anchors (anchor order is the reference's tie-break) ----
+  int base = 0, eq_base = 0;
   for (int a0 = 0; a0 < A; a0 += kNmsThreads) {
     const int a = a0 + tid;
     float conf = -INFINITY;
     int j = 0;
-    if (a < A) {
-      for (int c = 0; c < nc; ++c) {
-        const float v = __ldg(P + (size_t)(4 + c) * A + a);
-        if (c == 0 || v > conf || v != v) { conf = v; j = c; }   // first maximum; NaN is sticky (torch.max) and fails the filter
+    if (a < A) conf = anchor_conf(a, j);
+    bool flag = (a < A) && (conf > conf_thres);
+    if (overflow) {
+      const unsigned key = flag ? orderable(conf) : 0u;
+      const bool eq = flag && key == thr_key;
+      // rank of this anchor among the ties on the threshold key, in anchor order
+      const unsigned eqb = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s.warp_tot[warp] = __popc(eqb);
+      __syncthreads();
+      int eoff = eq_base, etot = 0;
+      for (int w = 0; w < kNmsThreads / 32; ++w) {
+        if (w < warp) eoff += s.warp_tot[w];
+        etot += s.warp_tot[w];
       }
+      __syncthreads();
+      const int erank = eoff + __popc(eqb & ((1u << lane) - 1u));
+      flag = flag && (key > thr_key || (eq && erank < n_eq));
+      eq_base += etot;
     }
-    const bool flag = (a < A) && (conf > conf_thres);
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     if (lane == 0) s.warp_tot[warp] = __popc(bal);
     __syncthreads();
@@ -71,10 +149,6 @@ nms_kernel(const float* __restrict__ pred, int A, int nc, int nm, float conf_thr
     base += tot;
     __syncthreads();
   }
-  if (base > kNmsCap) {                      // capacity exceeded: report, do not guess
-    if (tid == 0) counts_out[b] = -base;
-    return;
-  }
   const int n = base;
   // ---- 2. boxes (xywh -> xyxy, class offset), areas, sort keys ----
   int n2 = 1;
@@ -89,9 +163,7 @@ nms_kernel(const float* __restrict__ pred, int A, int nc, int nm, float conf_thr
       const float x2 = __fadd_rn(__fadd_rn(x, hw), c), y2 = __fadd_rn(__fadd_rn(y, hh), c);
       s.box[t][0] = x1; s.box[t][1] = y1; s.box[t][2] = x2; s.box[t][3] = y2;
       s.area[t] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
-      unsigned u = __float_as_uint(s.score[t]);
-      u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;        // ascending-orderable; inverted below for descending
-      s.key[t] = ((unsigned long long)(~u) << 32) | (unsigned)t;
+      s.key[t] = ((unsigned long long)(~orderable(s.score[t])) << 32) | (unsigned)t;   // ascending key = descending score
     } else {
       s.key[t] = ~0ull;
     }
@@ -146,7 +218,8 @@ nms_kernel(const float* __restrict__ pred, int A, int nc, int nm, float conf_thr
   __syncthreads();
   // ---- 4. rows of the survivors in keep order: what process_mask / va_run_fused take ----
   const int k = min(s.nkept, min(max_det, max_n));
-  if (tid == 0) counts_out[b] = k;
+  // candidates were dropped and fewer than max_det survived: the dropped ones could have survived too - report
+  if (tid == 0) counts_out[b] = (overflow && s.nkept < max_det) ? -total : k;
   for (int t = tid; t < max_n * 4; t += kNmsThreads) {
     const int slot = t >> 2, c = t & 3;
     float v = 0.f;
