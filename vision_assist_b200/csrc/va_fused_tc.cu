@@ -5,23 +5,27 @@
 //
 // Reference semantics: ops.process_mask (testing/old/segmenting_using_tflite/ops.py:707-737).
 //
-// Work item = (frame, band of prototype rows).  Inside a CTA, warp-specialised roles connected by
-// mbarriers (no CTA-wide barrier inside the steady state):
+// Work item = (band of prototype rows, frame, group of 8 / 16 instances), stolen dynamically from a global
+// counter.  Inside a CTA (16 warps), warp-specialised roles connected only by mbarriers:
 //
-//   warp 0      TMA producer  : [32 prototypes x 128 pixels] fp32 boxes of the pixel-contiguous [K, P]
-//                               prototype matrix into a staging ring (kStagesHi stages).
-//   warp 1      MMA issuer    : D[128 px, N inst] = A * B^T with kind::tf32, M=128, N=16, K=8 per
-//                               instruction, both operands K-major with 128B swizzle (tcgen05 does not
-//                               transpose 32-bit operands: an MN-major tf32 A returns zeros, measured with
-//                               tests/micro/umma_probe.cu).  fp32-class accuracy comes from a 3-pass split
-//                               A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, hi = top 19 bits (what the tensor core
-//                               reads; it truncates, measured), lo = x - hi.  Accumulators: kAcc TMEM tiles.
-//   warps 2-5   split+epilogue: (front) transpose the staged [k][px] box into the K-major [px][k] operand
-//                               tiles A_hi / A_lo (one pixel row per thread, swizzled 16 B chunks), per-frame
-//                               B tiles (coefficients hi/lo) ; (back, lagging) tcgen05.ld of finished
-//                               accumulators, box crop, store of the cropped logits into row-chunk buffers.
-//   warps 6-15  upsample      : per chunk of PR row pairs: 4-tap blend with torch's exact roundings,
-//                               > 0, 16-byte mask stores, area / bbox / lattice reductions.
+//   warp 0      work stealing + TMA producer: takes the next item, reduces the group's boxes to their hull in
+//               prototype rows (rows outside it are zero after crop_mask: neither loaded nor multiplied), publishes
+//               {item, live chunk range, instance count} to a shared-memory ring, then loads [32 prototypes x 128
+//               pixels] fp32 boxes of the pixel-contiguous [K, P] prototype matrix into a staging ring.
+//   warps 1-4   split + MMA issue: one pixel (= TMEM lane) per thread: 32 ld.shared, hi = the raw word (the tensor
+//               core truncates fp32 to tf32, measured), lo = x - trunc(x), both written to TENSOR MEMORY with
+//               tcgen05.st (tcgen05 does not transpose 32-bit operands - an MN-major tf32 A returns zeros, measured
+//               with tests/micro/umma_probe.cu - so the K-major A operand is produced by threads).  Lane 0 of warps
+//               1 and 2 issue D[128 px, 32] = A * [B_hi ; B_lo]^T (kind::tf32, A from TMEM, B from smem, K = 8 x 4):
+//               issuer 0 with A_hi, issuer 1 with A_lo, into separate accumulators (3xTF32-style split, fp32-class
+//               accuracy); MMAs issued from different warps overlap (tests/micro/umma_2issuers.cu).
+//   warps 5-8   epilogue: tcgen05.ld of the four partial products, sum, box crop with integer bounds, store of the
+//               cropped logits into row-chunk buffers in shared memory (instances far from the tile rows skipped).
+//   warps 9-15  upsample: per chunk of `pr` row pairs: 4-tap blend with torch's exact roundings, > 0, 16-byte mask
+//               stores, area / bbox / lattice reductions; dead (chunk, instance) pairs and rows outside the hull
+//               are bulk zero-filled (cp.async.bulk shared -> global).
+//
+// The last CTA to finish re-arms the work counter; the tail kernel is a programmatic dependent launch.
 #include <cuda.h>
 
 #include <cstdio>
@@ -51,7 +55,7 @@ constexpr int kFirstEpiWarp = kFirstSplitWarp + kWarpsSplit;
 constexpr int kFirstUpWarp = kFirstEpiWarp + kWarpsEpi;
 constexpr int kThreads = 32 * (kFirstUpWarp + kWarpsUp);   // 512
 constexpr int kUpThreadsTc = 32 * kWarpsUp;
-constexpr int kMaxInstTc = 16;              // instances this kernel handles (N = 16)
+constexpr int kMaxInstTc = 16;              // instances per group (accumulator columns of one pass: N = 16)
 constexpr int kTmemAOff = 0;                // TMEM columns [0, 128): A ring
 constexpr int kIssuers = 2;                 // MMA-issuing threads (lane 0 of split warps 0 and 1): tcgen05.mma from different warps overlap
 constexpr int kAccCols = kIssuers * kNMma;  // accumulator columns per tile: [hi pass | lo pass], each [B_hi | B_lo]
