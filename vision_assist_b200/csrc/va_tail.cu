@@ -12,8 +12,11 @@
 //   ProtrusionDetector._create_binary_image / _find_peak / __call__  :38-158, :419-535 in the
 //       grid-level closed form (oracle/protrusion.py::peaks_closed_form)
 //
+//   utils.get_closest_grid_to_point as _find_paths calls it (FrameProcessor.py:236-239) and the grid_lookup
+//       row table behind _create_graph (:184-207): path start / end cells and the implicit A* graph
+//
 // Rows are bit masks (32 columns per word): run extents along a row are clz/ffs operations, the
-// vertical walks read one broadcast word per step.
+// vertical walks read one broadcast word per step.  Launched as a programmatic dependent of the mask kernel.
 #include <climits>
 #include <cmath>
 
