@@ -9,7 +9,7 @@ B = int(os.environ.get("VA_B", "256")); n = int(os.environ.get("VA_N", "8"))
 M = int(os.environ.get("VA_M", "160")); S = 4 * M
 HH, WW = (int(v) for v in os.environ.get("VA_HW", f"{S}x{S}").split("x"))
 tc = os.environ.get("VA_TC", "1") == "1"
-eng = MaskGridEngine(H=HH, W=WW, mh=M, mw=M, max_n=n, gs=20, max_batch=B, tensor_core=tc)
+eng = MaskGridEngine(H=HH, W=WW, mh=M, mw=M, max_n=n, gs=int(os.environ.get("VA_GS", "20")), max_batch=B, tensor_core=tc)
 hp, hc, hb, hn = synth.make_batch(0, 32, n, HH, WW, M, M, max_n=n)
 reps = B // 32
 protos = hp.repeat(reps, 1, 1, 1).cuda(); coefs = hc.repeat(reps, 1, 1).cuda(); boxes = hb.repeat(reps, 1, 1).cuda(); counts = hn.repeat(reps).cuda()

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "va_common.cuh"
 
@@ -70,6 +71,7 @@ static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, s
   d.H = c.H; d.W = c.W; d.mh = c.mh; d.mw = c.mw; d.K = c.K; d.max_n = c.max_n; d.gs = c.gs;
   d.flags = c.flags;
   if (const char* e = getenv("VA_TAIL_TIMING")) { if (e[0] == '1') d.flags |= 1 << 30; }   // developer diagnostic (va_tail.cu)
+  if (const char* e = getenv("VA_TAIL_ROLES")) { if (e[0] == '3') d.flags |= 1 << 29; }    // tuning aid (va_tail.cu)
   const int half = c.gs / 2;
   d.lat_rows = ceil_div(c.H - half, c.gs);
   d.lat_cols = ceil_div(c.W - half, c.gs);
@@ -154,6 +156,20 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
   if (chunk > cfg->max_batch) chunk = cfg->max_batch;
   c->logits_chunk = chunk;
   VA_CREATE_CUDA(cudaMalloc(&c->scratch.logits, per_frame * chunk));
+  {
+    // quotient table for the penalty ratios (PenaltyCalculator.py:98-110): positions and run lengths are small
+    // integers in cell units, and (double)m / (double)den computed here is the correctly rounded quotient the
+    // reference's pixel-unit division yields (same rational) - the kernel looks it up instead of dividing
+    const int N = (d.cmax > 2 * d.rmax) ? d.cmax : 2 * d.rmax;
+    std::vector<double> tab((size_t)(N + 1) * (N + 1));
+    for (int m = 0; m <= N; ++m)
+      for (int den = 0; den <= N; ++den) tab[(size_t)m * (N + 1) + den] = den ? (double)m / (double)den : 0.5;
+    double* dev = nullptr;
+    VA_CREATE_CUDA(cudaMalloc(&dev, tab.size() * sizeof(double)));
+    c->d.ratio = dev;
+    c->d.ratio_n = N;
+    VA_CREATE_CUDA(cudaMemcpy(dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   c->plan = nullptr;
   if (!(cfg->flags & VA_CFG_NO_TENSOR_CORE)) {
     char perr[256] = "";
@@ -184,6 +200,7 @@ extern "C" void va_destroy(va_ctx* c) {
   cudaFree(c->scratch.stats);
   cudaFree(c->scratch.lattice);
   cudaFree(c->scratch.logits);
+  cudaFree(const_cast<double*>(c->d.ratio));
   if (c->prof_ev[0][0])
     for (int i = 0; i < kProfMax; ++i)
       for (int j = 0; j < 3; ++j) cudaEventDestroy(c->prof_ev[i][j]);

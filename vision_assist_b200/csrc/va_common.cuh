@@ -33,6 +33,8 @@ struct Dims {
   int flags;                           // VA_CFG_*
   float wr, hr;                        // fl32(mw/W), fl32(mh/H): box scale, ops.py:725-732
   float sx, sy;                        // fl32(mw)/W, fl32(mh)/H: bilinear scales (ATen area_pixel_compute_scale)
+  const double* ratio;                 // [ratio_n + 1][ratio_n + 1]: ratio[m][den] = (double)m / (double)den (host-built, exact)
+  int ratio_n;
 };
 
 struct Scratch {

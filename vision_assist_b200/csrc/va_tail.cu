@@ -33,12 +33,13 @@ constexpr int kTailMaxThreads = 512;
 // developer diagnostic (VA_TAIL_TIMING=1): cycle stamps of block 0 at the phase boundaries, printed by the kernel
 constexpr int kTailDebugFlag = 1 << 30;
 __device__ long long g_tail_t[16];
-#define TT(k) do { if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 32))) g_tail_t[(k) % 100] = clock64(); } while (0)
+#define TT(k) do { if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 64))) g_tail_t[(k) % 100] = clock64(); } while (0)
 
 struct TailSmem {
   // "created rows" table: ids [0, 2*rmax)
   int* row_y;        // [T]
   int* row_attr;     // [T]
+  int* row_ly;       // [T]      row_y / gs (filled by finish_record: the penalty cells use lookup-row units)
   unsigned* occ;     // [T][cwords]
   unsigned* art;     // [T][cwords]
   int* list_ids;     // [rmax]   FrameProcessor.grids (list order) -> created id
@@ -61,7 +62,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   const int T = 2 * d.rmax, PL = plane_cap(d);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
-  const size_t o_y = take(sizeof(int) * T), o_a = take(sizeof(int) * T);
+  const size_t o_y = take(sizeof(int) * T), o_a = take(sizeof(int) * T), o_ly = take(sizeof(int) * T);
   const size_t o_occ = take(sizeof(unsigned) * T * d.cwords), o_art = take(sizeof(unsigned) * T * d.cwords);
   const size_t o_l = take(sizeof(int) * d.rmax), o_p = take(sizeof(int) * PL);
   const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * max(d.rmax, d.cwords));
@@ -69,7 +70,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   const size_t o_or = take(sizeof(int) * d.rmax), o_of = take(sizeof(int) * T), o_sc = take(sizeof(int) * S_COUNT);
   const size_t o_best = take(sizeof(unsigned long long) * (d.pmax + 1));
   if (s) {
-    s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a);
+    s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a); s->row_ly = (int*)(base + o_ly);
     s->occ = (unsigned*)(base + o_occ); s->art = (unsigned*)(base + o_art);
     s->list_ids = (int*)(base + o_l); s->plane_owner = (int*)(base + o_p);
     s->erow_first = (int*)(base + o_ef); s->erow_last = (int*)(base + o_el);
@@ -111,10 +112,14 @@ __device__ __forceinline__ int run_right(const unsigned* row, int c, int C) {
   }
 }
 
-__device__ __forceinline__ double seg_penalty(int pos, int lo, int hi) {
-  // PenaltyCalculator.py:98-110
-  const int den = hi - lo;
-  const double ratio = (den == 0) ? 0.5 : __ddiv_rn((double)(pos - lo), (double)den);
+// PenaltyCalculator.py:98-110 with position and run ends in CELL units (m = pos - lo, den = hi - lo): the pixel
+// coordinates the reference divides are these times gs, the same rational, hence the same correctly rounded
+// double - taken from the host-built quotient table when both are in range (the usual case), divided otherwise.
+__device__ __forceinline__ double seg_penalty(const Dims& d, int m, int den) {
+  double ratio;
+  if (den == 0) ratio = 0.5;
+  else if ((unsigned)m <= (unsigned)d.ratio_n && (unsigned)den <= (unsigned)d.ratio_n) ratio = __ldg(d.ratio + (size_t)m * (d.ratio_n + 1) + den);
+  else ratio = __ddiv_rn((double)m, (double)den);
   return __dmul_rn(2.0, fabs(__dsub_rn(ratio, 0.5)));
 }
 
@@ -134,6 +139,7 @@ __device__ __forceinline__ double blend_penalty(double rp, double cp) {
 // ---------------------------------------------------------------------------------------------
 __device__ void easy_segments(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords;
+  for (int id = threadIdx.x; id < s.sc[S_NCREATED]; id += (int)blockDim.x) s.row_ly[id] = s.row_y[id] / d.gs;
   const bool use = s.sc[S_USE_EASY] != 0;
   for (int k = threadIdx.x; k < d.rmax; k += (int)blockDim.x) {
     int first = -1, last = -1, cnt = 0;
@@ -177,10 +183,18 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   uint8_t* occ_out = rec + d.off_occ;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const int cells = d.rmax * d.cmax;
-  for (int u = tid; u < cells; u += nt) {
-    // cell (k, c) with the columns rotated by the row: a thread stride that is a multiple of cmax (224 = 7 * 32,
-    // 480 = 5 * 96) would otherwise pin every thread to one column, and the cost of a cell depends on its column
-    const int k = u / d.cmax, c = (u - k * d.cmax + k) % d.cmax;
+  // cell u = tid, tid + nt, ... decoded incrementally as (k, c0) - no division per cell - with the columns rotated by
+  // the row, c = (c0 + k) mod cmax: a thread stride that is a multiple of cmax (224 = 7 * 32, 480 = 5 * 96) would
+  // otherwise pin every thread to one column, and the cost of a cell depends on its column
+  const int dk = nt / d.cmax, dc = nt - dk * d.cmax;
+  int k = tid / d.cmax, c0 = tid - k * d.cmax, kmod = k % d.cmax;
+  const int dkmod = dk % d.cmax;
+  for (int u = tid; u < cells; u += nt, k += dk, c0 += dc, kmod += dkmod) {
+    if (c0 >= d.cmax) { c0 -= d.cmax; ++k; ++kmod; }
+    if (kmod >= d.cmax) kmod -= d.cmax;
+    if (kmod >= d.cmax) kmod -= d.cmax;
+    int c = c0 + kmod;
+    if (c >= d.cmax) c -= d.cmax;
     const int t = k * d.cmax + c;
     double p = qnan;
     uint8_t ob = 0;
@@ -190,31 +204,31 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
       const bool filled = bit_at(own, c);
       ob = (filled ? 1 : 0) | (bit_at(s.art + (size_t)id * cw, c) ? 2 : 0);
       if (filled && k < R) {
-        const int y = s.row_y[id], attr = s.row_attr[id], x = x0 + c * gs;
-        const int ly = y / gs;
-        // ---- row direction (PenaltyCalculator.py:68-69, else :73-95 on grid_lookup) ----
+        const int attr = s.row_attr[id];
+        const int ly = s.row_ly[id];                     // rows sit on multiples of gs (validated for caller-given grids)
+        // ---- row direction (PenaltyCalculator.py:68-69, else :73-95 on grid_lookup), in column units ----
         int lo, hi;
         if (attr >= 0 && attr < R && s.erow_first[attr] >= 0) {
-          lo = x0 + s.erow_first[attr] * gs;
-          hi = x0 + s.erow_last[attr] * gs;
+          lo = s.erow_first[attr];
+          hi = s.erow_last[attr];
         } else {
           const unsigned* prow = s.occ + (size_t)s.plane_owner[ly] * cw;
-          lo = x0 + run_left(prow, c) * gs;
-          hi = x0 + run_right(prow, c, C) * gs;
+          lo = run_left(prow, c);
+          hi = run_right(prow, c, C);
         }
-        const double rp = seg_penalty(x, lo, hi);
-        // ---- column direction ----
+        const double rp = seg_penalty(d, c - lo, hi - lo);
+        // ---- column direction, in lookup-row units ----
         if (s.ecol_first[c] >= 0) {
-          lo = s.row_y[s.list_ids[s.ecol_first[c]]];
-          hi = s.row_y[s.list_ids[s.ecol_last[c]]];
+          lo = s.row_ly[s.list_ids[s.ecol_first[c]]];
+          hi = s.row_ly[s.list_ids[s.ecol_last[c]]];
         } else {
           int a = ly, b = ly;
           while (a - 1 >= 0 && s.plane_owner[a - 1] >= 0 && bit_at(s.occ + (size_t)s.plane_owner[a - 1] * cw, c)) --a;
           while (b + 1 < PL && s.plane_owner[b + 1] >= 0 && bit_at(s.occ + (size_t)s.plane_owner[b + 1] * cw, c)) ++b;
-          lo = a * gs;
-          hi = b * gs;
+          lo = a;
+          hi = b;
         }
-        const double cp = seg_penalty(y, lo, hi);
+        const double cp = seg_penalty(d, ly - lo, hi - lo);
         p = blend_penalty(rp, cp);
       }
     }
@@ -325,33 +339,56 @@ __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   }
 }
 
+// Closest non-empty cell of one list row to the point (px, py): along a row the distance only depends on the column,
+// so the candidates are the nearest set bit at or left of the point's column and the nearest one right of it
+// (equal distances: the left one comes first in the reference's scan, the key order takes care of it).
+__device__ __forceinline__ unsigned long long row_best_key(const unsigned* row, int cw, int C, int k, int cmax, int px, int py,
+                                                           int x0, int y, int gs) {
+  const int half = gs >> 1;
+  int cfl = floor_div(px - x0 - half, gs);               // column whose centre is at or left of px
+  cfl = max(-1, min(cfl, C - 1));
+  int cl = -1, cr = -1;
+  for (int w = cfl >> 5; w >= 0 && cfl >= 0; --w) {      // nearest set bit <= cfl
+    unsigned v = row[w];
+    if (w == (cfl >> 5) && (cfl & 31) != 31) v &= (2u << (cfl & 31)) - 1u;
+    if (v) { cl = (w << 5) + 31 - __clz(v); break; }
+  }
+  for (int w = (cfl + 1) >> 5; w < cw; ++w) {            // nearest set bit > cfl
+    unsigned v = row[w];
+    if (w == ((cfl + 1) >> 5)) v &= 0xffffffffu << ((cfl + 1) & 31);
+    if (v) { cr = (w << 5) + __ffs(v) - 1; break; }
+  }
+  const long long dy = py - (y + half);
+  unsigned long long best = ~0ull;
+  if (cl >= 0) {
+    const long long dx = px - (x0 + cl * gs + half);
+    best = ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * cmax + cl);
+  }
+  if (cr >= 0 && cr < C) {
+    const long long dx = px - (x0 + cr * gs + half);
+    best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * cmax + cr));
+  }
+  return best;
+}
+
 // SURVEY 8(f1), executed by warp 0 right after find_peaks (while the other warps compute penalty cells).
 // Path start / end cells: utils.get_closest_grid_to_point (utils.py:6-32) as _find_paths calls it
 // (FrameProcessor.py:236-239) - the non-empty LIST cell whose centre is closest to the point, first minimum in list
 // order.  The reference compares np.sqrt of exact integers; the squared integer distances order the same way.
 // One 64-bit key per candidate, (distance^2 << 32) | (k * cmax + c), minimised per lane and then over the warp.
 // Also the grid_lookup row table that makes the _create_graph neighbourhood (:184-207) implicit in the record.
-__device__ void start_goals_lookup(const Dims& d, const TailSmem& s, uint8_t* rec) {
+// `first_pt .. last_pt` of the points {0: path start (W/2, H), 1 + q: peak q}; one warp, lane = list row.
+__device__ void closest_cells(const Dims& d, const TailSmem& s, uint8_t* rec, int first_pt, int last_pt) {
   const int lane = threadIdx.x & 31;
-  __syncwarp();                                                           // lane 0's peaks / S_NPEAKS are visible
-  const int R = s.sc[S_R], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0], half = gs >> 1;
-  const int npk = s.sc[S_NPEAKS], norph = s.sc[S_NORPH], T = 2 * d.rmax, PL = plane_cap(d);
+  const int R = s.sc[S_R], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
   const int* peaks = reinterpret_cast<const int*>(rec + d.off_peaks);     // written by lane 0 in find_peaks
   int* goals = reinterpret_cast<int*>(rec + d.off_goals);
-  for (int pt = 0; pt <= npk; ++pt) {
+  for (int pt = first_pt; pt <= last_pt; ++pt) {
     const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
     unsigned long long best = ~0ull;
-    for (int t = lane; t < R * cw; t += 32) {
-      const int k = t / cw, w = t - k * cw;
+    for (int k = lane; k < R; k += 32) {
       const int id = s.list_ids[k];
-      unsigned v = s.occ[(size_t)id * cw + w];
-      const long long dy = py - (s.row_y[id] + half);
-      while (v) {
-        const int c = 32 * w + __ffs(v) - 1;
-        v &= v - 1;
-        const long long dx = px - (x0 + c * gs + half);
-        best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * d.cmax + c));
-      }
+      best = min(best, row_best_key(s.occ + (size_t)id * cw, cw, s.sc[S_C], k, d.cmax, px, py, x0, s.row_y[id], gs));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -362,7 +399,23 @@ __device__ void start_goals_lookup(const Dims& d, const TailSmem& s, uint8_t* re
       else { goals[2 * (pt - 1)] = gk; goals[2 * (pt - 1) + 1] = gc; }
     }
   }
+}
+
+// warp 0, after find_peaks: the end cell of every peak
+__device__ void goals_for_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();                                                           // lane 0's peaks / S_NPEAKS are visible
+  const int npk = s.sc[S_NPEAKS];
+  closest_cells(d, s, rec, 1, npk);
+  int* goals = reinterpret_cast<int*>(rec + d.off_goals);
   for (int q = npk + lane; q < d.pmax; q += 32) { goals[2 * q] = 0; goals[2 * q + 1] = 0; }
+}
+
+// warp 1 (independent of the peaks): the path start cell and the grid_lookup row table
+__device__ void start_and_lookup(const Dims& d, const TailSmem& s, uint8_t* rec) {
+  const int lane = threadIdx.x & 31;
+  const int R = s.sc[S_R], norph = s.sc[S_NORPH], T = 2 * d.rmax, PL = plane_cap(d);
+  closest_cells(d, s, rec, 0, 0);
   // created id -> record row (first list position, or R + j for the j-th orphan)
   for (int t = lane; t < T; t += 32) s.oflag[t] = INT_MAX;
   __syncwarp();
@@ -375,7 +428,6 @@ __device__ void start_goals_lookup(const Dims& d, const TailSmem& s, uint8_t* re
     const int v = (owner >= 0) ? s.oflag[owner] : -1;
     lookup[ly] = (v == INT_MAX) ? -1 : v;
   }
-  __syncwarp();
 }
 
 // The same for large grids (small cells / large frames), by the whole block after the penalty phase: one work item
@@ -390,17 +442,9 @@ __device__ void start_goals_lookup_block(const Dims& d, const TailSmem& s, uint8
   for (int pt = 0; pt < P; ++pt) {           // per point: per-thread minimum, warp minimum, one shared atomic per warp
     const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
     unsigned long long best = ~0ull;
-    for (int t = threadIdx.x; t < R * cw; t += (int)blockDim.x) {
-      const int k = t / cw, w = t - k * cw;
+    for (int k = threadIdx.x; k < R; k += (int)blockDim.x) {
       const int id = s.list_ids[k];
-      unsigned v = s.occ[(size_t)id * cw + w];
-      const long long dy = py - (s.row_y[id] + half);
-      while (v) {
-        const int c = 32 * w + __ffs(v) - 1;
-        v &= v - 1;
-        const long long dx = px - (x0 + c * gs + half);
-        best = min(best, ((unsigned long long)(dx * dx + dy * dy) << 32) | (unsigned)(k * d.cmax + c));
-      }
+      best = min(best, row_best_key(s.occ + (size_t)id * cw, cw, s.sc[S_C], k, d.cmax, px, py, x0, s.row_y[id], gs));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -448,17 +492,29 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
   }
   TT(6);
   if (d.rmax * d.cwords <= 128) {
-    if (threadIdx.x < 32) {
-      // warp 0: peaks, path start / end cells, lookup rows, header - concurrently with the other warps' penalty cells
+    // warp 0: peaks, the end cell of every peak, the path start cell and the lookup rows - concurrently with the other
+    // warps' penalty cells; joined by a barrier before the header
+    if (!(d.flags & (1 << 29))) {       // default: warp 0 does all the cell searches (VA_TAIL_ROLES=3 splits them; measured slower)
+      if (threadIdx.x < 32) {
+        find_peaks(d, s, rec);
+        goals_for_peaks(d, s, rec);
+        start_and_lookup(d, s, rec);
+      } else {
+        penalties_and_record(d, s, rec, (int)threadIdx.x - 32, (int)blockDim.x - 32);
+      }
+    } else if (threadIdx.x < 32) {
       find_peaks(d, s, rec);
       TT(7);
-      start_goals_lookup(d, s, rec);
+      goals_for_peaks(d, s, rec);
       TT(8);
-      if (threadIdx.x == 0) write_header(s, rec);
+    } else if (threadIdx.x < 64) {
+      start_and_lookup(d, s, rec);
     } else {
-      penalties_and_record(d, s, rec, (int)threadIdx.x - 32, (int)blockDim.x - 32);
+      penalties_and_record(d, s, rec, (int)threadIdx.x - 64, (int)blockDim.x - 64);
       TT(110);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) write_header(s, rec);
   } else {
     // large grids: the cell search is shared by the whole block
     if (threadIdx.x < 32) find_peaks(d, s, rec);
