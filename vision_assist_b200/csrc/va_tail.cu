@@ -28,7 +28,7 @@
 namespace va {
 
 constexpr int kTailThreads = 256;       // smallest CTA size (tuning aid VA_TAIL_THREADS); the launch uses kTailMaxThreads
-constexpr int kTailMaxThreads = 512;
+constexpr int kTailMaxThreads = 1024;
 
 // developer diagnostic (VA_TAIL_TIMING=1): cycle stamps of block 0 at the phase boundaries, printed by the kernel
 constexpr int kTailDebugFlag = 1 << 30;
@@ -811,12 +811,17 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// the penalty cells (fp64 divisions, dependent chains) are the long phase: as many threads as the register file allows
-static int tail_threads(const Dims& d) {
-  const int cells = d.rmax * d.cmax;
-  if (const char* e = getenv("VA_TAIL_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512) return v; }   // tuning aid
-  (void)cells;
-  return kTailMaxThreads;   // measured: 512 threads beat 256 also at 640^2 / gs = 20 (31 -> 23 us per 256 frames); 1024 are slower
+static int tail_threads(const Dims& d, int B) {
+  (void)d;
+  if (const char* e = getenv("VA_TAIL_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) return v; }   // tuning aid
+  // measured: 512 threads beat 256 also at 640^2 / gs = 20 (31 -> 23 us per 256 frames).  1024 are slower when every SM
+  // holds a frame, faster when most SMs would idle (cfg2: 32 frames of 6048 cells, 45 -> 35 us; one frame: 21.5 -> 20.5 us)
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return (2 * B <= sms) ? kTailMaxThreads : 512;
 }
 
 cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice,
@@ -829,7 +834,7 @@ cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stat
   // launched with programmatic stream serialization: see griddepcontrol.wait in the kernel
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B);
-  cfg.blockDim = dim3(tail_threads(d));
+  cfg.blockDim = dim3(tail_threads(d, B));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -849,7 +854,7 @@ cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int*
     cudaError_t e = cudaFuncSetAttribute(grid_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  grid_mode_kernel<<<B, tail_threads(d), smem, st>>>(d, hdr, row_y, row_attr, occ, plane_y, plane_occ, records);
+  grid_mode_kernel<<<B, tail_threads(d, B), smem, st>>>(d, hdr, row_y, row_attr, occ, plane_y, plane_occ, records);
   return cudaGetLastError();
 }
 
