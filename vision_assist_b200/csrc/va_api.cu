@@ -290,7 +290,9 @@ static int assemble(va_ctx* c, const float* protos, const float* coefs, const fl
   const size_t P = (size_t)d.mh * d.mw;
   const size_t fr_protos = (size_t)d.K * P, fr_coefs = (size_t)d.max_n * d.K, fr_boxes = (size_t)d.max_n * 4;
   const size_t fr_logits = (size_t)d.max_n * P, fr_masks = (size_t)d.max_n * d.H * d.W;
-  const int step = logits_out ? B : c->logits_chunk;
+  // L2-sized sub-batches of equal size (32 frames with room for 14: 11 + 11 + 10 rather than 14 + 14 + 4)
+  const int nsub = (B + c->logits_chunk - 1) / c->logits_chunk;
+  const int step = logits_out ? B : (B + nsub - 1) / nsub;
   for (int b0 = 0; b0 < B; b0 += step) {
     const int nb = (B - b0 < step) ? B - b0 : step;
     float* lg = logits_out ? logits_out + b0 * fr_logits : c->scratch.logits;
