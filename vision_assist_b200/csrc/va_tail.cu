@@ -320,9 +320,12 @@ __device__ void write_header(const TailSmem& s, uint8_t* rec) {
 __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], n = s.sc[S_NCREATED];
   int* s_flags = s.oflag;
+  for (int id = threadIdx.x; id < n; id += (int)blockDim.x) s_flags[id] = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < R; k += (int)blockDim.x) s_flags[s.list_ids[k]] = 1;      // rows still in the list
+  __syncthreads();
   for (int id = threadIdx.x; id < n; id += (int)blockDim.x) {
-    bool in_list = false;
-    for (int k = 0; k < R && !in_list; ++k) in_list = (s.list_ids[k] == id);
+    const bool in_list = s_flags[id] != 0;
     const int ly = s.row_y[id] / d.gs;
     s_flags[id] = (!in_list && ly >= 0 && ly < plane_cap(d) && s.plane_owner[ly] == id) ? 1 : 0;
   }
