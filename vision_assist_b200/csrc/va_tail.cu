@@ -40,6 +40,7 @@ struct TailSmem {
   int* row_y;        // [T]
   int* row_attr;     // [T]
   int* row_ly;       // [T]      row_y / gs (filled by finish_record: the penalty cells use lookup-row units)
+  unsigned* colocc;  // [cmax][plw] grid_lookup occupancy transposed: bit ly of column c (vertical runs by clz / ffs)
   unsigned* occ;     // [T][cwords]
   unsigned* art;     // [T][cwords]
   int* list_ids;     // [rmax]   FrameProcessor.grids (list order) -> created id
@@ -63,6 +64,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
   const size_t o_y = take(sizeof(int) * T), o_a = take(sizeof(int) * T), o_ly = take(sizeof(int) * T);
+  const size_t o_co = take(sizeof(unsigned) * d.cmax * ((PL + 31) / 32));
   const size_t o_occ = take(sizeof(unsigned) * T * d.cwords), o_art = take(sizeof(unsigned) * T * d.cwords);
   const size_t o_l = take(sizeof(int) * d.rmax), o_p = take(sizeof(int) * PL);
   const size_t o_ef = take(sizeof(int) * d.rmax), o_el = take(sizeof(int) * max(d.rmax, d.cwords));
@@ -70,7 +72,7 @@ __host__ __device__ inline size_t tail_smem_layout(const Dims& d, TailSmem* s, u
   const size_t o_or = take(sizeof(int) * d.rmax), o_of = take(sizeof(int) * T), o_sc = take(sizeof(int) * S_COUNT);
   const size_t o_best = take(sizeof(unsigned long long) * (d.pmax + 1));
   if (s) {
-    s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a); s->row_ly = (int*)(base + o_ly);
+    s->row_y = (int*)(base + o_y); s->row_attr = (int*)(base + o_a); s->row_ly = (int*)(base + o_ly); s->colocc = (unsigned*)(base + o_co);
     s->occ = (unsigned*)(base + o_occ); s->art = (unsigned*)(base + o_art);
     s->list_ids = (int*)(base + o_l); s->plane_owner = (int*)(base + o_p);
     s->erow_first = (int*)(base + o_ef); s->erow_last = (int*)(base + o_el);
@@ -140,6 +142,27 @@ __device__ __forceinline__ double blend_penalty(double rp, double cp) {
 __device__ void easy_segments(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords;
   for (int id = threadIdx.x; id < s.sc[S_NCREATED]; id += (int)blockDim.x) s.row_ly[id] = s.row_y[id] / d.gs;
+  {
+    // grid_lookup occupancy by column: the vertical traversal of PenaltyCalculator.py:73-95 becomes the same
+    // clz / ffs run search as the horizontal one instead of a cell-by-cell walk
+    const int PL = plane_cap(d), plw = (PL + 31) >> 5;
+    // 32 x 32 bit blocks transposed with ballots: lane = lookup row of the block, bit q of its word = column q
+    const int lane = threadIdx.x & 31, nwarps = (int)blockDim.x >> 5;
+    for (int blk = nwarps - 1 - ((int)threadIdx.x >> 5); blk < plw * cw; blk += nwarps) {   // last warps first: the first ones scan rows / columns below
+      const int w = blk / cw, cwd = blk - w * cw;
+      const int ly = 32 * w + lane;
+      const int o = (ly < PL) ? s.plane_owner[ly] : -1;
+      const unsigned word = (o >= 0) ? s.occ[(size_t)o * cw + cwd] : 0u;
+      unsigned mine = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, (word >> q) & 1u);
+        if (lane == q) mine = m;
+      }
+      const int c = 32 * cwd + lane;
+      if (c < d.cmax) s.colocc[(size_t)c * plw + w] = mine;
+    }
+  }
   const bool use = s.sc[S_USE_EASY] != 0;
   for (int k = threadIdx.x; k < d.rmax; k += (int)blockDim.x) {
     int first = -1, last = -1, cnt = 0;
@@ -222,11 +245,9 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
           lo = s.row_ly[s.list_ids[s.ecol_first[c]]];
           hi = s.row_ly[s.list_ids[s.ecol_last[c]]];
         } else {
-          int a = ly, b = ly;
-          while (a - 1 >= 0 && s.plane_owner[a - 1] >= 0 && bit_at(s.occ + (size_t)s.plane_owner[a - 1] * cw, c)) --a;
-          while (b + 1 < PL && s.plane_owner[b + 1] >= 0 && bit_at(s.occ + (size_t)s.plane_owner[b + 1] * cw, c)) ++b;
-          lo = a;
-          hi = b;
+          const unsigned* col = s.colocc + (size_t)c * ((PL + 31) >> 5);
+          lo = run_left(col, ly);
+          hi = run_right(col, ly, PL);
         }
         const double cp = seg_penalty(d, ly - lo, hi - lo);
         p = blend_penalty(rp, cp);
