@@ -62,3 +62,23 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_integration_md_binding_matches_the_library():
+    """The reference-side ctypes stub shown in INTEGRATION.md declares the same structures (field order, sizes) as
+    the product's own binding and only names entry points the library exports."""
+    from vision_assist_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = text[text.index("```python\n# vision_assist/_va_sm100.py"):]
+    code = code[len("```python\n"):code.index("\n```")]
+    # the two structure definitions, executed as written
+    decl = code[code.index("class VaConfig"):code.index("vp = C.c_void_p")]
+    ns = {"C": C}
+    exec(decl, ns)
+    assert [f[0] for f in ns["VaConfig"]._fields_] == [f[0] for f in _lib.VaConfig._fields_]
+    assert C.sizeof(ns["VaLayout"]) == C.sizeof(_lib.VaLayout) == 64
+    mine = [f[0] for f in _lib.VaLayout._fields_]
+    theirs = [f[0] for f in ns["VaLayout"]._fields_]
+    assert [t if t != "alg_bytes_n1" else "algorithmic_bytes_per_frame_n1" for t in theirs] == mine
+    for name in set(re.findall(r"lib\.(va_\w+)", code)):
+        assert name in _lib.EXPORTS, name
