@@ -7,15 +7,20 @@ record.  Two routes from masks to the grid:
 
   route="contour" : the reference's own route - masks2segments (cv2.findContours, contour with
                     most points) -> scale_coords -> contourArea-largest polygon -> fillPoly.
-  route="direct"  : what the CUDA path does - instance with the largest PIXEL AREA (first max),
+  route="lut"     : the same result computed the way the CUDA path does (oracle.contour): hole-filled top-level
+                    components, table-driven point counts and doubled areas, no contour tracing.  Must equal
+                    "contour" on every input (tests/test_contour_model.py).
+  route="direct"  : round-1 approximation kept for comparison - instance with the largest PIXEL AREA (first max),
                     its pixel bounding box and the mask itself as raster.  Equal to "contour"
-                    for hole-free single-blob masks; tests count the frames where they differ.
+                    for hole-free single-blob masks only.
 """
 from __future__ import annotations
 
+import cv2
 import numpy as np
 import torch
 
+from . import contour as ocontour
 from . import graph as ograph
 from . import grid as ogrid
 from . import mask_assembly as oma
@@ -25,7 +30,8 @@ from . import protrusion as oprot
 FLAG_EMPTY = 1            # no grid produced (reference returns [] at FrameProcessor.py:328-332)
 FLAG_CENTRE_OOB = 2       # reference raises IndexError at FrameProcessor.py:97
 FLAG_LIST_OOB = 4         # reference raises IndexError at FrameProcessor.py:163 (negative index)
-FLAG_NON_SIMPLE = 8       # selected mask is not one hole-free blob (Euler number != 1)
+FLAG_NON_SIMPLE = 8       # selected mask is not one hole-free blob
+FLAG_NO_POLYGON = 32      # the selected polygon has no points: reference raises cv2.error in fillPoly (FrameProcessor.py:86)
 
 
 def state_to_result(st: ogrid.GridState | None, flags: int = 0, sel: int = -1) -> dict:
@@ -85,6 +91,16 @@ def frame_from_masks(masks: np.ndarray, gs: int, route: str = "contour", frame_s
         if route == "contour":
             polys = oma.masks_to_polygons(masks, frame_shape) if n else None
             st = ogrid.extract_grid_from_polygons(polys, frame_shape[0], frame_shape[1], gs)
+        elif route == "lut":
+            sel, poly = ocontour.select_instance(masks) if n else (-1, None)
+            if n and poly is None:
+                return state_to_result(None, flags | FLAG_NO_POLYGON, sel)
+            if poly is not None:
+                x0, y0, x1, y1 = poly["bbox"]
+                if not poly["simple"]:
+                    flags |= FLAG_NON_SIMPLE
+                st = ogrid.extract_grid_from_raster(poly["raster"].astype(np.uint8), (x0, y0, x1 - x0 + 1, y1 - y0 + 1),
+                                                    gs=gs)
         else:
             if n:
                 areas = masks.reshape(n, -1).sum(axis=1, dtype=np.int64)
@@ -96,6 +112,8 @@ def frame_from_masks(masks: np.ndarray, gs: int, route: str = "contour", frame_s
     except IndexError as e:
         flags |= FLAG_CENTRE_OOB if "centre" in str(e) else FLAG_LIST_OOB
         return state_to_result(None, flags, sel)
+    except cv2.error:
+        return state_to_result(None, flags | FLAG_NO_POLYGON, sel)
     return state_to_result(st, flags, sel)
 
 
