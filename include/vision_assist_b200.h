@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VA_ABI_VERSION 1
+#define VA_ABI_VERSION 2
 #if defined(__GNUC__)
 #define VA_API __attribute__((visibility("default")))
 #else
@@ -50,8 +50,8 @@ enum {
 
 /* va_config.flags */
 enum {
-  VA_CFG_CHECK_SIMPLE = 1,  /* also compute the Euler number of the selected mask (extra H*W read
-                               per frame) and set VA_FLAG_NON_SIMPLE when it is not one hole-free blob */
+  VA_CFG_CHECK_SIMPLE = 1,  /* accepted and ignored since ABI 2: the contour step always classifies the masks
+                               (VA_FLAG_NON_SIMPLE) and is exact on all of them */
   VA_CFG_NO_TENSOR_CORE = 2 /* debug: force the CUDA-core (FFMA) contraction instead of tcgen05 */
 };
 
@@ -60,8 +60,14 @@ enum {
   VA_FLAG_EMPTY = 1,       /* no grid: reference returns [] (FrameProcessor.py:99-101, :328-332) */
   VA_FLAG_CENTRE_OOB = 2,  /* reference raises IndexError at FrameProcessor.py:97 (cell centre outside frame) */
   VA_FLAG_LIST_OOB = 4,    /* reference raises IndexError at FrameProcessor.py:163 (negative list index) */
-  VA_FLAG_NON_SIMPLE = 8,  /* selected mask is not a single hole-free 8-connected blob */
-  VA_FLAG_OVERFLOW = 16    /* record capacity exceeded (cannot happen for frames the context was sized for) */
+  VA_FLAG_NON_SIMPLE = 8,  /* informational: the selected mask is not a single hole-free 8-connected blob; the record is
+                              still exact - it is built from the polygon the reference keeps (external contour with
+                              the most points of masks2segments, ops.py:837-859, filled: FrameProcessor.py:85-86) */
+  VA_FLAG_OVERFLOW = 16,   /* record capacity exceeded (cannot happen for frames the context was sized for), or more
+                              than H*W/8 pixel runs in one mask (cannot happen for 4x-upsampled masks) */
+  VA_FLAG_NO_POLYGON = 32  /* the selected instance's mask is empty: masks2segments yields a polygon without points
+                              and the reference raises cv2.error in cv2.fillPoly (FrameProcessor.py:86); set with
+                              VA_FLAG_EMPTY */
 };
 
 typedef struct va_ctx va_ctx;
@@ -96,16 +102,17 @@ typedef struct va_config {
  * Cell (k, c) has Grid.coords = (x0 + c*gs, row_y[k]) and Grid.col = c. */
 typedef struct va_frame_header {
   int32_t flags;      /* VA_FLAG_* */
-  int32_t sel;        /* selected instance (largest pixel area, first max), -1 if none */
+  int32_t sel;        /* selected instance: largest cv2.contourArea of the kept polygons, first maximum
+                         (FrameProcessor.py:72-73); -1 if the frame has no instance */
   int32_t x0, y0;     /* snapped bbox origin (FrameProcessor.py:79-80) */
   int32_t n_cols;     /* C */
   int32_t n_rows;     /* R = len(FrameProcessor.grids) */
   int32_t n_orphans;
   int32_t n_peaks;
-  int32_t area;       /* pixel area of the selected mask */
+  int32_t area;       /* pixels set in the selected instance's mask */
   int32_t n_mask_rows;
-  int32_t minx, miny, maxx, maxy; /* pixel bbox of the selected mask */
-  int32_t euler;      /* Euler number when VA_CFG_CHECK_SIMPLE, else 0 */
+  int32_t minx, miny, maxx, maxy; /* cv2.boundingRect of the kept polygon (FrameProcessor.py:76) */
+  int32_t contour_area2; /* 2 * cv2.contourArea of the kept polygon (exact integer) */
   int32_t start_cell; /* (list row << 16) | column of the path start cell, -1 if none: the non-empty list cell
                          closest to (W/2, H) - utils.get_closest_grid_to_point as called at FrameProcessor.py:236 */
 } va_frame_header;
@@ -150,10 +157,11 @@ VA_API int va_assemble_masks(va_ctx* ctx, const float* protos, const float* coef
                       const int32_t* counts, int32_t B, uint8_t* masks_out, float* logits_out,
                       void* stream);
 
-/* Whole path in one call: mask assembly -> grid -> penalties -> peaks.
- * Replaces model.predict()'s process_mask + FrameProcessor._extract_grid_information +
- * _calculate_penalties + ProtrusionDetector.__call__ (FrameProcessor.py:322-341).
- *   masks_out may be NULL ("grid-only" mode: masks never touch HBM).
+/* Whole path in one call: mask assembly -> kept polygon per instance -> grid -> penalties -> peaks.
+ * Replaces model.predict()'s process_mask + Results.masks.xy (masks2segments) + FrameProcessor.
+ * _extract_grid_information + _calculate_penalties + ProtrusionDetector.__call__ (FrameProcessor.py:322-341).
+ *   masks_out may be NULL ("grid-only" mode: the u8 masks never touch HBM; a bit-packed copy, 1/8 of the bytes,
+ *   goes to context scratch for the contour step).
  *   records_out [B][record_bytes] */
 VA_API int va_run_fused(va_ctx* ctx, const float* protos, const float* coefs, const float* boxes,
                  const int32_t* counts, int32_t B, uint8_t* masks_out, uint8_t* records_out,

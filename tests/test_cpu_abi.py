@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.va_abi_version() == 1
+    assert lib.va_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

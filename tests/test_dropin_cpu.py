@@ -22,7 +22,7 @@ from vision_assist_b200.materialise import objects_to_grid_input, record_to_obje
 def record_from_oracle(res: dict) -> FrameRecord:
     R = res["R"]
     return FrameRecord(flags=res["flags"], sel=res["sel"], x0=res["x0"], y0=res["y0"], C=res["C"], R=R,
-                       n_orphans=len(res["orphan_y"]), area=0, bbox=(0, 0, 0, 0), euler=0,
+                       n_orphans=len(res["orphan_y"]), area=0, bbox=(0, 0, 0, 0), contour_area2=0,
                        rows_y=res["rows_y"], rows_attr=res["rows_attr"], occ=res["occ"], penalty=res["penalty"],
                        peaks=res["peaks"], orphan_y=res["orphan_y"], orphan_occ=res["orphan_occ"],
                        start=tuple(res["start"]), goals=res["goals"], lookup_row=res["lookup_row"])

@@ -90,14 +90,17 @@ def test_frames_golden(tc):
         records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
         recs = eng.decode(records)
         for k, rec in enumerate(recs):
-            assert rec.area == int(z[f"{ci}/areas"][k].max())
+            if fam == "sidewalk":
+                assert rec.area == int(z[f"{ci}/areas"][k].max())
             R, C = int(z[f"{ci}/R"][k]), int(z[f"{ci}/C"][k])
             case = dict(R=R, C=C, x0=int(z[f"{ci}/x0"][k]), rows_y=z[f"{ci}/rows_y"][k][:R],
                         rows_attr=z[f"{ci}/rows_attr"][k][:R], occ=z[f"{ci}/occ"][k][:R, :C],
                         pen=z[f"{ci}/pen"][k][:R, :C], peaks=z[f"{ci}/peaks"][k][:int(z[f"{ci}/npk"][k])])
-            if fam == "sidewalk":      # single hole-free blobs: the reference's contour route == ours
+            # golden = the reference's own contour route (masks2segments -> contourArea -> fillPoly): every family,
+            # multi-component masks with holes included
+            if fam == "sidewalk":
                 assert not (rec.flags & opl.FLAG_NON_SIMPLE)
-                goldenio.assert_result_matches(rec.as_dict(), case, f"golden frame {ci}/{k}")
+            goldenio.assert_result_matches(rec.as_dict(), case, f"golden frame {ci}/{k}")
 
 
 @pytest.mark.parametrize("tc", PATHS)
@@ -113,22 +116,32 @@ def test_run_fused_vs_oracle(tc, family):
     records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
     recs = eng.decode(records)
     masks = masks.cpu().numpy()
-    n_contour_diff = 0
+    n_nonsimple = n_band_frames = 0
     for b in range(B):
         nb = int(counts[b])
-        res = opl.frame_from_masks(masks[b, :nb], 20, "direct")        # same masks: grid path must be bit-exact
+        # the reference's contour route (OpenCV) on the SAME masks: bit-exact on every family - components, holes,
+        # contour point counts, contourArea selection
+        res = opl.frame_from_masks(masks[b, :nb], 20, "contour")
         assert_record_equals_oracle(recs[b], res, f"{family} frame {b}")
-        assert bool(recs[b].flags & opl.FLAG_NON_SIMPLE) == bool(res["flags"] & opl.FLAG_NON_SIMPLE)
+        lut = opl.frame_from_masks(masks[b, :nb], 20, "lut")
+        assert bool(recs[b].flags & opl.FLAG_NON_SIMPLE) == bool(lut["flags"] & opl.FLAG_NON_SIMPLE), (family, b)
+        assert bool(recs[b].flags & opl.FLAG_NO_POLYGON) == bool(lut["flags"] & opl.FLAG_NO_POLYGON), (family, b)
+        n_nonsimple += bool(recs[b].flags & opl.FLAG_NON_SIMPLE)
         if nb:
-            assert recs[b].sel == res["sel"]
+            assert recs[b].sel == lut["sel"], (family, b, recs[b].sel, lut["sel"])
+        # and from the tensors: identical whenever no mask pixel sits inside the 1e-4 band
         full = opl.frame_from_tensors(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W), 20, "contour")
-        assert (masks[b, :nb] != full["masks"]).sum() <= 64
-        try:
-            assert_record_equals_oracle(recs[b], full)
-        except AssertionError:
-            n_contour_diff += 1
-            assert family == "noise"
-    print(f"[parity] {family}: {n_contour_diff}/{B} frames differ from the reference's contour route")
+        if np.array_equal(masks[b, :nb], full["masks"]):
+            assert_record_equals_oracle(recs[b], full, f"{family} frame {b} (from tensors)")
+        else:
+            n_band_frames += 1
+            up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
+            assert band_mismatch_report(masks[b, :nb], up)[1] == 0
+    assert n_band_frames <= 2
+    if family == "noise":
+        assert n_nonsimple >= B // 2          # the family does exercise the general path
+    print(f"[parity] {family}: {B}/{B} records bit-exact vs the reference's contour route; {n_nonsimple} non-simple frames, "
+          f"{n_band_frames} frames with in-band mask pixels")
 
 
 @pytest.mark.parametrize("tc", PATHS)
@@ -141,13 +154,20 @@ def test_cfg1_full_batch_256(tc):
     dev = to_dev(protos, coefs, boxes, counts)
     records, masks = eng.run(*dev)
     recs = eng.decode(records)
-    band_pixels = 0
+    band_pixels = n_general = 0
+    masks_h = masks.cpu().numpy()
     for b in range(B):
         full = opl.frame_from_tensors(protos[b], coefs[b], boxes[b], (H, W), 20, "contour")
         assert_record_equals_oracle(recs[b], full, f"cfg1 frame {b}")
-        if b % 16 == 0:
-            band_pixels += int((masks[b].cpu().numpy() != full["masks"]).sum())
-    print(f"[parity] cfg1: 256/256 records bit-exact; {band_pixels} differing mask pixels in 16 sampled frames")
+        # binary-mask rule of the north star on EVERY frame: bit-exact except pixels within 1e-4 of the threshold
+        if not np.array_equal(masks_h[b], full["masks"]):
+            up = oma.upsampled_logits(protos[b], coefs[b], boxes[b], (H, W)).numpy()
+            nd, nout = band_mismatch_report(masks_h[b], up)
+            assert nout == 0, (b, nd, nout)
+            band_pixels += nd
+        n_general += bool(recs[b].flags & opl.FLAG_NON_SIMPLE)
+    print(f"[parity] cfg1: 256/256 records bit-exact; {band_pixels} in-band mask pixels over all 256 frames; "
+          f"{n_general} non-simple frames")
     # size-independent properties: idempotence (scratch reset), batch-split invariance, grid-only mode
     records2, _ = eng.run(*dev)
     assert torch.equal(records, records2)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VA_LIB_PATH") or os.path.join(_HERE, "libva_sm100.so"
 
 VA_OK, VA_ERR_INVALID, VA_ERR_CUDA, VA_ERR_CAPACITY, VA_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 VA_CFG_CHECK_SIMPLE, VA_CFG_NO_TENSOR_CORE = 1, 2
-VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG_OVERFLOW = 1, 2, 4, 8, 16
+VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG_OVERFLOW, VA_FLAG_NO_POLYGON = 1, 2, 4, 8, 16, 32
 
 EXPORTS = ["va_abi_version", "va_create", "va_destroy", "va_last_error", "va_get_layout", "va_assemble_masks",
            "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks", "va_nms",

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "va_common.cuh"
+#include "va_contour_core.h"
 
 using namespace va;
 
@@ -16,6 +17,7 @@ struct va_ctx {
   Dims d;
   va_layout layout;
   Scratch scratch;
+  int num_sms;
   int logits_chunk;            // frames of logits scratch (CUDA-core path)
   FusedPlan* plan;             // tcgen05 path, nullptr when unavailable / disabled
   int last_launches;
@@ -76,6 +78,8 @@ static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, s
   d.lat_rows = ceil_div(c.H - half, c.gs);
   d.lat_cols = ceil_div(c.W - half, c.gs);
   d.lat_words = ceil_div(d.lat_cols, 32);
+  d.nblk = ceil_div(c.W, cc::kRowBlock);
+  d.bit_words = ceil_div(c.W, 32);
   d.plane_rows = ceil_div(c.H, c.gs);
   int s = (int)((long long)c.H * 7 / 8);                   // int(H * 0.875), FrameProcessor.py:126
   s = s + (c.gs - s % c.gs) % c.gs;                        // :127
@@ -149,6 +153,24 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
   VA_CREATE_CUDA(cudaMalloc(&c->scratch.stats, ns * sizeof(InstStats)));
   VA_CREATE_CUDA(cudaMalloc(&c->scratch.lattice, ns * d.lat_rows * d.lat_words * sizeof(unsigned)));
   VA_CREATE_CUDA(launch_init_scratch(d, cfg->max_batch, c->scratch.stats, c->scratch.lattice, 0));
+  {
+    // contour step (va_contour.cu): per-row summaries, per-instance results, work list and the general path's slabs
+    int sms = 0;
+    VA_CREATE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    c->num_sms = sms;
+    VA_CREATE_CUDA(cudaMalloc(&c->scratch.rowsum, ns * d.H * d.nblk * sizeof(uint32_t)));
+    VA_CREATE_CUDA(cudaMalloc(&c->scratch.contour, ns * sizeof(cc::InstContour)));
+    VA_CREATE_CUDA(cudaMemset(c->scratch.contour, 0, ns * sizeof(cc::InstContour)));
+    VA_CREATE_CUDA(cudaMalloc(&c->scratch.worklist, (2 + ns) * sizeof(int)));
+    VA_CREATE_CUDA(cudaMemset(c->scratch.worklist, 0, (2 + ns) * sizeof(int)));
+    // run capacity: a 4x-upsampled mask row has at most W / 8 runs (one sign change per proto cell)
+    int cap = (int)(((size_t)d.H * d.W) / 8);
+    if (cap < 4096) cap = 4096;
+    c->scratch.cc_cap = cap;
+    c->scratch.cc_ctas = (int)((ns < (size_t)sms) ? ns : (size_t)sms);
+    c->scratch.cc_slab_bytes = (contour_slab_bytes(d, cap) + 255) & ~(size_t)255;
+    VA_CREATE_CUDA(cudaMalloc(&c->scratch.cc_slab, c->scratch.cc_slab_bytes * c->scratch.cc_ctas));
+  }
   // logits scratch for the CUDA-core path: keep one chunk (<= ~48 MB) so that it stays L2-resident
   const size_t per_frame = (size_t)d.max_n * d.mh * d.mw * sizeof(float);
   int chunk = (int)((48u << 20) / per_frame);
@@ -200,6 +222,11 @@ extern "C" void va_destroy(va_ctx* c) {
   cudaFree(c->scratch.stats);
   cudaFree(c->scratch.lattice);
   cudaFree(c->scratch.logits);
+  cudaFree(c->scratch.rowsum);
+  cudaFree(c->scratch.bits);
+  cudaFree(c->scratch.contour);
+  cudaFree(c->scratch.worklist);
+  cudaFree(c->scratch.cc_slab);
   cudaFree(const_cast<double*>(c->d.ratio));
   if (c->prof_ev[0][0])
     for (int i = 0; i < kProfMax; ++i)
@@ -279,10 +306,18 @@ static int check_batch(va_ctx* c, int B, const void* a, const void* b, const voi
 static int assemble(va_ctx* c, const float* protos, const float* coefs, const float* boxes, const int* counts, int B,
                     uint8_t* masks, float* logits_out, cudaStream_t st) {
   const Dims& d = c->d;
+  if (!masks && !c->scratch.bits) {
+    // grid-only mode: the contour step still needs the pixels of non-trivial masks - the kernels write them bit-packed
+    // (1/8 of the mask bytes) into context scratch instead
+    const size_t ns = (size_t)c->cfg.max_batch * d.max_n;
+    VA_CUDA(c, cudaMalloc(&c->scratch.bits, ns * d.H * d.bit_words * sizeof(uint32_t)));
+  }
+  MaskSinks sinks;
+  sinks.stats = c->scratch.stats; sinks.lattice = c->scratch.lattice; sinks.rowsum = c->scratch.rowsum;
+  sinks.bits = masks ? nullptr : c->scratch.bits;
   if (c->plan) {
     char perr[256] = "";
-    cudaError_t e = launch_fused(c->plan, d, protos, coefs, boxes, counts, B, masks, logits_out, c->scratch.stats,
-                                 c->scratch.lattice, st, perr, sizeof(perr));
+    cudaError_t e = launch_fused(c->plan, d, protos, coefs, boxes, counts, B, masks, logits_out, sinks, st, perr, sizeof(perr));
     if (e != cudaSuccess) { set_err(c, "fused kernel launch failed: %s %s", cudaGetErrorString(e), perr); return VA_ERR_CUDA; }
     c->last_launches += 1;
     return VA_OK;
@@ -297,9 +332,12 @@ static int assemble(va_ctx* c, const float* protos, const float* coefs, const fl
     const int nb = (B - b0 < step) ? B - b0 : step;
     float* lg = logits_out ? logits_out + b0 * fr_logits : c->scratch.logits;
     VA_CUDA(c, launch_logits(d, protos + b0 * fr_protos, coefs + b0 * fr_coefs, boxes + b0 * fr_boxes, counts + b0, nb, lg, st));
-    VA_CUDA(c, launch_upsample(d, lg, boxes + b0 * fr_boxes, counts + b0, nb, masks ? masks + b0 * fr_masks : nullptr,
-                               c->scratch.stats + (size_t)b0 * d.max_n,
-                               c->scratch.lattice + (size_t)b0 * d.max_n * d.lat_rows * d.lat_words, st));
+    MaskSinks sub = sinks;
+    sub.stats += (size_t)b0 * d.max_n;
+    sub.lattice += (size_t)b0 * d.max_n * d.lat_rows * d.lat_words;
+    sub.rowsum += (size_t)b0 * d.max_n * d.H * d.nblk;
+    if (sub.bits) sub.bits += (size_t)b0 * d.max_n * d.H * d.bit_words;
+    VA_CUDA(c, launch_upsample(d, lg, boxes + b0 * fr_boxes, counts + b0, nb, masks ? masks + b0 * fr_masks : nullptr, sub, st));
     c->last_launches += 2;
   }
   return VA_OK;
@@ -336,9 +374,10 @@ extern "C" int va_run_fused(va_ctx* c, const float* protos, const float* coefs, 
   rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, nullptr, st);
   if (rc != VA_OK) return rc;
   if (prof) VA_CUDA(c, cudaEventRecord(ev[1], st));
-  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, masks_out, nullptr, nullptr, records_out, st));
+  VA_CUDA(c, launch_contour(c->d, counts, B, c->scratch, masks_out, st));
+  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, c->scratch.contour, nullptr, nullptr, records_out, st));
   if (prof) { VA_CUDA(c, cudaEventRecord(ev[2], st)); c->prof_count++; }
-  c->last_launches += 1;
+  c->last_launches += 3;
   return VA_OK;
 }
 
@@ -351,9 +390,12 @@ extern "C" int va_mask_to_records(va_ctx* c, const uint8_t* masks, const int32_t
   cudaStream_t st = (cudaStream_t)stream;
   VA_CUDA(c, cudaSetDevice(c->cfg.device));
   c->last_launches = 0;
-  VA_CUDA(c, launch_mask_stats(c->d, masks, counts, B, c->scratch.stats, c->scratch.lattice, st));
-  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, masks, rects, sel, records_out, st));
-  c->last_launches = 2;
+  MaskSinks sinks;
+  sinks.stats = c->scratch.stats; sinks.lattice = c->scratch.lattice; sinks.rowsum = c->scratch.rowsum; sinks.bits = nullptr;
+  VA_CUDA(c, launch_mask_stats(c->d, masks, counts, B, sinks, st));
+  VA_CUDA(c, launch_contour(c->d, counts, B, c->scratch, masks, st));
+  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, c->scratch.contour, rects, sel, records_out, st));
+  c->last_launches = 4;
   return VA_OK;
 }
 
@@ -435,9 +477,10 @@ extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* 
     rc = assemble(c, c->d_protos[s], c->d_coefs[s], c->d_boxes[s], c->d_counts[s], nb,
                   h_masks_out ? c->d_masks[s] : nullptr, nullptr, c->s_compute);
     if (rc != VA_OK) return rc;
-    VA_CUDA(c, launch_tail(d, c->d_counts[s], nb, c->scratch.stats, c->scratch.lattice,
-                           h_masks_out ? c->d_masks[s] : nullptr, nullptr, nullptr, c->d_records[s], c->s_compute));
-    launches += c->last_launches + 1;
+    VA_CUDA(c, launch_contour(d, c->d_counts[s], nb, c->scratch, h_masks_out ? c->d_masks[s] : nullptr, c->s_compute));
+    VA_CUDA(c, launch_tail(d, c->d_counts[s], nb, c->scratch.stats, c->scratch.lattice, c->scratch.contour, nullptr, nullptr,
+                           c->d_records[s], c->s_compute));
+    launches += c->last_launches + 3;
     VA_CUDA(c, cudaEventRecord(c->ev_done[s], c->s_compute));
     VA_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_done[s], 0));
     VA_CUDA(c, cudaMemcpyAsync(h_records_out + (size_t)b0 * d.record_bytes, c->d_records[s], (size_t)d.record_bytes * nb,

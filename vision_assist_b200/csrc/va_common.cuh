@@ -26,6 +26,8 @@ static_assert(sizeof(InstStats) == 32, "InstStats is 32 B");
 struct Dims {
   int H, W, mh, mw, K, max_n, gs;
   int lat_rows, lat_cols, lat_words;   // cell-centre lattice: point (gs*lx+gs/2, gs*ly+gs/2)
+  int nblk;                            // 128-pixel blocks per row (per-row summaries, va_contour_core.h)
+  int bit_words;                       // 32-pixel words per row of the bit-packed masks (grid-only mode)
   int plane_rows;                      // ceil(H/gs): rows of the grid_lookup plane
   int rmax, cmax, pmax, cwords;        // record capacity; cwords = ceil(cmax/32)
   int record_bytes, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ, off_goals, off_lookup;
@@ -41,6 +43,23 @@ struct Scratch {
   InstStats* stats;        // [max_batch][max_n]
   unsigned int* lattice;   // [max_batch][max_n][lat_rows][lat_words]
   float* logits;           // [max_batch][max_n][mh][mw] (CUDA-core path only)
+  uint32_t* rowsum;        // [max_batch][max_n][H][nblk] per-(row, 128 px block) summaries of the masks
+  uint32_t* bits;          // [max_batch][max_n][H][bit_words] bit-packed masks, written INSTEAD of the u8 masks in
+                           // grid-only mode (allocated on first use)
+  void* contour;           // [max_batch][max_n] cc::InstContour - result of the contour step
+  int* worklist;           // [0] entries, [1] finished CTAs, [2 ...] (frame * max_n + instance) of the general path
+  unsigned char* cc_slab;  // general-path scratch, one slab per CTA of the contour kernel
+  size_t cc_slab_bytes;
+  int cc_cap;              // run capacity per instance
+  int cc_ctas;
+};
+
+// Where the mask kernels leave their by-products (besides the u8 masks).
+struct MaskSinks {
+  InstStats* stats;
+  unsigned int* lattice;
+  uint32_t* rowsum;
+  uint32_t* bits;          // nullptr when the u8 masks are written
 };
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -59,16 +78,19 @@ cudaError_t launch_logits(const Dims& d, const float* protos, const float* coefs
                           const int* counts, int B, float* logits, cudaStream_t st);
 // bilinear upsample + threshold (+ stats / lattice) from proto-resolution logits (ops.py:736-737)
 cudaError_t launch_upsample(const Dims& d, const float* logits, const float* boxes, const int* counts, int B, uint8_t* masks,
-                            InstStats* stats, unsigned int* lattice, cudaStream_t st);
-// stats / lattice from caller-provided binary masks
-cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, InstStats* stats,
-                              unsigned int* lattice, cudaStream_t st);
+                            const MaskSinks& sinks, cudaStream_t st);
+// stats / lattice / row summaries from caller-provided binary masks
+cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, const MaskSinks& sinks,
+                              cudaStream_t st);
+// contour step (va_contour.cu): per instance the polygon the reference keeps - doubled contourArea, bounding box,
+// lattice samples of its fillPoly raster.  masks may be nullptr (then scratch.bits holds the pixels).
+cudaError_t launch_contour(const Dims& d, const int* counts, int B, const Scratch& sc, const uint8_t* masks, cudaStream_t st);
+size_t contour_slab_bytes(const Dims& d, int cap);
 cudaError_t launch_init_scratch(const Dims& d, int max_batch, InstStats* stats, unsigned int* lattice,
                                 cudaStream_t st);
 // selection -> grid -> penalties -> peaks -> record; resets stats / lattice
-cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned int* lattice,
-                        const uint8_t* masks, const int* rects, const int* sel, uint8_t* records,
-                        cudaStream_t st);
+cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned int* lattice, const void* contour,
+                        const int* rects, const int* sel, uint8_t* records, cudaStream_t st);
 cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,
                              const uint8_t* occ, const int* plane_y, const uint8_t* plane_occ, int B,
                              uint8_t* records, cudaStream_t st);
@@ -84,7 +106,7 @@ struct FusedPlan;  // opaque, owned by the context
 FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen);
 void fused_plan_destroy(FusedPlan* p);
 cudaError_t launch_fused(FusedPlan* p, const Dims& d, const float* protos, const float* coefs, const float* boxes,
-                         const int* counts, int B, uint8_t* masks, float* logits_dbg, InstStats* stats,
-                         unsigned int* lattice, cudaStream_t st, char* err, size_t errlen);
+                         const int* counts, int B, uint8_t* masks, float* logits_dbg, const MaskSinks& sinks,
+                         cudaStream_t st, char* err, size_t errlen);
 
 }  // namespace va

@@ -1,0 +1,553 @@
+// Contour semantics of the reference without contour tracing - the algorithm shared by the CUDA kernels
+// (va_contour.cu) and a host build that the CPU tests drive (tests/native/contour_host.cpp).
+//
+// Reference behaviour reproduced (bit-exact, see oracle/contour.py for the model and its OpenCV pin):
+//   masks2segments          vendored ultralytics ops.py:837-859   findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE),
+//                                                                 contour with the most points (first maximum)
+//   polygon selection       FrameProcessor.py:72-73               largest cv2.contourArea (first maximum)
+//   boundingRect, fillPoly  FrameProcessor.py:75-86               bbox and raster of the kept contour
+//
+// Per instance mask:  G = complement of the 4-connected background region that touches the frame.  Its 8-connected
+// components are the top-level components with holes filled; one RETR_EXTERNAL contour each.  Points and doubled
+// shoelace area of a component are sums of a 3x3 table (va_contour_lut.h) over its pixels; the kept component is the
+// one with the most points (ties: last in raster order = OpenCV's first); its pixels ARE the fillPoly raster.
+//
+// Two paths:
+//   * certificate (contour_certify): every mask row of the instance is ONE run and consecutive rows touch -> one
+//     hole-free component; its doubled area follows in closed form from the per-row run ends (2N - L - 2 with L the
+//     number of border moves).  Input: the per-row summaries the mask kernels emit - no pixel is re-read.
+//   * general (Work / phase_*): run-based connected components on a bit image of the mask's bounding box:
+//     background gaps united 4-connectedly (union-find, node 0 = the outside) -> holes; foreground runs united
+//     8-connectedly and across holes -> components of G; table sums per component; selection; bbox; lattice samples.
+//     Written as barrier-separated phases `phase(w, tid, nthreads)` so the same code runs as one CTA per instance on
+//     the GPU and as a plain loop on the host.
+#pragma once
+
+#include <stdint.h>
+
+#include "va_contour_lut.h"
+
+#if defined(__CUDACC__)
+#define VA_HD __host__ __device__ __forceinline__
+#else
+#define VA_HD inline
+#endif
+
+namespace va {
+namespace cc {
+
+// ---------------------------------------------------------------------------------------------
+// portable intrinsics / atomics (the host build is single-threaded)
+// ---------------------------------------------------------------------------------------------
+VA_HD int popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+VA_HD int ffs32(uint32_t v) {   // 1-based index of the lowest set bit, 0 if none
+#ifdef __CUDA_ARCH__
+  return __ffs((int)v);
+#else
+  return v ? __builtin_ctz(v) + 1 : 0;
+#endif
+}
+VA_HD int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __clz((int)v);
+#else
+  return v ? __builtin_clz(v) : 32;
+#endif
+}
+VA_HD int atom_min(int* p, int v) {
+#ifdef __CUDA_ARCH__
+  return atomicMin(p, v);
+#else
+  const int o = *p; if (v < o) *p = v; return o;
+#endif
+}
+VA_HD int atom_max(int* p, int v) {
+#ifdef __CUDA_ARCH__
+  return atomicMax(p, v);
+#else
+  const int o = *p; if (v > o) *p = v; return o;
+#endif
+}
+VA_HD int atom_add(int* p, int v) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, v);
+#else
+  const int o = *p; *p = o + v; return o;
+#endif
+}
+VA_HD unsigned atom_or(unsigned* p, unsigned v) {
+#ifdef __CUDA_ARCH__
+  return atomicOr(p, v);
+#else
+  const unsigned o = *p; *p = o | v; return o;
+#endif
+}
+VA_HD unsigned long long atom_max64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  return atomicMax(p, v);
+#else
+  const unsigned long long o = *p; if (v > o) *p = v; return o;
+#endif
+}
+VA_HD int imin(int a, int b) { return a < b ? a : b; }
+VA_HD int imax(int a, int b) { return a > b ? a : b; }
+VA_HD int iabs(int a) { return a < 0 ? -a : a; }
+
+// ---------------------------------------------------------------------------------------------
+// per-row summaries written by the mask kernels: one entry per (row, 128-pixel block)
+//   bits 0-7 pixels set in the block (0 = none), bits 8-14 first set pixel, bits 15-21 last set pixel (block-relative)
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowBlock = 128;
+VA_HD uint32_t rowsum_pack(int cnt, int first, int last) { return (uint32_t)cnt | ((uint32_t)first << 8) | ((uint32_t)last << 15); }
+
+struct RowRun { int cnt, a, b; };   // pixels set in the row, first and last set pixel (a > b when empty)
+
+VA_HD RowRun rowsum_combine(const uint32_t* e, int nblk) {
+  RowRun r; r.cnt = 0; r.a = 1 << 30; r.b = -1;
+  for (int k = 0; k < nblk; ++k) {
+    const uint32_t v = e[k];
+    const int c = (int)(v & 0xffu);
+    if (c) {
+      if (r.cnt == 0) r.a = k * kRowBlock + (int)((v >> 8) & 0x7fu);
+      r.b = k * kRowBlock + (int)((v >> 15) & 0x7fu);
+      r.cnt += c;
+    }
+  }
+  return r;
+}
+
+// Result of the contour step for one instance (consumed by the tail kernel's selection).
+struct InstContour {
+  int area2;        // doubled cv2.contourArea of the kept polygon
+  int state;        // kEmpty / kSimple / kGeneral / kPending / kOverflow
+  int minx, miny, maxx, maxy;   // cv2.boundingRect of the kept polygon (pixel bbox of the kept component)
+  int points;       // CHAIN_APPROX_SIMPLE points of the kept contour (general path; 0 on the certificate path)
+  int n_components; // top-level components (general path; 1 on the certificate path)
+};
+enum { kEmpty = 0, kSimple = 1, kGeneral = 2, kPending = 3, kOverflow = 4 };
+
+// Certificate terms of one row y (miny <= y <= maxy) given its run and the previous row's run.
+struct CertTerms { int ok, n, l, minx, maxx; };
+VA_HD CertTerms cert_row(const RowRun& cur, const RowRun& prev, bool first_row, bool last_row) {
+  CertTerms t; t.ok = 1; t.n = cur.cnt; t.l = 0; t.minx = cur.a; t.maxx = cur.b;
+  if (cur.cnt == 0 || cur.cnt != cur.b - cur.a + 1) { t.ok = 0; return t; }       // empty row inside the range / several runs
+  if (!first_row) {
+    if (prev.cnt == 0 || prev.cnt != prev.b - prev.a + 1) { t.ok = 0; return t; }
+    if (!(cur.a <= prev.b + 1 && cur.b >= prev.a - 1)) { t.ok = 0; return t; }   // rows do not touch (8-connectivity)
+    t.l += imax(1, iabs(cur.a - prev.a)) + imax(1, iabs(cur.b - prev.b));       // border moves down the left and the right side
+  }
+  if (first_row) t.l += cur.b - cur.a;                                          // moves along the top run
+  if (last_row) t.l += cur.b - cur.a;                                           // ... and back along the bottom run
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// general path
+// ---------------------------------------------------------------------------------------------
+struct Work {
+  // ---- input ----
+  int H, W;                 // frame
+  int fmt;                  // 0: u8 mask (non-zero = set), 1: bit rows (bit x&31 of word x>>5)
+  const uint8_t* px;        // fmt 0: [H][W] of this instance
+  const uint32_t* bits;     // fmt 1: [H][bit_words] of this instance
+  int bit_words;
+  int y0, x0w;              // region origin: first row, first 32-pixel word
+  int R, Wd;                // region rows / words (covers the pixel bbox of the mask)
+  int gs, lat_rows, lat_cols, lat_words;
+  // ---- scratch (shared or global memory) ----
+  uint32_t* Mfg;            // [R][Wd] foreground bits
+  uint32_t* G;              // [R][Wd] foreground + holes
+  uint16_t* S;              // [R][Wd] runs of the row that start before word k
+  int* rowoff;              // [R + 1] first run id of the row
+  int cap;                  // run capacity
+  uint16_t* rs;             // [cap] first / last pixel (region-relative) and row of a run; ids are in raster order
+  uint16_t* re;
+  uint16_t* ry;
+  int* pF;                  // [cap] union-find over runs: components of G (root = smallest id = raster-first run)
+  int* pG;                  // [cap + 1] union-find over background gaps: node 0 = outside, node id+1 = gap right of run id
+  int* accP;                // [cap] per root: points
+  int* accA;                // [cap] per root: signed doubled area
+  int* seg;                 // [33] scan scratch
+  // ---- scalars (one copy per CTA, shared memory) ----
+  int* sc;                  // see enum
+  unsigned long long* best; // [1] (points << 32) | root id
+  // ---- output ----
+  unsigned* lattice;        // [lat_rows][lat_words] of this instance (overwritten)
+  InstContour* out;
+};
+enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_COUNT };
+
+VA_HD uint32_t word_at(const uint32_t* bm, const Work& w, int r, int k) {
+  return (r < 0 || r >= w.R || k < 0 || k >= w.Wd) ? 0u : bm[r * w.Wd + k];
+}
+VA_HD uint32_t rise_at(const Work& w, int r, int k) {      // bits where a foreground run starts
+  const uint32_t m = word_at(w.Mfg, w, r, k), p = word_at(w.Mfg, w, r, k - 1);
+  return m & ~((m << 1) | (p >> 31));
+}
+VA_HD bool fg_at(const Work& w, int r, int x) {
+  if (x < 0 || x >= 32 * w.Wd) return false;
+  return (w.Mfg[r * w.Wd + (x >> 5)] >> (x & 31)) & 1u;
+}
+VA_HD int row_runs(const Work& w, int r) { return w.rowoff[r + 1] - w.rowoff[r]; }
+// number of runs of row r that start at a pixel <= x
+VA_HD int ns(const Work& w, int r, int x) {
+  if (x < 0) return 0;
+  if (x >= 32 * w.Wd) return row_runs(w, r);
+  const int k = x >> 5;
+  return (int)w.S[r * w.Wd + k] + popc32(rise_at(w, r, k) & (0xffffffffu >> (31 - (x & 31))));
+}
+
+VA_HD int uf_find(const int* p, int x) {
+  while (true) {
+    const int q = p[x];
+    if (q == x) return x;
+    x = q;
+  }
+}
+// roots are the smallest ids: lock-free union by atomicMin on the larger root
+VA_HD void uf_union(int* p, int a, int b) {
+  while (true) {
+    a = uf_find(p, a);
+    b = uf_find(p, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atom_min(&p[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// ---- phase 0: scalars ----
+VA_HD void phase_init(Work& w, int tid, int nt) {
+  (void)nt;
+  if (tid == 0) {
+    for (int q = 0; q < W_COUNT; ++q) w.sc[q] = 0;
+    w.sc[W_MINX] = 1 << 30; w.sc[W_MINY] = 1 << 30; w.sc[W_MAXX] = -1; w.sc[W_MAXY] = -1;
+    w.sc[W_CHOSEN] = -1;
+    w.best[0] = 0ull;
+  }
+}
+
+// ---- phase 1: bit image of the region ----
+VA_HD void phase_load(Work& w, int tid, int nt) {
+  for (int t = tid; t < w.R * w.Wd; t += nt) {
+    const int r = t / w.Wd, k = t - r * w.Wd;
+    const int y = w.y0 + r, xw = w.x0w + k;
+    uint32_t m = 0;
+    if (w.fmt == 1) {
+      m = (xw < w.bit_words) ? w.bits[(size_t)y * w.bit_words + xw] : 0u;
+      const int rem = w.W - 32 * xw;
+      if (rem < 32) m &= (rem <= 0) ? 0u : (0xffffffffu >> (32 - rem));
+    } else {
+      const uint8_t* p = w.px + (size_t)y * w.W + 32 * xw;
+      const int rem = w.W - 32 * xw;
+      if (rem >= 32 && (w.W & 3) == 0 && (reinterpret_cast<uintptr_t>(w.px) & 3) == 0) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t u = q[j];
+          u |= u >> 4; u |= u >> 2; u |= u >> 1;
+          u &= 0x01010101u;                                   // byte != 0 -> 1
+          m |= ((u * 0x01020408u) >> 24) << (4 * j);          // 4 byte flags -> 4 bits
+        }
+      } else {
+        for (int j = 0; j < 32 && j < rem; ++j) m |= (uint32_t)(p[j] != 0) << j;
+      }
+    }
+    w.Mfg[t] = m;
+    w.G[t] = m;
+  }
+}
+
+// ---- phase 2: runs per word / row ----
+VA_HD void phase_count(Work& w, int tid, int nt) {
+  for (int r = tid; r < w.R; r += nt) {
+    int acc = 0;
+    for (int k = 0; k < w.Wd; ++k) {
+      w.S[r * w.Wd + k] = (uint16_t)acc;
+      acc += popc32(rise_at(w, r, k));
+    }
+    w.rowoff[r] = acc;
+  }
+}
+// ---- phase 3a-c: exclusive scan of the row counts (32 segments) ----
+VA_HD void phase_scan_a(Work& w, int tid, int nt) {
+  const int segl = (w.R + 31) / 32;
+  for (int s = tid; s < 32; s += nt) {
+    int acc = 0;
+    for (int r = s * segl; r < imin((s + 1) * segl, w.R); ++r) acc += w.rowoff[r];
+    w.seg[s] = acc;
+  }
+}
+VA_HD void phase_scan_b(Work& w, int tid, int nt) {
+  (void)nt;
+  if (tid == 0) {
+    int acc = 0;
+    for (int s = 0; s < 32; ++s) { const int v = w.seg[s]; w.seg[s] = acc; acc += v; }
+    w.seg[32] = acc;
+    w.sc[W_NR] = acc;
+    if (acc > w.cap) w.sc[W_OVERFLOW] = 1;
+  }
+}
+VA_HD void phase_scan_c(Work& w, int tid, int nt) {
+  const int segl = (w.R + 31) / 32;
+  for (int s = tid; s < 32; s += nt) {
+    int acc = w.seg[s];
+    for (int r = s * segl; r < imin((s + 1) * segl, w.R); ++r) { const int v = w.rowoff[r]; w.rowoff[r] = acc; acc += v; }
+  }
+  if (tid == 0) w.rowoff[w.R] = w.seg[32];
+}
+
+// ---- phase 4: run table ----
+VA_HD void phase_runs(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  if (tid == 0) w.pG[0] = 0;                          // the outside
+  for (int t = tid; t < w.R * w.Wd; t += nt) {
+    const int r = t / w.Wd, k = t - r * w.Wd;
+    uint32_t rise = rise_at(w, r, k);
+    int id = w.rowoff[r] + (int)w.S[t];
+    const int last_id = w.rowoff[r + 1] - 1;
+    while (rise) {
+      const int b = ffs32(rise) - 1;
+      rise &= rise - 1;
+      // end of the run: first zero after bit b, possibly in a later word
+      int kk = k;
+      uint32_t z = ~w.Mfg[r * w.Wd + kk] & ((b == 31) ? 0u : (0xffffffffu << (b + 1)));
+      while (!z && kk + 1 < w.Wd) { ++kk; z = ~w.Mfg[r * w.Wd + kk]; }
+      const int end = z ? 32 * kk + ffs32(z) - 2 : 32 * w.Wd - 1;
+      w.rs[id] = (uint16_t)(32 * k + b);
+      w.re[id] = (uint16_t)end;
+      w.ry[id] = (uint16_t)r;
+      w.pF[id] = id;
+      w.pG[id + 1] = (id == last_id) ? 0 : id + 1;     // the gap after the last run of a row is the outside
+      w.accP[id] = 0;
+      w.accA[id] = 0;
+      ++id;
+    }
+  }
+}
+
+// ---- phase 5: background gaps, 4-connectivity; gaps that reach the frame / region border join node 0 ----
+VA_HD void phase_gaps(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  for (int id = tid; id < NR; id += nt) {
+    const int r = w.ry[id];
+    if (id == w.rowoff[r + 1] - 1) continue;            // no gap to the right
+    const int g0 = w.re[id] + 1, g1 = w.rs[id + 1] - 1;
+    for (int dr = -1; dr <= 1; dr += 2) {
+      const int rr = r + dr;
+      if (rr < 0 || rr >= w.R) { uf_union(w.pG, id + 1, 0); continue; }
+      const int n2 = row_runs(w, rr), o2 = w.rowoff[rr];
+      int xa = g0, xb = g1;
+      if (fg_at(w, rr, xa)) xa = w.re[o2 + ns(w, rr, xa) - 1] + 1;       // first background pixel >= g0 in row rr
+      if (xa > xb) continue;
+      if (fg_at(w, rr, xb)) xb = w.rs[o2 + ns(w, rr, xb) - 1] - 1;       // last background pixel <= g1
+      if (xa > xb) continue;
+      const int qa = ns(w, rr, xa), qb = ns(w, rr, xb);                  // gap q lies between runs q-1 and q
+      for (int q = qa; q <= qb; ++q) uf_union(w.pG, id + 1, (q == 0 || q == n2) ? 0 : o2 + q);
+    }
+  }
+}
+// ---- phase 6: holes known -> runs separated by a hole belong together ----
+VA_HD void phase_holes(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  for (int id = tid; id < NR; id += nt) {
+    const int r = w.ry[id];
+    if (id == w.rowoff[r + 1] - 1) continue;
+    if (uf_find(w.pG, id + 1) != 0) {
+      uf_union(w.pF, id, id + 1);
+      atom_add(&w.sc[W_HOLES], 1);
+      // fill the hole pixels into G
+      const int g0 = w.re[id] + 1, g1 = w.rs[id + 1] - 1;
+      for (int k = g0 >> 5; k <= (g1 >> 5); ++k) {
+        uint32_t m = 0xffffffffu;
+        if (k == (g0 >> 5)) m &= 0xffffffffu << (g0 & 31);
+        if (k == (g1 >> 5)) m &= 0xffffffffu >> (31 - (g1 & 31));
+        atom_or(&w.G[r * w.Wd + k], m);
+      }
+    }
+  }
+}
+// ---- phase 7: foreground runs, 8-connectivity with the row above ----
+VA_HD void phase_link(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  for (int id = tid; id < NR; id += nt) {
+    const int r = w.ry[id];
+    if (r == 0) continue;
+    const int lo = (int)w.rs[id] - 1, hi = imin((int)w.re[id] + 1, 32 * w.Wd - 1);
+    const int o2 = w.rowoff[r - 1];
+    const int jlo = (lo >= 0 && fg_at(w, r - 1, lo)) ? ns(w, r - 1, lo) - 1 : ns(w, r - 1, lo);
+    const int jhi = ns(w, r - 1, hi) - 1;
+    for (int j = jlo; j <= jhi; ++j) uf_union(w.pF, id, o2 + j);
+  }
+}
+// ---- phase 8: flatten ----
+VA_HD void phase_flatten(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  for (int id = tid; id < NR; id += nt) {
+    const int root = uf_find(w.pF, id);
+    if (root == id) atom_add(&w.sc[W_ROOTS], 1);
+    // compress only after every find of this phase is done?  Safe either way: parents only ever move towards the root.
+    w.pF[id] = root;
+  }
+}
+// ---- phase 9: table sums over the border pixels of G ----
+VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  for (int t = tid; t < w.R * w.Wd; t += nt) {
+    const int r = t / w.Wd, k = t - r * w.Wd;
+    const uint32_t M = w.G[t];
+    if (!M) continue;
+    const uint32_t U = word_at(w.G, w, r - 1, k), D = word_at(w.G, w, r + 1, k);
+    const uint32_t Up = word_at(w.G, w, r - 1, k - 1), Un = word_at(w.G, w, r - 1, k + 1);
+    const uint32_t Mp = word_at(w.G, w, r, k - 1), Mn = word_at(w.G, w, r, k + 1);
+    const uint32_t Dp = word_at(w.G, w, r + 1, k - 1), Dn = word_at(w.G, w, r + 1, k + 1);
+    const uint32_t Ul = (U << 1) | (Up >> 31), Ur = (U >> 1) | (Un << 31);
+    const uint32_t Ml = (M << 1) | (Mp >> 31), Mr = (M >> 1) | (Mn << 31);
+    const uint32_t Dl = (D << 1) | (Dp >> 31), Dr = (D >> 1) | (Dn << 31);
+    uint32_t border = M & ~(Ul & U & Ur & Ml & Mr & Dl & D & Dr);
+    int cur_root = -1, pts = 0, a2 = 0;
+    while (border) {
+      const int b = ffs32(border) - 1;
+      border &= border - 1;
+      const uint32_t code = ((Ul >> b) & 1u) | (((U >> b) & 1u) << 1) | (((Ur >> b) & 1u) << 2) | (((Ml >> b) & 1u) << 3) |
+                            (((Mr >> b) & 1u) << 4) | (((Dl >> b) & 1u) << 5) | (((D >> b) & 1u) << 6) | (((Dr >> b) & 1u) << 7);
+      const uint32_t e = lut[code];
+      const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+      if (!(p | dxs | dys)) continue;                   // a hole pixel touching the outside diagonally: no visit
+      const int lx = 32 * k + b;
+      const int root = w.pF[w.rowoff[r] + ns(w, r, lx) - 1];
+      if (root != cur_root) {
+        if (cur_root >= 0) { atom_add(&w.accP[cur_root], pts); atom_add(&w.accA[cur_root], a2); }
+        cur_root = root; pts = 0; a2 = 0;
+      }
+      pts += p;
+      a2 += lx * dys - r * dxs;                         // region-relative coordinates: the area is translation invariant
+    }
+    if (cur_root >= 0) { atom_add(&w.accP[cur_root], pts); atom_add(&w.accA[cur_root], a2); }
+  }
+}
+// ---- phase 10: the component whose contour has the most points; ties: the last in raster order ----
+VA_HD void phase_select(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  unsigned long long best = 0ull;
+  bool any = false;
+  for (int id = tid; id < NR; id += nt) {
+    if (w.pF[id] != id) continue;
+    const unsigned long long key = ((unsigned long long)(unsigned)w.accP[id] << 32) | (unsigned)(id + 1);
+    if (!any || key > best) { best = key; any = true; }
+  }
+  if (any) atom_max64(w.best, best);
+}
+// ---- phase 11: bounding box of the kept component ----
+VA_HD void phase_bbox(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  const int chosen = (int)(unsigned)(w.best[0] & 0xffffffffull) - 1;
+  if (tid == 0) w.sc[W_CHOSEN] = chosen;
+  if (chosen < 0) return;
+  int minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
+  for (int id = tid; id < NR; id += nt) {
+    if (w.pF[id] != chosen) continue;
+    minx = imin(minx, (int)w.rs[id]); maxx = imax(maxx, (int)w.re[id]);
+    miny = imin(miny, (int)w.ry[id]); maxy = imax(maxy, (int)w.ry[id]);
+  }
+  if (maxx >= 0) {
+    atom_min(&w.sc[W_MINX], minx); atom_max(&w.sc[W_MAXX], maxx);
+    atom_min(&w.sc[W_MINY], miny); atom_max(&w.sc[W_MAXY], maxy);
+  }
+}
+// ---- phase 12: cell-centre lattice samples of the kept component (= the fillPoly raster) + result ----
+VA_HD void phase_output(Work& w, int tid, int nt) {
+  const int half = w.gs >> 1;
+  const bool ok = !w.sc[W_OVERFLOW] && w.sc[W_CHOSEN] >= 0;
+  const int chosen = w.sc[W_CHOSEN];
+  for (int t = tid; t < w.lat_rows * w.lat_words; t += nt) {
+    const int ly = t / w.lat_words, lw = t - ly * w.lat_words;
+    const int y = w.gs * ly + half, r = y - w.y0;
+    unsigned word = 0;
+    if (ok && r >= 0 && r < w.R) {
+      for (int q = 0; q < 32; ++q) {
+        const int lx = 32 * lw + q;
+        if (lx >= w.lat_cols) break;
+        const int x = w.gs * lx + half - 32 * w.x0w;          // region-relative pixel
+        if (x < 0 || x >= 32 * w.Wd) continue;
+        if (!((w.G[r * w.Wd + (x >> 5)] >> (x & 31)) & 1u)) continue;
+        const int j = ns(w, r, x) - 1;                        // the run at or left of x (x is in it or in the hole after it)
+        if (j >= 0 && w.pF[w.rowoff[r] + j] == chosen) word |= 1u << q;
+      }
+    }
+    w.lattice[t] = word;
+  }
+  if (tid == 0) {
+    InstContour o;
+    o.area2 = 0; o.state = kEmpty; o.minx = 0; o.miny = 0; o.maxx = -1; o.maxy = -1; o.points = 0; o.n_components = 0;
+    if (w.sc[W_OVERFLOW]) {
+      o.state = kOverflow;
+    } else if (chosen >= 0) {
+      const int a = w.accA[chosen];
+      o.area2 = a < 0 ? -a : a;
+      o.points = w.accP[chosen];
+      o.n_components = w.sc[W_ROOTS];
+      o.state = (w.sc[W_ROOTS] == 1 && w.sc[W_HOLES] == 0) ? kSimple : kGeneral;
+      o.minx = 32 * w.x0w + w.sc[W_MINX]; o.maxx = 32 * w.x0w + w.sc[W_MAXX];
+      o.miny = w.y0 + w.sc[W_MINY]; o.maxy = w.y0 + w.sc[W_MAXY];
+    }
+    *w.out = o;
+  }
+}
+
+// Scratch layout in two parts, each placed in shared memory when it fits and in a global slab otherwise:
+// the grid part (bit images, per-word run counts, row offsets) and the run part (run table, union-find, sums).
+struct GridLayout { size_t Mfg, G, S, rowoff, seg, total; };
+struct RunLayout { size_t rs, re, ry, pF, pG, accP, accA, total; };
+VA_HD size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+VA_HD GridLayout grid_layout(int R, int Wd) {
+  GridLayout l;
+  size_t o = 0;
+  l.Mfg = o; o += align16(sizeof(uint32_t) * R * Wd);
+  l.G = o; o += align16(sizeof(uint32_t) * R * Wd);
+  l.S = o; o += align16(sizeof(uint16_t) * R * Wd);
+  l.rowoff = o; o += align16(sizeof(int) * (R + 1));
+  l.seg = o; o += align16(sizeof(int) * 33);
+  l.total = o;
+  return l;
+}
+VA_HD RunLayout run_layout(int cap) {
+  RunLayout l;
+  size_t o = 0;
+  l.rs = o; o += align16(sizeof(uint16_t) * cap);
+  l.re = o; o += align16(sizeof(uint16_t) * cap);
+  l.ry = o; o += align16(sizeof(uint16_t) * cap);
+  l.pF = o; o += align16(sizeof(int) * cap);
+  l.pG = o; o += align16(sizeof(int) * (cap + 1));
+  l.accP = o; o += align16(sizeof(int) * cap);
+  l.accA = o; o += align16(sizeof(int) * cap);
+  l.total = o;
+  return l;
+}
+VA_HD void bind_grid(Work& w, unsigned char* base, const GridLayout& l) {
+  w.Mfg = reinterpret_cast<uint32_t*>(base + l.Mfg); w.G = reinterpret_cast<uint32_t*>(base + l.G);
+  w.S = reinterpret_cast<uint16_t*>(base + l.S); w.rowoff = reinterpret_cast<int*>(base + l.rowoff);
+  w.seg = reinterpret_cast<int*>(base + l.seg);
+}
+VA_HD void bind_runs(Work& w, unsigned char* base, const RunLayout& l) {
+  w.rs = reinterpret_cast<uint16_t*>(base + l.rs); w.re = reinterpret_cast<uint16_t*>(base + l.re);
+  w.ry = reinterpret_cast<uint16_t*>(base + l.ry);
+  w.pF = reinterpret_cast<int*>(base + l.pF); w.pG = reinterpret_cast<int*>(base + l.pG);
+  w.accP = reinterpret_cast<int*>(base + l.accP); w.accA = reinterpret_cast<int*>(base + l.accA);
+}
+
+}  // namespace cc
+}  // namespace va

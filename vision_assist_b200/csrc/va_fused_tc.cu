@@ -71,6 +71,8 @@ struct FusedParams {
   float* logits_dbg;
   InstStats* stats;
   unsigned* lattice;
+  uint32_t* rowsum;  // [B][max_n][H][nblk] per-(row, 128 px block) summaries (va_contour_core.h)
+  uint16_t* bits16;  // [B][max_n][H][2 * bit_words] bit-packed masks, written when the u8 masks are not (else nullptr)
   int B;
   int nbands;        // bands per frame
   int ppb;           // row pairs per band
@@ -851,9 +853,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           for (; g8w < ng8w; g8w += kWarpsUp) {
           const int g = (g8w * subs + sub) * 8 + gl;
           const bool active = (g < NG) && (pair < npairs);
-          ThreadStats ts;
+          const size_t inst = (size_t)it.b * d.max_n + it.i0 + i;
+          RowPats rp;                                   // this lane's 16-pixel patterns of dst rows jbeg .. nrows_out-1 (slot = j - jbeg)
           if (active) {
-            const size_t inst = (size_t)it.b * d.max_n + it.i0 + i;
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
             // every proto pixel this task reads (rows r, r+1, cols 4g-1 .. 4g+4) is outside the instance's box:
             // crop_mask zeroed them, the masks are 0 - store and skip everything else
@@ -889,7 +891,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
               const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
               const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
               if (uni_neg || uni_pos) {
-                const int Yfirst = (jbeg < 0) ? 0 : 4 * r + 2, Ylast = 4 * r + 1 + nrows_out;
+                const int Ylast = 4 * r + 1 + nrows_out;
                 if (kWriteMasks) {
                   const uint4 w = uni_pos ? ones : zeros;
 #pragma unroll 1
@@ -899,9 +901,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                   }
                 }
                 if (uni_pos) {
-                  ts.area = 16u * (unsigned)(nrows_out - jbeg);
-                  ts.orw[0] = ts.orw[1] = ts.orw[2] = ts.orw[3] = 0x01010101u;
-                  ts.miny = Yfirst; ts.maxy = Ylast;
+                  const int nrow = nrows_out - jbeg;                       // 2, 4 or 6 rows of ones
+                  rp.lo = (nrow >= 4) ? ~0ull : 0xffffffffull;
+                  rp.hi = (nrow == 6) ? ~0u : 0u;
                   if (laty >= 0 && laty <= Ylast) lattice_row(ones, laty, 16 * g, d, lat);
                 }
               } else {
@@ -923,36 +925,36 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                     w = vblend(hA, hB, 1.0f - l1, l1);
                   }
                   if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
-                  ts.add_row(w, Y);
+                  rp.set(j - jbeg, pat16(w));
                   if (Y == laty && (w.x | w.y | w.z | w.w)) lattice_row(w, Y, 16 * g, d, lat);
                 }
-                ts.flush();
               }
             }
           }
-          // warp-level reduction (all lanes of a warp task share the instance), one set of smem atomics per warp
+          // Per-row by-products for the contour step: the 8 lanes of a slot hold one 128-pixel block of the same dst
+          // rows.  Three warp reductions per row (pixels set, first, last) -> one 4-byte summary per (row, block);
+          // the group leaders also carry the instance's area / bbox.  Grid-only mode writes the bit patterns too.
           __syncwarp();
-          const unsigned area = __reduce_add_sync(0xffffffffu, ts.area);
-          if (area) {
-            int minx = INT_MAX, maxx = -1;
-#pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) {
-              if (ts.orw[w4]) {
-                minx = min(minx, 16 * g + 4 * w4 + ((__ffs(ts.orw[w4]) - 1) >> 3));
-                maxx = max(maxx, 16 * g + 4 * w4 + ((31 - __clz(ts.orw[w4])) >> 3));
-              }
+          {
+            const unsigned gmask = 0xffu << (lane & 24);
+            const int nrow = active ? nrows_out - jbeg : 0;
+            const int srows = (r0 == 0) ? 6 : 4;                           // warp-uniform bound (pair 0 of the frame owns 6 rows)
+            uint32_t* rs_inst = p.rowsum + inst * (size_t)d.H * d.nblk;
+            LeaderStats ls;
+#pragma unroll 1
+            for (int sidx = 0; sidx < srows; ++sidx) {
+              const unsigned pat = rp.get(sidx);
+              const int Y = (jbeg < 0) ? sidx : 4 * r + 2 + sidx;
+              if (!kWriteMasks && sidx < nrow) p.bits16[(inst * d.H + Y) * (size_t)(2 * d.bit_words) + g] = (uint16_t)pat;
+              emit_row_summary(pat, gl, gmask, sidx < nrow, Y, g >> 3, rs_inst, d.nblk, ls);
             }
-            minx = __reduce_min_sync(0xffffffffu, minx);
-            maxx = __reduce_max_sync(0xffffffffu, maxx);
-            const int miny = __reduce_min_sync(0xffffffffu, ts.miny);
-            const int maxy = __reduce_max_sync(0xffffffffu, ts.maxy);
-            if (lane == 0) {
+            if (gl == 0 && ls.area) {
               const uint32_t st = wstat + i * 32;
-              atoms_add(st, (int)area);
-              atoms_min(st + 4, minx);
-              atoms_min(st + 8, miny);
-              atoms_max(st + 12, maxx);
-              atoms_max(st + 16, maxy);
+              atoms_add(st, (int)ls.area);
+              atoms_min(st + 4, ls.minx);
+              atoms_min(st + 8, ls.miny);
+              atoms_max(st + 12, ls.maxx);
+              atoms_max(st + 16, ls.maxy);
             }
           }
           }   // tasks of instance i
@@ -1097,7 +1099,7 @@ void fused_plan_destroy(FusedPlan* p) {
 }
 
 cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, const float* coefs, const float* boxes,
-                         const int* counts, int B, uint8_t* masks, float* logits_dbg, InstStats* stats, unsigned* lattice,
+                         const int* counts, int B, uint8_t* masks, float* logits_dbg, const MaskSinks& sinks,
                          cudaStream_t st, char* err, size_t errlen) {
   const size_t P = (size_t)d.mh * d.mw;
   if (pl->map_ptr != protos || pl->map_B != B) {
@@ -1115,7 +1117,10 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   }
   FusedParams p;
   p.d = d; p.coefs = coefs; p.boxes = boxes; p.counts = counts; p.masks = masks; p.logits_dbg = logits_dbg;
-  p.stats = stats; p.lattice = lattice; p.B = B;
+  p.stats = sinks.stats; p.lattice = sinks.lattice; p.B = B;
+  p.rowsum = sinks.rowsum;
+  p.bits16 = reinterpret_cast<uint16_t*>(sinks.bits);
+  if (!masks && !sinks.bits) { snprintf(err, errlen, "grid-only launch without a bit-mask buffer"); return cudaErrorInvalidValue; }
   p.timing = pl->timing;
   p.work_counter = pl->work_counter;
   p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = pl->ni; p.gsize = pl->ni; p.groups = pl->groups; p.chunk_floats = pl->chunk_floats; p.nbuf = pl->nbuf;

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "va_common.cuh"
+#include "va_contour_core.h"
 
 namespace va {
 
@@ -332,7 +333,7 @@ __device__ void write_header(const TailSmem& s, uint8_t* rec) {
   h.n_cols = s.sc[S_C]; h.n_rows = s.sc[S_R]; h.n_orphans = s.sc[S_NORPH]; h.n_peaks = s.sc[S_NPEAKS];
   h.area = s.sc[S_AREA]; h.n_mask_rows = s.sc[S_RM];
   h.minx = s.sc[S_MINX]; h.miny = s.sc[S_MINY]; h.maxx = s.sc[S_MAXX]; h.maxy = s.sc[S_MAXY];
-  h.euler = s.sc[S_EULER]; h.start_cell = s.sc[S_START];
+  h.contour_area2 = s.sc[S_EULER]; h.start_cell = s.sc[S_START];
   *reinterpret_cast<va_frame_header*>(rec) = h;
 }
 
@@ -553,33 +554,9 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
 // ---------------------------------------------------------------------------------------------
 // mask-driven tail
 // ---------------------------------------------------------------------------------------------
-__device__ int euler_number(const Dims& d, const uint8_t* m) {
-  // 8-connectivity Euler number by bit-quad counting (Gray): (Q1 - Q3 - 2*QD) / 4 over the
-  // zero-padded image.
-  int acc = 0;
-  const int total = (d.H + 1) * (d.W + 1);
-  for (int t = threadIdx.x; t < total; t += (int)blockDim.x) {
-    const int y = t / (d.W + 1) - 1, x = t % (d.W + 1) - 1;
-    const int a = (y >= 0 && x >= 0) ? (m[(size_t)y * d.W + x] != 0) : 0;
-    const int b = (y >= 0 && x + 1 < d.W) ? (m[(size_t)y * d.W + x + 1] != 0) : 0;
-    const int c = (y + 1 < d.H && x >= 0) ? (m[(size_t)(y + 1) * d.W + x] != 0) : 0;
-    const int e = (y + 1 < d.H && x + 1 < d.W) ? (m[(size_t)(y + 1) * d.W + x + 1] != 0) : 0;
-    const int sum = a + b + c + e;
-    if (sum == 1) acc += 1;
-    else if (sum == 3) acc -= 1;
-    else if (sum == 2 && a == e) acc -= 2;
-  }
-  __shared__ int s_red;
-  if (threadIdx.x == 0) s_red = 0;
-  __syncthreads();
-  atomicAdd(&s_red, acc);
-  __syncthreads();
-  return s_red / 4;
-}
-
 __global__ void __launch_bounds__(kTailMaxThreads)
 tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stats, unsigned* __restrict__ lattice,
-            const uint8_t* __restrict__ masks, const int* __restrict__ rects, const int* __restrict__ sel_in,
+            const cc::InstContour* __restrict__ contour, const int* __restrict__ rects, const int* __restrict__ sel_in,
             uint8_t* __restrict__ records) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TailSmem s;
@@ -593,43 +570,53 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   TT(0);
 
   __shared__ unsigned s_area[kMaxInst];
+  __shared__ int s_area2[kMaxInst], s_state[kMaxInst];
   __shared__ int s_bbox[kMaxInst][4];
   for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
   for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
-  // Programmatic dependent launch: this kernel may become resident while the mask kernel is still draining (its
-  // CTAs finish at different times); everything above touched only shared memory and kernel inputs.  Wait here for
-  // the mask kernel's writes (statistics, lattice bits, masks).
+  // Programmatic dependent launch: this kernel may become resident while the kernels before it are still draining;
+  // everything above touched only shared memory and kernel inputs.  Wait here for their writes (contour results,
+  // lattice bits, statistics).
   asm volatile("griddepcontrol.wait;" ::: "memory");
   TT(1);
-  if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
+  if (threadIdx.x < kMaxInst) {      // all per-instance results in one parallel round of global loads
     const int i = threadIdx.x;
-    InstStats v;
-    v.area = 0; v.minx = 0; v.miny = 0; v.maxx = -1; v.maxy = -1;
-    if (i < n) v = st[i];
-    s_area[i] = v.area;
+    cc::InstContour v;
+    v.area2 = 0; v.state = cc::kEmpty; v.minx = 0; v.miny = 0; v.maxx = -1; v.maxy = -1;
+    unsigned area = 0;
+    if (i < n) { v = contour[(size_t)b * d.max_n + i]; area = st[i].area; }
+    s_area[i] = area;
+    s_area2[i] = (v.state == cc::kSimple || v.state == cc::kGeneral) ? v.area2 : 0;
+    s_state[i] = v.state;
     s_bbox[i][0] = v.minx; s_bbox[i][1] = v.miny; s_bbox[i][2] = v.maxx; s_bbox[i][3] = v.maxy;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
     s.sc[S_USE_EASY] = 1;
-    // ---- instance selection: largest pixel area, first maximum (FrameProcessor.py:71-73 uses
-    //      cv2.contourArea of the polygon; see DESIGN.md "selection").  Areas were pre-loaded in parallel. ----
+    // ---- instance selection (FrameProcessor.py:71-73): the polygon with the largest cv2.contourArea, first maximum;
+    //      a single instance is taken as it is.  Areas come from the contour step (doubled, exact integers); an empty
+    //      polygon has area 0. ----
     int sel = -1;
-    unsigned best = 0;
     if (sel_in) {
       sel = sel_in[b];
-      if (sel < 0 || sel >= n) sel = -1; else best = s_area[sel];
-    } else {
-      for (int i = 0; i < n; ++i) if (s_area[i] > best) { best = s_area[i]; sel = i; }
-      if (sel < 0 && n > 0) sel = 0;
+      if (sel < 0 || sel >= n) sel = -1;
+    } else if (n > 0) {
+      sel = 0;
+      for (int i = 1; i < n; ++i) if (s_area2[i] > s_area2[sel]) sel = i;
     }
     s.sc[S_SEL] = sel;
-    s.sc[S_AREA] = (int)best;
+    s.sc[S_AREA] = sel >= 0 ? (int)s_area[sel] : 0;
+    s.sc[S_EULER] = sel >= 0 ? s_area2[sel] : 0;
     int flags = 0;
-    if (sel < 0 || best == 0) {
+    if (sel < 0) {
       flags = VA_FLAG_EMPTY;
+    } else if (s_state[sel] == cc::kEmpty) {
+      flags = VA_FLAG_EMPTY | VA_FLAG_NO_POLYGON;     // cv2.fillPoly raises on the empty polygon (FrameProcessor.py:86)
+    } else if (s_state[sel] != cc::kSimple && s_state[sel] != cc::kGeneral) {
+      flags = VA_FLAG_EMPTY | VA_FLAG_OVERFLOW;       // run capacity of the contour step exceeded
     } else {
+      if (s_state[sel] == cc::kGeneral) flags |= VA_FLAG_NON_SIMPLE;
       int x, y, w, h;
       if (rects) { x = rects[4 * b]; y = rects[4 * b + 1]; w = rects[4 * b + 2]; h = rects[4 * b + 3]; }
       else { x = s_bbox[sel][0]; y = s_bbox[sel][1]; w = s_bbox[sel][2] - x + 1; h = s_bbox[sel][3] - y + 1; }
@@ -641,9 +628,9 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       if (h % gs != 0) h += gs - h % gs;             // :83
       const int C = ceil_div(w, gs), Rm = ceil_div(h, gs);   // len(arange(x, x+w, gs))
       s.sc[S_X0] = x; s.sc[S_Y0] = y; s.sc[S_C] = C; s.sc[S_RM] = Rm;
-      if (C <= 0 || Rm <= 0) flags = VA_FLAG_EMPTY;
-      else if (y + (Rm - 1) * gs + gs / 2 >= d.H || x + (C - 1) * gs + gs / 2 >= d.W) flags = VA_FLAG_CENTRE_OOB;  // :97
-      else if (C > d.cmax || Rm > d.rmax) flags = VA_FLAG_OVERFLOW | VA_FLAG_EMPTY;
+      if (C <= 0 || Rm <= 0) flags |= VA_FLAG_EMPTY;
+      else if (y + (Rm - 1) * gs + gs / 2 >= d.H || x + (C - 1) * gs + gs / 2 >= d.W) flags |= VA_FLAG_CENTRE_OOB;  // :97
+      else if (C > d.cmax || Rm > d.rmax) flags |= VA_FLAG_OVERFLOW | VA_FLAG_EMPTY;
     }
     s.sc[S_FLAGS] = flags;
     TT(2);
@@ -729,13 +716,6 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     }
   }
   __syncthreads();
-  if ((d.flags & VA_CFG_CHECK_SIMPLE) && masks && sel >= 0 && s.sc[S_AREA] > 0) {
-    const int e = euler_number(d, masks + ((size_t)b * d.max_n + sel) * (size_t)d.H * d.W);
-    if (threadIdx.x == 0) {
-      s.sc[S_EULER] = e;
-      if (e != 1) s.sc[S_FLAGS] |= VA_FLAG_NON_SIMPLE;
-    }
-  }
   TT(4);
   finish_record(d, s, rec);
   TT(13);
@@ -848,8 +828,8 @@ static int tail_threads(const Dims& d, int B) {
   return (2 * B <= sms) ? kTailMaxThreads : 512;
 }
 
-cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice,
-                        const uint8_t* masks, const int* rects, const int* sel, uint8_t* records, cudaStream_t st) {
+cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice, const void* contour,
+                        const int* rects, const int* sel, uint8_t* records, cudaStream_t st) {
   const size_t smem = tail_smem_bytes(d);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -867,7 +847,7 @@ cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stat
   cfg.attrs = attr;
   static const bool no_pdl = getenv("VA_NO_PDL") != nullptr;   // tuning aid: plain stream-ordered launch
   cfg.numAttrs = no_pdl ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, tail_kernel, d, counts, stats, lattice, masks, rects, sel, records);
+  return cudaLaunchKernelEx(&cfg, tail_kernel, d, counts, stats, lattice, reinterpret_cast<const cc::InstContour*>(contour), rects, sel, records);
 }
 
 cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,

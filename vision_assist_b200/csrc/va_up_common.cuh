@@ -6,6 +6,7 @@
 #include <climits>
 
 #include "va_common.cuh"
+#include "va_contour_core.h"
 
 namespace va {
 
@@ -84,6 +85,83 @@ static __device__ __noinline__ void lattice_row_impl(unsigned w0, unsigned w1, u
 }
 __device__ __forceinline__ void lattice_row(const uint4& w, int Y, int xbase, const Dims& d, unsigned* lat) {
   lattice_row_impl(w.x, w.y, w.z, w.w, Y, xbase, d.gs, d.lat_cols, d.lat_words, lat);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row by-products for the contour step (va_contour_core.h): every mask kernel maps the 8 lanes of a lane group
+// (lane & 7 = 16-pixel piece, lane >> 3 = row slot) to one 128-pixel block of one dst row
+// ---------------------------------------------------------------------------------------------
+// 16 mask bytes (0 / 1) -> 16 bits
+__device__ __forceinline__ unsigned pat16(const uint4& w) {
+  return ((w.x * 0x01020408u) >> 24) | (((w.y * 0x01020408u) >> 24) << 4) | (((w.z * 0x01020408u) >> 24) << 8) |
+         (((w.w * 0x01020408u) >> 24) << 12);
+}
+// 16 bits -> 16 mask bytes
+__device__ __forceinline__ uint4 bytes16(unsigned pat) {
+  auto ex = [](unsigned n) { return ((n & 0xfu) * 0x00204081u) & 0x01010101u; };
+  return make_uint4(ex(pat), ex(pat >> 4), ex(pat >> 8), ex(pat >> 12));
+}
+
+// 16-pixel patterns of up to 6 dst rows of one lane (slot s = row ordinal inside the task), three registers
+struct RowPats {
+  unsigned long long lo = 0ull;
+  unsigned hi = 0u;
+  __device__ __forceinline__ void set(int s, unsigned pat) {
+    if (s < 4) lo |= (unsigned long long)pat << (16 * s);
+    else hi |= pat << (16 * (s - 4));
+  }
+  __device__ __forceinline__ unsigned get(int s) const {
+    return (s < 4) ? (unsigned)(lo >> (16 * s)) & 0xffffu : (hi >> (16 * (s - 4))) & 0xffffu;
+  }
+};
+
+// what the leader lane (lane & 7 == 0) of a group accumulates for the instance's InstStats
+struct LeaderStats {
+  unsigned area = 0;
+  int minx = INT_MAX, miny = INT_MAX, maxx = -1, maxy = -1;
+};
+
+// One dst row of a lane group: reduce the 8 patterns to the (row, block) summary, store it, feed the leader's stats.
+// ALL 32 lanes of the warp must call (with their own group's mask); `exists` = this lane's row is a real row.
+__device__ __forceinline__ void emit_row_summary(unsigned pat, int gl, unsigned gmask, bool exists, int Y, int blk,
+                                                 uint32_t* __restrict__ rowsum_inst, int nblk, LeaderStats& ls) {
+  const int c = (int)__reduce_add_sync(gmask, (unsigned)__popc(pat));
+  const int f = __reduce_min_sync(gmask, pat ? 16 * gl + __ffs((int)pat) - 1 : 255);
+  const int l = __reduce_max_sync(gmask, pat ? 16 * gl + 31 - __clz((int)pat) : -1);
+  if (exists && gl == 0) {
+    rowsum_inst[(size_t)Y * nblk + blk] = c ? cc::rowsum_pack(c, f, l) : 0u;
+    if (c) {
+      ls.area += (unsigned)c;
+      ls.minx = min(ls.minx, cc::kRowBlock * blk + f);
+      ls.maxx = max(ls.maxx, cc::kRowBlock * blk + l);
+      ls.miny = min(ls.miny, Y);
+      ls.maxy = max(ls.maxy, Y);
+    }
+  }
+}
+
+__device__ __forceinline__ void publish_leader(const LeaderStats& ls, InstStats* dst) {
+  if (ls.area) {
+    atomicAdd(&dst->area, ls.area);
+    atomicMin(&dst->minx, ls.minx);
+    atomicMin(&dst->miny, ls.miny);
+    atomicMax(&dst->maxx, ls.maxx);
+    atomicMax(&dst->maxy, ls.maxy);
+  }
+}
+
+// lattice samples from a 16-bit pattern (see lattice_row)
+static __device__ __noinline__ void lattice_row_pat(unsigned pat, int Y, int xbase, int gs, int lat_cols, int lat_words,
+                                                    unsigned* lat) {
+  const int half = gs >> 1;
+  const int ly = (Y - half) / gs;
+  int lx = (xbase - half + gs - 1) / gs;
+  if (lx < 0) lx = 0;
+  for (; lx < lat_cols; ++lx) {
+    const int pos = gs * lx + half - xbase;
+    if (pos > 15) break;
+    if ((pat >> pos) & 1u) atomicOr(&lat[ly * lat_words + (lx >> 5)], 1u << (lx & 31));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

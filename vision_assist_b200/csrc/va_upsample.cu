@@ -21,10 +21,33 @@ struct RowState {
   bool hvalid;
 };
 
+// Common sink of one finished dst row of a lane: lattice sample, bit-packed row (grid-only mode) and the
+// (row, 128 px block) summary.  Called by ALL lanes of a lane group at the same point (warp reductions inside).
+struct RowSink {
+  const Dims& d;
+  uint32_t* rowsum_inst;
+  uint16_t* bits_inst;      // nullptr unless grid-only
+  unsigned* lat;
+  int g, gl;
+  unsigned gmask;
+  bool gok;                 // this lane's 16-pixel piece exists (g < NG)
+  LeaderStats ls;
+  __device__ __forceinline__ void row(unsigned pat, int Y, bool exists) {
+    const bool ex = exists && gok;
+    if (ex && pat) {
+      const int t = Y - (d.gs >> 1);
+      if (t >= 0 && t % d.gs == 0) lattice_row_pat(pat, Y, 16 * g, d.gs, d.lat_cols, d.lat_words, lat);
+    }
+    if (ex && bits_inst) bits_inst[(size_t)Y * (2 * d.bit_words) + g] = (uint16_t)pat;
+    // the leader's piece always exists when any piece of the group does (pieces are numbered left to right)
+    emit_row_summary(ex ? pat : 0u, gl, gmask, exists, Y, g >> 3, rowsum_inst, d.nblk, ls);
+  }
+};
+
 template <bool kWriteMasks>
 __global__ void __launch_bounds__(kUpThreads, 3)
 upsample4x_kernel(Dims d, const float* __restrict__ logits, const int* __restrict__ counts, uint8_t* __restrict__ masks,
-                  InstStats* __restrict__ stats, unsigned* __restrict__ lattice) {
+                  MaskSinks sk) {
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= min(counts[b], d.max_n)) return;
   const int NG = d.W >> 4;                        // 16-px groups per row
@@ -37,100 +60,103 @@ upsample4x_kernel(Dims d, const float* __restrict__ logits, const int* __restric
   const int strip = (wt / NG8) * 4 + (lane >> 3);
   const int r_begin = strip * kStrip;
   const int r_end = min(r_begin + kStrip, d.mh);
-  const bool active = (g < NG) && (r_begin < d.mh);
+  if (r_begin >= d.mh) return;                    // the whole lane group leaves together
+  const bool gok = g < NG;
+  const int ge = gok ? g : NG - 1;                // lanes past the row width follow the group with a clamped piece
 
   const size_t inst = (size_t)b * d.max_n + i;
   const float* L = logits + inst * d.mh * d.mw;
-  uint8_t* M = kWriteMasks ? masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
-  unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
-  const int half = d.gs >> 1;
-  ThreadStats ts;
+  uint8_t* M = kWriteMasks ? masks + inst * (size_t)d.H * d.W + 16 * ge : nullptr;
+  RowSink sink{d, sk.rowsum + inst * (size_t)d.H * d.nblk,
+               (!kWriteMasks && sk.bits) ? reinterpret_cast<uint16_t*>(sk.bits) + inst * (size_t)d.H * (2 * d.bit_words) : nullptr,
+               sk.lattice + inst * (size_t)d.lat_rows * d.lat_words, g, lane & 7, 0xffu << (lane & 24), gok, LeaderStats()};
 
-  if (active) {
-    const bool left = (g == 0);
-    RowState A, Bq;
-    load6(L + (size_t)r_begin * d.mw, g, d.mw, A.s, A.mn, A.mx);
-    A.hvalid = false;
+  const bool left = (ge == 0);
+  RowState A, Bq;
+  load6(L + (size_t)r_begin * d.mw, ge, d.mw, A.s, A.mn, A.mx);
+  A.hvalid = false;
+  auto store = [&](const uint4& w, int Y) {
+    if (kWriteMasks && gok) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
+  };
+  const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  const uint4 zeros = make_uint4(0, 0, 0, 0);
 
-    // rows are emitted in increasing Y: keep the next cell-centre row instead of a modulo per row
-    const int Yfirst = (r_begin == 0) ? 0 : 4 * r_begin + 2;
-    int next_lat = (Yfirst <= half) ? half : half + ceil_div(Yfirst - half, d.gs) * d.gs;
-    auto emit = [&](const uint4& w, int Y) {
-      if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
-      ts.add_row(w, Y);
-      if (Y == next_lat) {
-        next_lat += d.gs;
-        if (w.x | w.y | w.z | w.w) lattice_row(w, Y, 16 * g, d, lat);
-      }
-    };
-    const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-    const uint4 zeros = make_uint4(0, 0, 0, 0);
-
-    if (r_begin == 0) {   // dst rows 0,1: src y clamps to 0 -> l0 = 1, l1 = 0 -> value = h(row 0)
-      uint4 w;
-      if (A.mn > kTiny) w = ones;
-      else if (A.mx <= 0.f) w = zeros;
-      else {
-        hinterp4(A.s, A.h, left);
-        A.hvalid = true;
-        w = make_uint4(pack4(A.h[0], A.h[1], A.h[2], A.h[3]), pack4(A.h[4], A.h[5], A.h[6], A.h[7]),
-                       pack4(A.h[8], A.h[9], A.h[10], A.h[11]), pack4(A.h[12], A.h[13], A.h[14], A.h[15]));
-      }
-      emit(w, 0);
-      emit(w, 1);
+  if (r_begin == 0) {   // dst rows 0,1: src y clamps to 0 -> l0 = 1, l1 = 0 -> value = h(row 0)
+    uint4 w;
+    if (A.mn > kTiny) w = ones;
+    else if (A.mx <= 0.f) w = zeros;
+    else {
+      hinterp4(A.s, A.h, left);
+      A.hvalid = true;
+      w = hpack(A.h);
     }
-
-    auto step = [&](RowState& P, RowState& Q, int r) {
-      // pair (r, r+1): dst rows 4r+2 .. 4r+5
-      load6(L + (size_t)(r + 1) * d.mw, g, d.mw, Q.s, Q.mn, Q.mx);
-      Q.hvalid = false;
-      const float mn = fminf(P.mn, Q.mn), mx = fmaxf(P.mx, Q.mx);
-      const int Y0 = 4 * r + 2;
-      if (mn > kTiny) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) emit(ones, Y0 + j);
-      } else if (mx <= 0.f) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) emit(zeros, Y0 + j);
-      } else {
-        if (!P.hvalid) { hinterp4(P.s, P.h, left); P.hvalid = true; }
-        hinterp4(Q.s, Q.h, left);
-        Q.hvalid = true;
-        emit(vblend(P.h, Q.h, 0.875f, 0.125f), Y0);
-        emit(vblend(P.h, Q.h, 0.625f, 0.375f), Y0 + 1);
-        emit(vblend(P.h, Q.h, 0.375f, 0.625f), Y0 + 2);
-        emit(vblend(P.h, Q.h, 0.125f, 0.875f), Y0 + 3);
-      }
-    };
-    auto last_step = [&](RowState& P) {
-      // bottom edge r = mh-1: src row r+1 clamps to r, only dst rows 4r+2, 4r+3 exist
-      const int Y0 = 4 * (d.mh - 1) + 2;
-      if (P.mn > kTiny) { emit(ones, Y0); emit(ones, Y0 + 1); }
-      else if (P.mx <= 0.f) { emit(zeros, Y0); emit(zeros, Y0 + 1); }
-      else {
-        if (!P.hvalid) { hinterp4(P.s, P.h, left); P.hvalid = true; }
-        emit(vblend(P.h, P.h, 0.875f, 0.125f), Y0);
-        emit(vblend(P.h, P.h, 0.625f, 0.375f), Y0 + 1);
-      }
-    };
-    const int r_pairs_end = min(r_end, d.mh - 1);   // pairs with a real second row
-    int r = r_begin;
-    for (; r + 1 < r_pairs_end; r += 2) {
-      step(A, Bq, r);
-      step(Bq, A, r + 1);
-    }
-    if (r < r_pairs_end) {
-      step(A, Bq, r);
-      if (r_end == d.mh) last_step(Bq);
-    } else if (r_end == d.mh) {
-      last_step(A);
-    }
+    store(w, 0);
+    store(w, 1);
+    const unsigned pat = pat16(w);
+    sink.row(pat, 0, true);
+    sink.row(pat, 1, true);
   }
-  publish_stats(ts, 16 * g, stats + inst);
+
+  auto step = [&](RowState& P, RowState& Q, int r) {
+    // pair (r, r+1): dst rows 4r+2 .. 4r+5
+    load6(L + (size_t)(r + 1) * d.mw, ge, d.mw, Q.s, Q.mn, Q.mx);
+    Q.hvalid = false;
+    const float mn = fminf(P.mn, Q.mn), mx = fmaxf(P.mx, Q.mx);
+    const int Y0 = 4 * r + 2;
+    unsigned pp[4];
+    if (mn > kTiny) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { store(ones, Y0 + j); pp[j] = 0xffffu; }
+    } else if (mx <= 0.f) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { store(zeros, Y0 + j); pp[j] = 0u; }
+    } else {
+      if (!P.hvalid) { hinterp4(P.s, P.h, left); P.hvalid = true; }
+      hinterp4(Q.s, Q.h, left);
+      Q.hvalid = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float l1 = 0.125f + 0.25f * (float)j;
+        const uint4 w = vblend(P.h, Q.h, 1.0f - l1, l1);
+        store(w, Y0 + j);
+        pp[j] = pat16(w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sink.row(pp[j], Y0 + j, true);
+  };
+  auto last_step = [&](RowState& P) {
+    // bottom edge r = mh-1: src row r+1 clamps to r, only dst rows 4r+2, 4r+3 exist
+    const int Y0 = 4 * (d.mh - 1) + 2;
+    unsigned pp[2];
+    if (P.mn > kTiny) { store(ones, Y0); store(ones, Y0 + 1); pp[0] = pp[1] = 0xffffu; }
+    else if (P.mx <= 0.f) { store(zeros, Y0); store(zeros, Y0 + 1); pp[0] = pp[1] = 0u; }
+    else {
+      if (!P.hvalid) { hinterp4(P.s, P.h, left); P.hvalid = true; }
+      const uint4 w0 = vblend(P.h, P.h, 0.875f, 0.125f), w1 = vblend(P.h, P.h, 0.625f, 0.375f);
+      store(w0, Y0); store(w1, Y0 + 1);
+      pp[0] = pat16(w0); pp[1] = pat16(w1);
+    }
+    sink.row(pp[0], Y0, true);
+    sink.row(pp[1], Y0 + 1, true);
+  };
+  const int r_pairs_end = min(r_end, d.mh - 1);   // pairs with a real second row
+  int r = r_begin;
+  for (; r + 1 < r_pairs_end; r += 2) {
+    step(A, Bq, r);
+    step(Bq, A, r + 1);
+  }
+  if (r < r_pairs_end) {
+    step(A, Bq, r);
+    if (r_end == d.mh) last_step(Bq);
+  } else if (r_end == d.mh) {
+    last_step(A);
+  }
+  if ((lane & 7) == 0) publish_leader(sink.ls, sk.stats + inst);
 }
 
 // ---------------------------------------------------------------------------------------------
-// generic-scale kernel: one thread = 16 consecutive dst pixels of one dst row
+// generic-scale kernel: one thread = 16 consecutive dst pixels of kGenRows dst rows
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
   float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
@@ -146,8 +172,7 @@ constexpr int kGenRows = 8;   // dst rows per thread (same 16 columns): the colu
 template <bool kWriteMasks>
 __global__ void __launch_bounds__(kUpThreads, 8)
 upsample_generic_kernel(Dims d, const float* __restrict__ logits, const float* __restrict__ boxes,
-                        const int* __restrict__ counts, uint8_t* __restrict__ masks, InstStats* __restrict__ stats,
-                        unsigned* __restrict__ lattice) {
+                        const int* __restrict__ counts, uint8_t* __restrict__ masks, MaskSinks sk) {
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= min(counts[b], d.max_n)) return;
   const size_t inst = (size_t)b * d.max_n + i;
@@ -179,105 +204,86 @@ upsample_generic_kernel(Dims d, const float* __restrict__ logits, const float* _
   const int g = (wt % NG8) * 8 + (lane & 7);
   const int Ybeg = ((wt / NG8) * 4 + (lane >> 3)) * kGenRows;
   const int Yend = min(Ybeg + kGenRows, d.H);
+  if (Ybeg >= d.H) return;                          // the whole lane group leaves together
+  const bool gok = g < NG;
   const float* L = logits + inst * d.mh * d.mw;
-  unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
-  ThreadStats ts;
-  if (g < NG && Ybeg < d.H) {
-    const int X0 = 16 * g, X1 = min(X0 + 15, d.W - 1);
-    const int npx = X1 - X0 + 1;
-    const bool col_in = !(X1 < rXa || X0 > rXb);
-    int xa = 0, xb = 0;                        // proto columns the 16 pixels can read
-    if (col_in) {
-      int t;
-      float f0, f1;
-      src_index(d.sx, X0, d.mw, xa, t, f0, f1);
-      src_index(d.sx, X1, d.mw, t, xb, f0, f1);
-    }
-    uint8_t* M = kWriteMasks ? masks + inst * (size_t)d.H * d.W + X0 : nullptr;
-    const bool vec = (npx == 16) && ((d.W & 15) == 0);
-    if (!col_in || Yend <= rYa || Ybeg > rYb) {
-      // whole thread tile outside the rectangle (the common case with many small instances): zeros, nothing else
-      if (kWriteMasks) {
-        uint8_t* Mr = M + (size_t)Ybeg * d.W;
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < kGenRows; ++j)
-            if (Ybeg + j < Yend) *reinterpret_cast<uint4*>(Mr + (size_t)j * d.W) = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          for (int Y = Ybeg; Y < Yend; ++Y, Mr += d.W)
-            for (int px = 0; px < npx; ++px) Mr[px] = 0;
-        }
-      }
-    } else {
-    int py0 = -1, py1 = -1;
-    float mn = 0.f, mx = 0.f;
-    // next lattice (cell-centre) row at or after Ybeg: rows gs/2, gs/2 + gs, ...
-    int Ylat = (d.gs >> 1) + ceil_div(max(Ybeg - (d.gs >> 1), 0), d.gs) * d.gs;
-#pragma unroll 1
-    for (int Y = Ybeg; Y < Yend; ++Y) {
-      unsigned ww[4] = {0u, 0u, 0u, 0u};
-      if (Y >= rYa && Y <= rYb) {
-        int y0, y1;
-        float ly0, ly1;
-        src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
-        const float* r0 = L + (size_t)y0 * d.mw;
-        const float* r1 = L + (size_t)y1 * d.mw;
-        if (y0 != py0 || y1 != py1) {            // sign range of every tap these 16 pixels can read in rows y0, y1
-          mn = INFINITY; mx = -INFINITY;
-          for (int x = xa; x <= xb; ++x) {
-            const float u = __ldg(r0 + x), v = __ldg(r1 + x);
-            mn = fminf(mn, fminf(u, v));
-            mx = fmaxf(mx, fmaxf(u, v));
-          }
-          py0 = y0; py1 = y1;
-        }
-        if (mn > kTiny) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int left = npx - 4 * q;        // pixels of this word that exist
-            ww[q] = left >= 4 ? 0x01010101u : left <= 0 ? 0u : (0x01010101u >> (8 * (4 - left)));
-          }
-        } else if (mx > 0.f) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            unsigned acc = 0;
-#pragma unroll 1
-            for (int k = 0; k < 4 && 4 * q + k < npx; ++k) {
-              int x0, x1;
-              float lx0, lx1;
-              src_index(d.sx, X0 + 4 * q + k, d.mw, x0, x1, lx0, lx1);
-              const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
-              const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
-              const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
-              if (o > 0.f) acc |= 1u << (8 * k);
-            }
-            ww[q] = acc;
-          }
-        }
-      }
-      const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
-      if (kWriteMasks) {
-        uint8_t* Mr = M + (size_t)Y * d.W;
-        if (vec) *reinterpret_cast<uint4*>(Mr) = w;
-        else for (int px = 0; px < npx; ++px) Mr[px] = (uint8_t)(((px < 4 ? w.x : px < 8 ? w.y : px < 12 ? w.z : w.w) >> (8 * (px & 3))) & 1u);
-      }
-      if (Y == Ylat) {
-        Ylat += d.gs;
-        if (ww[0] | ww[1] | ww[2] | ww[3]) lattice_row(w, Y, X0, d, lat);
-      }
-      ts.add_row(w, Y);
-    }
-    }
+  RowSink sink{d, sk.rowsum + inst * (size_t)d.H * d.nblk,
+               (!kWriteMasks && sk.bits) ? reinterpret_cast<uint16_t*>(sk.bits) + inst * (size_t)d.H * (2 * d.bit_words) : nullptr,
+               sk.lattice + inst * (size_t)d.lat_rows * d.lat_words, g, lane & 7, 0xffu << (lane & 24), gok, LeaderStats()};
+  const int X0 = 16 * g, X1 = min(X0 + 15, d.W - 1);
+  const int npx = gok ? X1 - X0 + 1 : 0;
+  const bool col_in = gok && !(X1 < rXa || X0 > rXb);
+  int xa = 0, xb = 0;                        // proto columns the 16 pixels can read
+  if (col_in) {
+    int t;
+    float f0, f1;
+    src_index(d.sx, X0, d.mw, xa, t, f0, f1);
+    src_index(d.sx, X1, d.mw, t, xb, f0, f1);
   }
-  if (__any_sync(0xffffffffu, ts.acc != 0)) publish_stats(ts, 16 * g, stats + inst);
+  uint8_t* M = (kWriteMasks && gok) ? masks + inst * (size_t)d.H * d.W + X0 : nullptr;
+  const bool vec = (npx == 16) && ((d.W & 15) == 0);
+  // whole thread tile outside the rectangle (the common case with many small instances): zeros, no logit is read
+  const bool tile_out = !col_in || Yend <= rYa || Ybeg > rYb;
+  int py0 = -1, py1 = -1;
+  float mn = 0.f, mx = 0.f;
+#pragma unroll 1
+  for (int Y = Ybeg; Y < Yend; ++Y) {
+    unsigned ww[4] = {0u, 0u, 0u, 0u};
+    if (!tile_out && Y >= rYa && Y <= rYb) {
+      int y0, y1;
+      float ly0, ly1;
+      src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
+      const float* r0 = L + (size_t)y0 * d.mw;
+      const float* r1 = L + (size_t)y1 * d.mw;
+      if (y0 != py0 || y1 != py1) {            // sign range of every tap these 16 pixels can read in rows y0, y1
+        mn = INFINITY; mx = -INFINITY;
+        for (int x = xa; x <= xb; ++x) {
+          const float u = __ldg(r0 + x), v = __ldg(r1 + x);
+          mn = fminf(mn, fminf(u, v));
+          mx = fmaxf(mx, fmaxf(u, v));
+        }
+        py0 = y0; py1 = y1;
+      }
+      if (mn > kTiny) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int left = npx - 4 * q;        // pixels of this word that exist
+          ww[q] = left >= 4 ? 0x01010101u : left <= 0 ? 0u : (0x01010101u >> (8 * (4 - left)));
+        }
+      } else if (mx > 0.f) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          unsigned acc = 0;
+#pragma unroll 1
+          for (int k = 0; k < 4 && 4 * q + k < npx; ++k) {
+            int x0, x1;
+            float lx0, lx1;
+            src_index(d.sx, X0 + 4 * q + k, d.mw, x0, x1, lx0, lx1);
+            const float top = fmaf(__ldg(r0 + x0), lx0, __fmul_rn(__ldg(r0 + x1), lx1));
+            const float bot = fmaf(__ldg(r1 + x0), lx0, __fmul_rn(__ldg(r1 + x1), lx1));
+            const float o = fmaf(top, ly0, __fmul_rn(bot, ly1));
+            if (o > 0.f) acc |= 1u << (8 * k);
+          }
+          ww[q] = acc;
+        }
+      }
+    }
+    const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+    if (M) {
+      uint8_t* Mr = M + (size_t)Y * d.W;
+      if (vec) *reinterpret_cast<uint4*>(Mr) = w;
+      else for (int px = 0; px < npx; ++px) Mr[px] = (uint8_t)(((px < 4 ? w.x : px < 8 ? w.y : px < 12 ? w.z : w.w) >> (8 * (px & 3))) & 1u);
+    }
+    sink.row(pat16(w), Y, true);
+  }
+  if ((lane & 7) == 0) publish_leader(sink.ls, sk.stats + inst);
 }
 
 // ---------------------------------------------------------------------------------------------
-// stats from caller-provided u8 masks (va_mask_to_records)
+// by-products from caller-provided u8 masks (va_mask_to_records)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kUpThreads)
-mask_stats_kernel(Dims d, const uint8_t* __restrict__ masks, const int* __restrict__ counts,
-                  InstStats* __restrict__ stats, unsigned* __restrict__ lattice) {
+mask_stats_kernel(Dims d, const uint8_t* __restrict__ masks, const int* __restrict__ counts, MaskSinks sk) {
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= min(counts[b], d.max_n)) return;
   const int NG = ceil_div(d.W, 16);
@@ -289,30 +295,29 @@ mask_stats_kernel(Dims d, const uint8_t* __restrict__ masks, const int* __restri
   const int g = (wt % NG8) * 8 + (lane & 7);
   const int Y = (wt / NG8) * 4 + (lane >> 3);
   const size_t inst = (size_t)b * d.max_n + i;
-  unsigned* lat = lattice + inst * (size_t)d.lat_rows * d.lat_words;
-  ThreadStats ts;
+  RowSink sink{d, sk.rowsum + inst * (size_t)d.H * d.nblk, nullptr, sk.lattice + inst * (size_t)d.lat_rows * d.lat_words,
+               g, lane & 7, 0xffu << (lane & 24), g < NG, LeaderStats()};
+  unsigned pat = 0;
   if (g < NG && Y < d.H) {
     const uint8_t* M = masks + inst * (size_t)d.H * d.W + (size_t)Y * d.W + 16 * g;
-    unsigned ww[4] = {0, 0, 0, 0};
     const int npx = min(16, d.W - 16 * g);
     if (npx == 16 && (d.W & 15) == 0) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(M));
       const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+      unsigned ww[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {   // normalise non-zero bytes to 1
         unsigned t = vv[q];
         t |= t >> 4; t |= t >> 2; t |= t >> 1;
         ww[q] = t & 0x01010101u;
       }
+      pat = pat16(make_uint4(ww[0], ww[1], ww[2], ww[3]));
     } else {
-      for (int px = 0; px < npx; ++px) if (M[px]) ww[px >> 2] |= 1u << (8 * (px & 3));
+      for (int px = 0; px < npx; ++px) if (M[px]) pat |= 1u << px;
     }
-    const uint4 w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
-    ts.add_row(w, Y);
-    const int t = Y - (d.gs >> 1);
-    if (t >= 0 && t % d.gs == 0 && (ww[0] | ww[1] | ww[2] | ww[3])) lattice_row(w, Y, 16 * g, d, lat);
   }
-  publish_stats(ts, 16 * g, stats + inst);
+  sink.row(pat, Y, Y < d.H);
+  if ((lane & 7) == 0) publish_leader(sink.ls, sk.stats + inst);
 }
 
 __global__ void init_scratch_kernel(InstStats* stats, size_t n_stats, unsigned* lattice, size_t n_lat) {
@@ -328,27 +333,27 @@ __global__ void init_scratch_kernel(InstStats* stats, size_t n_stats, unsigned* 
 
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_upsample(const Dims& d, const float* logits, const float* boxes, const int* counts, int B, uint8_t* masks,
-                            InstStats* stats, unsigned* lattice, cudaStream_t st) {
+                            const MaskSinks& sk, cudaStream_t st) {
   const bool x4 = (d.H == 4 * d.mh) && (d.W == 4 * d.mw) && (d.mw % 4 == 0);
   if (x4) {
     const int warps = ceil_div(d.W >> 4, 8) * ceil_div(d.mh, 4 * kStrip);
     dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
-    if (masks) upsample4x_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
-    else upsample4x_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, stats, lattice);
+    if (masks) upsample4x_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, sk);
+    else upsample4x_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, counts, masks, sk);
   } else {
     const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4 * kGenRows);
     dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
-    if (masks) upsample_generic_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, stats, lattice);
-    else upsample_generic_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, stats, lattice);
+    if (masks) upsample_generic_kernel<true><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, sk);
+    else upsample_generic_kernel<false><<<grid, kUpThreads, 0, st>>>(d, logits, boxes, counts, masks, sk);
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, InstStats* stats,
-                              unsigned* lattice, cudaStream_t st) {
+cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, const MaskSinks& sk,
+                              cudaStream_t st) {
   const int warps = ceil_div(ceil_div(d.W, 16), 8) * ceil_div(d.H, 4);
   dim3 grid(ceil_div(warps, kUpThreads / 32), d.max_n, B);
-  mask_stats_kernel<<<grid, kUpThreads, 0, st>>>(d, masks, counts, stats, lattice);
+  mask_stats_kernel<<<grid, kUpThreads, 0, st>>>(d, masks, counts, sk);
   return cudaGetLastError();
 }
 

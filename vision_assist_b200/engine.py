@@ -26,7 +26,7 @@ class FrameRecord:
     n_orphans: int
     area: int
     bbox: tuple
-    euler: int
+    contour_area2: int      # 2 * cv2.contourArea of the kept polygon (FrameProcessor.py:72-73)
     rows_y: np.ndarray      # int32 [R]
     rows_attr: np.ndarray   # int32 [R]
     occ: np.ndarray         # uint8 [R, C]   bit0 = non-empty, bit1 = artificial
@@ -75,6 +75,9 @@ class FrameRecord:
             raise IndexError("index out of bounds: cell centre outside the frame (FrameProcessor.py:97)")
         if self.flags & _lib.VA_FLAG_LIST_OOB:
             raise IndexError("list assignment index out of range (FrameProcessor.py:163)")
+        if self.flags & _lib.VA_FLAG_NO_POLYGON:
+            import cv2
+            raise cv2.error("fillPoly: the selected polygon has no points (FrameProcessor.py:86)")
         if self.flags & _lib.VA_FLAG_OVERFLOW:
             raise RuntimeError("record capacity exceeded")
 
@@ -286,14 +289,14 @@ class MaskGridEngine:
 def decode_record(blob: np.ndarray, L, gs: int = 20) -> FrameRecord:
     blob = np.ascontiguousarray(blob)
     h = blob[:64].view(np.int32)
-    flags, sel, x0, y0, Cc, R, norph, npk, area, rm, minx, miny, maxx, maxy, euler, start = (int(v) for v in h[:16])
+    flags, sel, x0, y0, Cc, R, norph, npk, area, rm, minx, miny, maxx, maxy, area2, start = (int(v) for v in h[:16])
     ry = blob[L.off_row_y:L.off_row_y + 4 * L.rmax].view(np.int32)
     ra = blob[L.off_row_attr:L.off_row_attr + 4 * L.rmax].view(np.int32)
     pen = blob[L.off_penalty:L.off_penalty + 8 * L.rmax * L.cmax].view(np.float64).reshape(L.rmax, L.cmax)
     pk = blob[L.off_peaks:L.off_peaks + 8 * L.pmax].view(np.int32).reshape(L.pmax, 2)
     occ = blob[L.off_occ:L.off_occ + L.rmax * L.cmax].reshape(L.rmax, L.cmax)
     return FrameRecord(flags=flags, sel=sel, x0=x0, y0=y0, C=Cc, R=R, n_orphans=norph, area=area,
-                       bbox=(minx, miny, maxx, maxy), euler=euler, rows_y=ry[:R].copy(), rows_attr=ra[:R].copy(),
+                       bbox=(minx, miny, maxx, maxy), contour_area2=area2, rows_y=ry[:R].copy(), rows_attr=ra[:R].copy(),
                        occ=occ[:R, :Cc].copy(), penalty=pen[:R, :Cc].copy(), peaks=pk[:npk].copy(),
                        orphan_y=ry[R:R + norph].copy(), orphan_occ=occ[R:R + norph, :Cc].copy(), _gs=gs,
                        start=(start >> 16, start & 0xffff) if start >= 0 else (-1, -1),
