@@ -211,6 +211,23 @@ typedef struct va_nms_params {
 VA_API int va_nms(va_ctx* ctx, const float* pred, int32_t A, const va_nms_params* prm, int32_t B, float* coefs_out,
                   float* boxes_out, float* conf_out, int32_t* cls_out, int32_t* counts_out, void* stream);
 
+/* Multi-GPU record sink (frames are sharded across the GPUs of one box, only the per-frame records are
+ * gathered).  Instead of a collective, every rank's tail kernel stores its records straight into the gathering
+ * rank's memory over NVLink: records_out of va_run_fused may be a PEER pointer obtained here.
+ *   va_peer_alloc   on the gathering rank: device buffer + a 64-byte handle to send to the other processes
+ *   va_peer_open    on the other ranks: map that buffer (peer access is enabled by the mapping); *dptr is valid in
+ *                   kernels of the context's device
+ *   va_signal       enqueue "flag = value" (system-scope release) after everything queued before it on the stream -
+ *                   the per-step "records of step k have landed" mark; flag may be a peer pointer
+ *   va_wait_flags   enqueue a wait until flags[i] >= value for all i < n (system-scope acquire) on the stream */
+#define VA_IPC_HANDLE_BYTES 64
+VA_API int va_peer_alloc(va_ctx* ctx, uint64_t bytes, void** dptr, uint8_t handle[VA_IPC_HANDLE_BYTES]);
+VA_API int va_peer_open(va_ctx* ctx, const uint8_t handle[VA_IPC_HANDLE_BYTES], void** dptr);
+VA_API int va_peer_close(va_ctx* ctx, void* dptr);
+VA_API int va_peer_free(va_ctx* ctx, void* dptr);
+VA_API int va_signal(va_ctx* ctx, int32_t* flag, int32_t value, void* stream);
+VA_API int va_wait_flags(va_ctx* ctx, const int32_t* flags, int32_t n, int32_t value, void* stream);
+
 /* Introspection for benchmarks: number of kernels launched by the last call, and which
  * contraction path the context uses (1 = tcgen05/TMEM, 0 = CUDA-core FFMA). */
 VA_API int va_last_launch_count(const va_ctx* ctx);

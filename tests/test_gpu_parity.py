@@ -139,7 +139,7 @@ def test_run_fused_vs_oracle(tc, family):
             assert band_mismatch_report(masks[b, :nb], up)[1] == 0
     assert n_band_frames <= 2
     if family == "noise":
-        assert n_nonsimple >= B // 2          # the family does exercise the general path
+        assert n_nonsimple >= B // 4          # the family does exercise the general path
     print(f"[parity] {family}: {B}/{B} records bit-exact vs the reference's contour route; {n_nonsimple} non-simple frames, "
           f"{n_band_frames} frames with in-band mask pixels")
 
@@ -195,7 +195,7 @@ def test_sixteen_instance_accumulator_path(tc):
         up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
         nd, nout = band_mismatch_report(masks[b, :nb], up)
         assert nout == 0, (nd, nout)
-        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "direct"), f"n=12 frame {b}")
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "contour"), f"n=12 frame {b}")
 
 
 @pytest.mark.parametrize("tc", PATHS)
@@ -228,7 +228,7 @@ def test_instance_groups_ragged_counts_and_dead_bands(tc):
             up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
             nd, nout = band_mismatch_report(masks[b, :nb], up)
             assert nout == 0, (b, nd, nout)
-        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "direct"), f"groups frame {b}")
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "contour"), f"groups frame {b}")
     r_nomask, _ = eng.run(*to_dev(protos, coefs, boxes, counts), write_masks=False)
     assert torch.equal(r_nomask, records)
 
@@ -289,7 +289,7 @@ def test_box_fuzz_masks_and_records(tc, max_n, seed):
             # a reference logit of exactly 0 comes from crop_mask: no tolerance there
             assert int(masks[b, :nb][up == 0].sum()) == 0, (b, int(masks[b, :nb][up == 0].sum()))
             n_band += nd
-        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "direct"), f"fuzz frame {b}")
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], 20, "contour"), f"fuzz frame {b}")
     r_nomask, _ = eng.run(*to_dev(protos, coefs, boxes, counts), write_masks=False)
     assert torch.equal(r_nomask, records)
     print(f"[parity] box fuzz max_n={max_n}: {n_band} mask pixels inside the 1e-4 band")
@@ -343,7 +343,7 @@ def test_generic_geometry_fuzz(H, W, mh, mw, gs):
             up = oma.upsampled_logits(protos[b], coefs[b, :nb], boxes[b, :nb], (H, W)).numpy()
             nd, nout = band_mismatch_report(masks[b, :nb], up)
             assert nout == 0, (fam, b, nd, nout)
-            assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], gs, "direct"), f"{fam} {H}x{W} frame {b}")
+            assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b, :nb], gs, "contour"), f"{fam} {H}x{W} frame {b}")
 
 
 @pytest.mark.parametrize("tc", PATHS)
@@ -461,7 +461,7 @@ def test_cfg2_1080p_generic_scale(tc):
         up = oma.upsampled_logits(protos[b], coefs[b], boxes[b], (H, W)).numpy()
         nd, nout = band_mismatch_report(masks[b], up)
         assert nout == 0 and nd < 50, (nd, nout)
-        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], 20, "direct"), f"1080p frame {b}")
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], 20, "contour"), f"1080p frame {b}")
 
 
 @pytest.mark.parametrize("tc", PATHS)
@@ -475,7 +475,7 @@ def test_cfg4_cell_size_sweep(tc, gs):
     recs = eng.decode(records)
     masks = masks.cpu().numpy()
     for b in range(B):
-        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], gs, "direct"), f"gs={gs} frame {b}")
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], gs, "contour"), f"gs={gs} frame {b}")
 
 
 @pytest.mark.parametrize("tc", PATHS)
@@ -492,7 +492,7 @@ def test_cfg4_proto_sweep(tc, m, n):
         up = oma.upsampled_logits(protos[b], coefs[b], boxes[b], (H, W)).numpy()
         nd, nout = band_mismatch_report(masks[b], up)
         assert nout == 0, (m, nd, nout)
-        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], eng.gs, "direct"), f"proto {m} frame {b}")
+        assert_record_equals_oracle(recs[b], opl.frame_from_masks(masks[b], eng.gs, "contour"), f"proto {m} frame {b}")
 
 
 def test_host_buffer_path_matches_device_path():

@@ -14,11 +14,13 @@ LIB_PATH = os.environ.get("VA_LIB_PATH") or os.path.join(_HERE, "libva_sm100.so"
 
 VA_OK, VA_ERR_INVALID, VA_ERR_CUDA, VA_ERR_CAPACITY, VA_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 VA_CFG_CHECK_SIMPLE, VA_CFG_NO_TENSOR_CORE = 1, 2
+VA_IPC_HANDLE_BYTES = 64
 VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG_OVERFLOW, VA_FLAG_NO_POLYGON = 1, 2, 4, 8, 16, 32
 
 EXPORTS = ["va_abi_version", "va_create", "va_destroy", "va_last_error", "va_get_layout", "va_assemble_masks",
            "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks", "va_nms",
-           "va_last_launch_count", "va_uses_tensor_core", "va_profile_enable", "va_profile_read"]
+           "va_last_launch_count", "va_uses_tensor_core", "va_profile_enable", "va_profile_read",
+           "va_peer_alloc", "va_peer_open", "va_peer_close", "va_peer_free", "va_signal", "va_wait_flags"]
 
 
 class VaConfig(C.Structure):
@@ -78,6 +80,12 @@ def load() -> C.CDLL:
     lib.va_uses_tensor_core.argtypes = [vp]
     lib.va_profile_enable.argtypes = [vp, i32]
     lib.va_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i32)]
+    lib.va_peer_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.c_char_p]
+    lib.va_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.va_peer_close.argtypes = [vp, vp]
+    lib.va_peer_free.argtypes = [vp, vp]
+    lib.va_signal.argtypes = [vp, vp, i32, vp]
+    lib.va_wait_flags.argtypes = [vp, vp, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
     _lib = lib

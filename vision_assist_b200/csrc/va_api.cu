@@ -290,6 +290,77 @@ extern "C" int va_nms(va_ctx* c, const float* pred, int32_t A, const va_nms_para
   return VA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU record sink: peer-mapped buffers + system-scope flags
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == VA_IPC_HANDLE_BYTES, "IPC handle size");
+
+__global__ void signal_kernel(int* flag, int value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void wait_flags_kernel(const int* flags, int n, int value) {
+  for (int i = threadIdx.x; i < n; i += (int)blockDim.x) {
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+      if (v < value) __nanosleep(200);
+    } while (v < value);
+  }
+  __threadfence_system();
+}
+
+extern "C" int va_peer_alloc(va_ctx* c, uint64_t bytes, void** dptr, uint8_t handle[VA_IPC_HANDLE_BYTES]) {
+  if (!c || !dptr || !handle || bytes == 0) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  void* p = nullptr;
+  VA_CUDA(c, cudaMalloc(&p, bytes));
+  VA_CUDA(c, cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); set_err(c, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return VA_ERR_CUDA; }
+  memcpy(handle, &h, sizeof(h));
+  VA_CUDA(c, cudaDeviceSynchronize());
+  *dptr = p;
+  return VA_OK;
+}
+extern "C" int va_peer_open(va_ctx* c, const uint8_t handle[VA_IPC_HANDLE_BYTES], void** dptr) {
+  if (!c || !dptr || !handle) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  VA_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dptr = p;
+  return VA_OK;
+}
+extern "C" int va_peer_close(va_ctx* c, void* dptr) {
+  if (!c || !dptr) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_CUDA(c, cudaIpcCloseMemHandle(dptr));
+  return VA_OK;
+}
+extern "C" int va_peer_free(va_ctx* c, void* dptr) {
+  if (!c || !dptr) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_CUDA(c, cudaFree(dptr));
+  return VA_OK;
+}
+extern "C" int va_signal(va_ctx* c, int32_t* flag, int32_t value, void* stream) {
+  if (!c || !flag) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+  VA_CUDA(c, cudaGetLastError());
+  return VA_OK;
+}
+extern "C" int va_wait_flags(va_ctx* c, const int32_t* flags, int32_t n, int32_t value, void* stream) {
+  if (!c || !flags || n < 1) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, value);
+  VA_CUDA(c, cudaGetLastError());
+  return VA_OK;
+}
+
 extern "C" int va_last_launch_count(const va_ctx* c) { return c ? c->last_launches : 0; }
 extern "C" int va_uses_tensor_core(const va_ctx* c) { return (c && c->plan) ? 1 : 0; }
 

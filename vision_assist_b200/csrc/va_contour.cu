@@ -28,35 +28,44 @@ namespace va {
 
 using cc::InstContour;
 
-constexpr int kCertWarps = 8;
+constexpr int kCertThreads = 128;
 constexpr int kGenThreads = 512;
 
 __device__ uint16_t g_contour_lut[256];
 
-__global__ void __launch_bounds__(32 * kCertWarps)
+// One CTA per (frame, instance): thread t takes mask rows miny + t, miny + t + 128, ...; a row needs its own summary
+// and the previous row's (a neighbour lane's, one extra load at the lane-0 seam).
+__global__ void __launch_bounds__(kCertThreads)
 contour_certify_kernel(Dims d, const int* __restrict__ counts, int B, const InstStats* __restrict__ stats,
                        const uint32_t* __restrict__ rowsum, InstContour* __restrict__ out, int* __restrict__ worklist) {
+  __shared__ int s_red[5];     // ok, n, l, minx, maxx
+  const int inst = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  const int inst = blockIdx.x * kCertWarps + (threadIdx.x >> 5);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (inst >= B * d.max_n) return;
   const int b = inst / d.max_n, i = inst - b * d.max_n;
   InstContour o;
   o.area2 = 0; o.state = cc::kEmpty; o.minx = 0; o.miny = 0; o.maxx = -1; o.maxy = -1; o.points = 0; o.n_components = 0;
   const InstStats st = stats[inst];
   if (i >= min(counts[b], d.max_n) || st.area == 0) {
-    if (lane == 0) out[inst] = o;
+    if (threadIdx.x == 0) out[inst] = o;
     return;
   }
+  if (threadIdx.x == 0) { s_red[0] = 1; s_red[1] = 0; s_red[2] = 0; s_red[3] = INT_MAX; s_red[4] = -1; }
+  __syncthreads();
   const uint32_t* rs = rowsum + (size_t)inst * d.H * d.nblk;
   int ok = 1, n = 0, l = 0, minx = INT_MAX, maxx = -1;
-  for (int y0 = st.miny; y0 <= st.maxy; y0 += 32) {
-    const int y = y0 + lane;
-    if (y <= st.maxy) {
-      const cc::RowRun cur = cc::rowsum_combine(rs + (size_t)y * d.nblk, d.nblk);
-      cc::RowRun prev; prev.cnt = 0; prev.a = 0; prev.b = -1;
-      if (y > st.miny) prev = cc::rowsum_combine(rs + (size_t)(y - 1) * d.nblk, d.nblk);
+  for (int y0 = st.miny; y0 <= st.maxy; y0 += kCertThreads) {
+    const int y = y0 + (int)threadIdx.x;
+    const bool live = y <= st.maxy;
+    cc::RowRun cur; cur.cnt = 0; cur.a = 0; cur.b = -1;
+    if (live) cur = cc::rowsum_combine(rs + (size_t)y * d.nblk, d.nblk);
+    cc::RowRun prev;
+    prev.cnt = __shfl_up_sync(0xffffffffu, cur.cnt, 1);
+    prev.a = __shfl_up_sync(0xffffffffu, cur.a, 1);
+    prev.b = __shfl_up_sync(0xffffffffu, cur.b, 1);
+    if (live && lane == 0 && y > st.miny) prev = cc::rowsum_combine(rs + (size_t)(y - 1) * d.nblk, d.nblk);
+    if (live) {
       const cc::CertTerms t = cc::cert_row(cur, prev, y == st.miny, y == st.maxy);
       ok &= t.ok; n += t.n; l += t.l;
       minx = min(minx, t.minx); maxx = max(maxx, t.maxx);
@@ -68,10 +77,16 @@ contour_certify_kernel(Dims d, const int* __restrict__ counts, int B, const Inst
   minx = __reduce_min_sync(0xffffffffu, minx);
   maxx = __reduce_max_sync(0xffffffffu, maxx);
   if (lane == 0) {
-    if (ok) {
+    if (!ok) atomicAnd(&s_red[0], 0);
+    atomicAdd(&s_red[1], n); atomicAdd(&s_red[2], l);
+    atomicMin(&s_red[3], minx); atomicMax(&s_red[4], maxx);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_red[0]) {
       o.state = cc::kSimple;
-      o.area2 = 2 * n - l - 2;
-      o.minx = minx; o.maxx = maxx; o.miny = st.miny; o.maxy = st.maxy;
+      o.area2 = 2 * s_red[1] - s_red[2] - 2;
+      o.minx = s_red[3]; o.maxx = s_red[4]; o.miny = st.miny; o.maxy = st.maxy;
       o.n_components = 1;
     } else {
       o.state = cc::kPending;
@@ -95,6 +110,7 @@ struct GenParams {
   size_t slab_bytes;
   int cap;                   // run capacity (global slab)
   int smem_bytes;            // dynamic shared memory available for the scratch parts
+  int timing;                // developer diagnostic (VA_CC_TIMING=1): CTA 0 prints the cycles of every phase of its first item
 };
 
 __global__ void __launch_bounds__(kGenThreads)
@@ -134,13 +150,17 @@ contour_general_kernel(const GenParams p) {
     cc::bind_grid(w, grid_in_smem ? smem_dyn : slab, gl);
     unsigned char* run_slab = slab + gl_full.total;
     cc::bind_runs(w, run_slab, cc::run_layout(p.cap));
+    long long tstamp[20];
+    int nst = 0;
+#define VA_TS() do { if (p.timing && blockIdx.x == 0 && tid == 0 && item == 0) tstamp[nst++] = clock64(); } while (0)
     __syncthreads();                                       // previous item done with the shared scalars
+    VA_TS();
     cc::phase_init(w, tid, nt);       __syncthreads();
-    cc::phase_load(w, tid, nt);       __syncthreads();
-    cc::phase_count(w, tid, nt);      __syncthreads();
+    cc::phase_load(w, tid, nt);       __syncthreads(); VA_TS();
+    cc::phase_count(w, tid, nt);      __syncthreads(); VA_TS();
     cc::phase_scan_a(w, tid, nt);     __syncthreads();
     cc::phase_scan_b(w, tid, nt);     __syncthreads();
-    cc::phase_scan_c(w, tid, nt);     __syncthreads();
+    cc::phase_scan_c(w, tid, nt);     __syncthreads(); VA_TS();
     {
       const int NR = s_sc[cc::W_NR];
       const size_t used = grid_in_smem ? gl.total : 0;
@@ -150,15 +170,28 @@ contour_general_kernel(const GenParams p) {
         cc::bind_runs(w, smem_dyn + used, rl);
       }
     }
-    cc::phase_runs(w, tid, nt);       __syncthreads();
-    cc::phase_gaps(w, tid, nt);       __syncthreads();
-    cc::phase_holes(w, tid, nt);      __syncthreads();
-    cc::phase_link(w, tid, nt);       __syncthreads();
-    cc::phase_flatten(w, tid, nt);    __syncthreads();
-    cc::phase_sums(w, s_lut, tid, nt); __syncthreads();
+    cc::phase_runs(w, tid, nt);       __syncthreads(); VA_TS();
+    cc::phase_gaps(w, tid, nt);       __syncthreads(); VA_TS();
+    cc::phase_holes(w, tid, nt);      __syncthreads(); VA_TS();
+    cc::phase_link(w, tid, nt);       __syncthreads(); VA_TS();
+    cc::phase_flatten(w, tid, nt);    __syncthreads(); VA_TS();
+    cc::phase_sums(w, s_lut, tid, nt); __syncthreads(); VA_TS();
     cc::phase_select(w, tid, nt);     __syncthreads();
-    cc::phase_bbox(w, tid, nt);       __syncthreads();
+    cc::phase_bbox(w, tid, nt);       __syncthreads(); VA_TS();
     cc::phase_output(w, tid, nt);
+    if (p.timing && blockIdx.x == 0 && item == 0) {
+      __syncthreads();
+      VA_TS();
+      if (tid == 0) {
+        printf("[va contour] items %d inst %d R %d Wd %d runs %d holes %d roots %d grid_smem %d | cycles: load %lld count %lld scan %lld runs %lld "
+               "gaps %lld holes %lld link %lld flatten %lld sums %lld select+bbox %lld output %lld | total %lld\n",
+               n_items, inst, w.R, w.Wd, s_sc[cc::W_NR], s_sc[cc::W_HOLES], s_sc[cc::W_ROOTS], (int)grid_in_smem,
+               tstamp[1] - tstamp[0], tstamp[2] - tstamp[1], tstamp[3] - tstamp[2], tstamp[4] - tstamp[3], tstamp[5] - tstamp[4],
+               tstamp[6] - tstamp[5], tstamp[7] - tstamp[6], tstamp[8] - tstamp[7], tstamp[9] - tstamp[8], tstamp[10] - tstamp[9],
+               tstamp[11] - tstamp[10], tstamp[11] - tstamp[0]);
+      }
+    }
+#undef VA_TS
   }
   // the last CTA to finish re-arms the work list for the next call (every CTA has read the count by now)
   __syncthreads();
@@ -192,8 +225,8 @@ cudaError_t launch_contour(const Dims& d, const int* counts, int B, const Scratc
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ceil_div(B * d.max_n, kCertWarps));
-    cfg.blockDim = dim3(32 * kCertWarps);
+    cfg.gridDim = dim3(B * d.max_n);
+    cfg.blockDim = dim3(kCertThreads);
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
@@ -215,6 +248,8 @@ cudaError_t launch_contour(const Dims& d, const int* counts, int B, const Scratc
     if (e != cudaSuccess) return e;
   }
   p.smem_bytes = smem_opt;
+  static const bool cc_timing = getenv("VA_CC_TIMING") != nullptr;
+  p.timing = cc_timing ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(sc.cc_ctas);
   cfg.blockDim = dim3(kGenThreads);

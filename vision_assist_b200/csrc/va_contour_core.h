@@ -203,11 +203,16 @@ VA_HD int ns(const Work& w, int r, int x) {
   return (int)w.S[r * w.Wd + k] + popc32(rise_at(w, r, k) & (0xffffffffu >> (31 - (x & 31))));
 }
 
-VA_HD int uf_find(const int* p, int x) {
+// find with path halving: every visited node is re-pointed at its grandparent.  The concurrent writes are benign -
+// a parent is only ever replaced by one of its ancestors, so chains only get shorter (a vertical stack of runs would
+// otherwise leave a chain as long as the mask is tall).
+VA_HD int uf_find(int* p, int x) {
   while (true) {
     const int q = p[x];
     if (q == x) return x;
-    x = q;
+    const int g = p[q];
+    if (g != q) p[x] = g;
+    x = g;
   }
 }
 // roots are the smallest ids: lock-free union by atomicMin on the larger root

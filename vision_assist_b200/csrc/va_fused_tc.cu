@@ -932,21 +932,60 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             }
           }
           // Per-row by-products for the contour step: the 8 lanes of a slot hold one 128-pixel block of the same dst
-          // rows.  Three warp reductions per row (pixels set, first, last) -> one 4-byte summary per (row, block);
-          // the group leaders also carry the instance's area / bbox.  Grid-only mode writes the bit patterns too.
+          // rows -> one 4-byte summary per (row, block), written by the group leader, which also carries the
+          // instance's area / bbox.  Most tasks lie entirely inside or outside the mask: two votes recognise blocks
+          // that are all ones / all zeros and their summaries are constants; only tasks that cross the outline
+          // gather the 128-bit block patterns (four shuffles per row, the rows' chains interleaved).
           __syncwarp();
           {
-            const unsigned gmask = 0xffu << (lane & 24);
             const int nrow = active ? nrows_out - jbeg : 0;
-            const int srows = (r0 == 0) ? 6 : 4;                           // warp-uniform bound (pair 0 of the frame owns 6 rows)
+            const unsigned long long full_lo = (nrow >= 4) ? ~0ull : (nrow == 2) ? 0xffffffffull : 0ull;
+            const unsigned full_hi = (nrow == 6) ? ~0u : 0u;
+            const bool is_zero = (rp.lo | rp.hi) == 0;
+            const bool is_full = active && rp.lo == full_lo && rp.hi == full_hi;
+            const unsigned zm = __ballot_sync(0xffffffffu, is_zero), fm = __ballot_sync(0xffffffffu, is_full || !active);
+            // per 8-lane group: every lane zero, or every lane full (lanes past the row end count as full: they only
+            // exist in the last block of a ragged row, where the exact path below is taken instead)
+            const unsigned gz = zm & (zm >> 4), gf = fm & (fm >> 4);
+            const unsigned gz2 = gz & (gz >> 2), gf2 = gf & (gf >> 2);
+            const unsigned gzall = gz2 & (gz2 >> 1) & 0x01010101u, gfall = gf2 & (gf2 >> 1) & 0x01010101u;   // bit 8q: group q
+            const bool ragged = (NG & 7) != 0;
             uint32_t* rs_inst = p.rowsum + inst * (size_t)d.H * d.nblk;
             LeaderStats ls;
+            if (!kWriteMasks) {
 #pragma unroll 1
-            for (int sidx = 0; sidx < srows; ++sidx) {
-              const unsigned pat = rp.get(sidx);
-              const int Y = (jbeg < 0) ? sidx : 4 * r + 2 + sidx;
-              if (!kWriteMasks && sidx < nrow) p.bits16[(inst * d.H + Y) * (size_t)(2 * d.bit_words) + g] = (uint16_t)pat;
-              emit_row_summary(pat, gl, gmask, sidx < nrow, Y, g >> 3, rs_inst, d.nblk, ls);
+              for (int sidx = 0; sidx < nrow; ++sidx) {
+                const int Y = (jbeg < 0) ? sidx : 4 * r + 2 + sidx;
+                p.bits16[(inst * d.H + Y) * (size_t)(2 * d.bit_words) + g] = (uint16_t)rp.get(sidx);
+              }
+            }
+            if (!ragged && ((gzall | gfall) == 0x01010101u)) {
+              if (gl == 0 && nrow > 0) {
+                const bool fullg = (gfall >> (lane & 24)) & 1u;
+                const int blk = g >> 3;
+                const uint32_t e = fullg ? cc::rowsum_pack(cc::kRowBlock, 0, cc::kRowBlock - 1) : 0u;
+#pragma unroll 1
+                for (int sidx = 0; sidx < nrow; ++sidx) {
+                  const int Y = (jbeg < 0) ? sidx : 4 * r + 2 + sidx;
+                  rs_inst[(size_t)Y * d.nblk + blk] = e;
+                }
+                if (fullg) {
+                  const int Y0 = (jbeg < 0) ? 0 : 4 * r + 2;
+                  ls.area = (unsigned)(cc::kRowBlock * nrow);
+                  ls.minx = cc::kRowBlock * blk; ls.maxx = cc::kRowBlock * blk + cc::kRowBlock - 1;
+                  ls.miny = Y0; ls.maxy = Y0 + nrow - 1;
+                }
+              }
+            } else {
+              const int Yb = (jbeg < 0) ? 0 : 4 * r + 2;
+#pragma unroll
+              for (int sidx = 0; sidx < 4; ++sidx)
+                emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yb + sidx, g >> 3, rs_inst, d.nblk, ls);
+              if (r0 == 0) {                                               // pair 0 of the frame owns 6 rows (warp-uniform)
+#pragma unroll
+                for (int sidx = 4; sidx < 6; ++sidx)
+                  emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yb + sidx, g >> 3, rs_inst, d.nblk, ls);
+              }
             }
             if (gl == 0 && ls.area) {
               const uint32_t st = wstat + i * 32;

@@ -121,23 +121,36 @@ struct LeaderStats {
   int minx = INT_MAX, miny = INT_MAX, maxx = -1, maxy = -1;
 };
 
-// One dst row of a lane group: reduce the 8 patterns to the (row, block) summary, store it, feed the leader's stats.
-// ALL 32 lanes of the warp must call (with their own group's mask); `exists` = this lane's row is a real row.
-__device__ __forceinline__ void emit_row_summary(unsigned pat, int gl, unsigned gmask, bool exists, int Y, int blk,
-                                                 uint32_t* __restrict__ rowsum_inst, int nblk, LeaderStats& ls) {
-  const int c = (int)__reduce_add_sync(gmask, (unsigned)__popc(pat));
-  const int f = __reduce_min_sync(gmask, pat ? 16 * gl + __ffs((int)pat) - 1 : 255);
-  const int l = __reduce_max_sync(gmask, pat ? 16 * gl + 31 - __clz((int)pat) : -1);
+// One dst row of a lane group: gather the 8 patterns into the block's 128-bit pattern (4 full-warp shuffles - a
+// warp reduction with a partial member mask would be serialised group by group), derive the (row, block) summary at
+// the leader, store it, feed the leader's stats.  ALL 32 lanes of the warp must call, converged; `exists` = this
+// lane's row is a real row.  Returns the block pattern (valid in every lane of the group).
+__device__ __forceinline__ uint4 emit_row_summary(unsigned pat, int gl, bool exists, int Y, int blk,
+                                                  uint32_t* __restrict__ rowsum_inst, int nblk, LeaderStats& ls) {
+  unsigned u = __shfl_xor_sync(0xffffffffu, pat, 1);
+  const unsigned w32 = (gl & 1) ? (u | (pat << 16)) : (pat | (u << 16));
+  u = __shfl_xor_sync(0xffffffffu, w32, 2);
+  const unsigned lo = (gl & 2) ? u : w32, hi = (gl & 2) ? w32 : u;
+  const unsigned ulo = __shfl_xor_sync(0xffffffffu, lo, 4), uhi = __shfl_xor_sync(0xffffffffu, hi, 4);
+  uint4 w;
+  w.x = (gl & 4) ? ulo : lo; w.y = (gl & 4) ? uhi : hi;
+  w.z = (gl & 4) ? lo : ulo; w.w = (gl & 4) ? hi : uhi;
   if (exists && gl == 0) {
-    rowsum_inst[(size_t)Y * nblk + blk] = c ? cc::rowsum_pack(c, f, l) : 0u;
+    const int c = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+    unsigned e = 0u;
     if (c) {
+      const int f = w.x ? __ffs((int)w.x) - 1 : w.y ? 31 + __ffs((int)w.y) : w.z ? 63 + __ffs((int)w.z) : 95 + __ffs((int)w.w);
+      const int l = w.w ? 127 - __clz((int)w.w) : w.z ? 95 - __clz((int)w.z) : w.y ? 63 - __clz((int)w.y) : 31 - __clz((int)w.x);
+      e = cc::rowsum_pack(c, f, l);
       ls.area += (unsigned)c;
       ls.minx = min(ls.minx, cc::kRowBlock * blk + f);
       ls.maxx = max(ls.maxx, cc::kRowBlock * blk + l);
       ls.miny = min(ls.miny, Y);
       ls.maxy = max(ls.maxy, Y);
     }
+    rowsum_inst[(size_t)Y * nblk + blk] = e;
   }
+  return w;
 }
 
 __device__ __forceinline__ void publish_leader(const LeaderStats& ls, InstStats* dst) {

@@ -29,7 +29,6 @@ struct RowSink {
   uint16_t* bits_inst;      // nullptr unless grid-only
   unsigned* lat;
   int g, gl;
-  unsigned gmask;
   bool gok;                 // this lane's 16-pixel piece exists (g < NG)
   LeaderStats ls;
   __device__ __forceinline__ void row(unsigned pat, int Y, bool exists) {
@@ -40,7 +39,7 @@ struct RowSink {
     }
     if (ex && bits_inst) bits_inst[(size_t)Y * (2 * d.bit_words) + g] = (uint16_t)pat;
     // the leader's piece always exists when any piece of the group does (pieces are numbered left to right)
-    emit_row_summary(ex ? pat : 0u, gl, gmask, exists, Y, g >> 3, rowsum_inst, d.nblk, ls);
+    emit_row_summary(ex ? pat : 0u, gl, exists, Y, g >> 3, rowsum_inst, d.nblk, ls);
   }
 };
 
@@ -69,7 +68,7 @@ upsample4x_kernel(Dims d, const float* __restrict__ logits, const int* __restric
   uint8_t* M = kWriteMasks ? masks + inst * (size_t)d.H * d.W + 16 * ge : nullptr;
   RowSink sink{d, sk.rowsum + inst * (size_t)d.H * d.nblk,
                (!kWriteMasks && sk.bits) ? reinterpret_cast<uint16_t*>(sk.bits) + inst * (size_t)d.H * (2 * d.bit_words) : nullptr,
-               sk.lattice + inst * (size_t)d.lat_rows * d.lat_words, g, lane & 7, 0xffu << (lane & 24), gok, LeaderStats()};
+               sk.lattice + inst * (size_t)d.lat_rows * d.lat_words, g, lane & 7, gok, LeaderStats()};
 
   const bool left = (ge == 0);
   RowState A, Bq;
@@ -209,7 +208,7 @@ upsample_generic_kernel(Dims d, const float* __restrict__ logits, const float* _
   const float* L = logits + inst * d.mh * d.mw;
   RowSink sink{d, sk.rowsum + inst * (size_t)d.H * d.nblk,
                (!kWriteMasks && sk.bits) ? reinterpret_cast<uint16_t*>(sk.bits) + inst * (size_t)d.H * (2 * d.bit_words) : nullptr,
-               sk.lattice + inst * (size_t)d.lat_rows * d.lat_words, g, lane & 7, 0xffu << (lane & 24), gok, LeaderStats()};
+               sk.lattice + inst * (size_t)d.lat_rows * d.lat_words, g, lane & 7, gok, LeaderStats()};
   const int X0 = 16 * g, X1 = min(X0 + 15, d.W - 1);
   const int npx = gok ? X1 - X0 + 1 : 0;
   const bool col_in = gok && !(X1 < rXa || X0 > rXb);
@@ -296,7 +295,7 @@ mask_stats_kernel(Dims d, const uint8_t* __restrict__ masks, const int* __restri
   const int Y = (wt / NG8) * 4 + (lane >> 3);
   const size_t inst = (size_t)b * d.max_n + i;
   RowSink sink{d, sk.rowsum + inst * (size_t)d.H * d.nblk, nullptr, sk.lattice + inst * (size_t)d.lat_rows * d.lat_words,
-               g, lane & 7, 0xffu << (lane & 24), g < NG, LeaderStats()};
+               g, lane & 7, g < NG, LeaderStats()};
   unsigned pat = 0;
   if (g < NG && Y < d.H) {
     const uint8_t* M = masks + inst * (size_t)d.H * d.W + (size_t)Y * d.W + 16 * g;

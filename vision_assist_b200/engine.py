@@ -199,16 +199,45 @@ class MaskGridEngine:
         return coefs, boxes, conf, cls, counts
 
     def run(self, protos, coefs, boxes, counts, masks_out: torch.Tensor | None = None,
-            records_out: torch.Tensor | None = None, write_masks: bool = True):
-        """Whole path; returns (records u8 [B, record_bytes], masks or None), all on the device."""
+            records_out: torch.Tensor | None = None, write_masks: bool = True, records_ptr: int | None = None):
+        """Whole path; returns (records u8 [B, record_bytes], masks or None), all on the device.
+        `records_ptr`: raw device address for the records instead of a tensor - e.g. a slot of another GPU's buffer
+        mapped with `peer_open` (the tail kernel then stores the records over NVLink); returns (None, masks)."""
         B, p, c, b, n = self._inputs(protos, coefs, boxes, counts)
-        if records_out is None:
+        if records_ptr is None and records_out is None:
             records_out = torch.empty((B, self.record_bytes), dtype=torch.uint8, device=protos.device)
         if write_masks and masks_out is None:
             masks_out = torch.empty((B, self.max_n, self.H, self.W), dtype=torch.uint8, device=protos.device)
         mptr = C.c_void_p(masks_out.data_ptr()) if (write_masks and masks_out is not None) else None
-        self._check(self.lib.va_run_fused(self._ctx, p, c, b, n, B, mptr, C.c_void_p(records_out.data_ptr()), self._stream()))
-        return records_out, (masks_out if write_masks else None)
+        rptr = C.c_void_p(records_ptr if records_ptr is not None else records_out.data_ptr())
+        self._check(self.lib.va_run_fused(self._ctx, p, c, b, n, B, mptr, rptr, self._stream()))
+        return (records_out if records_ptr is None else None), (masks_out if write_masks else None)
+
+    # -- multi-GPU record sink (peer memory over NVLink, C ABI va_peer_* / va_signal / va_wait_flags) ---------
+    def peer_alloc(self, nbytes: int) -> tuple[int, bytes]:
+        """-> (device address, 64-byte IPC handle) of a zeroed buffer other processes can map with peer_open."""
+        ptr, h = C.c_void_p(), C.create_string_buffer(_lib.VA_IPC_HANDLE_BYTES)
+        self._check(self.lib.va_peer_alloc(self._ctx, int(nbytes), C.byref(ptr), h))
+        return int(ptr.value), bytes(h.raw)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.va_peer_open(self._ctx, C.create_string_buffer(handle, _lib.VA_IPC_HANDLE_BYTES), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int) -> None:
+        self._check(self.lib.va_peer_close(self._ctx, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int) -> None:
+        self._check(self.lib.va_peer_free(self._ctx, C.c_void_p(ptr)))
+
+    def signal(self, flag_ptr: int, value: int) -> None:
+        """Enqueue `*flag = value` (system scope) behind everything already queued on the current stream."""
+        self._check(self.lib.va_signal(self._ctx, C.c_void_p(flag_ptr), int(value), self._stream()))
+
+    def wait_flags(self, flags_ptr: int, n: int, value: int) -> None:
+        """Enqueue a wait on the current stream until flags[i] >= value for i < n."""
+        self._check(self.lib.va_wait_flags(self._ctx, C.c_void_p(flags_ptr), int(n), int(value), self._stream()))
 
     def masks_to_records(self, masks, counts, rects: torch.Tensor | None = None, sel: torch.Tensor | None = None):
         B = masks.shape[0]

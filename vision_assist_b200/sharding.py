@@ -77,3 +77,62 @@ class RecordGatherer:
             if self.work[slot] is not None:
                 self.work[slot].wait()
                 self.work[slot] = None
+
+
+def device_view(ptr: int, nbytes: int, device) -> torch.Tensor:
+    """Zero-copy u8 tensor over raw device memory (used for buffers allocated through the C ABI)."""
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_Raw(), device=device)
+
+
+class PeerRecordSink:
+    """Records of every rank land in ONE buffer on rank `dst` without a collective: the buffer is allocated through the
+    C ABI on `dst` (va_peer_alloc), its IPC handle is broadcast once, every other rank maps it (va_peer_open) and hands
+    its slot's address to `va_run_fused` as records_out - the tail kernel's stores go over NVLink, no NCCL kernel
+    competes with the persistent mask kernel for the SMs.  After every step each rank raises its per-rank flag
+    (va_signal); `dst` can wait for a step with `wait(step)`.
+
+    Layout on `dst`: [depth][world][n_local][record_bytes] then world int32 flags.  `depth` slots rotate (a frame
+    stream keeps depth = number of chunks, i.e. every record has its own place)."""
+
+    def __init__(self, eng, n_local: int, depth: int, group=None, dst: int = 0):
+        self.eng, self.group, self.dst, self.depth, self.n_local = eng, group, dst, depth, n_local
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rb = eng.record_bytes
+        self.slot_bytes = self.world * n_local * self.rb
+        self.flags_off = (depth * self.slot_bytes + 255) // 256 * 256
+        total = self.flags_off + 4 * self.world
+        box = [None]
+        if self.rank == dst:
+            self.base, handle = eng.peer_alloc(total)
+            box[0] = handle
+        dist.broadcast_object_list(box, src=dst, group=group)
+        if self.rank != dst:
+            self.base = eng.peer_open(box[0])
+        self.total = total
+        self.step = 0
+
+    def records_ptr(self) -> int:
+        """Address this rank writes the records of the current step to."""
+        return self.base + (self.step % self.depth) * self.slot_bytes + self.rank * self.n_local * self.rb
+
+    def commit(self) -> None:
+        """Call after va_run_fused of the current step was enqueued: raises this rank's flag to step + 1."""
+        self.step += 1
+        self.eng.signal(self.base + self.flags_off + 4 * self.rank, self.step)
+
+    def wait(self, step: int | None = None) -> None:
+        """`dst` only: the current stream waits until every rank has committed `step` (default: the latest) steps."""
+        self.eng.wait_flags(self.base + self.flags_off, self.world, self.step if step is None else step)
+
+    def view(self, slot: int) -> torch.Tensor:
+        """`dst` only: [world * n_local, record_bytes] u8 view of a slot."""
+        v = device_view(self.base + slot * self.slot_bytes, self.slot_bytes, torch.device("cuda", self.eng.device))
+        return v.view(self.world * self.n_local, self.rb)
+
+    def close(self) -> None:
+        if self.rank == self.dst:
+            self.eng.peer_free(self.base)
+        else:
+            self.eng.peer_close(self.base)

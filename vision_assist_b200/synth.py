@@ -140,3 +140,94 @@ def make_head_output(first_idx: int, B: int, A: int = 8400, nc: int = 1, K: int 
             p[4 + cls, idx] = conf
         out[b] = p
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# on-device generator for frame STREAMS (BASELINE configs[3]: 65,536 frames do not fit in HBM at once and must not
+# cross PCIe in the timed region): the same "sidewalk" family, every random number a counter-based hash of
+# (SEED_BASE + frame index, draw index) - a frame's tensors depend on its index only, not on the chunking, the shard
+# or the GPU that generates it.  (Not bit-identical to make_frame's CPU torch.Generator stream; parity tests use
+# make_frame, throughput streams use this.)
+# ---------------------------------------------------------------------------------------------
+def _hash_u32(x: torch.Tensor) -> torch.Tensor:
+    """splitmix-style avalanche on int64 lanes holding 32-bit values."""
+    m = 0xFFFFFFFF
+    x = (x ^ (x >> 16)) * 0x7FEB352D & m
+    x = (x ^ (x >> 15)) * 0x846CA68B & m
+    return (x ^ (x >> 16)) & m
+
+
+def _uniform(seed: torch.Tensor, k: int, draws: int) -> torch.Tensor:
+    """seed int64 [B] -> float32 [B, draws] in (0, 1), stream k."""
+    idx = torch.arange(draws, device=seed.device, dtype=torch.int64)[None, :]
+    h = _hash_u32(_hash_u32(seed[:, None] & 0xFFFFFFFF) ^ (idx * 0x9E3779B1 + k * 0x85EBCA6B & 0xFFFFFFFF))
+    return ((h.to(torch.float64) + 0.5) / 4294967296.0).to(torch.float32)
+
+
+def _normal(seed: torch.Tensor, k: int, draws: int) -> torch.Tensor:
+    u1, u2 = _uniform(seed, 2 * k + 100, draws), _uniform(seed, 2 * k + 101, draws)
+    return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(6.283185307179586 * u2)
+
+
+def make_batch_device(first_idx: int, B: int, n: int, H: int, W: int, mh: int, mw: int, K: int = 32, device="cuda"):
+    """-> protos [B,K,mh,mw], coefs [B,n,K], boxes [B,n,4], counts [B] on `device` ("sidewalk" family)."""
+    dev = torch.device(device)
+    seed = (SEED_BASE + first_idx + torch.arange(B, device=dev, dtype=torch.int64))
+    u = _uniform(seed, 0, 16)
+    nrm = _normal(seed, 1, 8)
+    sx, sy = W / mw, H / mh
+    ys = torch.arange(mh, device=dev, dtype=torch.float32)[None, :, None]
+    xs = torch.arange(mw, device=dev, dtype=torch.float32)[None, None, :]
+    col = lambda t: t[:, None, None]
+    cx0 = col(mw / 2 + nrm[:, 0] * mw / 8)
+    y_top = col(mh * (0.125 + 0.375 * u[:, 0]))
+    hw_top = col(mw * (1 / 16 + u[:, 1] / 8))
+    hw_bot = col(mw * (0.25 + 0.25 * u[:, 2]))
+    shear = col(0.3 * nrm[:, 1])
+    t = ((ys - y_top) / (mh - 1 - y_top).clamp(min=1.0)).clamp(0, 1)
+    halfw = hw_top + (hw_bot - hw_top) * t
+    cx = cx0 + shear * (ys - y_top)
+    field = torch.minimum(halfw - (xs - cx).abs(), ys - y_top + 0.5)            # [B, mh, mw]
+    protos = torch.empty(B, K, mh, mw, device=dev)
+    protos[:, 0] = field
+    discs = []
+    for d in range(N_DISC_CH):
+        dcx, dcy = col(mw * (0.1 + 0.8 * u[:, 3 + 2 * d])), col(mh * (0.1 + 0.8 * u[:, 4 + 2 * d]))
+        rad = col(mw * (1 / 16 + u[:, 9 + d] / 16))
+        protos[:, 1 + d] = rad - ((xs - dcx) ** 2 + (ys - dcy) ** 2).sqrt()
+        discs.append((dcx[:, 0, 0], dcy[:, 0, 0], rad[:, 0, 0]))
+    n_noise = K - 1 - N_DISC_CH
+    z = _normal(seed, 2, n_noise * 36).view(B, n_noise, 6, 6)
+    protos[:, 1 + N_DISC_CH:] = 0.3 * F.interpolate(z, (mh, mw), mode="bicubic", align_corners=False)
+    coefs = torch.zeros(B, n, K, device=dev)
+    coefs[:, :, 1 + N_DISC_CH:] = 0.3 * _normal(seed, 3, n * n_noise).view(B, n, n_noise)
+    boxes = torch.zeros(B, n, 4, device=dev)
+    jit = _uniform(seed, 4, n * 4).view(B, n, 4) * 8.0
+    amp = 0.75 + 0.5 * _uniform(seed, 5, n)
+    pos = field > -1.0
+    anyy, anyx = pos.any(2), pos.any(1)                                         # [B, mh], [B, mw]
+    ar_y, ar_x = torch.arange(mh, device=dev), torch.arange(mw, device=dev)
+    big = 1 << 20
+    y1 = torch.where(anyy, ar_y, big).min(1).values.float() * sy
+    y2 = (torch.where(anyy, ar_y, -1).max(1).values.float() + 1) * sy
+    x1 = torch.where(anyx, ar_x, big).min(1).values.float() * sx
+    x2 = (torch.where(anyx, ar_x, -1).max(1).values.float() + 1) * sx
+    none = ~anyy.any(1)
+    for i in range(n):
+        if i == 0:
+            coefs[:, 0, 0] = 1.0
+            b = torch.stack([torch.where(none, 0.0, x1), torch.where(none, 0.0, y1),
+                             torch.where(none, W - 1.0, x2), torch.where(none, H - 1.0, y2)], 1)
+        else:
+            d = (i - 1) % N_DISC_CH
+            coefs[:, i, 1 + d] = amp[:, i]
+            dcx, dcy, rad = discs[d]
+            shrink = 1.0 / (1 + (i - 1) // N_DISC_CH)
+            b = torch.stack([(dcx - rad * shrink) * sx, (dcy - rad * shrink) * sy, (dcx + rad * shrink) * sx,
+                             (dcy + rad * shrink) * sy], 1)
+        b = b + jit[:, i] * torch.tensor([-1.0, -1.0, 1.0, 1.0], device=dev)
+        b[:, 0::2] = b[:, 0::2].clamp(0, W - 1.0)
+        b[:, 1::2] = b[:, 1::2].clamp(0, H - 1.0)
+        boxes[:, i] = b
+    counts = torch.full((B,), n, dtype=torch.int32, device=dev)
+    return protos.contiguous(), coefs.contiguous(), boxes.contiguous(), counts
