@@ -81,6 +81,7 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       } else {
         w.px = mask;
       }
+      w.rowsum = rowsum.data(); w.nblk = nblk;
       w.y0 = bbox[1]; w.x0w = bbox[0] >> 5; w.R = bbox[3] - bbox[1] + 1; w.Wd = (bbox[2] >> 5) - w.x0w + 1;
       w.cap = cap;
       const GridLayout gl = grid_layout(w.R, w.Wd);
@@ -103,7 +104,8 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       PHASE(phase_gaps(w, tid, nt));
       PHASE(phase_holes(w, tid, nt));
       PHASE(phase_link(w, tid, nt));
-      PHASE(phase_flatten(w, tid, nt));
+      PHASE(phase_flatten_a(w, tid, nt));
+      PHASE(phase_flatten_b(w, tid, nt));
       PHASE(phase_sums(w, kContourLutHost, tid, nt));
       PHASE(phase_select(w, tid, nt));
       PHASE(phase_bbox(w, tid, nt));

@@ -27,9 +27,9 @@ def make_engine(tc, **kw):
     e = MaskGridEngine(tensor_core=tc, **kw)
     if tc and not e.uses_tensor_core:
         why = e.lib.va_last_error(e._ctx).decode()
-        # documented limit of the tcgen05 kernel: exact-4x geometry (H = 4*mh, W = 4*mw);
-        # those configurations run on the CUDA-core contraction and are covered by the other id
-        if "needs H=4*mh" in why or "max_n <=" in why:
+        # documented limits of the tcgen05 kernel: up-sampling scales with W % 16 == 0, mw >= 52 and at
+        # most 8 dst rows per prototype row; other configurations run on the CUDA-core contraction (the other id)
+        if any(k in why for k in ("needs H=4*mh", "max_n <=", "mw >= 52", "vertical scales", "owns no dst row", "W % 16", "mw % 4")):
             pytest.skip(why)
         pytest.fail("tcgen05 plan unavailable: " + why)
     return e
@@ -325,13 +325,15 @@ def test_band_count_invariance():
 
 @pytest.mark.parametrize("H,W,mh,mw,gs", [(270, 480, 40, 40, 10), (333, 500, 48, 64, 20), (200, 304, 100, 152, 8),
                                            (96, 128, 96, 128, 8), (80, 96, 160, 192, 4), (1000, 1000, 36, 52, 20),
-                                           (641, 643, 160, 160, 20)])
-def test_generic_geometry_fuzz(H, W, mh, mw, gs):
-    """Generic-scale path (CUDA-core contraction + generic upsample): non-integer, anisotropic, unit and
-    down-sampling scales, widths that are not a multiple of 16 (ragged right edge) or of the cell size."""
+                                           (641, 643, 160, 160, 20), (540, 960, 80, 160, 20), (405, 720, 60, 120, 10),
+                                           (300, 1024, 100, 64, 8)])
+@pytest.mark.parametrize("tc", PATHS)
+def test_generic_geometry_fuzz(tc, H, W, mh, mw, gs):
+    """Generic-scale paths (tcgen05 kernel with the row table where its limits allow, CUDA-core contraction + generic
+    upsample everywhere): non-integer, anisotropic, unit and down-sampling scales, widths that are not a multiple of
+    16 (ragged right edge) or of the cell size."""
     B, n = 4, 5
-    eng = MaskGridEngine(H=H, W=W, mh=mh, mw=mw, max_n=8, gs=gs, max_batch=B)
-    assert not eng.uses_tensor_core or (H == 4 * mh and W == 4 * mw)
+    eng = make_engine(tc, H=H, W=W, mh=mh, mw=mw, max_n=8, gs=gs, max_batch=B)
     for fam, first in (("sidewalk", 1200), ("noise", 1300)):
         protos, coefs, boxes, counts = synth.make_batch(first, B, n, H, W, mh, mw, family=fam, max_n=8)
         counts[1] = 2
@@ -453,6 +455,7 @@ def test_repeatability_soak(H, W, mh, mw, n, B):
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
     eng = make_engine(tc, H=H, W=W, mh=160, mw=160, max_n=32, gs=20, max_batch=B)
+    assert eng.uses_tensor_core == tc          # BASELINE configs[2] runs on the tcgen05 kernel (generic scale 6.75 x 12)
     protos, coefs, boxes, counts = synth.make_batch(7000, B, n, H, W, 160, 160, max_n=32)
     records, masks = eng.run(*to_dev(protos, coefs, boxes, counts))
     recs = eng.decode(records)

@@ -29,7 +29,7 @@ namespace va {
 using cc::InstContour;
 
 constexpr int kCertThreads = 128;
-constexpr int kGenThreads = 512;
+constexpr int kGenThreads = 1024;
 
 __device__ uint16_t g_contour_lut[256];
 
@@ -102,6 +102,7 @@ struct GenParams {
   Dims d;
   const uint8_t* masks;      // [B][max_n][H][W] or nullptr
   const uint32_t* bits;      // [B][max_n][H][bit_words] when masks == nullptr
+  const uint32_t* rowsum;    // [B][max_n][H][nblk]
   const InstStats* stats;
   unsigned* lattice;
   InstContour* out;
@@ -136,6 +137,7 @@ contour_general_kernel(const GenParams p) {
     w.px = p.masks ? p.masks + (size_t)inst * d.H * d.W : nullptr;
     w.bits = p.masks ? nullptr : p.bits + (size_t)inst * d.H * d.bit_words;
     w.bit_words = d.bit_words;
+    w.rowsum = p.rowsum + (size_t)inst * d.H * d.nblk; w.nblk = d.nblk;
     w.y0 = st.miny; w.x0w = st.minx >> 5;
     w.R = st.maxy - st.miny + 1; w.Wd = (st.maxx >> 5) - w.x0w + 1;
     w.gs = d.gs; w.lat_rows = d.lat_rows; w.lat_cols = d.lat_cols; w.lat_words = d.lat_words;
@@ -174,7 +176,8 @@ contour_general_kernel(const GenParams p) {
     cc::phase_gaps(w, tid, nt);       __syncthreads(); VA_TS();
     cc::phase_holes(w, tid, nt);      __syncthreads(); VA_TS();
     cc::phase_link(w, tid, nt);       __syncthreads(); VA_TS();
-    cc::phase_flatten(w, tid, nt);    __syncthreads(); VA_TS();
+    cc::phase_flatten_a(w, tid, nt);  __syncthreads();
+    cc::phase_flatten_b(w, tid, nt);  __syncthreads(); VA_TS();
     cc::phase_sums(w, s_lut, tid, nt); __syncthreads(); VA_TS();
     cc::phase_select(w, tid, nt);     __syncthreads();
     cc::phase_bbox(w, tid, nt);       __syncthreads(); VA_TS();
@@ -235,7 +238,7 @@ cudaError_t launch_contour(const Dims& d, const int* counts, int B, const Scratc
     if (e != cudaSuccess) return e;
   }
   GenParams p;
-  p.d = d; p.masks = masks; p.bits = sc.bits; p.stats = sc.stats; p.lattice = sc.lattice;
+  p.d = d; p.masks = masks; p.bits = sc.bits; p.rowsum = sc.rowsum; p.stats = sc.stats; p.lattice = sc.lattice;
   p.out = reinterpret_cast<InstContour*>(sc.contour); p.worklist = sc.worklist;
   p.slab = sc.cc_slab; p.slab_bytes = sc.cc_slab_bytes; p.cap = sc.cc_cap;
   static int smem_opt = -1;

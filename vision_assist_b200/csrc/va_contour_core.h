@@ -150,6 +150,9 @@ VA_HD CertTerms cert_row(const RowRun& cur, const RowRun& prev, bool first_row, 
 // ---------------------------------------------------------------------------------------------
 // general path
 // ---------------------------------------------------------------------------------------------
+// Rows whose summary says "one run" (or "empty") never touch the pixels: their bit words are synthesised from the run
+// ends, their run table entry is written directly, and run look-ups on them are two comparisons.  Only rows with
+// several runs are read back (u8 masks or bit rows) and scanned word by word.
 struct Work {
   // ---- input ----
   int H, W;                 // frame
@@ -157,13 +160,17 @@ struct Work {
   const uint8_t* px;        // fmt 0: [H][W] of this instance
   const uint32_t* bits;     // fmt 1: [H][bit_words] of this instance
   int bit_words;
+  const uint32_t* rowsum;   // [H][nblk] per-(row, 128 px block) summaries of this instance
+  int nblk;
   int y0, x0w;              // region origin: first row, first 32-pixel word
   int R, Wd;                // region rows / words (covers the pixel bbox of the mask)
   int gs, lat_rows, lat_cols, lat_words;
   // ---- scratch (shared or global memory) ----
   uint32_t* Mfg;            // [R][Wd] foreground bits
   uint32_t* G;              // [R][Wd] foreground + holes
-  uint16_t* S;              // [R][Wd] runs of the row that start before word k
+  uint16_t* S;              // [R][Wd] runs of the row that start before word k (rows with several runs only)
+  int16_t* one_a;           // [R] first pixel of the row's only run (region-relative); kRowEmpty / kRowMulti otherwise
+  int16_t* one_b;           // [R] last pixel of the row's only run
   int* rowoff;              // [R + 1] first run id of the row
   int cap;                  // run capacity
   uint16_t* rs;             // [cap] first / last pixel (region-relative) and row of a run; ids are in raster order
@@ -182,6 +189,7 @@ struct Work {
   InstContour* out;
 };
 enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_COUNT };
+constexpr int kRowEmpty = -1, kRowMulti = -2;
 
 VA_HD uint32_t word_at(const uint32_t* bm, const Work& w, int r, int k) {
   return (r < 0 || r >= w.R || k < 0 || k >= w.Wd) ? 0u : bm[r * w.Wd + k];
@@ -190,17 +198,31 @@ VA_HD uint32_t rise_at(const Work& w, int r, int k) {      // bits where a foreg
   const uint32_t m = word_at(w.Mfg, w, r, k), p = word_at(w.Mfg, w, r, k - 1);
   return m & ~((m << 1) | (p >> 31));
 }
+VA_HD uint32_t fall_at(const Work& w, int r, int k) {      // bits where a foreground run ends
+  const uint32_t m = word_at(w.Mfg, w, r, k), n = word_at(w.Mfg, w, r, k + 1);
+  return m & ~((m >> 1) | (n << 31));
+}
 VA_HD bool fg_at(const Work& w, int r, int x) {
   if (x < 0 || x >= 32 * w.Wd) return false;
+  const int a = w.one_a[r];
+  if (a != kRowMulti) return a >= 0 && x >= a && x <= (int)w.one_b[r];
   return (w.Mfg[r * w.Wd + (x >> 5)] >> (x & 31)) & 1u;
 }
 VA_HD int row_runs(const Work& w, int r) { return w.rowoff[r + 1] - w.rowoff[r]; }
 // number of runs of row r that start at a pixel <= x
 VA_HD int ns(const Work& w, int r, int x) {
   if (x < 0) return 0;
+  const int a = w.one_a[r];
+  if (a != kRowMulti) return (a >= 0 && x >= a) ? 1 : 0;
   if (x >= 32 * w.Wd) return row_runs(w, r);
   const int k = x >> 5;
   return (int)w.S[r * w.Wd + k] + popc32(rise_at(w, r, k) & (0xffffffffu >> (31 - (x & 31))));
+}
+// bits [a, b] of word k (pixels 32k .. 32k+31), a <= b
+VA_HD uint32_t span_bits(int a, int b, int k) {
+  const int lo = imax(a, 32 * k), hi = imin(b, 32 * k + 31);
+  if (lo > hi) return 0u;
+  return (0xffffffffu << (lo & 31)) & (0xffffffffu >> (31 - (hi & 31)));
 }
 
 // find with path halving: every visited node is re-pointed at its grandparent.  The concurrent writes are benign -
@@ -228,14 +250,21 @@ VA_HD void uf_union(int* p, int a, int b) {
   }
 }
 
-// ---- phase 0: scalars ----
+// ---- phase 0: scalars + row classes from the summaries ----
 VA_HD void phase_init(Work& w, int tid, int nt) {
-  (void)nt;
   if (tid == 0) {
     for (int q = 0; q < W_COUNT; ++q) w.sc[q] = 0;
     w.sc[W_MINX] = 1 << 30; w.sc[W_MINY] = 1 << 30; w.sc[W_MAXX] = -1; w.sc[W_MAXY] = -1;
     w.sc[W_CHOSEN] = -1;
     w.best[0] = 0ull;
+  }
+  for (int r = tid; r < w.R; r += nt) {
+    const RowRun rr = rowsum_combine(w.rowsum + (size_t)(w.y0 + r) * w.nblk, w.nblk);
+    int a = kRowMulti, b = 0;
+    if (rr.cnt == 0) { a = kRowEmpty; }
+    else if (rr.cnt == rr.b - rr.a + 1) { a = rr.a - 32 * w.x0w; b = rr.b - 32 * w.x0w; }
+    w.one_a[r] = (int16_t)a;
+    w.one_b[r] = (int16_t)b;
   }
 }
 
@@ -245,7 +274,10 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
     const int r = t / w.Wd, k = t - r * w.Wd;
     const int y = w.y0 + r, xw = w.x0w + k;
     uint32_t m = 0;
-    if (w.fmt == 1) {
+    const int a = w.one_a[r];
+    if (a != kRowMulti) {
+      if (a >= 0) m = span_bits(a, (int)w.one_b[r], k);
+    } else if (w.fmt == 1) {
       m = (xw < w.bit_words) ? w.bits[(size_t)y * w.bit_words + xw] : 0u;
       const int rem = w.W - 32 * xw;
       if (rem < 32) m &= (rem <= 0) ? 0u : (0xffffffffu >> (32 - rem));
@@ -273,10 +305,15 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
 // ---- phase 2: runs per word / row ----
 VA_HD void phase_count(Work& w, int tid, int nt) {
   for (int r = tid; r < w.R; r += nt) {
+    const int a = w.one_a[r];
     int acc = 0;
-    for (int k = 0; k < w.Wd; ++k) {
-      w.S[r * w.Wd + k] = (uint16_t)acc;
-      acc += popc32(rise_at(w, r, k));
+    if (a != kRowMulti) {
+      acc = (a >= 0) ? 1 : 0;
+    } else {
+      for (int k = 0; k < w.Wd; ++k) {
+        w.S[r * w.Wd + k] = (uint16_t)acc;
+        acc += popc32(rise_at(w, r, k));
+      }
     }
     w.rowoff[r] = acc;
   }
@@ -309,31 +346,47 @@ VA_HD void phase_scan_c(Work& w, int tid, int nt) {
   if (tid == 0) w.rowoff[w.R] = w.seg[32];
 }
 
-// ---- phase 4: run table ----
+VA_HD void run_init(Work& w, int id, int start, int r, bool last_in_row) {
+  w.rs[id] = (uint16_t)start;
+  w.ry[id] = (uint16_t)r;
+  w.pF[id] = id;
+  w.pG[id + 1] = last_in_row ? 0 : id + 1;           // the gap after the last run of a row is the outside
+  w.accP[id] = 0;
+  w.accA[id] = 0;
+}
+// ---- phase 4: run table.  The j-th run start of a row pairs with its j-th run end, so starts and ends are written
+//      independently word by word (no search for the end of a run) ----
 VA_HD void phase_runs(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   if (tid == 0) w.pG[0] = 0;                          // the outside
-  for (int t = tid; t < w.R * w.Wd; t += nt) {
+  for (int r = tid; r < w.R; r += nt) {               // rows with one run
+    const int a = w.one_a[r];
+    if (a < 0) continue;
+    const int id = w.rowoff[r];
+    run_init(w, id, a, r, true);
+    w.re[id] = (uint16_t)w.one_b[r];
+  }
+  for (int t = tid; t < w.R * w.Wd; t += nt) {        // rows with several runs
     const int r = t / w.Wd, k = t - r * w.Wd;
+    if (w.one_a[r] != kRowMulti) continue;
+    const int base = w.rowoff[r], last_id = w.rowoff[r + 1] - 1;
     uint32_t rise = rise_at(w, r, k);
-    int id = w.rowoff[r] + (int)w.S[t];
-    const int last_id = w.rowoff[r + 1] - 1;
+    int id = base + (int)w.S[t];
     while (rise) {
       const int b = ffs32(rise) - 1;
       rise &= rise - 1;
-      // end of the run: first zero after bit b, possibly in a later word
-      int kk = k;
-      uint32_t z = ~w.Mfg[r * w.Wd + kk] & ((b == 31) ? 0u : (0xffffffffu << (b + 1)));
-      while (!z && kk + 1 < w.Wd) { ++kk; z = ~w.Mfg[r * w.Wd + kk]; }
-      const int end = z ? 32 * kk + ffs32(z) - 2 : 32 * w.Wd - 1;
-      w.rs[id] = (uint16_t)(32 * k + b);
-      w.re[id] = (uint16_t)end;
-      w.ry[id] = (uint16_t)r;
-      w.pF[id] = id;
-      w.pG[id + 1] = (id == last_id) ? 0 : id + 1;     // the gap after the last run of a row is the outside
-      w.accP[id] = 0;
-      w.accA[id] = 0;
+      run_init(w, id, 32 * k + b, r, id == last_id);
       ++id;
+    }
+    // run ends: as many ends as starts lie before this word, minus the run still open at the word's left edge
+    uint32_t fall = fall_at(w, r, k);
+    const int open = (k > 0) ? (int)(w.Mfg[t - 1] >> 31) & (int)(w.Mfg[t] & 1u) : 0;
+    int ie = base + (int)w.S[t] - open;
+    while (fall) {
+      const int b = ffs32(fall) - 1;
+      fall &= fall - 1;
+      w.re[ie] = (uint16_t)(32 * k + b);
+      ++ie;
     }
   }
 }
@@ -372,12 +425,7 @@ VA_HD void phase_holes(Work& w, int tid, int nt) {
       atom_add(&w.sc[W_HOLES], 1);
       // fill the hole pixels into G
       const int g0 = w.re[id] + 1, g1 = w.rs[id + 1] - 1;
-      for (int k = g0 >> 5; k <= (g1 >> 5); ++k) {
-        uint32_t m = 0xffffffffu;
-        if (k == (g0 >> 5)) m &= 0xffffffffu << (g0 & 31);
-        if (k == (g1 >> 5)) m &= 0xffffffffu >> (31 - (g1 & 31));
-        atom_or(&w.G[r * w.Wd + k], m);
-      }
+      for (int k = g0 >> 5; k <= (g1 >> 5); ++k) atom_or(&w.G[r * w.Wd + k], span_bits(g0, g1, k));
     }
   }
 }
@@ -395,15 +443,21 @@ VA_HD void phase_link(Work& w, int tid, int nt) {
     for (int j = jlo; j <= jhi; ++j) uf_union(w.pF, id, o2 + j);
   }
 }
-// ---- phase 8: flatten ----
-VA_HD void phase_flatten(Work& w, int tid, int nt) {
+// ---- phase 8: flatten, in two barrier-separated steps: the finds of step a still re-point nodes (path halving) and
+//      would undo another thread's flattened entry, so the roots are parked in accA first ----
+VA_HD void phase_flatten_a(Work& w, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  const int NR = w.sc[W_NR];
+  for (int id = tid; id < NR; id += nt) w.accA[id] = uf_find(w.pF, id);
+}
+VA_HD void phase_flatten_b(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
   for (int id = tid; id < NR; id += nt) {
-    const int root = uf_find(w.pF, id);
+    const int root = w.accA[id];
     if (root == id) atom_add(&w.sc[W_ROOTS], 1);
-    // compress only after every find of this phase is done?  Safe either way: parents only ever move towards the root.
     w.pF[id] = root;
+    w.accA[id] = 0;
   }
 }
 // ---- phase 9: table sums over the border pixels of G ----
@@ -411,6 +465,18 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   for (int t = tid; t < w.R * w.Wd; t += nt) {
     const int r = t / w.Wd, k = t - r * w.Wd;
+    // Rows r-1, r, r+1 each one run (or empty) and no hole: the pixels of [a, b] that have all eight neighbours
+    // are [max(a, ua, da) + 1, min(b, ub, db) - 1]; words inside that range have no border pixel.
+    {
+      const int a = w.one_a[r];
+      if (a == kRowEmpty) continue;
+      const int ua = (r > 0) ? (int)w.one_a[r - 1] : kRowEmpty, da = (r + 1 < w.R) ? (int)w.one_a[r + 1] : kRowEmpty;
+      if (a >= 0 && ua >= 0 && da >= 0) {
+        const int lo = imax(a, imax(ua, da)) + 1;
+        const int hi = imin((int)w.one_b[r], imin((int)w.one_b[r - 1], (int)w.one_b[r + 1])) - 1;
+        if (32 * k >= lo && 32 * k + 31 <= hi) continue;
+      }
+    }
     const uint32_t M = w.G[t];
     if (!M) continue;
     const uint32_t U = word_at(w.G, w, r - 1, k), D = word_at(w.G, w, r + 1, k);
@@ -444,6 +510,7 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
 }
 // ---- phase 10: the component whose contour has the most points; ties: the last in raster order ----
 VA_HD void phase_select(Work& w, int tid, int nt) {
+  for (int t = tid; t < w.lat_rows * w.lat_words; t += nt) w.lattice[t] = 0u;     // rebuilt by phase_output
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
   unsigned long long best = 0ull;
@@ -478,22 +545,22 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
   const int half = w.gs >> 1;
   const bool ok = !w.sc[W_OVERFLOW] && w.sc[W_CHOSEN] >= 0;
   const int chosen = w.sc[W_CHOSEN];
-  for (int t = tid; t < w.lat_rows * w.lat_words; t += nt) {
-    const int ly = t / w.lat_words, lw = t - ly * w.lat_words;
-    const int y = w.gs * ly + half, r = y - w.y0;
-    unsigned word = 0;
-    if (ok && r >= 0 && r < w.R) {
-      for (int q = 0; q < 32; ++q) {
-        const int lx = 32 * lw + q;
-        if (lx >= w.lat_cols) break;
+  if (ok) {
+    // lattice points inside the region only: rows ly0 .. ly1, columns lx0 .. lx1
+    const int ly0 = imax(0, (w.y0 - half + w.gs - 1) / w.gs), ly1 = imin(w.lat_rows - 1, (w.y0 + w.R - 1 - half) / w.gs);
+    const int lx0 = imax(0, (32 * w.x0w - half + w.gs - 1) / w.gs), lx1 = imin(w.lat_cols - 1, (32 * (w.x0w + w.Wd) - 1 - half) / w.gs);
+    const int nly = ly1 - ly0 + 1, nlx = lx1 - lx0 + 1;
+    if (w.y0 + w.R - 1 >= half && nly > 0 && nlx > 0) {
+      for (int t = tid; t < nly * nlx; t += nt) {
+        const int ly = ly0 + t / nlx, lx = lx0 + t % nlx;
+        const int r = w.gs * ly + half - w.y0;
         const int x = w.gs * lx + half - 32 * w.x0w;          // region-relative pixel
-        if (x < 0 || x >= 32 * w.Wd) continue;
+        if (r < 0 || r >= w.R || x < 0 || x >= 32 * w.Wd) continue;
         if (!((w.G[r * w.Wd + (x >> 5)] >> (x & 31)) & 1u)) continue;
         const int j = ns(w, r, x) - 1;                        // the run at or left of x (x is in it or in the hole after it)
-        if (j >= 0 && w.pF[w.rowoff[r] + j] == chosen) word |= 1u << q;
+        if (j >= 0 && w.pF[w.rowoff[r] + j] == chosen) atom_or(&w.lattice[ly * w.lat_words + (lx >> 5)], 1u << (lx & 31));
       }
     }
-    w.lattice[t] = word;
   }
   if (tid == 0) {
     InstContour o;
@@ -514,8 +581,9 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
 }
 
 // Scratch layout in two parts, each placed in shared memory when it fits and in a global slab otherwise:
-// the grid part (bit images, per-word run counts, row offsets) and the run part (run table, union-find, sums).
-struct GridLayout { size_t Mfg, G, S, rowoff, seg, total; };
+// the grid part (bit images, per-word run counts, row classes, row offsets) and the run part (run table, union-find,
+// sums).
+struct GridLayout { size_t Mfg, G, S, one_a, one_b, rowoff, seg, total; };
 struct RunLayout { size_t rs, re, ry, pF, pG, accP, accA, total; };
 VA_HD size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 VA_HD GridLayout grid_layout(int R, int Wd) {
@@ -524,6 +592,8 @@ VA_HD GridLayout grid_layout(int R, int Wd) {
   l.Mfg = o; o += align16(sizeof(uint32_t) * R * Wd);
   l.G = o; o += align16(sizeof(uint32_t) * R * Wd);
   l.S = o; o += align16(sizeof(uint16_t) * R * Wd);
+  l.one_a = o; o += align16(sizeof(int16_t) * R);
+  l.one_b = o; o += align16(sizeof(int16_t) * R);
   l.rowoff = o; o += align16(sizeof(int) * (R + 1));
   l.seg = o; o += align16(sizeof(int) * 33);
   l.total = o;
@@ -544,7 +614,9 @@ VA_HD RunLayout run_layout(int cap) {
 }
 VA_HD void bind_grid(Work& w, unsigned char* base, const GridLayout& l) {
   w.Mfg = reinterpret_cast<uint32_t*>(base + l.Mfg); w.G = reinterpret_cast<uint32_t*>(base + l.G);
-  w.S = reinterpret_cast<uint16_t*>(base + l.S); w.rowoff = reinterpret_cast<int*>(base + l.rowoff);
+  w.S = reinterpret_cast<uint16_t*>(base + l.S);
+  w.one_a = reinterpret_cast<int16_t*>(base + l.one_a); w.one_b = reinterpret_cast<int16_t*>(base + l.one_b);
+  w.rowoff = reinterpret_cast<int*>(base + l.rowoff);
   w.seg = reinterpret_cast<int*>(base + l.seg);
 }
 VA_HD void bind_runs(Work& w, unsigned char* base, const RunLayout& l) {

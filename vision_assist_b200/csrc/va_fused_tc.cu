@@ -84,6 +84,9 @@ struct FusedParams {
   int nst;           // instance stride of the chunk buffers (= gsize)
   int chunk_floats;  // floats per chunk buffer = (pr+1) * nst * mw
   int nbuf;          // chunk buffers in the ring (3 or 4)
+  int zero_bytes;    // size of the shared-memory zero buffer (source of the bulk zero fills), a multiple of W
+  int zero_rows;     // = zero_bytes / W
+  int max_rows;      // generic scale: most dst rows owned by one prototype row pair (<= 8)
   int* work_counter;            // [0] global work-stealing counter, [1] finished CTAs (the last one resets both)
   unsigned long long* timing;   // developer diagnostic (VA_FUSED_TIMING=1): [grid][5 roles][8] cycle counters, or nullptr
 };
@@ -244,7 +247,7 @@ struct SmemMap {
   uint32_t zeros;     // [(4*pr+2) * W] bytes of 0: source of the bulk zero-fill stores
   uint32_t zero_bytes;
   uint32_t stat;      // [kWarpsUp][kMaxInstTc][8] i32: area, minx, miny, maxx, maxy (private per upsample warp)
-  uint32_t latrow;    // [H] i16: lattice row index of dst row Y, -1 if none
+  uint32_t latrow;    // [H] i16; generic scale: [mh + 1] first dst row of every prototype row pair (ytab)
   uint32_t bars;      // [BAR_COUNT] u64
   uint32_t tmem_slot;
   uint32_t items;     // [kItemRing][4] i32
@@ -265,7 +268,7 @@ enum {
   BAR_COUNT = BAR_ITEM + kItemRing
 };
 
-__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int nbuf, int H, int zero_bytes) {
+__host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int nbuf, int H, int mh, int zero_bytes) {
   SmemMap m;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes, uint32_t align) { o = (o + align - 1) / align * align; uint32_t r = o; o += bytes; return r; };
@@ -274,7 +277,7 @@ __host__ __device__ inline SmemMap fused_smem_map(int chunk_floats, int nbuf, in
   m.chunks = take((uint32_t)nbuf * chunk_floats * 4, 16);
   m.box = take(2 * kMaxInstTc * 4 * 4, 16);
   m.ubox = take(kWarpsUp * kMaxInstTc * 4 * 4, 16);
-  m.latpair = take((uint32_t)(H / 4 + 8) * 2, 16);
+  m.latpair = take((uint32_t)(mh + 8) * 2, 16);
   m.zero_bytes = (uint32_t)zero_bytes;
   m.zeros = take((uint32_t)zero_bytes, 128);
   m.stat = take(kWarpsUp * kMaxInstTc * 8 * 4, 16);
@@ -414,13 +417,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
-template <bool kWriteMasks, int kNI, bool kDiag, int kNBuf>
+// kGeneric = false: exact 4x geometry (H = 4 mh, W = 4 mw), constant blend weights.  kGeneric = true: any up-sampling
+// scale (ATen's source index / lambda arithmetic per row and per pixel), dst rows assigned to prototype row pairs by a
+// shared-memory table.
+template <bool kWriteMasks, int kNI, bool kDiag, int kNBuf, bool kGeneric>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   // dynamic shared memory is only guaranteed 16 B aligned: round the shared address up to 1024
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const SmemMap sm = fused_smem_map(p.chunk_floats, kNBuf, p.d.H, (4 * p.pr + 2) * p.d.W);
+  const SmemMap sm = fused_smem_map(p.chunk_floats, kNBuf, p.d.H, p.d.mh, p.zero_bytes);
   const Dims& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bars = sbase + sm.bars;
@@ -450,6 +456,21 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       if (t >= 0 && t % d.gs == 0 && 4 * r + 2 + j < d.H) ly = 4 * r + 2 + j;
     }
     sts_s16(sbase + sm.latpair + 2 * r, (short)ly);
+  }
+  if (kGeneric) {
+    // ytab[r] = first dst row whose upper source row is r (ATen source index, monotone in Y, steps of at most 1 for
+    // up-sampling scales); ytab[mh] = H.  Pair r owns dst rows ytab[r] .. ytab[r+1]-1.
+    for (int Y = threadIdx.x; Y < d.H; Y += kThreads) {
+      int y0, y1, q0, q1;
+      float l0, l1;
+      src_index(d.sy, Y, d.mh, y0, y1, l0, l1);
+      if (Y == 0) { sts_s16(sbase + sm.latrow, 0); }
+      else {
+        src_index(d.sy, Y - 1, d.mh, q0, q1, l0, l1);
+        if (q0 != y0) sts_s16(sbase + sm.latrow + 2 * y0, (short)Y);
+      }
+    }
+    if (threadIdx.x == 0) sts_s16(sbase + sm.latrow + 2 * d.mh, (short)d.H);
   }
   for (uint32_t t = threadIdx.x * 16u; t < sm.zero_bytes; t += kThreads * 16u) sts_v4(sbase + sm.zeros + t, make_float4(0.f, 0.f, 0.f, 0.f));
   fence_proxy_async();
@@ -749,6 +770,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     const uint4 zeros = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t inst_stride = (uint32_t)d.mw * 4;
     const uint32_t row_stride = (uint32_t)p.nst * inst_stride;
+    // first dst row of prototype row pair r (pair r owns dst rows YT(r) .. YT(r+1)-1; YT(mh) = H)
+    auto YT = [&](int r) -> int {
+      if (kGeneric) return lds_s16(sbase + sm.latrow + 2 * r);
+      return (r == 0) ? 0 : min(4 * r + 2, d.H);
+    };
+    // bulk zero fill of dst rows [Ya, Yb] of one instance, in pieces of at most zero_rows rows
+    auto zero_rows_bulk = [&](uint8_t* inst_base, int Ya, int Yb) {
+      for (int y = Ya; y <= Yb; y += p.zero_rows) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(inst_base + (size_t)y * d.W),
+                     "r"(sbase + sm.zeros), "r"((uint32_t)(min(p.zero_rows, Yb + 1 - y) * d.W))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
     RoleTimer tm; tm.begin((kDiag && p.timing && ut == 0) ? p.timing + ((size_t)blockIdx.x * 5 + 4) * 8 : nullptr);
     uint32_t gc = 0;
     int base = 0;                        // (live task count) % kWarpsUp
@@ -782,21 +817,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
       }
       if (kWriteMasks) {
         // Parts of the band the hull of the boxes excluded (no chunk exists for them): zero for every instance.
-        // Pieces of <= zero_bytes, one per lane; the instances go round the upsample warps.
-        const int rows_per = 4 * p.pr + 2;
+        // Pieces of <= zero_rows rows, one per lane; the instances go round the upsample warps.
 #pragma unroll 1
         for (int part = 0; part < 2; ++part) {
           const int A = part ? it.pb : it.band_pa, Bp = part ? it.band_pb : it.pa;
           if (A >= Bp) continue;
-          const int Ya = (A == 0) ? 0 : 4 * A + 2;
-          const int Yb = min(4 * (Bp - 1) + 5, d.H - 1);
+          const int Ya = YT(A);
+          const int Yb = YT(Bp) - 1;
 #pragma unroll 1
           for (int i = 0; i < n; ++i) {
             if (zw == uw) {
               uint8_t* base = p.masks + ((size_t)it.b * d.max_n + it.i0 + i) * (size_t)d.H * d.W;
-              for (int y = Ya + lane * rows_per; y <= Yb; y += 32 * rows_per) {
+              for (int y = Ya + lane * p.zero_rows; y <= Yb; y += 32 * p.zero_rows) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t)y * d.W),
-                             "r"(sbase + sm.zeros), "r"((uint32_t)(min(rows_per, Yb + 1 - y) * d.W))
+                             "r"(sbase + sm.zeros), "r"((uint32_t)(min(p.zero_rows, Yb + 1 - y) * d.W))
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
@@ -813,9 +847,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
         const int npairs = min(p.pr, it.pb - r0);
         const int r = r0 + pair;
         const bool last = (r == d.mh - 1);
-        const int nrows_out = last ? 2 : 4;
-        const int jbeg = (r == 0) ? -2 : 0;                     // pair 0 also owns dst rows 0,1
-        const int laty = (pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
+        // dst rows of this lane's pair: Yfirst .. Yfirst + nrows - 1 (exact 4x: 4, 6 for pair 0, 2 for the last pair)
+        const int Yfirst = (pair < npairs) ? YT(r) : 0;
+        const int nrows = (pair < npairs) ? YT(r + 1) - Yfirst : 0;
+        const int laty = (!kGeneric && pair < npairs) ? lds_s16(sbase + sm.latpair + 2 * r) : -1;
         // Warp tasks: (live instance, block of 8*subs column groups), numbered consecutively and dealt round-robin:
         // task wq = live_ordinal * ng8w + g8w belongs to warp wq % kWarpsUp.  The numbering runs on across chunks
         // and items, so the warps that get one task more than the others rotate.
@@ -826,16 +861,12 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           if (kq < 0) kq += kWarpsUp;
           unsigned dead = ~live & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u)) & (0x10204081u << kq);
           if (lane == 0) {
-            const int Ya = (r0 == 0) ? 0 : 4 * r0 + 2;
-            const int Yb = min(4 * (r0 + npairs - 1) + 5, d.H - 1);
+            const int Ya = YT(r0);
+            const int Yb = YT(r0 + npairs) - 1;
             while (dead) {
               const int i = __ffs(dead) - 1;
               dead &= dead - 1;
-              uint8_t* dst = p.masks + (((size_t)it.b * d.max_n + it.i0 + i) * d.H + Ya) * (size_t)d.W;
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sbase + sm.zeros),
-                           "r"((uint32_t)((Yb - Ya + 1) * d.W))
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              zero_rows_bulk(p.masks + ((size_t)it.b * d.max_n + it.i0 + i) * (size_t)d.H * d.W, Ya, Yb);
             }
           }
           __syncwarp();
@@ -854,79 +885,135 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           const int g = (g8w * subs + sub) * 8 + gl;
           const bool active = (g < NG) && (pair < npairs);
           const size_t inst = (size_t)it.b * d.max_n + it.i0 + i;
-          RowPats rp;                                   // this lane's 16-pixel patterns of dst rows jbeg .. nrows_out-1 (slot = j - jbeg)
+          RowPats<kGeneric> rp;                         // this lane's 16-pixel patterns of its dst rows (slot = row - Yfirst)
           if (active) {
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
-            // every proto pixel this task reads (rows r, r+1, cols 4g-1 .. 4g+4) is outside the instance's box:
-            // crop_mask zeroed them, the masks are 0 - store and skip everything else
-            const bool outside = ((float)(r + 1) < q.y) || ((float)r >= q.w) || ((float)(4 * g + 4) < q.x) || ((float)(4 * g - 1) >= q.z);
-            if (outside) {
-              if (kWriteMasks) {
+            unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
+            const uint32_t rowA = cb + pair * row_stride + i * inst_stride;
+            const uint32_t rowB = last ? rowA : rowA + row_stride;
+            if (!kGeneric) {
+              // every proto pixel this task reads (rows r, r+1, cols 4g-1 .. 4g+4) is outside the instance's box:
+              // crop_mask zeroed them, the masks are 0 - store and skip everything else
+              const bool outside = ((float)(r + 1) < q.y) || ((float)r >= q.w) || ((float)(4 * g + 4) < q.x) || ((float)(4 * g - 1) >= q.z);
+              if (outside) {
+                if (kWriteMasks) {
 #pragma unroll 1
-                for (int j = jbeg; j < nrows_out; ++j) {
-                  const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
-                  *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = zeros;
+                  for (int j = 0; j < nrows; ++j) *reinterpret_cast<uint4*>(M + (size_t)(Yfirst + j) * d.W) = zeros;
+                }
+              } else {
+                const uint32_t pA = rowA + g * 16, pB = rowB + g * 16;
+                float sA[6], sB[6];
+                {
+                  const float4 v = lds_v4(pA);
+                  sA[1] = v.x; sA[2] = v.y; sA[3] = v.z; sA[4] = v.w;
+                  sA[0] = (g > 0) ? lds_f32(pA - 4) : v.x;
+                  sA[5] = (4 * g + 4 < d.mw) ? lds_f32(pA + 16) : v.w;
+                  const float4 u = lds_v4(pB);
+                  sB[1] = u.x; sB[2] = u.y; sB[3] = u.z; sB[4] = u.w;
+                  sB[0] = (g > 0) ? lds_f32(pB - 4) : u.x;
+                  sB[5] = (4 * g + 4 < d.mw) ? lds_f32(pB + 16) : u.w;
+                }
+                const float mnA = fminf(fminf(fminf(sA[0], sA[1]), fminf(sA[2], sA[3])), fminf(sA[4], sA[5]));
+                const float mxA = fmaxf(fmaxf(fmaxf(sA[0], sA[1]), fmaxf(sA[2], sA[3])), fmaxf(sA[4], sA[5]));
+                const float mnB = fminf(fminf(fminf(sB[0], sB[1]), fminf(sB[2], sB[3])), fminf(sB[4], sB[5]));
+                const float mxB = fmaxf(fmaxf(fmaxf(sB[0], sB[1]), fmaxf(sB[2], sB[3])), fmaxf(sB[4], sB[5]));
+                const bool left = (g == 0);
+                const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
+                const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
+                if (uni_neg || uni_pos) {
+                  if (kWriteMasks) {
+                    const uint4 w = uni_pos ? ones : zeros;
+#pragma unroll 1
+                    for (int j = 0; j < nrows; ++j) *reinterpret_cast<uint4*>(M + (size_t)(Yfirst + j) * d.W) = w;
+                  }
+                  if (uni_pos) {
+                    rp.fill(nrows);
+                    if (laty >= 0 && laty < Yfirst + nrows) lattice_row(ones, laty, 16 * g, d, lat);
+                  }
+                } else {
+                  // mixed signs: the exact 4-tap blend.  One compact, rolled loop (code size matters: the roles
+                  // share the instruction cache).
+                  float hA[16], hB[16];
+                  hinterp4(sA, hA, left);
+                  hinterp4(sB, hB, left);
+                  const int jbeg = (r == 0) ? -2 : 0;     // pair 0 also owns dst rows 0,1: h(row 0) unchanged (src y clamps to 0)
+#pragma unroll 1
+                  for (int j = jbeg; j < nrows + jbeg; ++j) {
+                    uint4 w;
+                    const int Y = Yfirst + j - jbeg;
+                    if (j < 0) {
+                      w = hpack(hA);
+                    } else {
+                      const float l1 = 0.125f + 0.25f * (float)j;     // .125 .375 .625 .875 (exact)
+                      w = vblend(hA, hB, 1.0f - l1, l1);
+                    }
+                    if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
+                    rp.set(j - jbeg, pat16(w));
+                    if (Y == laty && (w.x | w.y | w.z | w.w)) lattice_row(w, Y, 16 * g, d, lat);
+                  }
                 }
               }
             } else {
-              const uint32_t rowA = cb + pair * row_stride + i * inst_stride + g * 16;
-              const uint32_t rowB = last ? rowA : rowA + row_stride;
-              float sA[6], sB[6];
-              {
-                const float4 v = lds_v4(rowA);
-                sA[1] = v.x; sA[2] = v.y; sA[3] = v.z; sA[4] = v.w;
-                sA[0] = (g > 0) ? lds_f32(rowA - 4) : v.x;
-                sA[5] = (4 * g + 4 < d.mw) ? lds_f32(rowA + 16) : v.w;
-                const float4 u = lds_v4(rowB);
-                sB[1] = u.x; sB[2] = u.y; sB[3] = u.z; sB[4] = u.w;
-                sB[0] = (g > 0) ? lds_f32(rowB - 4) : u.x;
-                sB[5] = (4 * g + 4 < d.mw) ? lds_f32(rowB + 16) : u.w;
-              }
-              const float mnA = fminf(fminf(fminf(sA[0], sA[1]), fminf(sA[2], sA[3])), fminf(sA[4], sA[5]));
-              const float mxA = fmaxf(fmaxf(fmaxf(sA[0], sA[1]), fmaxf(sA[2], sA[3])), fmaxf(sA[4], sA[5]));
-              const float mnB = fminf(fminf(fminf(sB[0], sB[1]), fminf(sB[2], sB[3])), fminf(sB[4], sB[5]));
-              const float mxB = fmaxf(fmaxf(fmaxf(sB[0], sB[1]), fmaxf(sB[2], sB[3])), fmaxf(sB[4], sB[5]));
-              unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
-              const bool left = (g == 0);
-              const bool uniA_pos = mnA > kTiny, uniA_neg = mxA <= 0.f;
-              const bool uni_pos = uniA_pos && (mnB > kTiny), uni_neg = uniA_neg && (mxB <= 0.f);
-              if (uni_neg || uni_pos) {
-                const int Ylast = 4 * r + 1 + nrows_out;
+              // ---- generic scale: the 16 pixels read proto columns xa .. xb of rows r, r+1 ----
+              const int X0 = 16 * g;
+              int xa, xb, tq;
+              float f0, f1;
+              src_index(d.sx, X0, d.mw, xa, tq, f0, f1);
+              src_index(d.sx, X0 + 15, d.mw, tq, xb, f0, f1);
+              const bool outside = ((float)(r + 1) < q.y) || ((float)r >= q.w) || ((float)xb < q.x) || ((float)xa >= q.z);
+              if (outside) {
                 if (kWriteMasks) {
-                  const uint4 w = uni_pos ? ones : zeros;
 #pragma unroll 1
-                  for (int j = jbeg; j < nrows_out; ++j) {
-                    const int Y = (j < 0) ? j + 2 : 4 * r + 2 + j;
-                    *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
-                  }
-                }
-                if (uni_pos) {
-                  const int nrow = nrows_out - jbeg;                       // 2, 4 or 6 rows of ones
-                  rp.lo = (nrow >= 4) ? ~0ull : 0xffffffffull;
-                  rp.hi = (nrow == 6) ? ~0u : 0u;
-                  if (laty >= 0 && laty <= Ylast) lattice_row(ones, laty, 16 * g, d, lat);
+                  for (int j = 0; j < nrows; ++j) *reinterpret_cast<uint4*>(M + (size_t)(Yfirst + j) * d.W) = zeros;
                 }
               } else {
-                // mixed signs: the exact 4-tap blend.  One compact, rolled loop (code size matters: the roles
-                // share the instruction cache).
-                float hA[16], hB[16];
-                hinterp4(sA, hA, left);
-                hinterp4(sB, hB, left);
+                float mn = INFINITY, mx = -INFINITY;
 #pragma unroll 1
-                for (int j = jbeg; j < nrows_out; ++j) {
-                  uint4 w;
-                  int Y;
-                  if (j < 0) {         // dst rows 0,1 take h(row 0) unchanged (src y clamps to 0)
-                    Y = j + 2;
-                    w = hpack(hA);
-                  } else {
-                    Y = 4 * r + 2 + j;
-                    const float l1 = 0.125f + 0.25f * (float)j;     // .125 .375 .625 .875 (exact)
-                    w = vblend(hA, hB, 1.0f - l1, l1);
+                for (int x = xa; x <= xb; ++x) {
+                  const float a = lds_f32(rowA + 4 * x), bq = lds_f32(rowB + 4 * x);
+                  mn = fminf(mn, fminf(a, bq));
+                  mx = fmaxf(mx, fmaxf(a, bq));
+                }
+                const bool uni_pos = mn > kTiny, uni_neg = mx <= 0.f;
+                const int half = d.gs >> 1;
+                if (uni_neg || uni_pos) {
+                  if (kWriteMasks) {
+                    const uint4 w = uni_pos ? ones : zeros;
+#pragma unroll 1
+                    for (int j = 0; j < nrows; ++j) *reinterpret_cast<uint4*>(M + (size_t)(Yfirst + j) * d.W) = w;
                   }
-                  if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
-                  rp.set(j - jbeg, pat16(w));
-                  if (Y == laty && (w.x | w.y | w.z | w.w)) lattice_row(w, Y, 16 * g, d, lat);
+                  if (uni_pos) {
+                    rp.fill(nrows);
+#pragma unroll 1
+                    for (int j = 0; j < nrows; ++j) {
+                      const int tl = Yfirst + j - half;
+                      if (tl >= 0 && tl % d.gs == 0) lattice_row(ones, Yfirst + j, X0, d, lat);
+                    }
+                  }
+                } else {
+                  // horizontal pass for both proto rows (ATen: top = fma(a, l0x, fl(b * l1x))), then one vertical
+                  // blend per dst row of the pair (out = fma(top, l0y, fl(bot * l1y)))
+                  float hA[16], hB[16];
+#pragma unroll
+                  for (int px = 0; px < 16; ++px) {
+                    int x0, x1;
+                    float lx0, lx1;
+                    src_index(d.sx, X0 + px, d.mw, x0, x1, lx0, lx1);
+                    hA[px] = fmaf(lds_f32(rowA + 4 * x0), lx0, __fmul_rn(lds_f32(rowA + 4 * x1), lx1));
+                    hB[px] = fmaf(lds_f32(rowB + 4 * x0), lx0, __fmul_rn(lds_f32(rowB + 4 * x1), lx1));
+                  }
+#pragma unroll 1
+                  for (int j = 0; j < nrows; ++j) {
+                    const int Y = Yfirst + j;
+                    int y0, y1;
+                    float ly0, ly1;
+                    src_index(d.sy, Y, d.mh, y0, y1, ly0, ly1);
+                    const uint4 w = vblend(hA, hB, ly0, ly1);
+                    if (kWriteMasks) *reinterpret_cast<uint4*>(M + (size_t)Y * d.W) = w;
+                    rp.set(j, pat16(w));
+                    const int tl = Y - half;
+                    if ((w.x | w.y | w.z | w.w) && tl >= 0 && tl % d.gs == 0) lattice_row(w, Y, X0, d, lat);
+                  }
                 }
               }
             }
@@ -938,11 +1025,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           // gather the 128-bit block patterns (four shuffles per row, the rows' chains interleaved).
           __syncwarp();
           {
-            const int nrow = active ? nrows_out - jbeg : 0;
-            const unsigned long long full_lo = (nrow >= 4) ? ~0ull : (nrow == 2) ? 0xffffffffull : 0ull;
-            const unsigned full_hi = (nrow == 6) ? ~0u : 0u;
-            const bool is_zero = (rp.lo | rp.hi) == 0;
-            const bool is_full = active && rp.lo == full_lo && rp.hi == full_hi;
+            const int nrow = active ? nrows : 0;
+            const bool is_zero = rp.is_zero();
+            const bool is_full = active && rp.is_full(nrow);
             const unsigned zm = __ballot_sync(0xffffffffu, is_zero), fm = __ballot_sync(0xffffffffu, is_full || !active);
             // per 8-lane group: every lane zero, or every lane full (lanes past the row end count as full: they only
             // exist in the last block of a ragged row, where the exact path below is taken instead)
@@ -954,10 +1039,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             LeaderStats ls;
             if (!kWriteMasks) {
 #pragma unroll 1
-              for (int sidx = 0; sidx < nrow; ++sidx) {
-                const int Y = (jbeg < 0) ? sidx : 4 * r + 2 + sidx;
-                p.bits16[(inst * d.H + Y) * (size_t)(2 * d.bit_words) + g] = (uint16_t)rp.get(sidx);
-              }
+              for (int sidx = 0; sidx < nrow; ++sidx)
+                p.bits16[(inst * d.H + Yfirst + sidx) * (size_t)(2 * d.bit_words) + g] = (uint16_t)rp.get(sidx);
             }
             if (!ragged && ((gzall | gfall) == 0x01010101u)) {
               if (gl == 0 && nrow > 0) {
@@ -965,26 +1048,22 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                 const int blk = g >> 3;
                 const uint32_t e = fullg ? cc::rowsum_pack(cc::kRowBlock, 0, cc::kRowBlock - 1) : 0u;
 #pragma unroll 1
-                for (int sidx = 0; sidx < nrow; ++sidx) {
-                  const int Y = (jbeg < 0) ? sidx : 4 * r + 2 + sidx;
-                  rs_inst[(size_t)Y * d.nblk + blk] = e;
-                }
+                for (int sidx = 0; sidx < nrow; ++sidx) rs_inst[(size_t)(Yfirst + sidx) * d.nblk + blk] = e;
                 if (fullg) {
-                  const int Y0 = (jbeg < 0) ? 0 : 4 * r + 2;
                   ls.area = (unsigned)(cc::kRowBlock * nrow);
                   ls.minx = cc::kRowBlock * blk; ls.maxx = cc::kRowBlock * blk + cc::kRowBlock - 1;
-                  ls.miny = Y0; ls.maxy = Y0 + nrow - 1;
+                  ls.miny = Yfirst; ls.maxy = Yfirst + nrow - 1;
                 }
               }
             } else {
-              const int Yb = (jbeg < 0) ? 0 : 4 * r + 2;
 #pragma unroll
               for (int sidx = 0; sidx < 4; ++sidx)
-                emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yb + sidx, g >> 3, rs_inst, d.nblk, ls);
-              if (r0 == 0) {                                               // pair 0 of the frame owns 6 rows (warp-uniform)
+                emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yfirst + sidx, g >> 3, rs_inst, d.nblk, ls);
+              // exact 4x: pair 0 of the frame owns 6 rows; generic scale: up to max_rows (both warp-uniform)
+              if (kGeneric ? (p.max_rows > 4) : (r0 == 0)) {
 #pragma unroll
-                for (int sidx = 4; sidx < 6; ++sidx)
-                  emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yb + sidx, g >> 3, rs_inst, d.nblk, ls);
+                for (int sidx = 4; sidx < (kGeneric ? 8 : 6); ++sidx)
+                  emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yfirst + sidx, g >> 3, rs_inst, d.nblk, ls);
               }
             }
             if (gl == 0 && ls.area) {
@@ -1056,6 +1135,9 @@ struct FusedPlan {
   int ni;            // instances per group = accumulator columns read back per tile (8 or 16)
   int groups;        // instance groups per frame = ceil(max_n / ni)
   int chunk_floats;
+  bool generic;      // any up-sampling scale (row table + per-pixel source indices) instead of exact 4x
+  int max_rows;      // generic: most dst rows owned by one prototype row pair
+  int zero_rows;     // rows of the shared-memory zero buffer
   size_t smem_bytes;
   unsigned long long* timing;   // device buffer when VA_FUSED_TIMING=1
   int* work_counter;
@@ -1066,11 +1148,33 @@ struct FusedPlan {
 };
 
 FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen) {
-  if (!(d.H == 4 * d.mh && d.W == 4 * d.mw)) { snprintf(err, errlen, "tcgen05 path needs H=4*mh, W=4*mw"); return nullptr; }
+  const bool exact4 = (d.H == 4 * d.mh && d.W == 4 * d.mw);
+  int max_rows = 6;
+  if (!exact4) {
+    // generic scale: up-sampling in both directions, whole 16-pixel pieces, at most 8 dst rows per prototype row pair
+    if (d.H < d.mh || d.W < d.mw || (d.W % 16) != 0) { snprintf(err, errlen, "tcgen05 path needs H=4*mh, W=4*mw, or an up-sampling scale with W %% 16 == 0"); return nullptr; }
+    if (d.H > 32767) { snprintf(err, errlen, "tcgen05 path: H <= 32767"); return nullptr; }
+    max_rows = 0;
+    int prev = -1, first = 0;
+    for (int Y = 0; Y <= d.H; ++Y) {                    // the same fp32 arithmetic the kernel uses for its row table
+      int y0 = d.mh;
+      if (Y < d.H) {
+        float src = fmaf(d.sy, (float)Y + 0.5f, -0.5f);
+        src = src < 0.f ? 0.f : src;
+        y0 = (int)src < d.mh - 1 ? (int)src : d.mh - 1;
+      }
+      if (y0 != prev) {
+        if (prev >= 0 && Y - first > max_rows) max_rows = Y - first;
+        if (prev >= 0 && y0 != prev + 1) { snprintf(err, errlen, "tcgen05 path: a prototype row owns no dst row"); return nullptr; }
+        prev = y0; first = Y;
+      }
+    }
+    if (max_rows > 8) { snprintf(err, errlen, "tcgen05 path handles vertical scales up to 7x (at most 8 dst rows per prototype row, got %d)", max_rows); return nullptr; }
+  }
   if (d.max_n > kMaxInst) { snprintf(err, errlen, "tcgen05 path handles max_n <= %d", kMaxInst); return nullptr; }
   if ((d.mw % 4) != 0 || (d.W % 16) != 0) { snprintf(err, errlen, "mw %% 4 / W %% 16"); return nullptr; }
   if (((size_t)d.mh * d.mw) % 4 != 0) { snprintf(err, errlen, "P %% 4"); return nullptr; }
-  if (d.mw * 5 < 2 * kTileM + 1) { snprintf(err, errlen, "tcgen05 path needs H=4*mh, W=4*mw with mw >= 52 (items of >= 2 tiles)"); return nullptr; }
+  if (d.mw * 5 < 2 * kTileM + 1) { snprintf(err, errlen, "tcgen05 path needs mw >= 52 (items of >= 2 tiles)"); return nullptr; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties failed"); return nullptr; }
   if (prop.major != 10) { snprintf(err, errlen, "device is sm_%d%d, tcgen05 needs sm_100", prop.major, prop.minor); return nullptr; }
@@ -1093,13 +1197,20 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   int pr = 0, nbuf = 0, ni = 0;
   int force_ni = 0;
   if (const char* e = getenv("VA_FUSED_GSIZE")) force_ni = atoi(e);   // tuning aid: 8 or 16
+  // rows of the zero buffer: a whole chunk's dst rows when that is small (exact 4x: 4 pr + 2), else pieces of <= 16 KB
+  auto zero_rows_for = [&](int cand) {
+    const int want = exact4 ? 4 * cand + 2 : cand * max_rows;
+    const int fit = (16 * 1024) / d.W > 0 ? (16 * 1024) / d.W : 1;
+    return (exact4 || want <= fit) ? want : fit;
+  };
+  int zrows = 0;
   for (int g : {16, 8}) {
     if (g == 16 && d.max_n <= 8) continue;
     if (force_ni && g != force_ni && d.max_n > 8) continue;
     for (int cand : {4, 2}) {
       for (int nb : {4, 3}) {
         const int cf = (cand + 1) * g * d.mw;
-        if ((size_t)fused_smem_map(cf, nb, d.H, (4 * cand + 2) * d.W).total + 1024 <= limit) { pr = cand; nbuf = nb; ni = g; break; }
+        if ((size_t)fused_smem_map(cf, nb, d.H, d.mh, zero_rows_for(cand) * d.W).total + 1024 <= limit) { pr = cand; nbuf = nb; ni = g; zrows = zero_rows_for(cand); break; }
       }
       if (pr) break;
     }
@@ -1111,10 +1222,14 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   pl->ni = ni;
   pl->groups = ceil_div(d.max_n, ni);
   pl->chunk_floats = (pr + 1) * ni * d.mw;
-  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, nbuf, d.H, (4 * pr + 2) * d.W).total + 1024;
+  pl->generic = !exact4;
+  pl->max_rows = max_rows;
+  pl->zero_rows = zrows;
+  pl->smem_bytes = (size_t)fused_smem_map(pl->chunk_floats, nbuf, d.H, d.mh, zrows * d.W).total + 1024;
   cudaError_t e = cudaSuccess;
 #define VA_ATTR(WM, NI, DG, NB) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)fused_tc_kernel<WM, NI, DG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes)
+  if (e == cudaSuccess) e = pl->generic ? cudaFuncSetAttribute((const void*)fused_tc_kernel<WM, NI, DG, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes) \
+                                        : cudaFuncSetAttribute((const void*)fused_tc_kernel<WM, NI, DG, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes)
 #define VA_ATTR4(NI, NB) VA_ATTR(true, NI, false, NB); VA_ATTR(false, NI, false, NB); VA_ATTR(true, NI, true, NB); VA_ATTR(false, NI, true, NB)
   if (pl->nbuf == 4) { if (pl->ni == 8) { VA_ATTR4(8, 4); } else { VA_ATTR4(16, 4); } }
   else               { if (pl->ni == 8) { VA_ATTR4(8, 3); } else { VA_ATTR4(16, 3); } }
@@ -1163,6 +1278,7 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.timing = pl->timing;
   p.work_counter = pl->work_counter;
   p.pr = pl->pr; p.pr_shift = pl->pr == 4 ? 2 : 1; p.nst = pl->ni; p.gsize = pl->ni; p.groups = pl->groups; p.chunk_floats = pl->chunk_floats; p.nbuf = pl->nbuf;
+  p.zero_rows = pl->zero_rows; p.zero_bytes = pl->zero_rows * d.W; p.max_rows = pl->max_rows;
   // Bands per frame: items are stolen dynamically, so what matters is enough items per CTA for a short tail
   // (>= ~8) against the one-row halo every band recomputes and re-reads (1/ppb).
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
@@ -1177,7 +1293,8 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.n_items = B * p.nbands * p.groups;
   const int grid = p.n_items < pl->num_sms ? p.n_items : pl->num_sms;
   const bool diag = (logits_dbg != nullptr) || (pl->timing != nullptr);   // debug logits / role timing: separate instantiation
-#define VA_LAUNCH(WM, NI, DG, NB) fused_tc_kernel<WM, NI, DG, NB><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p)
+#define VA_LAUNCH(WM, NI, DG, NB) do { if (pl->generic) fused_tc_kernel<WM, NI, DG, NB, true><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p); \
+                                       else fused_tc_kernel<WM, NI, DG, NB, false><<<grid, kThreads, pl->smem_bytes, st>>>(pl->map, p); } while (0)
 #define VA_LAUNCH_NB(WM, NI, DG) do { if (pl->nbuf == 4) VA_LAUNCH(WM, NI, DG, 4); else VA_LAUNCH(WM, NI, DG, 3); } while (0)
   if (pl->ni == 8) {
     if (diag) { if (masks) VA_LAUNCH_NB(true, 8, true); else VA_LAUNCH_NB(false, 8, true); }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <climits>
+#include <type_traits>
 
 #include "va_common.cuh"
 #include "va_contour_core.h"
@@ -102,16 +103,29 @@ __device__ __forceinline__ uint4 bytes16(unsigned pat) {
   return make_uint4(ex(pat), ex(pat >> 4), ex(pat >> 8), ex(pat >> 12));
 }
 
-// 16-pixel patterns of up to 6 dst rows of one lane (slot s = row ordinal inside the task), three registers
+// 16-pixel patterns of the dst rows of one lane (slot s = row ordinal inside the task): up to 6 rows in three
+// registers (exact 4x), up to 8 rows in four (generic scale)
+template <bool kWide>
 struct RowPats {
   unsigned long long lo = 0ull;
-  unsigned hi = 0u;
+  typename std::conditional<kWide, unsigned long long, unsigned>::type hi = 0;
   __device__ __forceinline__ void set(int s, unsigned pat) {
     if (s < 4) lo |= (unsigned long long)pat << (16 * s);
-    else hi |= pat << (16 * (s - 4));
+    else hi |= (decltype(hi))pat << (16 * (s - 4));
   }
   __device__ __forceinline__ unsigned get(int s) const {
-    return (s < 4) ? (unsigned)(lo >> (16 * s)) & 0xffffu : (hi >> (16 * (s - 4))) & 0xffffu;
+    return (s < 4) ? (unsigned)(lo >> (16 * s)) & 0xffffu : (unsigned)(hi >> (16 * (s - 4))) & 0xffffu;
+  }
+  // the first n rows all ones
+  __device__ __forceinline__ void fill(int n) {
+    lo = (n >= 4) ? ~0ull : ((1ull << (16 * n)) - 1ull);
+    hi = (n <= 4) ? 0 : (n >= 4 + (int)(sizeof(hi) / 2)) ? ~(decltype(hi))0 : (decltype(hi))((1ull << (16 * (n - 4))) - 1ull);
+  }
+  __device__ __forceinline__ bool is_zero() const { return (lo | hi) == 0; }
+  __device__ __forceinline__ bool is_full(int n) const {
+    RowPats f;
+    f.fill(n);
+    return lo == f.lo && hi == f.hi;
   }
 };
 
@@ -206,6 +220,16 @@ __device__ __forceinline__ void load6(const float* __restrict__ row, int g, int 
   s[5] = (4 * g + 4 < mw) ? __ldg(row + 4 * g + 4) : v.w;
   mn = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(s[4], s[5]));
   mx = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), fmaxf(s[4], s[5]));
+}
+
+// ATen's align_corners=False source index and lambdas (area_pixel_compute_source_index + guard_index_and_lambda)
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
+  src = fmaxf(src, 0.f);
+  i0 = min((int)src, in_size - 1);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+  l0 = 1.0f - l1;
 }
 
 constexpr float kTiny = 1e-30f;   // below this a positive product could underflow: take the exact path

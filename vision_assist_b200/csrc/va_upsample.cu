@@ -157,15 +157,6 @@ upsample4x_kernel(Dims d, const float* __restrict__ logits, const int* __restric
 // ---------------------------------------------------------------------------------------------
 // generic-scale kernel: one thread = 16 consecutive dst pixels of kGenRows dst rows
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
-  float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
-  src = fmaxf(src, 0.f);
-  i0 = min((int)src, in_size - 1);
-  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
-  l0 = 1.0f - l1;
-}
-
 constexpr int kGenRows = 8;   // dst rows per thread (same 16 columns): the column span and its sign range are reused
 
 template <bool kWriteMasks>
