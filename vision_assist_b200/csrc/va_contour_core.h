@@ -461,8 +461,15 @@ VA_HD void phase_flatten_b(Work& w, int tid, int nt) {
   }
 }
 // ---- phase 9: table sums over the border pixels of G ----
+// Sums are kept per thread across all its words and flushed when the component changes; on the GPU the last flush
+// is aggregated over the warp first (generic atomics that land on one shared-memory word serialise - with one
+// component per mask every thread would hit the same two words).
+VA_HD void sums_flush(Work& w, int root, int pts, int a2) {
+  if (root >= 0) { atom_add(&w.accP[root], pts); atom_add(&w.accA[root], a2); }
+}
 VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
+  int cur_root = -1, pts = 0, a2 = 0;
   for (int t = tid; t < w.R * w.Wd; t += nt) {
     const int r = t / w.Wd, k = t - r * w.Wd;
     // Rows r-1, r, r+1 each one run (or empty) and no hole: the pixels of [a, b] that have all eight neighbours
@@ -487,7 +494,6 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
     const uint32_t Ml = (M << 1) | (Mp >> 31), Mr = (M >> 1) | (Mn << 31);
     const uint32_t Dl = (D << 1) | (Dp >> 31), Dr = (D >> 1) | (Dn << 31);
     uint32_t border = M & ~(Ul & U & Ur & Ml & Mr & Dl & D & Dr);
-    int cur_root = -1, pts = 0, a2 = 0;
     while (border) {
       const int b = ffs32(border) - 1;
       border &= border - 1;
@@ -499,14 +505,24 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
       const int lx = 32 * k + b;
       const int root = w.pF[w.rowoff[r] + ns(w, r, lx) - 1];
       if (root != cur_root) {
-        if (cur_root >= 0) { atom_add(&w.accP[cur_root], pts); atom_add(&w.accA[cur_root], a2); }
+        sums_flush(w, cur_root, pts, a2);
         cur_root = root; pts = 0; a2 = 0;
       }
       pts += p;
       a2 += lx * dys - r * dxs;                         // region-relative coordinates: the area is translation invariant
     }
-    if (cur_root >= 0) { atom_add(&w.accP[cur_root], pts); atom_add(&w.accA[cur_root], a2); }
   }
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+  const int rmax = __reduce_max_sync(0xffffffffu, cur_root);
+  if (__all_sync(0xffffffffu, cur_root == rmax || cur_root < 0)) {     // one component in this warp (the usual case)
+    const int sp = (int)__reduce_add_sync(0xffffffffu, (unsigned)(cur_root >= 0 ? pts : 0));
+    const int sa = (int)__reduce_add_sync(0xffffffffu, (unsigned)(cur_root >= 0 ? a2 : 0));
+    if ((tid & 31) == 0) sums_flush(w, rmax, sp, sa);
+    return;
+  }
+#endif
+  sums_flush(w, cur_root, pts, a2);
 }
 // ---- phase 10: the component whose contour has the most points; ties: the last in raster order ----
 VA_HD void phase_select(Work& w, int tid, int nt) {

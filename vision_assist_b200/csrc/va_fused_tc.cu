@@ -86,7 +86,7 @@ struct FusedParams {
   int nbuf;          // chunk buffers in the ring (3 or 4)
   int zero_bytes;    // size of the shared-memory zero buffer (source of the bulk zero fills), a multiple of W
   int zero_rows;     // = zero_bytes / W
-  int max_rows;      // generic scale: most dst rows owned by one prototype row pair (<= 8)
+  int max_rows;      // generic scale: most dst rows owned by one prototype row pair (<= 12)
   int* work_counter;            // [0] global work-stealing counter, [1] finished CTAs (the last one resets both)
   unsigned long long* timing;   // developer diagnostic (VA_FUSED_TIMING=1): [grid][5 roles][8] cycle counters, or nullptr
 };
@@ -1056,15 +1056,12 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                 }
               }
             } else {
-#pragma unroll
-              for (int sidx = 0; sidx < 4; ++sidx)
+              // rolled on purpose (code size: the roles share the instruction cache); exact 4x: pair 0 of the frame
+              // owns 6 rows, generic scale: up to max_rows (both bounds warp-uniform)
+              const int srows = kGeneric ? p.max_rows : ((r0 == 0) ? 6 : 4);
+#pragma unroll 1
+              for (int sidx = 0; sidx < srows; ++sidx)
                 emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yfirst + sidx, g >> 3, rs_inst, d.nblk, ls);
-              // exact 4x: pair 0 of the frame owns 6 rows; generic scale: up to max_rows (both warp-uniform)
-              if (kGeneric ? (p.max_rows > 4) : (r0 == 0)) {
-#pragma unroll
-                for (int sidx = 4; sidx < (kGeneric ? 8 : 6); ++sidx)
-                  emit_row_summary(rp.get(sidx), gl, sidx < nrow, Yfirst + sidx, g >> 3, rs_inst, d.nblk, ls);
-              }
             }
             if (gl == 0 && ls.area) {
               const uint32_t st = wstat + i * 32;
@@ -1169,7 +1166,7 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
         prev = y0; first = Y;
       }
     }
-    if (max_rows > 8) { snprintf(err, errlen, "tcgen05 path handles vertical scales up to 7x (at most 8 dst rows per prototype row, got %d)", max_rows); return nullptr; }
+    if (max_rows > 12) { snprintf(err, errlen, "tcgen05 path handles vertical scales up to 8x (at most 12 dst rows per prototype row, got %d)", max_rows); return nullptr; }
   }
   if (d.max_n > kMaxInst) { snprintf(err, errlen, "tcgen05 path handles max_n <= %d", kMaxInst); return nullptr; }
   if ((d.mw % 4) != 0 || (d.W % 16) != 0) { snprintf(err, errlen, "mw %% 4 / W %% 16"); return nullptr; }

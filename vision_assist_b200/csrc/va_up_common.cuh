@@ -104,28 +104,58 @@ __device__ __forceinline__ uint4 bytes16(unsigned pat) {
 }
 
 // 16-pixel patterns of the dst rows of one lane (slot s = row ordinal inside the task): up to 6 rows in three
-// registers (exact 4x), up to 8 rows in four (generic scale)
+// registers (exact 4x), up to 12 rows in six (generic scale: the first prototype row pair also owns the dst rows whose
+// source row clamps to 0, about 1.5 x the vertical scale)
 template <bool kWide>
-struct RowPats {
+struct RowPats;
+template <>
+struct RowPats<false> {
+  static constexpr int kSlots = 6;
   unsigned long long lo = 0ull;
-  typename std::conditional<kWide, unsigned long long, unsigned>::type hi = 0;
+  unsigned hi = 0u;
   __device__ __forceinline__ void set(int s, unsigned pat) {
     if (s < 4) lo |= (unsigned long long)pat << (16 * s);
-    else hi |= (decltype(hi))pat << (16 * (s - 4));
+    else hi |= pat << (16 * (s - 4));
   }
   __device__ __forceinline__ unsigned get(int s) const {
-    return (s < 4) ? (unsigned)(lo >> (16 * s)) & 0xffffu : (unsigned)(hi >> (16 * (s - 4))) & 0xffffu;
+    return (s < 4) ? (unsigned)(lo >> (16 * s)) & 0xffffu : (hi >> (16 * (s - 4))) & 0xffffu;
   }
-  // the first n rows all ones
-  __device__ __forceinline__ void fill(int n) {
-    lo = (n >= 4) ? ~0ull : ((1ull << (16 * n)) - 1ull);
-    hi = (n <= 4) ? 0 : (n >= 4 + (int)(sizeof(hi) / 2)) ? ~(decltype(hi))0 : (decltype(hi))((1ull << (16 * (n - 4))) - 1ull);
+  __device__ __forceinline__ void fill(int n) {      // the first n rows all ones (n = 2, 4 or 6)
+    lo = (n >= 4) ? ~0ull : 0xffffffffull;
+    hi = (n == 6) ? ~0u : 0u;
   }
   __device__ __forceinline__ bool is_zero() const { return (lo | hi) == 0; }
   __device__ __forceinline__ bool is_full(int n) const {
     RowPats f;
     f.fill(n);
-    return lo == f.lo && hi == f.hi;
+    return n > 0 && lo == f.lo && hi == f.hi;
+  }
+};
+template <>
+struct RowPats<true> {
+  static constexpr int kSlots = 12;
+  unsigned long long q0 = 0ull, q1 = 0ull, q2 = 0ull;
+  static __device__ __forceinline__ unsigned long long ones(int n) {      // n rows of 16 ones, 0 <= n <= 4
+    return (n >= 4) ? ~0ull : ((1ull << (16 * n)) - 1ull);
+  }
+  __device__ __forceinline__ void set(int s, unsigned pat) {
+    const unsigned long long v = (unsigned long long)pat << (16 * (s & 3));
+    if (s < 4) q0 |= v; else if (s < 8) q1 |= v; else q2 |= v;
+  }
+  __device__ __forceinline__ unsigned get(int s) const {
+    const unsigned long long q = (s < 4) ? q0 : (s < 8) ? q1 : q2;
+    return (unsigned)(q >> (16 * (s & 3))) & 0xffffu;
+  }
+  __device__ __forceinline__ void fill(int n) {
+    q0 = ones(min(n, 4));
+    q1 = ones(max(min(n - 4, 4), 0));
+    q2 = ones(max(min(n - 8, 4), 0));
+  }
+  __device__ __forceinline__ bool is_zero() const { return (q0 | q1 | q2) == 0; }
+  __device__ __forceinline__ bool is_full(int n) const {
+    RowPats f;
+    f.fill(n);
+    return n > 0 && q0 == f.q0 && q1 == f.q1 && q2 == f.q2;
   }
 };
 

@@ -104,12 +104,27 @@ class PeerRecordSink:
         self.flags_off = (depth * self.slot_bytes + 255) // 256 * 256
         total = self.flags_off + 4 * self.world
         box = [None]
+        self.base, err = 0, ""
         if self.rank == dst:
-            self.base, handle = eng.peer_alloc(total)
-            box[0] = handle
+            try:
+                self.base, handle = eng.peer_alloc(total)
+                box[0] = handle
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
         dist.broadcast_object_list(box, src=dst, group=group)
-        if self.rank != dst:
-            self.base = eng.peer_open(box[0])
+        if self.rank != dst and box[0] is not None:
+            try:
+                self.base = eng.peer_open(box[0])
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+        # every rank must agree on whether the mapping exists
+        ok = torch.tensor([1 if self.base else 0], dtype=torch.int32, device=torch.device("cuda", eng.device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if self.base:
+                (eng.peer_free if self.rank == dst else eng.peer_close)(self.base)
+                self.base = 0
+            raise RuntimeError("peer mapping of the record buffer failed on at least one rank: " + (err or "see other ranks"))
         self.total = total
         self.step = 0
 
