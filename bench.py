@@ -204,7 +204,7 @@ def _events():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=None, sampler=None):
+def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=None, sampler=None, gatherer=None):
     """`steps` timed steps of va_run_fused on device-resident inputs.  With a PeerRecordSink every step's records go
     to rank 0 over NVLink and rank 0 waits for all flags inside the timed region.  -> dict(ms, kernel_ms, tail_ms, calls)"""
     import torch
@@ -212,7 +212,11 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
     protos, coefs, boxes, counts = tensors
 
     def step():
-        if sink is None:
+        if gatherer is not None:          # fallback: NCCL gather of every step's records, overlapped with the next step
+            buf = gatherer.next_buffer()
+            eng.run(protos, coefs, boxes, counts, masks_out=masks, records_out=buf, write_masks=masks is not None)
+            gatherer.gather()
+        elif sink is None:
             eng.run(protos, coefs, boxes, counts, masks_out=masks, records_out=records, write_masks=masks is not None)
         else:
             eng.run(protos, coefs, boxes, counts, masks_out=masks, write_masks=masks is not None, records_ptr=sink.records_ptr())
@@ -222,8 +226,10 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
         step()
     if sink is not None and sink.rank == sink.dst:
         sink.wait()
+    if gatherer is not None:
+        gatherer.flush()
     torch.cuda.synchronize()
-    if sink is not None:
+    if sink is not None or gatherer is not None:
         dist.barrier()
     eng.profile(8 if steps >= 64 else 1)
     e0, e1 = _events()
@@ -234,13 +240,15 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
         step()
     if sink is not None and sink.rank == sink.dst:
         sink.wait()                        # every rank's records of the last step have landed on rank 0
+    if gatherer is not None:
+        gatherer.flush()
     e1.record()
     torch.cuda.synchronize()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
     asm_ms, tail_ms, calls = eng.profile_read()
     eng.profile(False)
-    if sink is not None:
+    if sink is not None or gatherer is not None:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -289,7 +297,9 @@ def run_stream(eng, wl, rank, world, sink_factory):
     non_simple = 0
     for mode in ("no_gather", "gather"):
         sink = sink_factory(n_chunks) if (mode == "gather" and world > 1) else None
-        allrec = torch.empty((n_chunks * B, eng.record_bytes), dtype=torch.uint8, device="cuda") if (mode == "gather" and world == 1) else None
+        nccl_fallback = mode == "gather" and world > 1 and sink is None
+        allrec = (torch.empty((n_chunks * B, eng.record_bytes), dtype=torch.uint8, device="cuda")
+                  if (mode == "gather" and (world == 1 or nccl_fallback)) else None)
         ms = 0.0
         evs = []
         for k in range(n_chunks):
@@ -313,6 +323,13 @@ def run_stream(eng, wl, rank, world, sink_factory):
             e0, e1 = _events()
             e0.record()
             sink.wait()
+            e1.record()
+            evs.append((e0, e1))
+        if nccl_fallback:                  # one NCCL gather of the whole shard at the end of the stream
+            from vision_assist_b200.sharding import gather_records
+            e0, e1 = _events()
+            e0.record()
+            gather_records(allrec[:hi - lo], total, dst=0)
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -342,7 +359,7 @@ def run_ours(args, wl):
 
     from vision_assist_b200 import synth
     from vision_assist_b200.engine import MaskGridEngine
-    from vision_assist_b200.sharding import PeerRecordSink
+    from vision_assist_b200.sharding import PeerRecordSink, RecordGatherer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -386,10 +403,11 @@ def run_ours(args, wl):
     in_bytes = hp.numel() * 4 + hc.numel() * 4 + hb.numel() * 4
 
     sink = sink_factory(2) if world > 1 else None
+    gatherer = RecordGatherer(B, eng.record_bytes, "cuda", dst=0, depth=2) if (world > 1 and sink is None) else None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    m = measure_device_resident(eng, tensors, masks, records, args.steps, args.warmup, sink, sampler)
+    m = measure_device_resident(eng, tensors, masks, records, args.steps, args.warmup, sink, sampler, gatherer)
     clocks = sampler.stop(m["t_begin"], m["t_end"]) if rank == 0 else None
     ms = m["ms"]
     value = B * world * args.steps / (ms / 1000.0)
@@ -452,6 +470,7 @@ def run_ours(args, wl):
                                "flags inside the timed region" if world > 1 else "single GPU",
                   "cpu_affinity": affinity,
                   "non_simple_frames_per_step": non_simple,
+                  **sink_note,
                   "contour_step": "exact: every record is built from the polygon the reference keeps (findContours RETR_EXTERNAL, "
                                   "most points, contourArea selection); non_simple = frames whose selected mask is not one hole-free blob"},
         "clocks": clocks,

@@ -244,6 +244,22 @@ class FrameProcessor:
                 unique.append(path)
         return unique
 
+    # -- FrameProcessor.py:272-299 (debug drawing; de-facto public: utilities/generate_testing_grids/run_on_main.py:196) --
+    def _draw_grid(self, grid, color) -> None:
+        """Fill one cell on self.frame (corners inclusive, as cv2.fillPoly draws them)."""
+        gs = config.grid_size
+        x, y = grid.coords.x, grid.coords.y
+        corners = np.array([[x, y], [x + gs, y], [x + gs, y + gs], [x, y + gs]], np.int32)
+        cv2.fillPoly(self.frame, [corners], color)
+
+    def _draw_non_path_grids(self) -> None:
+        """Every non-empty cell in its penalty colour (PenaltyCalculator.get_penalty_colour, config.py:4-17)."""
+        for grid_row in self.grids:
+            for grid in grid_row:
+                if grid.empty:
+                    continue
+                self._draw_grid(grid, penalty_calculator.get_penalty_colour(grid.penalty or 0))
+
     # -- FrameProcessor.py:301-360 ---------------------------------------------------------------
     def __call__(self, frame: np.ndarray):
         self.frame = frame
@@ -262,7 +278,8 @@ class FrameProcessor:
         paths = self._find_paths(protrusion_peaks, graph)
         final_answer = self.path_analyser(frame.shape[0], frame.shape[1], paths)
         if self.debug:
+            self._draw_non_path_grids()                                                      # :352
             if self.path_visualiser is not None:
-                self.frame = self.path_visualiser(self.frame, paths)
+                self.frame = self.path_visualiser(self.frame, paths)                         # :355
             return self.frame, final_answer
         return final_answer

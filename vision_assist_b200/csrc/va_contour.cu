@@ -29,7 +29,7 @@ namespace va {
 using cc::InstContour;
 
 constexpr int kCertThreads = 128;
-constexpr int kGenThreads = 1024;
+constexpr int kGenThreads = 512;
 
 __device__ uint16_t g_contour_lut[256];
 

@@ -191,8 +191,18 @@ struct Work {
 enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_COUNT };
 constexpr int kRowEmpty = -1, kRowMulti = -2;
 
+// bits [a, b] of word k (pixels 32k .. 32k+31), a <= b
+VA_HD uint32_t span_bits(int a, int b, int k) {
+  const int lo = imax(a, 32 * k), hi = imin(b, 32 * k + 31);
+  if (lo > hi) return 0u;
+  return (0xffffffffu << (lo & 31)) & (0xffffffffu >> (31 - (hi & 31)));
+}
+// word k of row r of a bit image: stored for rows with several runs, made up from the run ends otherwise
 VA_HD uint32_t word_at(const uint32_t* bm, const Work& w, int r, int k) {
-  return (r < 0 || r >= w.R || k < 0 || k >= w.Wd) ? 0u : bm[r * w.Wd + k];
+  if (r < 0 || r >= w.R || k < 0 || k >= w.Wd) return 0u;
+  const int a = w.one_a[r];
+  if (a == kRowMulti) return bm[r * w.Wd + k];
+  return (a >= 0) ? span_bits(a, (int)w.one_b[r], k) : 0u;
 }
 VA_HD uint32_t rise_at(const Work& w, int r, int k) {      // bits where a foreground run starts
   const uint32_t m = word_at(w.Mfg, w, r, k), p = word_at(w.Mfg, w, r, k - 1);
@@ -217,12 +227,6 @@ VA_HD int ns(const Work& w, int r, int x) {
   if (x >= 32 * w.Wd) return row_runs(w, r);
   const int k = x >> 5;
   return (int)w.S[r * w.Wd + k] + popc32(rise_at(w, r, k) & (0xffffffffu >> (31 - (x & 31))));
-}
-// bits [a, b] of word k (pixels 32k .. 32k+31), a <= b
-VA_HD uint32_t span_bits(int a, int b, int k) {
-  const int lo = imax(a, 32 * k), hi = imin(b, 32 * k + 31);
-  if (lo > hi) return 0u;
-  return (0xffffffffu << (lo & 31)) & (0xffffffffu >> (31 - (hi & 31)));
 }
 
 // find with path halving: every visited node is re-pointed at its grandparent.  The concurrent writes are benign -
@@ -250,6 +254,17 @@ VA_HD void uf_union(int* p, int a, int b) {
   }
 }
 
+// (row, word) tasks t = tid, tid + nt, ... without a division per task
+struct WordIter {
+  int t, r, k, dr, dk, nt, Wd, end;
+  VA_HD WordIter(const Work& w, int tid, int nthreads) {
+    Wd = w.Wd; nt = nthreads; end = w.R * w.Wd;
+    t = tid; r = tid / Wd; k = tid - r * Wd; dr = nt / Wd; dk = nt - dr * Wd;
+  }
+  VA_HD bool valid() const { return t < end; }
+  VA_HD void next() { t += nt; r += dr; k += dk; if (k >= Wd) { k -= Wd; ++r; } }
+};
+
 // ---- phase 0: scalars + row classes from the summaries ----
 VA_HD void phase_init(Work& w, int tid, int nt) {
   if (tid == 0) {
@@ -268,16 +283,14 @@ VA_HD void phase_init(Work& w, int tid, int nt) {
   }
 }
 
-// ---- phase 1: bit image of the region ----
+// ---- phase 1: bit rows of the rows with several runs (every other row is made up from its run ends on demand) ----
 VA_HD void phase_load(Work& w, int tid, int nt) {
-  for (int t = tid; t < w.R * w.Wd; t += nt) {
-    const int r = t / w.Wd, k = t - r * w.Wd;
+  for (WordIter it(w, tid, nt); it.valid(); it.next()) {
+    const int r = it.r, k = it.k, t = it.t;
+    if (w.one_a[r] != kRowMulti) continue;
     const int y = w.y0 + r, xw = w.x0w + k;
     uint32_t m = 0;
-    const int a = w.one_a[r];
-    if (a != kRowMulti) {
-      if (a >= 0) m = span_bits(a, (int)w.one_b[r], k);
-    } else if (w.fmt == 1) {
+    if (w.fmt == 1) {
       m = (xw < w.bit_words) ? w.bits[(size_t)y * w.bit_words + xw] : 0u;
       const int rem = w.W - 32 * xw;
       if (rem < 32) m &= (rem <= 0) ? 0u : (0xffffffffu >> (32 - rem));
@@ -366,8 +379,8 @@ VA_HD void phase_runs(Work& w, int tid, int nt) {
     run_init(w, id, a, r, true);
     w.re[id] = (uint16_t)w.one_b[r];
   }
-  for (int t = tid; t < w.R * w.Wd; t += nt) {        // rows with several runs
-    const int r = t / w.Wd, k = t - r * w.Wd;
+  for (WordIter it(w, tid, nt); it.valid(); it.next()) {   // rows with several runs
+    const int r = it.r, k = it.k, t = it.t;
     if (w.one_a[r] != kRowMulti) continue;
     const int base = w.rowoff[r], last_id = w.rowoff[r + 1] - 1;
     uint32_t rise = rise_at(w, r, k);
@@ -461,30 +474,71 @@ VA_HD void phase_flatten_b(Work& w, int tid, int nt) {
   }
 }
 // ---- phase 9: table sums over the border pixels of G ----
-// Sums are kept per thread across all its words and flushed when the component changes; on the GPU the last flush
-// is aggregated over the warp first (generic atomics that land on one shared-memory word serialise - with one
-// component per mask every thread would hit the same two words).
+// Sums are kept per thread across all its work and flushed when the component changes; on the GPU the last flush
+// is aggregated over the warp first (with one component per mask every thread would hit the same two words).
 VA_HD void sums_flush(Work& w, int root, int pts, int a2) {
   if (root >= 0) { atom_add(&w.accP[root], pts); atom_add(&w.accA[root], a2); }
+}
+VA_HD bool row_is_multi(const Work& w, int r) { return r >= 0 && r < w.R && w.one_a[r] == kRowMulti; }
+// a row with one run whose two neighbour rows have at most one run each: no hole touches it, its border pixels and
+// their 3x3 codes follow from the three pairs of run ends
+VA_HD bool row_is_plain(const Work& w, int r) { return w.one_a[r] >= 0 && !row_is_multi(w, r - 1) && !row_is_multi(w, r + 1); }
+struct Span { int a, b; };     // a > b: empty
+VA_HD Span row_span(const Work& w, int r) {
+  Span s; s.a = 1; s.b = 0;
+  if (r >= 0 && r < w.R && w.one_a[r] >= 0) { s.a = w.one_a[r]; s.b = w.one_b[r]; }
+  return s;
+}
+VA_HD uint32_t span_code(const Span& u, const Span& c, const Span& d, int x) {
+  auto in = [](const Span& s, int v) -> uint32_t { return (v >= s.a && v <= s.b) ? 1u : 0u; };
+  return in(u, x - 1) | (in(u, x) << 1) | (in(u, x + 1) << 2) | (in(c, x - 1) << 3) | (in(c, x + 1) << 4) |
+         (in(d, x - 1) << 5) | (in(d, x) << 6) | (in(d, x + 1) << 7);
 }
 VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   int cur_root = -1, pts = 0, a2 = 0;
-  for (int t = tid; t < w.R * w.Wd; t += nt) {
-    const int r = t / w.Wd, k = t - r * w.Wd;
-    // Rows r-1, r, r+1 each one run (or empty) and no hole: the pixels of [a, b] that have all eight neighbours
-    // are [max(a, ua, da) + 1, min(b, ub, db) - 1]; words inside that range have no border pixel.
-    {
-      const int a = w.one_a[r];
-      if (a == kRowEmpty) continue;
-      const int ua = (r > 0) ? (int)w.one_a[r - 1] : kRowEmpty, da = (r + 1 < w.R) ? (int)w.one_a[r + 1] : kRowEmpty;
-      if (a >= 0 && ua >= 0 && da >= 0) {
-        const int lo = imax(a, imax(ua, da)) + 1;
-        const int hi = imin((int)w.one_b[r], imin((int)w.one_b[r - 1], (int)w.one_b[r + 1])) - 1;
-        if (32 * k >= lo && 32 * k + 31 <= hi) continue;
-      }
+  auto add = [&](int root, int p, int v) {
+    if (root != cur_root) { sums_flush(w, cur_root, pts, a2); cur_root = root; pts = 0; a2 = 0; }
+    pts += p; a2 += v;
+  };
+  // (a) plain rows: the 3x3 code is constant between the pixels next to a run end of the three rows - evaluate those
+  //     pixels one by one and every stretch between them once (count * table entry, sum of x in closed form)
+  for (int r = tid; r < w.R; r += nt) {
+    if (!row_is_plain(w, r)) continue;
+    const Span c = row_span(w, r), u = row_span(w, r - 1), d = row_span(w, r + 1);
+    const int root = w.pF[w.rowoff[r]];
+    int bp[14], n = 0;
+    bp[n++] = c.a; bp[n++] = c.b;
+    if (u.a <= u.b) { for (int q = -1; q <= 1; ++q) { bp[n++] = u.a + q; bp[n++] = u.b + q; } }
+    if (d.a <= d.b) { for (int q = -1; q <= 1; ++q) { bp[n++] = d.a + q; bp[n++] = d.b + q; } }
+    for (int i = 1; i < n; ++i) {                       // insertion sort (<= 14 values)
+      const int v = bp[i];
+      int j = i - 1;
+      while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
+      bp[j + 1] = v;
     }
-    const uint32_t M = w.G[t];
+    int prev = c.a - 1;                                 // last pixel already accounted for
+    for (int i = 0; i < n; ++i) {
+      const int x = bp[i];
+      if (x < c.a || x > c.b || x <= prev) continue;
+      if (x - 1 > prev) {                               // stretch prev+1 .. x-1: constant code
+        const int lo = prev + 1, hi = x - 1, cnt = hi - lo + 1;
+        const uint32_t e = lut[span_code(u, c, d, lo)];
+        const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+        if (p | dxs | dys) add(root, p * cnt, dys * ((lo + hi) * cnt / 2) - r * dxs * cnt);
+      }
+      const uint32_t e = lut[span_code(u, c, d, x)];
+      const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+      if (p | dxs | dys) add(root, p, x * dys - r * dxs);
+      prev = x;
+    }
+    // c.b is a breakpoint, so the row is complete here
+  }
+  // (b) every other row, word by word on the bit image
+  for (WordIter it(w, tid, nt); it.valid(); it.next()) {
+    const int r = it.r, k = it.k;
+    if (w.one_a[r] == kRowEmpty || row_is_plain(w, r)) continue;
+    const uint32_t M = word_at(w.G, w, r, k);
     if (!M) continue;
     const uint32_t U = word_at(w.G, w, r - 1, k), D = word_at(w.G, w, r + 1, k);
     const uint32_t Up = word_at(w.G, w, r - 1, k - 1), Un = word_at(w.G, w, r - 1, k + 1);
@@ -503,13 +557,7 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
       const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
       if (!(p | dxs | dys)) continue;                   // a hole pixel touching the outside diagonally: no visit
       const int lx = 32 * k + b;
-      const int root = w.pF[w.rowoff[r] + ns(w, r, lx) - 1];
-      if (root != cur_root) {
-        sums_flush(w, cur_root, pts, a2);
-        cur_root = root; pts = 0; a2 = 0;
-      }
-      pts += p;
-      a2 += lx * dys - r * dxs;                         // region-relative coordinates: the area is translation invariant
+      add(w.pF[w.rowoff[r] + ns(w, r, lx) - 1], p, lx * dys - r * dxs);   // region-relative coordinates: the area is translation invariant
     }
   }
 #ifdef __CUDA_ARCH__
@@ -572,7 +620,7 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
         const int r = w.gs * ly + half - w.y0;
         const int x = w.gs * lx + half - 32 * w.x0w;          // region-relative pixel
         if (r < 0 || r >= w.R || x < 0 || x >= 32 * w.Wd) continue;
-        if (!((w.G[r * w.Wd + (x >> 5)] >> (x & 31)) & 1u)) continue;
+        if (!((word_at(w.G, w, r, x >> 5) >> (x & 31)) & 1u)) continue;
         const int j = ns(w, r, x) - 1;                        // the run at or left of x (x is in it or in the hole after it)
         if (j >= 0 && w.pF[w.rowoff[r] + j] == chosen) atom_or(&w.lattice[ly * w.lat_words + (lx >> 5)], 1u << (lx & 31));
       }
