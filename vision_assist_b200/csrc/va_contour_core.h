@@ -60,39 +60,58 @@ VA_HD int clz32(uint32_t v) {
   return v ? __builtin_clz(v) : 32;
 #endif
 }
-VA_HD int atom_min(int* p, int v) {
+// Atomics on scratch that lives in shared memory when it fits and in a global slab otherwise.  A generic atomic
+// (ATOM.E) that lands in the shared window is far slower than the shared-space instruction, so the device versions
+// test the address space and issue atom / red .shared explicitly.
 #ifdef __CUDA_ARCH__
+#define VA_SH(p) ((unsigned)__cvta_generic_to_shared(p))
+#endif
+VA_HD int atom_min(int* p, int v) {        // returns the old value
+#ifdef __CUDA_ARCH__
+  if (__isShared(p)) { int o; asm volatile("atom.shared.min.s32 %0, [%1], %2;" : "=r"(o) : "r"(VA_SH(p)), "r"(v) : "memory"); return o; }
   return atomicMin(p, v);
 #else
   const int o = *p; if (v < o) *p = v; return o;
 #endif
 }
-VA_HD int atom_max(int* p, int v) {
+VA_HD void atom_max(int* p, int v) {
 #ifdef __CUDA_ARCH__
-  return atomicMax(p, v);
+  if (__isShared(p)) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(VA_SH(p)), "r"(v) : "memory"); return; }
+  atomicMax(p, v);
 #else
-  const int o = *p; if (v > o) *p = v; return o;
+  if (v > *p) *p = v;
 #endif
 }
-VA_HD int atom_add(int* p, int v) {
+VA_HD void atom_min_nr(int* p, int v) {
 #ifdef __CUDA_ARCH__
-  return atomicAdd(p, v);
+  if (__isShared(p)) { asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(VA_SH(p)), "r"(v) : "memory"); return; }
+  atomicMin(p, v);
 #else
-  const int o = *p; *p = o + v; return o;
+  if (v < *p) *p = v;
 #endif
 }
-VA_HD unsigned atom_or(unsigned* p, unsigned v) {
+VA_HD void atom_add(int* p, int v) {
 #ifdef __CUDA_ARCH__
-  return atomicOr(p, v);
+  if (__isShared(p)) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(VA_SH(p)), "r"(v) : "memory"); return; }
+  atomicAdd(p, v);
 #else
-  const unsigned o = *p; *p = o | v; return o;
+  *p += v;
 #endif
 }
-VA_HD unsigned long long atom_max64(unsigned long long* p, unsigned long long v) {
+VA_HD void atom_or(unsigned* p, unsigned v) {
 #ifdef __CUDA_ARCH__
-  return atomicMax(p, v);
+  if (__isShared(p)) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(VA_SH(p)), "r"(v) : "memory"); return; }
+  atomicOr(p, v);
 #else
-  const unsigned long long o = *p; if (v > o) *p = v; return o;
+  *p |= v;
+#endif
+}
+VA_HD void atom_max64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  if (__isShared(p)) { asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(VA_SH(p)), "l"(v) : "memory"); return; }
+  atomicMax(p, v);
+#else
+  if (v > *p) *p = v;
 #endif
 }
 VA_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -600,8 +619,8 @@ VA_HD void phase_bbox(Work& w, int tid, int nt) {
     miny = imin(miny, (int)w.ry[id]); maxy = imax(maxy, (int)w.ry[id]);
   }
   if (maxx >= 0) {
-    atom_min(&w.sc[W_MINX], minx); atom_max(&w.sc[W_MAXX], maxx);
-    atom_min(&w.sc[W_MINY], miny); atom_max(&w.sc[W_MAXY], maxy);
+    atom_min_nr(&w.sc[W_MINX], minx); atom_max(&w.sc[W_MAXX], maxx);
+    atom_min_nr(&w.sc[W_MINY], miny); atom_max(&w.sc[W_MAXY], maxy);
   }
 }
 // ---- phase 12: cell-centre lattice samples of the kept component (= the fillPoly raster) + result ----

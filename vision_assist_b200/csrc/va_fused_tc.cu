@@ -1024,7 +1024,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           // that are all ones / all zeros and their summaries are constants; only tasks that cross the outline
           // gather the 128-bit block patterns (four shuffles per row, the rows' chains interleaved).
           __syncwarp();
-          {
+          if (p.rowsum != nullptr) {                      // nullptr: developer A/B switch (VA_NO_ROWSUM=1), records are then meaningless
             const int nrow = active ? nrows : 0;
             const bool is_zero = rp.is_zero();
             const bool is_full = active && rp.is_full(nrow);
@@ -1270,6 +1270,8 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   p.d = d; p.coefs = coefs; p.boxes = boxes; p.counts = counts; p.masks = masks; p.logits_dbg = logits_dbg;
   p.stats = sinks.stats; p.lattice = sinks.lattice; p.B = B;
   p.rowsum = sinks.rowsum;
+  static const bool no_rowsum = getenv("VA_NO_ROWSUM") != nullptr;     // developer A/B switch: cost of the per-row by-products
+  if (no_rowsum) p.rowsum = nullptr;
   p.bits16 = reinterpret_cast<uint16_t*>(sinks.bits);
   if (!masks && !sinks.bits) { snprintf(err, errlen, "grid-only launch without a bit-mask buffer"); return cudaErrorInvalidValue; }
   p.timing = pl->timing;
