@@ -91,10 +91,11 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       bind_runs(w, scratch2.data(), rl);
       int sc[W_COUNT];
       unsigned long long best = 0;
-      w.sc = sc; w.best = &best; w.lattice = lattice; w.out = &res;
+      w.sc = sc; w.best = &best; w.lattice = lattice; w.out = &res; w.dbg = nullptr;
       const int nt = nthreads;
 #define PHASE(call) for (int tid = 0; tid < nt; ++tid) { call; }
       PHASE(phase_init(w, tid, nt));
+      PHASE(phase_lists(w, tid, nt));
       PHASE(phase_load(w, tid, nt));
       PHASE(phase_count(w, tid, nt));
       PHASE(phase_scan_a(w, tid, nt));

@@ -120,6 +120,7 @@ contour_general_kernel(const GenParams p) {
   __shared__ int s_sc[cc::W_COUNT];
   __shared__ unsigned long long s_best;
   __shared__ uint16_t s_lut[256];
+  __shared__ unsigned long long s_dbg[4];
   const Dims& d = p.d;
   const int tid = threadIdx.x, nt = blockDim.x;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -145,6 +146,8 @@ contour_general_kernel(const GenParams p) {
     w.sc = s_sc; w.best = &s_best;
     w.lattice = p.lattice + (size_t)inst * d.lat_rows * d.lat_words;
     w.out = p.out + inst;
+    w.dbg = (p.timing && blockIdx.x == 0 && item == blockIdx.x) ? s_dbg : nullptr;
+    if (w.dbg && tid < 4) s_dbg[tid] = 0ull;
     // grid part: shared memory when it fits; the run part follows it there when the runs fit too (known after the scan)
     const cc::GridLayout gl = cc::grid_layout(w.R, w.Wd);
     const cc::GridLayout gl_full = cc::grid_layout(d.H, d.bit_words);
@@ -158,6 +161,7 @@ contour_general_kernel(const GenParams p) {
     __syncthreads();                                       // previous item done with the shared scalars
     VA_TS();
     cc::phase_init(w, tid, nt);       __syncthreads();
+    cc::phase_lists(w, tid, nt);      __syncthreads();
     cc::phase_load(w, tid, nt);       __syncthreads(); VA_TS();
     cc::phase_count(w, tid, nt);      __syncthreads(); VA_TS();
     cc::phase_scan_a(w, tid, nt);     __syncthreads();
@@ -186,6 +190,7 @@ contour_general_kernel(const GenParams p) {
       __syncthreads();
       VA_TS();
       if (tid == 0) {
+        printf("[va contour] sums sections (max cycles over threads): rows %llu words %llu flush %llu\n", s_dbg[0], s_dbg[1], s_dbg[2]);
         printf("[va contour] items %d inst %d R %d Wd %d runs %d holes %d roots %d grid_smem %d | cycles: load %lld count %lld scan %lld runs %lld "
                "gaps %lld holes %lld link %lld flatten %lld sums %lld select+bbox %lld output %lld | total %lld\n",
                n_items, inst, w.R, w.Wd, s_sc[cc::W_NR], s_sc[cc::W_HOLES], s_sc[cc::W_ROOTS], (int)grid_in_smem,

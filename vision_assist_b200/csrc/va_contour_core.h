@@ -190,6 +190,8 @@ struct Work {
   uint16_t* S;              // [R][Wd] runs of the row that start before word k (rows with several runs only)
   int16_t* one_a;           // [R] first pixel of the row's only run (region-relative); kRowEmpty / kRowMulti otherwise
   int16_t* one_b;           // [R] last pixel of the row's only run
+  int16_t* mlist;           // [R] rows with several runs (sc[W_NM] entries, any order)
+  int16_t* nplist;          // [R] non-empty rows that are not "plain" (sc[W_NNP] entries): summed word by word
   int* rowoff;              // [R + 1] first run id of the row
   int cap;                  // run capacity
   uint16_t* rs;             // [cap] first / last pixel (region-relative) and row of a run; ids are in raster order
@@ -206,8 +208,9 @@ struct Work {
   // ---- output ----
   unsigned* lattice;        // [lat_rows][lat_words] of this instance (overwritten)
   InstContour* out;
+  unsigned long long* dbg;  // developer diagnostic (device only): per-section maximum cycles over the threads, or nullptr
 };
-enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_COUNT };
+enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_NM, W_NNP, W_COUNT };
 constexpr int kRowEmpty = -1, kRowMulti = -2;
 
 // bits [a, b] of word k (pixels 32k .. 32k+31), a <= b
@@ -284,6 +287,11 @@ struct WordIter {
   VA_HD void next() { t += nt; r += dr; k += dk; if (k >= Wd) { k -= Wd; ++r; } }
 };
 
+VA_HD bool row_is_multi(const Work& w, int r) { return r >= 0 && r < w.R && w.one_a[r] == kRowMulti; }
+// a row with one run whose two neighbour rows have at most one run each: no hole touches it, its border pixels and
+// their 3x3 codes follow from the three pairs of run ends
+VA_HD bool row_is_plain(const Work& w, int r) { return w.one_a[r] >= 0 && !row_is_multi(w, r - 1) && !row_is_multi(w, r + 1); }
+
 // ---- phase 0: scalars + row classes from the summaries ----
 VA_HD void phase_init(Work& w, int tid, int nt) {
   if (tid == 0) {
@@ -302,11 +310,27 @@ VA_HD void phase_init(Work& w, int tid, int nt) {
   }
 }
 
+// ---- phase 0b: the (few) rows that need word-level work ----
+VA_HD int atom_inc(int* p) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, 1);
+#else
+  return (*p)++;
+#endif
+}
+VA_HD void phase_lists(Work& w, int tid, int nt) {
+  for (int r = tid; r < w.R; r += nt) {
+    const int a = w.one_a[r];
+    if (a == kRowMulti) w.mlist[atom_inc(&w.sc[W_NM])] = (int16_t)r;
+    if (a != kRowEmpty && !row_is_plain(w, r)) w.nplist[atom_inc(&w.sc[W_NNP])] = (int16_t)r;
+  }
+}
+
 // ---- phase 1: bit rows of the rows with several runs (every other row is made up from its run ends on demand) ----
 VA_HD void phase_load(Work& w, int tid, int nt) {
-  for (WordIter it(w, tid, nt); it.valid(); it.next()) {
-    const int r = it.r, k = it.k, t = it.t;
-    if (w.one_a[r] != kRowMulti) continue;
+  const int ntask = w.sc[W_NM] * w.Wd;
+  for (int q = tid; q < ntask; q += nt) {
+    const int r = w.mlist[q / w.Wd], k = q % w.Wd, t = r * w.Wd + k;
     const int y = w.y0 + r, xw = w.x0w + k;
     uint32_t m = 0;
     if (w.fmt == 1) {
@@ -398,9 +422,9 @@ VA_HD void phase_runs(Work& w, int tid, int nt) {
     run_init(w, id, a, r, true);
     w.re[id] = (uint16_t)w.one_b[r];
   }
-  for (WordIter it(w, tid, nt); it.valid(); it.next()) {   // rows with several runs
-    const int r = it.r, k = it.k, t = it.t;
-    if (w.one_a[r] != kRowMulti) continue;
+  const int ntask = w.sc[W_NM] * w.Wd;
+  for (int q = tid; q < ntask; q += nt) {              // rows with several runs
+    const int r = w.mlist[q / w.Wd], k = q % w.Wd, t = r * w.Wd + k;
     const int base = w.rowoff[r], last_id = w.rowoff[r + 1] - 1;
     uint32_t rise = rise_at(w, r, k);
     int id = base + (int)w.S[t];
@@ -498,10 +522,6 @@ VA_HD void phase_flatten_b(Work& w, int tid, int nt) {
 VA_HD void sums_flush(Work& w, int root, int pts, int a2) {
   if (root >= 0) { atom_add(&w.accP[root], pts); atom_add(&w.accA[root], a2); }
 }
-VA_HD bool row_is_multi(const Work& w, int r) { return r >= 0 && r < w.R && w.one_a[r] == kRowMulti; }
-// a row with one run whose two neighbour rows have at most one run each: no hole touches it, its border pixels and
-// their 3x3 codes follow from the three pairs of run ends
-VA_HD bool row_is_plain(const Work& w, int r) { return w.one_a[r] >= 0 && !row_is_multi(w, r - 1) && !row_is_multi(w, r + 1); }
 struct Span { int a, b; };     // a > b: empty
 VA_HD Span row_span(const Work& w, int r) {
   Span s; s.a = 1; s.b = 0;
@@ -515,17 +535,39 @@ VA_HD uint32_t span_code(const Span& u, const Span& c, const Span& d, int x) {
 }
 VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
+#ifdef __CUDA_ARCH__
+  long long tdbg0 = w.dbg ? clock64() : 0;
+#define VA_DBG(slot) do { if (w.dbg) { const long long n__ = clock64(); atomicMax(w.dbg + (slot), (unsigned long long)(n__ - tdbg0)); tdbg0 = n__; } } while (0)
+#else
+#define VA_DBG(slot) do { } while (0)
+#endif
   int cur_root = -1, pts = 0, a2 = 0;
   auto add = [&](int root, int p, int v) {
     if (root != cur_root) { sums_flush(w, cur_root, pts, a2); cur_root = root; pts = 0; a2 = 0; }
     pts += p; a2 += v;
   };
-  // (a) plain rows: the 3x3 code is constant between the pixels next to a run end of the three rows - evaluate those
-  //     pixels one by one and every stretch between them once (count * table entry, sum of x in closed form)
+  // (a) plain rows.  All pixels of [a, b] that miss a neighbour lie in [a, la] and [lb, b] with la = max(a, ua, da) + 1,
+  //     lb = min(b, ub, db) - 1 (the whole run when a neighbour row is empty).  Slanted outlines make both ranges a
+  //     few pixels long: evaluated pixel by pixel.  Long ranges (flat edges) are evaluated at the pixels next to a run
+  //     end of the three rows and once per stretch in between, where the 3x3 code is constant (count * table entry,
+  //     sum of x in closed form).
   for (int r = tid; r < w.R; r += nt) {
     if (!row_is_plain(w, r)) continue;
     const Span c = row_span(w, r), u = row_span(w, r - 1), d = row_span(w, r + 1);
     const int root = w.pF[w.rowoff[r]];
+    auto pixel = [&](int x) {
+      const uint32_t e = lut[span_code(u, c, d, x)];
+      const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+      if (p | dxs | dys) add(root, p, x * dys - r * dxs);
+    };
+    const bool both = (u.a <= u.b) && (d.a <= d.b);
+    const int la = both ? imin(c.b, imax(c.a, imax(u.a, d.a)) + 1) : c.b;
+    const int lb = both ? imax(c.a, imin(c.b, imin(u.b, d.b)) - 1) : c.a;
+    if (both && la - c.a < 8 && c.b - lb < 8) {
+      for (int x = c.a; x <= la; ++x) pixel(x);
+      for (int x = imax(lb, la + 1); x <= c.b; ++x) pixel(x);
+      continue;
+    }
     int bp[14], n = 0;
     bp[n++] = c.a; bp[n++] = c.b;
     if (u.a <= u.b) { for (int q = -1; q <= 1; ++q) { bp[n++] = u.a + q; bp[n++] = u.b + q; } }
@@ -546,17 +588,16 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
         const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
         if (p | dxs | dys) add(root, p * cnt, dys * ((lo + hi) * cnt / 2) - r * dxs * cnt);
       }
-      const uint32_t e = lut[span_code(u, c, d, x)];
-      const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
-      if (p | dxs | dys) add(root, p, x * dys - r * dxs);
+      pixel(x);
       prev = x;
     }
     // c.b is a breakpoint, so the row is complete here
   }
-  // (b) every other row, word by word on the bit image
-  for (WordIter it(w, tid, nt); it.valid(); it.next()) {
-    const int r = it.r, k = it.k;
-    if (w.one_a[r] == kRowEmpty || row_is_plain(w, r)) continue;
+  VA_DBG(0);
+  // (b) every other non-empty row (rows with several runs and their neighbours), word by word on the bit image
+  const int ntask = w.sc[W_NNP] * w.Wd;
+  for (int q = tid; q < ntask; q += nt) {
+    const int r = w.nplist[q / w.Wd], k = q % w.Wd;
     const uint32_t M = word_at(w.G, w, r, k);
     if (!M) continue;
     const uint32_t U = word_at(w.G, w, r - 1, k), D = word_at(w.G, w, r + 1, k);
@@ -579,6 +620,7 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
       add(w.pF[w.rowoff[r] + ns(w, r, lx) - 1], p, lx * dys - r * dxs);   // region-relative coordinates: the area is translation invariant
     }
   }
+  VA_DBG(1);
 #ifdef __CUDA_ARCH__
   __syncwarp();
   const int rmax = __reduce_max_sync(0xffffffffu, cur_root);
@@ -586,10 +628,13 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
     const int sp = (int)__reduce_add_sync(0xffffffffu, (unsigned)(cur_root >= 0 ? pts : 0));
     const int sa = (int)__reduce_add_sync(0xffffffffu, (unsigned)(cur_root >= 0 ? a2 : 0));
     if ((tid & 31) == 0) sums_flush(w, rmax, sp, sa);
+    VA_DBG(2);
     return;
   }
 #endif
   sums_flush(w, cur_root, pts, a2);
+  VA_DBG(2);
+#undef VA_DBG
 }
 // ---- phase 10: the component whose contour has the most points; ties: the last in raster order ----
 VA_HD void phase_select(Work& w, int tid, int nt) {
@@ -666,7 +711,7 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
 // Scratch layout in two parts, each placed in shared memory when it fits and in a global slab otherwise:
 // the grid part (bit images, per-word run counts, row classes, row offsets) and the run part (run table, union-find,
 // sums).
-struct GridLayout { size_t Mfg, G, S, one_a, one_b, rowoff, seg, total; };
+struct GridLayout { size_t Mfg, G, S, one_a, one_b, mlist, nplist, rowoff, seg, total; };
 struct RunLayout { size_t rs, re, ry, pF, pG, accP, accA, total; };
 VA_HD size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 VA_HD GridLayout grid_layout(int R, int Wd) {
@@ -677,6 +722,8 @@ VA_HD GridLayout grid_layout(int R, int Wd) {
   l.S = o; o += align16(sizeof(uint16_t) * R * Wd);
   l.one_a = o; o += align16(sizeof(int16_t) * R);
   l.one_b = o; o += align16(sizeof(int16_t) * R);
+  l.mlist = o; o += align16(sizeof(int16_t) * R);
+  l.nplist = o; o += align16(sizeof(int16_t) * R);
   l.rowoff = o; o += align16(sizeof(int) * (R + 1));
   l.seg = o; o += align16(sizeof(int) * 33);
   l.total = o;
@@ -699,6 +746,7 @@ VA_HD void bind_grid(Work& w, unsigned char* base, const GridLayout& l) {
   w.Mfg = reinterpret_cast<uint32_t*>(base + l.Mfg); w.G = reinterpret_cast<uint32_t*>(base + l.G);
   w.S = reinterpret_cast<uint16_t*>(base + l.S);
   w.one_a = reinterpret_cast<int16_t*>(base + l.one_a); w.one_b = reinterpret_cast<int16_t*>(base + l.one_b);
+  w.mlist = reinterpret_cast<int16_t*>(base + l.mlist); w.nplist = reinterpret_cast<int16_t*>(base + l.nplist);
   w.rowoff = reinterpret_cast<int*>(base + l.rowoff);
   w.seg = reinterpret_cast<int*>(base + l.seg);
 }
