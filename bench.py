@@ -14,8 +14,8 @@ One "step" = one pass of the hot path over one batch of synthetic frames (cfg1: 
                  configs[3] (a 65,536-frame stream generated on the device, sharded over the ranks, frames/s with
                  and without landing every record on rank 0)
 N > 1 (torchrun): every rank runs the same per-GPU batch on its own frames (weak scaling), no collective inside
-the path; every rank's tail kernel stores its records straight into rank 0's buffer over NVLink (peer mapping
-through the C ABI, one flag per rank and step) inside the timed region.
+the path; every step's records are moved by a copy engine into rank 0's peer-mapped buffer over NVLink (C ABI
+va_peer_*, one flag per rank and step) inside the timed region; NCCL only for the rendezvous and the timing reduction.
 --impl reference times the reference algorithm's CPU implementation (oracle port) instead.
 """
 from __future__ import annotations
@@ -224,6 +224,8 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
 
     for _ in range(max(warmup, 3)):
         step()
+    if sink is not None:
+        sink.drain()
     if sink is not None and sink.rank == sink.dst:
         sink.wait()
     if gatherer is not None:
@@ -238,8 +240,10 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
     e0.record()
     for _ in range(steps):
         step()
-    if sink is not None and sink.rank == sink.dst:
-        sink.wait()                        # every rank's records of the last step have landed on rank 0
+    if sink is not None:
+        sink.drain()                       # this rank's copies to rank 0 are inside its clock
+        if sink.rank == sink.dst:
+            sink.wait()                    # every rank's records of the last step have landed on rank 0
     if gatherer is not None:
         gatherer.flush()
     e1.record()
@@ -310,7 +314,7 @@ def run_stream(eng, wl, rank, world, sink_factory):
             e0.record()
             if sink is not None:
                 eng.run(p, c, b, cnt, masks_out=masks[:nb], write_masks=True, records_ptr=sink.records_ptr())
-                sink.commit()
+                sink.commit(nb)
             elif allrec is not None:
                 eng.run(p, c, b, cnt, masks_out=masks[:nb], records_out=allrec[k * B:k * B + nb], write_masks=True)
             else:
@@ -319,10 +323,12 @@ def run_stream(eng, wl, rank, world, sink_factory):
             evs.append((e0, e1))
             if mode == "no_gather" and k % 32 == 0:
                 non_simple += int((local[:nb, 0] & 8).ne(0).sum().item())
-        if sink is not None and rank == 0:
+        if sink is not None:
             e0, e1 = _events()
             e0.record()
-            sink.wait()
+            sink.drain()
+            if rank == 0:
+                sink.wait()
             e1.record()
             evs.append((e0, e1))
         if nccl_fallback:                  # one NCCL gather of the whole shard at the end of the stream
@@ -465,9 +471,9 @@ def run_ours(args, wl):
         "vs_baseline": None, "dtype": "f32 (tf32x3 tensor-core contraction, fp32 blend, f64 penalties, u8 masks)",
         "data": "synthetic", "config": cfg,
         "notes": {"contraction": "tcgen05" if eng.uses_tensor_core else "cuda-core",
-                  "multi_gpu": "frames sharded per rank, no collective in the path; every rank's tail kernel stores its records into "
-                               "rank 0's peer-mapped buffer over NVLink (one flag per rank and step), rank 0 waits for the last "
-                               "flags inside the timed region" if world > 1 else "single GPU",
+                  "multi_gpu": "frames sharded per rank, no collective in the path; every step's records are moved by a copy engine "
+                               "into rank 0's peer-mapped buffer over NVLink (side stream, one flag per rank and step), rank 0 waits "
+                               "for the last flags inside the timed region" if world > 1 else "single GPU",
                   "cpu_affinity": affinity,
                   "non_simple_frames_per_step": non_simple,
                   **sink_note,

@@ -217,6 +217,9 @@ VA_API int va_nms(va_ctx* ctx, const float* pred, int32_t A, const va_nms_params
  *   va_peer_alloc   on the gathering rank: device buffer + a 64-byte handle to send to the other processes
  *   va_peer_open    on the other ranks: map that buffer (peer access is enabled by the mapping); *dptr is valid in
  *                   kernels of the context's device
+ *   va_peer_put     enqueue a device-to-device copy of finished records into the (peer) buffer: runs on a copy engine,
+ *                   no SM is involved (the other way to fill the buffer is to pass a peer pointer as records_out -
+ *                   fewer steps, but the tail kernel's small stores then cross NVLink one by one)
  *   va_signal       enqueue "flag = value" (system-scope release) after everything queued before it on the stream -
  *                   the per-step "records of step k have landed" mark; flag may be a peer pointer
  *   va_wait_flags   enqueue a wait until flags[i] >= value for all i < n (system-scope acquire) on the stream */
@@ -225,6 +228,7 @@ VA_API int va_peer_alloc(va_ctx* ctx, uint64_t bytes, void** dptr, uint8_t handl
 VA_API int va_peer_open(va_ctx* ctx, const uint8_t handle[VA_IPC_HANDLE_BYTES], void** dptr);
 VA_API int va_peer_close(va_ctx* ctx, void* dptr);
 VA_API int va_peer_free(va_ctx* ctx, void* dptr);
+VA_API int va_peer_put(va_ctx* ctx, void* dst, const void* src, uint64_t bytes, void* stream);
 VA_API int va_signal(va_ctx* ctx, int32_t* flag, int32_t value, void* stream);
 VA_API int va_wait_flags(va_ctx* ctx, const int32_t* flags, int32_t n, int32_t value, void* stream);
 

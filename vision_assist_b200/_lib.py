@@ -20,7 +20,7 @@ VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG
 EXPORTS = ["va_abi_version", "va_create", "va_destroy", "va_last_error", "va_get_layout", "va_assemble_masks",
            "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks", "va_nms",
            "va_last_launch_count", "va_uses_tensor_core", "va_profile_enable", "va_profile_read",
-           "va_peer_alloc", "va_peer_open", "va_peer_close", "va_peer_free", "va_signal", "va_wait_flags"]
+           "va_peer_alloc", "va_peer_open", "va_peer_close", "va_peer_free", "va_peer_put", "va_signal", "va_wait_flags"]
 
 
 class VaConfig(C.Structure):
@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     lib.va_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.va_peer_close.argtypes = [vp, vp]
     lib.va_peer_free.argtypes = [vp, vp]
+    lib.va_peer_put.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.va_signal.argtypes = [vp, vp, i32, vp]
     lib.va_wait_flags.argtypes = [vp, vp, i32, i32, vp]
     for name in EXPORTS:

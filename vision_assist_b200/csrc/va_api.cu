@@ -346,6 +346,12 @@ extern "C" int va_peer_free(va_ctx* c, void* dptr) {
   VA_CUDA(c, cudaFree(dptr));
   return VA_OK;
 }
+extern "C" int va_peer_put(va_ctx* c, void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (!c || !dst || !src) return VA_ERR_INVALID;
+  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return VA_OK;
+}
 extern "C" int va_signal(va_ctx* c, int32_t* flag, int32_t value, void* stream) {
   if (!c || !flag) return VA_ERR_INVALID;
   VA_CUDA(c, cudaSetDevice(c->cfg.device));

@@ -231,6 +231,10 @@ class MaskGridEngine:
     def peer_free(self, ptr: int) -> None:
         self._check(self.lib.va_peer_free(self._ctx, C.c_void_p(ptr)))
 
+    def peer_put(self, dst_ptr: int, src_ptr: int, nbytes: int) -> None:
+        """Enqueue a device-to-device copy (copy engine) into a local or peer-mapped buffer on the current stream."""
+        self._check(self.lib.va_peer_put(self._ctx, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(nbytes), self._stream()))
+
     def signal(self, flag_ptr: int, value: int) -> None:
         """Enqueue `*flag = value` (system scope) behind everything already queued on the current stream."""
         self._check(self.lib.va_signal(self._ctx, C.c_void_p(flag_ptr), int(value), self._stream()))

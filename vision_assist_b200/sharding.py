@@ -88,10 +88,11 @@ def device_view(ptr: int, nbytes: int, device) -> torch.Tensor:
 
 class PeerRecordSink:
     """Records of every rank land in ONE buffer on rank `dst` without a collective: the buffer is allocated through the
-    C ABI on `dst` (va_peer_alloc), its IPC handle is broadcast once, every other rank maps it (va_peer_open) and hands
-    its slot's address to `va_run_fused` as records_out - the tail kernel's stores go over NVLink, no NCCL kernel
-    competes with the persistent mask kernel for the SMs.  After every step each rank raises its per-rank flag
-    (va_signal); `dst` can wait for a step with `wait(step)`.
+    C ABI on `dst` (va_peer_alloc), its IPC handle is broadcast once, every other rank maps it (va_peer_open).  A step's
+    records are written by the tail kernel into a LOCAL staging buffer (two rotate); a copy engine then moves them over
+    NVLink into the rank's slot on `dst` (va_peer_put on a side stream, overlapped with the next step) and the rank's
+    flag is raised behind the copy (va_signal) - no SM is spent on the gather and no NCCL kernel competes with the
+    persistent mask kernel.  `dst` writes its own slot directly and can wait for a step with `wait(step)`.
 
     Layout on `dst`: [depth][world][n_local][record_bytes] then world int32 flags.  `depth` slots rotate (a frame
     stream keeps depth = number of chunks, i.e. every record has its own place)."""
@@ -127,15 +128,51 @@ class PeerRecordSink:
             raise RuntimeError("peer mapping of the record buffer failed on at least one rank: " + (err or "see other ranks"))
         self.total = total
         self.step = 0
+        dev = torch.device("cuda", eng.device)
+        self.remote = self.rank != dst
+        if self.remote:
+            self.stage = [torch.empty(n_local * self.rb, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.copied = [None, None]
+            self.side = torch.cuda.Stream(device=dev)
 
-    def records_ptr(self) -> int:
-        """Address this rank writes the records of the current step to."""
+    def _slot_ptr(self) -> int:
         return self.base + (self.step % self.depth) * self.slot_bytes + self.rank * self.n_local * self.rb
 
-    def commit(self) -> None:
-        """Call after va_run_fused of the current step was enqueued: raises this rank's flag to step + 1."""
+    def records_ptr(self) -> int:
+        """Address the tail kernel writes the records of the current step to: the rank's slot itself on `dst`, a local
+        staging buffer elsewhere (waits, on the current stream, until the copy that last used it has finished)."""
+        if not self.remote:
+            return self._slot_ptr()
+        s = self.step & 1
+        if self.copied[s] is not None:
+            torch.cuda.current_stream().wait_event(self.copied[s])
+        return self.stage[s].data_ptr()
+
+    def commit(self, n_frames: int | None = None) -> None:
+        """Call after va_run_fused of the current step was enqueued: moves the step's records to `dst` (copy engine,
+        side stream) and raises this rank's flag to step + 1 behind the copy."""
+        flag = self.base + self.flags_off + 4 * self.rank
+        if not self.remote:
+            self.step += 1
+            self.eng.signal(flag, self.step)
+            return
+        s = self.step & 1
+        nbytes = (self.n_local if n_frames is None else n_frames) * self.rb
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        self.side.wait_event(done)
+        dst_ptr = self._slot_ptr()
         self.step += 1
-        self.eng.signal(self.base + self.flags_off + 4 * self.rank, self.step)
+        with torch.cuda.stream(self.side):
+            self.eng.peer_put(dst_ptr, self.stage[s].data_ptr(), nbytes)
+            self.eng.signal(flag, self.step)
+            self.copied[s] = torch.cuda.Event()
+            self.copied[s].record(self.side)
+
+    def drain(self) -> None:
+        """The current stream waits for this rank's outstanding copies (no-op on `dst`)."""
+        if self.remote:
+            torch.cuda.current_stream().wait_stream(self.side)
 
     def wait(self, step: int | None = None) -> None:
         """`dst` only: the current stream waits until every rank has committed `step` (default: the latest) steps."""
@@ -147,6 +184,8 @@ class PeerRecordSink:
         return v.view(self.world * self.n_local, self.rb)
 
     def close(self) -> None:
+        if self.remote:
+            self.side.synchronize()
         if self.rank == self.dst:
             self.eng.peer_free(self.base)
         else:
