@@ -326,11 +326,19 @@ def run_stream(eng, wl, rank, world, sink_factory):
         if sink is not None:
             e0, e1 = _events()
             e0.record()
-            sink.drain()
-            if rank == 0:
-                sink.wait()
+            sink.drain()                   # this rank's copies to rank 0 have completed: inside its clock
             e1.record()
             evs.append((e0, e1))
+            # the chunks are generated (untimed, ~10 ms each) between the timed regions, so the ranks drift apart by
+            # milliseconds: line them up before rank 0 checks the flags, or that drift would be billed to the gather
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                e0, e1 = _events()
+                e0.record()
+                sink.wait()
+                e1.record()
+                evs.append((e0, e1))
         if nccl_fallback:                  # one NCCL gather of the whole shard at the end of the stream
             from vision_assist_b200.sharding import gather_records
             e0, e1 = _events()
