@@ -84,9 +84,11 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       w.rowsum = rowsum.data(); w.nblk = nblk;
       w.y0 = bbox[1]; w.x0w = bbox[0] >> 5; w.R = bbox[3] - bbox[1] + 1; w.Wd = (bbox[2] >> 5) - w.x0w + 1;
       w.cap = cap;
+      const RowLayout wl = row_layout(w.R);
       const GridLayout gl = grid_layout(w.R, w.Wd);
       const RunLayout rl = run_layout(cap);
-      std::vector<unsigned char> scratch(gl.total + 64, 0xcd), scratch2(rl.total + 64, 0xcd);   // poison: the phases must initialise what they read
+      std::vector<unsigned char> scratch0(wl.total + 64, 0xcd), scratch(gl.total + 64, 0xcd), scratch2(rl.total + 64, 0xcd);   // poison: the phases must initialise what they read
+      bind_rows(w, scratch0.data(), wl);
       bind_grid(w, scratch.data(), gl);
       bind_runs(w, scratch2.data(), rl);
       int sc[W_COUNT];

@@ -148,12 +148,20 @@ contour_general_kernel(const GenParams p) {
     w.out = p.out + inst;
     w.dbg = (p.timing && blockIdx.x == 0 && item == blockIdx.x) ? s_dbg : nullptr;
     if (w.dbg && tid < 4) s_dbg[tid] = 0ull;
-    // grid part: shared memory when it fits; the run part follows it there when the runs fit too (known after the scan)
+    // row part, word part, run part: each in shared memory when it fits behind the previous one, else in the CTA's
+    // slab (L2-resident); the run part is placed after the scan, when the number of runs is known
+    const cc::RowLayout wl = cc::row_layout(w.R);
     const cc::GridLayout gl = cc::grid_layout(w.R, w.Wd);
+    const cc::RowLayout wl_full = cc::row_layout(d.H);
     const cc::GridLayout gl_full = cc::grid_layout(d.H, d.bit_words);
-    const bool grid_in_smem = gl.total <= (size_t)p.smem_bytes;
-    cc::bind_grid(w, grid_in_smem ? smem_dyn : slab, gl);
-    unsigned char* run_slab = slab + gl_full.total;
+    size_t used = 0;
+    const bool rows_in_smem = wl.total <= (size_t)p.smem_bytes;
+    cc::bind_rows(w, rows_in_smem ? smem_dyn : slab, wl);
+    if (rows_in_smem) used += wl.total;
+    const bool grid_in_smem = used + gl.total <= (size_t)p.smem_bytes;
+    cc::bind_grid(w, grid_in_smem ? smem_dyn + used : slab + wl_full.total, gl);
+    if (grid_in_smem) used += gl.total;
+    unsigned char* run_slab = slab + wl_full.total + gl_full.total;
     cc::bind_runs(w, run_slab, cc::run_layout(p.cap));
     long long tstamp[20];
     int nst = 0;
@@ -169,7 +177,6 @@ contour_general_kernel(const GenParams p) {
     cc::phase_scan_c(w, tid, nt);     __syncthreads(); VA_TS();
     {
       const int NR = s_sc[cc::W_NR];
-      const size_t used = grid_in_smem ? gl.total : 0;
       const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
       if (NR <= p.cap && used + rl.total <= (size_t)p.smem_bytes) {
         w.cap = NR > 0 ? NR : 1;
@@ -213,7 +220,7 @@ contour_general_kernel(const GenParams p) {
 }
 
 size_t contour_slab_bytes(const Dims& d, int cap) {
-  return cc::grid_layout(d.H, d.bit_words).total + cc::run_layout(cap).total + 256;
+  return cc::row_layout(d.H).total + cc::grid_layout(d.H, d.bit_words).total + cc::run_layout(cap).total + 256;
 }
 
 static bool g_lut_loaded[64] = {false};

@@ -708,24 +708,31 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
   }
 }
 
-// Scratch layout in two parts, each placed in shared memory when it fits and in a global slab otherwise:
-// the grid part (bit images, per-word run counts, row classes, row offsets) and the run part (run table, union-find,
-// sums).
-struct GridLayout { size_t Mfg, G, S, one_a, one_b, mlist, nplist, rowoff, seg, total; };
+// Scratch layout in three parts, each placed in shared memory when it fits and in a global slab otherwise: the row
+// part (row classes, row offsets, row lists - touched by every phase), the word part (bit images and per-word run
+// counts - only rows with several runs use it) and the run part (run table, union-find, sums).
+struct RowLayout { size_t one_a, one_b, mlist, nplist, rowoff, seg, total; };
+struct GridLayout { size_t Mfg, G, S, total; };
 struct RunLayout { size_t rs, re, ry, pF, pG, accP, accA, total; };
 VA_HD size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-VA_HD GridLayout grid_layout(int R, int Wd) {
-  GridLayout l;
+VA_HD RowLayout row_layout(int R) {
+  RowLayout l;
   size_t o = 0;
-  l.Mfg = o; o += align16(sizeof(uint32_t) * R * Wd);
-  l.G = o; o += align16(sizeof(uint32_t) * R * Wd);
-  l.S = o; o += align16(sizeof(uint16_t) * R * Wd);
   l.one_a = o; o += align16(sizeof(int16_t) * R);
   l.one_b = o; o += align16(sizeof(int16_t) * R);
   l.mlist = o; o += align16(sizeof(int16_t) * R);
   l.nplist = o; o += align16(sizeof(int16_t) * R);
   l.rowoff = o; o += align16(sizeof(int) * (R + 1));
   l.seg = o; o += align16(sizeof(int) * 33);
+  l.total = o;
+  return l;
+}
+VA_HD GridLayout grid_layout(int R, int Wd) {
+  GridLayout l;
+  size_t o = 0;
+  l.Mfg = o; o += align16(sizeof(uint32_t) * R * Wd);
+  l.G = o; o += align16(sizeof(uint32_t) * R * Wd);
+  l.S = o; o += align16(sizeof(uint16_t) * R * Wd);
   l.total = o;
   return l;
 }
@@ -742,13 +749,15 @@ VA_HD RunLayout run_layout(int cap) {
   l.total = o;
   return l;
 }
-VA_HD void bind_grid(Work& w, unsigned char* base, const GridLayout& l) {
-  w.Mfg = reinterpret_cast<uint32_t*>(base + l.Mfg); w.G = reinterpret_cast<uint32_t*>(base + l.G);
-  w.S = reinterpret_cast<uint16_t*>(base + l.S);
+VA_HD void bind_rows(Work& w, unsigned char* base, const RowLayout& l) {
   w.one_a = reinterpret_cast<int16_t*>(base + l.one_a); w.one_b = reinterpret_cast<int16_t*>(base + l.one_b);
   w.mlist = reinterpret_cast<int16_t*>(base + l.mlist); w.nplist = reinterpret_cast<int16_t*>(base + l.nplist);
   w.rowoff = reinterpret_cast<int*>(base + l.rowoff);
   w.seg = reinterpret_cast<int*>(base + l.seg);
+}
+VA_HD void bind_grid(Work& w, unsigned char* base, const GridLayout& l) {
+  w.Mfg = reinterpret_cast<uint32_t*>(base + l.Mfg); w.G = reinterpret_cast<uint32_t*>(base + l.G);
+  w.S = reinterpret_cast<uint16_t*>(base + l.S);
 }
 VA_HD void bind_runs(Work& w, unsigned char* base, const RunLayout& l) {
   w.rs = reinterpret_cast<uint16_t*>(base + l.rs); w.re = reinterpret_cast<uint16_t*>(base + l.re);

@@ -38,8 +38,32 @@ struct RowSink {
       if (t >= 0 && t % d.gs == 0) lattice_row_pat(pat, Y, 16 * g, d.gs, d.lat_cols, d.lat_words, lat);
     }
     if (ex && bits_inst) bits_inst[(size_t)Y * (2 * d.bit_words) + g] = (uint16_t)pat;
-    // the leader's piece always exists when any piece of the group does (pieces are numbered left to right)
-    emit_row_summary(ex ? pat : 0u, gl, exists, Y, g >> 3, rowsum_inst, d.nblk, ls);
+    // Most rows of most blocks are all zeros or all ones: two votes find the 8-lane groups for which that holds and
+    // their summaries are constants; only a warp with a block that crosses the outline gathers the patterns.
+    // (A lane past the row end, or a row that does not exist, counts as both - its leader then writes nothing.)
+    const unsigned p = ex ? pat : 0u;
+    const unsigned zm = __ballot_sync(0xffffffffu, p == 0u), fm = __ballot_sync(0xffffffffu, p == 0xffffu || !ex);
+    const unsigned gz = zm & (zm >> 4), gf = fm & (fm >> 4);
+    const unsigned gz2 = gz & (gz >> 2), gf2 = gf & (gf >> 2);
+    const unsigned gzall = gz2 & (gz2 >> 1) & 0x01010101u, gfall = gf2 & (gf2 >> 1) & 0x01010101u;
+    if ((gzall | gfall) == 0x01010101u) {
+      if (gl == 0 && ex) {             // the leader's piece exists whenever any piece of its group does
+        const bool fullg = ((gfall >> ((threadIdx.x & 31) & 24)) & 1u) && !((gzall >> ((threadIdx.x & 31) & 24)) & 1u);
+        const int blk = g >> 3;
+        // a "full" group whose last pieces lie past the row end is a ragged block: count its real pixels
+        const int npx = min(cc::kRowBlock, d.W - cc::kRowBlock * blk);
+        rowsum_inst[(size_t)Y * d.nblk + blk] = fullg ? cc::rowsum_pack(npx, 0, npx - 1) : 0u;
+        if (fullg) {
+          ls.area += (unsigned)npx;
+          ls.minx = min(ls.minx, cc::kRowBlock * blk);
+          ls.maxx = max(ls.maxx, cc::kRowBlock * blk + npx - 1);
+          ls.miny = min(ls.miny, Y);
+          ls.maxy = max(ls.maxy, Y);
+        }
+      }
+      return;
+    }
+    emit_row_summary(p, gl, exists, Y, g >> 3, rowsum_inst, d.nblk, ls);
   }
 };
 
