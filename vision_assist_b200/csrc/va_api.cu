@@ -159,6 +159,7 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
     VA_CREATE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     c->num_sms = sms;
     VA_CREATE_CUDA(cudaMalloc(&c->scratch.rowsum, ns * d.H * d.nblk * sizeof(uint32_t)));
+    VA_CREATE_CUDA(cudaMemset(c->scratch.rowsum, 0, ns * d.H * d.nblk * sizeof(uint32_t)));
     VA_CREATE_CUDA(cudaMalloc(&c->scratch.contour, ns * sizeof(cc::InstContour)));
     VA_CREATE_CUDA(cudaMemset(c->scratch.contour, 0, ns * sizeof(cc::InstContour)));
     VA_CREATE_CUDA(cudaMalloc(&c->scratch.worklist, (2 + ns) * sizeof(int)));
@@ -432,6 +433,7 @@ extern "C" int va_assemble_masks(va_ctx* c, const float* protos, const float* co
   if (rc != VA_OK) return rc;
   // masks-only call: the reductions are not consumed by a tail, reset them
   VA_CUDA(c, launch_init_scratch(c->d, B, c->scratch.stats, c->scratch.lattice, st));
+  VA_CUDA(c, cudaMemsetAsync(c->scratch.rowsum, 0, (size_t)B * c->d.max_n * c->d.H * c->d.nblk * sizeof(uint32_t), st));
   c->last_launches += 1;
   return VA_OK;
 }

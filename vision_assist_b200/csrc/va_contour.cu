@@ -37,7 +37,7 @@ __device__ uint16_t g_contour_lut[256];
 // and the previous row's (a neighbour lane's, one extra load at the lane-0 seam).
 __global__ void __launch_bounds__(kCertThreads)
 contour_certify_kernel(Dims d, const int* __restrict__ counts, int B, const InstStats* __restrict__ stats,
-                       const uint32_t* __restrict__ rowsum, InstContour* __restrict__ out, int* __restrict__ worklist) {
+                       uint32_t* __restrict__ rowsum, InstContour* __restrict__ out, int* __restrict__ worklist) {
   __shared__ int s_red[5];     // ok, n, l, minx, maxx
   const int inst = blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -53,7 +53,7 @@ contour_certify_kernel(Dims d, const int* __restrict__ counts, int B, const Inst
   }
   if (threadIdx.x == 0) { s_red[0] = 1; s_red[1] = 0; s_red[2] = 0; s_red[3] = INT_MAX; s_red[4] = -1; }
   __syncthreads();
-  const uint32_t* rs = rowsum + (size_t)inst * d.H * d.nblk;
+  uint32_t* rs = rowsum + (size_t)inst * d.H * d.nblk;
   int ok = 1, n = 0, l = 0, minx = INT_MAX, maxx = -1;
   for (int y0 = st.miny; y0 <= st.maxy; y0 += kCertThreads) {
     const int y = y0 + (int)threadIdx.x;
@@ -82,6 +82,11 @@ contour_certify_kernel(Dims d, const int* __restrict__ counts, int B, const Inst
     atomicMin(&s_red[3], minx); atomicMax(&s_red[4], maxx);
   }
   __syncthreads();
+  if (s_red[0]) {
+    // certified: nobody else reads this instance's summaries - put them back to their resting state (pending
+    // instances are reset by the general path after it has read them)
+    for (int t = threadIdx.x; t < (st.maxy - st.miny + 1) * d.nblk; t += kCertThreads) rs[(size_t)st.miny * d.nblk + t] = 0u;
+  }
   if (threadIdx.x == 0) {
     if (s_red[0]) {
       o.state = cc::kSimple;
@@ -102,7 +107,7 @@ struct GenParams {
   Dims d;
   const uint8_t* masks;      // [B][max_n][H][W] or nullptr
   const uint32_t* bits;      // [B][max_n][H][bit_words] when masks == nullptr
-  const uint32_t* rowsum;    // [B][max_n][H][nblk]
+  uint32_t* rowsum;          // [B][max_n][H][nblk]
   const InstStats* stats;
   unsigned* lattice;
   InstContour* out;
@@ -245,7 +250,7 @@ cudaError_t launch_contour(const Dims& d, const int* counts, int B, const Scratc
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    e = cudaLaunchKernelEx(&cfg, contour_certify_kernel, d, counts, B, (const InstStats*)sc.stats, (const uint32_t*)sc.rowsum,
+    e = cudaLaunchKernelEx(&cfg, contour_certify_kernel, d, counts, B, (const InstStats*)sc.stats, sc.rowsum,
                            reinterpret_cast<InstContour*>(sc.contour), sc.worklist);
     if (e != cudaSuccess) return e;
   }

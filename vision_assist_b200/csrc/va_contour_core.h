@@ -121,6 +121,8 @@ VA_HD int iabs(int a) { return a < 0 ? -a : a; }
 // ---------------------------------------------------------------------------------------------
 // per-row summaries written by the mask kernels: one entry per (row, 128-pixel block)
 //   bits 0-7 pixels set in the block (0 = none), bits 8-14 first set pixel, bits 15-21 last set pixel (block-relative)
+// Protocol: the array is all zero between calls; a mask kernel only stores the non-zero entries, and whoever consumes
+// an instance's rows (certificate kernel, general path) stores zeros back.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowBlock = 128;
 VA_HD uint32_t rowsum_pack(int cnt, int first, int last) { return (uint32_t)cnt | ((uint32_t)first << 8) | ((uint32_t)last << 15); }
@@ -179,7 +181,7 @@ struct Work {
   const uint8_t* px;        // fmt 0: [H][W] of this instance
   const uint32_t* bits;     // fmt 1: [H][bit_words] of this instance
   int bit_words;
-  const uint32_t* rowsum;   // [H][nblk] per-(row, 128 px block) summaries of this instance
+  uint32_t* rowsum;         // [H][nblk] per-(row, 128 px block) summaries of this instance (read, then reset to 0)
   int nblk;
   int y0, x0w;              // region origin: first row, first 32-pixel word
   int R, Wd;                // region rows / words (covers the pixel bbox of the mask)
@@ -301,7 +303,9 @@ VA_HD void phase_init(Work& w, int tid, int nt) {
     w.best[0] = 0ull;
   }
   for (int r = tid; r < w.R; r += nt) {
-    const RowRun rr = rowsum_combine(w.rowsum + (size_t)(w.y0 + r) * w.nblk, w.nblk);
+    uint32_t* e = w.rowsum + (size_t)(w.y0 + r) * w.nblk;
+    const RowRun rr = rowsum_combine(e, w.nblk);
+    for (int k = 0; k < w.nblk; ++k) e[k] = 0u;       // the summaries are all zero between calls: the mask kernels only write non-zero ones
     int a = kRowMulti, b = 0;
     if (rr.cnt == 0) { a = kRowEmpty; }
     else if (rr.cnt == rr.b - rr.a + 1) { a = rr.a - 32 * w.x0w; b = rr.b - 32 * w.x0w; }

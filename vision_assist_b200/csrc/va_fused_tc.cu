@@ -1043,17 +1043,14 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                 p.bits16[(inst * d.H + Yfirst + sidx) * (size_t)(2 * d.bit_words) + g] = (uint16_t)rp.get(sidx);
             }
             if (!ragged && ((gzall | gfall) == 0x01010101u)) {
-              if (gl == 0 && nrow > 0) {
-                const bool fullg = (gfall >> (lane & 24)) & 1u;
+              if (gl == 0 && nrow > 0 && ((gfall >> (lane & 24)) & 1u)) {     // all-zero blocks: nothing to store (resting state)
                 const int blk = g >> 3;
-                const uint32_t e = fullg ? cc::rowsum_pack(cc::kRowBlock, 0, cc::kRowBlock - 1) : 0u;
+                const uint32_t e = cc::rowsum_pack(cc::kRowBlock, 0, cc::kRowBlock - 1);
 #pragma unroll 1
                 for (int sidx = 0; sidx < nrow; ++sidx) rs_inst[(size_t)(Yfirst + sidx) * d.nblk + blk] = e;
-                if (fullg) {
-                  ls.area = (unsigned)(cc::kRowBlock * nrow);
-                  ls.minx = cc::kRowBlock * blk; ls.maxx = cc::kRowBlock * blk + cc::kRowBlock - 1;
-                  ls.miny = Yfirst; ls.maxy = Yfirst + nrow - 1;
-                }
+                ls.area = (unsigned)(cc::kRowBlock * nrow);
+                ls.minx = cc::kRowBlock * blk; ls.maxx = cc::kRowBlock * blk + cc::kRowBlock - 1;
+                ls.miny = Yfirst; ls.maxy = Yfirst + nrow - 1;
               }
             } else {
               // rolled on purpose (code size: the roles share the instruction cache); exact 4x: pair 0 of the frame

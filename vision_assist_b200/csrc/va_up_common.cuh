@@ -192,7 +192,7 @@ __device__ __forceinline__ uint4 emit_row_summary(unsigned pat, int gl, bool exi
       ls.miny = min(ls.miny, Y);
       ls.maxy = max(ls.maxy, Y);
     }
-    rowsum_inst[(size_t)Y * nblk + blk] = e;
+    if (e) rowsum_inst[(size_t)Y * nblk + blk] = e;      // zero entries are the array's resting state
   }
   return w;
 }

@@ -52,8 +52,8 @@ struct RowSink {
         const int blk = g >> 3;
         // a "full" group whose last pieces lie past the row end is a ragged block: count its real pixels
         const int npx = min(cc::kRowBlock, d.W - cc::kRowBlock * blk);
-        rowsum_inst[(size_t)Y * d.nblk + blk] = fullg ? cc::rowsum_pack(npx, 0, npx - 1) : 0u;
         if (fullg) {
+          rowsum_inst[(size_t)Y * d.nblk + blk] = cc::rowsum_pack(npx, 0, npx - 1);
           ls.area += (unsigned)npx;
           ls.minx = min(ls.minx, cc::kRowBlock * blk);
           ls.maxx = max(ls.maxx, cc::kRowBlock * blk + npx - 1);
@@ -238,6 +238,21 @@ upsample_generic_kernel(Dims d, const float* __restrict__ logits, const float* _
   const bool vec = (npx == 16) && ((d.W & 15) == 0);
   // whole thread tile outside the rectangle (the common case with many small instances): zeros, no logit is read
   const bool tile_out = !col_in || Yend <= rYa || Ybeg > rYb;
+  if (__all_sync(0xffffffffu, tile_out || !gok)) {
+    // the whole warp tile (128 px x 32 rows) lies outside the instance's rectangle: zeros in the masks (and the bit
+    // rows), no summary entry to write - the array rests at zero
+    if (gok) {
+      for (int Y = Ybeg; Y < Yend; ++Y) {
+        if (M) {
+          uint8_t* Mr = M + (size_t)Y * d.W;
+          if (vec) *reinterpret_cast<uint4*>(Mr) = make_uint4(0u, 0u, 0u, 0u);
+          else for (int px = 0; px < npx; ++px) Mr[px] = 0;
+        }
+        if (sink.bits_inst) sink.bits_inst[(size_t)Y * (2 * d.bit_words) + g] = 0;
+      }
+    }
+    return;
+  }
   int py0 = -1, py1 = -1;
   float mn = 0.f, mx = 0.f;
 #pragma unroll 1
