@@ -1198,7 +1198,11 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
     return (exact4 || want <= fit) ? want : fit;
   };
   int zrows = 0;
-  for (int g : {16, 8}) {
+  // measured (cfg2, 1080p, n = 32): with the generic blend groups of 8 beat groups of 16 (0.60 -> 0.51 ms at equal band
+  // counts: the 16-column instantiation spills), so the generic plan tries 8 first
+  const int order_exact[2] = {16, 8}, order_generic[2] = {8, 16};
+  for (int gi = 0; gi < 2; ++gi) {
+    const int g = exact4 ? order_exact[gi] : order_generic[gi];
     if (g == 16 && d.max_n <= 8) continue;
     if (force_ni && g != force_ni && d.max_n > 8) continue;
     for (int cand : {4, 2}) {
@@ -1279,7 +1283,11 @@ cudaError_t launch_fused(FusedPlan* pl, const Dims& d, const float* protos, cons
   // (>= ~8) against the one-row halo every band recomputes and re-reads (1/ppb).
   const int max_bands = (d.mh / (2 * pl->pr)) > 0 ? d.mh / (2 * pl->pr) : 1;
   int nb = 1;
-  while (nb < max_bands && nb < 8 && (long)B * nb * pl->groups < 8L * pl->num_sms) ++nb;
+  // generic scale (store-dominated, 6-12 dst rows per prototype row): many short bands - measured at cfg2: 8 bands
+  // (3.5 items per SM) 0.80 ms, 20 bands 0.48 ms, 40 bands 0.45 ms
+  const int band_cap = pl->generic ? ((d.mh / pl->pr) > 0 ? d.mh / pl->pr : 1) : (max_bands < 8 ? max_bands : 8);
+  const long want_items = (pl->generic ? 32L : 8L) * pl->num_sms;
+  while (nb < band_cap && (long)B * nb * pl->groups < want_items) ++nb;
   // tiny batches (single-frame latency): more, shorter bands - down to one chunk of pr row pairs - until every SM has an item
   const int max_bands_tiny = (d.mh / pl->pr) > 0 ? d.mh / pl->pr : 1;
   while (nb < max_bands_tiny && (long)B * nb * pl->groups < (long)pl->num_sms) ++nb;
