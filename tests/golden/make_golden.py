@@ -21,6 +21,7 @@ Files:
 """
 from __future__ import annotations
 
+import importlib.util
 import inspect
 import os
 import sys
@@ -286,6 +287,81 @@ def gen_nms(ref):
     print("nms.npz:", len(NMS_CASES), "cases,", total, "kept rows")
 
 
+CFG0_FRAMES, CFG0_EVERY, CFG0_SEED = 30, 5, 9000
+
+
+def cfg0_clip_frame(i: int, H: int = 640, W: int = 640) -> np.ndarray:
+    """Deterministic synthetic BGR frame i of the MockCamera clip (a moving gradient with the index stamped in)."""
+    ys, xs = np.mgrid[0:H, 0:W]
+    f = np.stack([(xs + 7 * i) % 256, (ys + 3 * i) % 256, (xs + ys) // 5 % 256], -1).astype(np.uint8)
+    cv2.putText(f, f"frame {i}", (40, 80), cv2.FONT_HERSHEY_SIMPLEX, 2.0, (255, 255, 255), 3)
+    return f
+
+
+def write_cfg0_clip(path: str, H: int = 640, W: int = 640) -> None:
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (W, H))
+    assert vw.isOpened()
+    for i in range(CFG0_FRAMES):
+        vw.write(cfg0_clip_frame(i, H, W))
+    vw.release()
+
+
+def gen_cfg0(ref):
+    """BASELINE configs[0]: a 30-frame 640x640 MJPG clip read through the reference's MockCamera; every 5th frame goes
+    through the UNMODIFIED reference FrameProcessor.__call__ (model = polygons of the reference's own mask assembly of
+    synthetic head tensors, seed 9000 + frame index).  Stored per processed frame: a checksum of the decoded frame, the
+    final answer, the grid state and the A* paths (cells + costs, after the similarity filter) - what the drop-in must
+    reproduce on the GPU box from the same clip and the same head tensors."""
+    import tempfile
+    import zlib
+    H = W = 640
+    d = tempfile.mkdtemp(prefix="va_cfg0_")
+    clip = os.path.join(d, "clip.avi")
+    write_cfg0_clip(clip, H, W)
+    mc_spec = importlib.util.spec_from_file_location("va_ref_mockcamera", os.path.join(refharness.REFERENCE_ROOT, "MockCamera.py"))
+    mc = importlib.util.module_from_spec(mc_spec)
+    mc_spec.loader.exec_module(mc)
+    cam = mc.MockCamera(clip, target_fps=10000)
+    assert cam.isOpened() and (cam.frame_width, cam.frame_height) == (W, H)
+    ref.PathFinder.path_finder.angle_cache.clear()
+    out = {"meta": np.array([CFG0_FRAMES, CFG0_EVERY, CFG0_SEED, H, W], np.int32)}
+    idx, k = 0, 0
+    answers = []
+    while True:
+        ret, frame = cam.read()
+        if not ret:
+            break
+        if idx % CFG0_EVERY == 0:
+            p, c, b = synth.make_frame(CFG0_SEED + idx, 8, H, W, 160, 160)
+            masks = ref.ops.process_mask(p, c, b, (H, W), upsample=True)
+            xy = [ref.ops.scale_coords((H, W), s_, (H, W), normalize=False) for s_ in ref.ops.masks2segments(masks)]
+            fp = refharness.new_frame_processor(ref, refharness.FakeModel(xy))
+            fp.frame = frame
+            fp._extract_grid_information(fp.model.predict(frame))
+            a = ref_state_arrays(fp, ref, H, W)
+            graph = fp._create_graph()
+            peaks = fp.protrusion_detector(frame, fp.grids, fp.grid_lookup)
+            paths = fp._find_paths(peaks, graph)
+            answer = ref.PathAnalyser.path_analyser(H, W, paths)
+            answers.append(str(answer))
+            cells = [np.array([(g.coords.x, g.coords.y) for g in pth.grids], np.int32) for pth in paths]
+            out[f"{k}/frame_index"] = np.int32(idx)
+            out[f"{k}/frame_crc"] = np.uint32(zlib.crc32(frame.tobytes()))
+            out[f"{k}/n_paths"] = np.int32(len(paths))
+            out[f"{k}/path_len"] = np.array([len(c_) for c_ in cells], np.int32)
+            out[f"{k}/path_cells"] = np.concatenate(cells, 0) if cells else np.zeros((0, 2), np.int32)
+            out[f"{k}/path_cost"] = np.array([pth.total_cost for pth in paths], np.float64)
+            for key in ("R", "C", "x0", "npk", "rows_y", "rows_attr", "occ", "pen", "peaks", "start", "goals"):
+                out[f"{k}/{key}"] = a[key]
+            k += 1
+        idx += 1
+    cam.release()
+    out["n"] = np.int32(k)
+    out["answers"] = np.array(answers)
+    np.savez_compressed(os.path.join(HERE, "cfg0.npz"), **out)
+    print("cfg0.npz:", k, "frames processed of", idx, "answers:", answers)
+
+
 if __name__ == "__main__":
     ref = refharness.load()
     torch.set_num_threads(1)
@@ -294,6 +370,7 @@ if __name__ == "__main__":
     gen_mask_assembly(ref)
     gen_frames(ref)
     gen_nms(ref)
+    gen_cfg0(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

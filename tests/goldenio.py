@@ -47,5 +47,5 @@ def assert_result_matches(res: dict, case: dict, what=""):
     if "start" in case and "start" in res:      # start / goal cells, graph neighbourhood
         assert tuple(int(v) for v in res["start"]) == tuple(int(v) for v in case["start"]), (what, res["start"], case["start"])
         assert np.array_equal(np.asarray(res["goals"]).reshape(-1, 2), case["goals"].reshape(-1, 2)), what
-        if "nbr" in res:
+        if "nbr" in res and "nbr" in case:
             assert np.array_equal(res["nbr"], case["nbr"]), what

@@ -93,6 +93,7 @@ class FrameProcessor:
             self.path_visualiser = None
             self.get_closest_grid_to_point = None
             self.Path = None
+            self.array_paths: list = []          # [(cells [(x, y), ...], cost)] of the last frame (array A*, no host stages)
 
     def bind_host_stages(self, path_finder=None, path_analyser=None, path_visualiser=None,
                          get_closest_grid_to_point=None, Path=None) -> None:
@@ -244,6 +245,36 @@ class FrameProcessor:
                 unique.append(path)
         return unique
 
+    # -- FrameProcessor.py:230-271 on the record's arrays -----------------------------
+    def _find_paths_arrays(self) -> list:
+        """A* from the record's start cell to every peak's end cell with the array-based port of the reference's
+        PathFinder (vision_assist_b200/PathFinder.py), then the reference's similarity filter (:255-269): longest paths
+        first, a path is dropped when it shares >= 90 % of its cells (Jaccard; 1.0 for a subset) with a kept one.
+        -> [(cells [(x, y), ...], total cost)]; no Grid object is created."""
+        from .PathFinder import path_finder as array_path_finder
+        rec = self.frame_record
+        if rec is None or rec.R == 0:
+            return []
+        found = [p for p in array_path_finder.find_paths(rec, config.grid_size)]
+        for p in found:
+            if p is None:
+                print("No path found.")
+        paths = sorted((p for p in found if p is not None), key=lambda pc: len(pc[0]), reverse=True)   # stable, as list.sort
+        unique = []
+        for cells, cost in paths:
+            a = set(cells)
+            ok = True
+            for other, _ in unique:
+                b = set(other)
+                inter = len(a & b)
+                sim = 0.0 if not a or not b else 1.0 if inter in (len(a), len(b)) else inter / len(a | b)
+                if sim >= 0.90:
+                    ok = False
+                    break
+            if ok:
+                unique.append((cells, cost))
+        return unique
+
     # -- FrameProcessor.py:272-299 (debug drawing; de-facto public: utilities/generate_testing_grids/run_on_main.py:196) --
     def _draw_grid(self, grid, color) -> None:
         """Fill one cell on self.frame (corners inclusive, as cv2.fillPoly draws them)."""
@@ -273,7 +304,8 @@ class FrameProcessor:
         if not protrusion_peaks:
             print("No protrusions detected.")
         if self.path_finder is None or self.path_analyser is None:
-            # grid producer only: hand the peaks back to the caller
+            # no host stages bound: paths from the array A* (kept in self.array_paths), the peaks go back to the caller
+            self.array_paths = self._find_paths_arrays()
             return (self.frame, protrusion_peaks) if self.debug else protrusion_peaks
         paths = self._find_paths(protrusion_peaks, graph)
         final_answer = self.path_analyser(frame.shape[0], frame.shape[1], paths)

@@ -60,6 +60,22 @@ static void set_err(va_ctx* c, const char* fmt, ...) {
 
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// Entry points run on the context's device and put the caller's current device back on every exit path (a process
+// that drives several GPUs from one thread must not find its current device switched by a library call).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err != cudaSuccess) { prev = -1; err = cudaSetDevice(device); }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define VA_ON_DEVICE(ctx)                                                                                   \
+  DeviceGuard guard__((ctx)->cfg.device);                                                                   \
+  if (guard__.err != cudaSuccess) { set_err((ctx), "cudaSetDevice(%d) failed: %s", (ctx)->cfg.device, cudaGetErrorString(guard__.err)); return VA_ERR_CUDA; }
+
 static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, size_t n) {
   if (c.K != kProtoK) { snprintf(why, n, "K must be %d (got %d)", kProtoK, c.K); return false; }
   if (c.max_n < 1 || c.max_n > kMaxInst) { snprintf(why, n, "max_n must be in [1,%d]", kMaxInst); return false; }
@@ -147,7 +163,8 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
       return VA_ERR_CUDA;                                                         \
     }                                                                             \
   } while (0)
-  VA_CREATE_CUDA(cudaSetDevice(cfg->device));
+  DeviceGuard guard__(cfg->device);
+  VA_CREATE_CUDA(guard__.err);
   const Dims& d = c->d;
   const size_t ns = (size_t)cfg->max_batch * d.max_n;
   VA_CREATE_CUDA(cudaMalloc(&c->scratch.stats, ns * sizeof(InstStats)));
@@ -158,6 +175,7 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
     int sms = 0;
     VA_CREATE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     c->num_sms = sms;
+    c->d.num_sms = sms;
     VA_CREATE_CUDA(cudaMalloc(&c->scratch.rowsum, ns * d.H * d.nblk * sizeof(uint32_t)));
     VA_CREATE_CUDA(cudaMemset(c->scratch.rowsum, 0, ns * d.H * d.nblk * sizeof(uint32_t)));
     VA_CREATE_CUDA(cudaMalloc(&c->scratch.contour, ns * sizeof(cc::InstContour)));
@@ -204,20 +222,27 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
   return VA_OK;
 }
 
+// releases whatever part of the host pipeline exists (also after a half-finished host_pipeline_init)
 static void host_pipeline_destroy(va_ctx* c) {
-  if (!c->host_ready) return;
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_protos[i]); cudaFree(c->d_coefs[i]); cudaFree(c->d_boxes[i]); cudaFree(c->d_counts[i]);
     cudaFree(c->d_records[i]); cudaFree(c->d_masks[i]);
-    cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_out[i]);
+    c->d_protos[i] = c->d_coefs[i] = c->d_boxes[i] = nullptr; c->d_counts[i] = nullptr; c->d_records[i] = c->d_masks[i] = nullptr;
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    c->ev_in[i] = c->ev_done[i] = c->ev_out[i] = nullptr;
   }
-  cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_out);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_compute) cudaStreamDestroy(c->s_compute);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  c->s_in = c->s_compute = c->s_out = nullptr;
   c->host_ready = false;
 }
 
 extern "C" void va_destroy(va_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->cfg.device);
+  DeviceGuard guard__(c->cfg.device);
   host_pipeline_destroy(c);
   if (c->plan) fused_plan_destroy(c->plan);
   cudaFree(c->scratch.stats);
@@ -245,7 +270,7 @@ extern "C" int va_get_layout(const va_ctx* c, va_layout* out) {
 
 extern "C" int va_profile_enable(va_ctx* c, int on) {
   if (!c) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   if (on && !c->prof_ev[0][0]) {
     for (int i = 0; i < kProfMax; ++i)
       for (int j = 0; j < 3; ++j) VA_CUDA(c, cudaEventCreate(&c->prof_ev[i][j]));
@@ -258,7 +283,7 @@ extern "C" int va_profile_enable(va_ctx* c, int on) {
 
 extern "C" int va_profile_read(va_ctx* c, float* assemble_ms, float* tail_ms, int32_t* calls) {
   if (!c || !assemble_ms || !tail_ms || !calls) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   float a = 0.f, t = 0.f;
   for (int i = 0; i < c->prof_count; ++i) {
     float ms = 0.f;
@@ -283,7 +308,7 @@ extern "C" int va_nms(va_ctx* c, const float* pred, int32_t A, const va_nms_para
     return VA_ERR_INVALID;
   }
   if (B == 0) return VA_OK;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   const float off = prm->agnostic ? 0.f : (float)prm->max_wh;
   VA_CUDA(c, launch_nms(pred, A, prm->nc, c->cfg.K, prm->conf_thres, prm->iou_thres, off, prm->max_det, c->cfg.max_n, B,
                         coefs_out, boxes_out, conf_out, cls_out, counts_out, (cudaStream_t)stream));
@@ -313,7 +338,7 @@ __global__ void wait_flags_kernel(const int* flags, int n, int value) {
 
 extern "C" int va_peer_alloc(va_ctx* c, uint64_t bytes, void** dptr, uint8_t handle[VA_IPC_HANDLE_BYTES]) {
   if (!c || !dptr || !handle || bytes == 0) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   void* p = nullptr;
   VA_CUDA(c, cudaMalloc(&p, bytes));
   VA_CUDA(c, cudaMemset(p, 0, bytes));
@@ -327,7 +352,7 @@ extern "C" int va_peer_alloc(va_ctx* c, uint64_t bytes, void** dptr, uint8_t han
 }
 extern "C" int va_peer_open(va_ctx* c, const uint8_t handle[VA_IPC_HANDLE_BYTES], void** dptr) {
   if (!c || !dptr || !handle) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, sizeof(h));
   void* p = nullptr;
@@ -337,32 +362,32 @@ extern "C" int va_peer_open(va_ctx* c, const uint8_t handle[VA_IPC_HANDLE_BYTES]
 }
 extern "C" int va_peer_close(va_ctx* c, void* dptr) {
   if (!c || !dptr) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   VA_CUDA(c, cudaIpcCloseMemHandle(dptr));
   return VA_OK;
 }
 extern "C" int va_peer_free(va_ctx* c, void* dptr) {
   if (!c || !dptr) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   VA_CUDA(c, cudaFree(dptr));
   return VA_OK;
 }
 extern "C" int va_peer_put(va_ctx* c, void* dst, const void* src, uint64_t bytes, void* stream) {
   if (!c || !dst || !src) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   VA_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   return VA_OK;
 }
 extern "C" int va_signal(va_ctx* c, int32_t* flag, int32_t value, void* stream) {
   if (!c || !flag) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
   VA_CUDA(c, cudaGetLastError());
   return VA_OK;
 }
 extern "C" int va_wait_flags(va_ctx* c, const int32_t* flags, int32_t n, int32_t value, void* stream) {
   if (!c || !flags || n < 1) return VA_ERR_INVALID;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, value);
   VA_CUDA(c, cudaGetLastError());
   return VA_OK;
@@ -427,7 +452,7 @@ extern "C" int va_assemble_masks(va_ctx* c, const float* protos, const float* co
   if (rc != VA_OK) return rc;
   if (B == 0) return VA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   c->last_launches = 0;
   rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, logits_out, st);
   if (rc != VA_OK) return rc;
@@ -445,7 +470,7 @@ extern "C" int va_run_fused(va_ctx* c, const float* protos, const float* coefs, 
   if (B == 0) return VA_OK;
   if (!records_out) { set_err(c, "records_out is null"); return VA_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   c->last_launches = 0;
   const bool prof = c->prof_on && (c->prof_calls++ % c->prof_on) == 0 && c->prof_count < kProfMax;
   cudaEvent_t* ev = prof ? c->prof_ev[c->prof_count] : nullptr;
@@ -467,7 +492,7 @@ extern "C" int va_mask_to_records(va_ctx* c, const uint8_t* masks, const int32_t
   if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
   if (B == 0) return VA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   c->last_launches = 0;
   MaskSinks sinks;
   sinks.stats = c->scratch.stats; sinks.lattice = c->scratch.lattice; sinks.rowsum = c->scratch.rowsum; sinks.bits = nullptr;
@@ -485,7 +510,7 @@ extern "C" int va_grid_to_penalty_peaks(va_ctx* c, const va_grid_input* hdr, con
   if (!hdr || !row_y || !row_attr || !occ || !records_out) { set_err(c, "null pointer"); return VA_ERR_INVALID; }
   if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
   if (B == 0) return VA_OK;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   VA_CUDA(c, launch_grid_mode(c->d, hdr, row_y, row_attr, occ, plane_y, plane_occ, B, records_out, (cudaStream_t)stream));
   c->last_launches = 1;
   return VA_OK;
@@ -494,8 +519,14 @@ extern "C" int va_grid_to_penalty_peaks(va_ctx* c, const va_grid_input* hdr, con
 // ---------------------------------------------------------------------------------------------
 // host-buffer pipeline
 // ---------------------------------------------------------------------------------------------
+static int host_pipeline_init_impl(va_ctx* c);
 static int host_pipeline_init(va_ctx* c) {
   if (c->host_ready) return VA_OK;
+  const int rc = host_pipeline_init_impl(c);
+  if (rc != VA_OK) host_pipeline_destroy(c);       // nothing of a half-built pipeline survives
+  return rc;
+}
+static int host_pipeline_init_impl(va_ctx* c) {
   const Dims& d = c->d;
   const size_t P = (size_t)d.mh * d.mw;
   const size_t fr_in = (size_t)d.K * P * 4;
@@ -527,7 +558,7 @@ extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* 
   if (rc != VA_OK) return rc;
   if (!h_records_out) { set_err(c, "h_records_out is null"); return VA_ERR_INVALID; }
   if (B == 0) return VA_OK;
-  VA_CUDA(c, cudaSetDevice(c->cfg.device));
+  VA_ON_DEVICE(c);
   rc = host_pipeline_init(c);
   if (rc != VA_OK) return rc;
   const Dims& d = c->d;
@@ -555,7 +586,10 @@ extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* 
     c->last_launches = 0;
     rc = assemble(c, c->d_protos[s], c->d_coefs[s], c->d_boxes[s], c->d_counts[s], nb,
                   h_masks_out ? c->d_masks[s] : nullptr, nullptr, c->s_compute);
-    if (rc != VA_OK) return rc;
+    if (rc != VA_OK) {               // copies of earlier chunks may still reference the caller's buffers: drain first
+      cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->s_compute); cudaStreamSynchronize(c->s_out);
+      return rc;
+    }
     VA_CUDA(c, launch_contour(d, c->d_counts[s], nb, c->scratch, h_masks_out ? c->d_masks[s] : nullptr, c->s_compute));
     VA_CUDA(c, launch_tail(d, c->d_counts[s], nb, c->scratch.stats, c->scratch.lattice, c->scratch.contour, nullptr, nullptr,
                            c->d_records[s], c->s_compute));

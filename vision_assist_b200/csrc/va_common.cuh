@@ -33,6 +33,7 @@ struct Dims {
   int record_bytes, off_row_y, off_row_attr, off_penalty, off_peaks, off_occ, off_goals, off_lookup;
   int band_start;                      // FrameProcessor.py:126-127 starting_y
   int flags;                           // VA_CFG_*
+  int num_sms;                         // of the context's device
   float wr, hr;                        // fl32(mw/W), fl32(mh/H): box scale, ops.py:725-732
   float sx, sy;                        // fl32(mw)/W, fl32(mh)/H: bilinear scales (ATen area_pixel_compute_scale)
   const double* ratio;                 // [ratio_n + 1][ratio_n + 1]: ratio[m][den] = (double)m / (double)den (host-built, exact)

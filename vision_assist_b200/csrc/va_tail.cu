@@ -816,15 +816,10 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
 
 // ---------------------------------------------------------------------------------------------
 static int tail_threads(const Dims& d, int B) {
-  (void)d;
   if (const char* e = getenv("VA_TAIL_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) return v; }   // tuning aid
   // measured: 512 threads beat 256 also at 640^2 / gs = 20 (31 -> 23 us per 256 frames).  1024 are slower when every SM
   // holds a frame, faster when most SMs would idle (cfg2: 32 frames of 6048 cells, 45 -> 35 us; one frame: 21.5 -> 20.5 us)
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
+  const int sms = d.num_sms > 0 ? d.num_sms : 148;
   return (2 * B <= sms) ? kTailMaxThreads : 512;
 }
 

@@ -72,6 +72,13 @@ class RecordGatherer:
         self.i += 1
         return self.out[slot].view(-1, self.send[slot].shape[1]) if self.rank == self.dst else None
 
+    def wait_latest(self) -> None:
+        """Make the view returned by the last gather() safe to read (the slot is reused `depth` steps later)."""
+        slot = (self.i - 1) % self.depth
+        if self.i and self.work[slot] is not None:
+            self.work[slot].wait()
+            self.work[slot] = None
+
     def flush(self) -> None:
         for slot in range(self.depth):
             if self.work[slot] is not None:
