@@ -11,7 +11,7 @@ The reference turns every instance mask into ONE polygon and picks one polygon p
 
 `oracle.mask_assembly.masks2segments` + `oracle.grid.extract_grid_from_polygons` call OpenCV for all of that (route
 "contour").  This module restates the same result WITHOUT tracing contours, the way the CUDA kernel computes it
-(vision_assist_b200/csrc/va_contour.cu), so that every intermediate (points, doubled area, bbox, filled raster) can be
+(vision_assist_b200/csrc/va_contour_core.h, run by the tail kernel), so that every intermediate (points, doubled area, bbox, filled raster) can be
 compared on the CPU, and so that the generated table is pinned against OpenCV itself (tests/test_contour_model.py):
 
   * G = complement of the 4-connected background region touching the frame; its 8-connected components are the
@@ -35,7 +35,7 @@ _HDR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 def load_table() -> np.ndarray:
     """The generated table (product data, vision_assist_b200/csrc/va_contour_lut.h) as uint16[256]."""
     txt = open(_HDR).read()
-    body = txt[txt.index("{") + 1:txt.rindex("}")]
+    body = txt[txt.index("#define VA_CONTOUR_LUT_VALUES"):txt.index("static const uint16_t kContourLutHost")]
     vals = [int(v, 16) for v in re.findall(r"0x([0-9a-fA-F]+)", body)]
     assert len(vals) == 256
     return np.array(vals, np.uint16)

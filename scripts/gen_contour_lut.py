@@ -131,10 +131,10 @@ def main() -> None:
         f.write("// Per-pixel border-following table indexed by the 3x3 neighbourhood code of a pixel in the hole-filled\n")
         f.write("// image (bits: 0 NW, 1 N, 2 NE, 3 W, 4 E, 5 SW, 6 S, 7 SE).  Entry: bits 0-2 CHAIN_APPROX_SIMPLE points,\n")
         f.write("// bits 3-5 sum(dx of outgoing moves)+2, bits 6-8 sum(dy)+2, bits 9-11 moves.  See the script for the proof.\n")
-        f.write("#pragma once\n#include <stdint.h>\n\nstatic const uint16_t kContourLutHost[256] = {\n")
+        f.write("#pragma once\n#include <stdint.h>\n\n#define VA_CONTOUR_LUT_VALUES \\\n")
         for r in range(16):
-            f.write("    " + ", ".join(f"0x{v:03x}" for v in table[16 * r:16 * r + 16]) + ",\n")
-        f.write("};\n")
+            f.write("    " + ", ".join(f"0x{v:03x}" for v in table[16 * r:16 * r + 16]) + (", \\\n" if r < 15 else "\n"))
+        f.write("\nstatic const uint16_t kContourLutHost[256] = {VA_CONTOUR_LUT_VALUES};\n")
     print("wrote", path)
 
 

@@ -1,4 +1,4 @@
-"""The table-driven contour model (oracle/contour.py = what va_contour.cu computes) against OpenCV itself.
+"""The table-driven contour model (oracle/contour.py = what va_contour_core.h computes) against OpenCV itself.
 
 Pins scripts/gen_contour_lut.py's table and the three structural facts the CUDA path relies on:
   (1) RETR_EXTERNAL contours <-> 8-connected components of the hole-filled image, in reverse raster order;

@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        --expt-relaxed-constexpr -Xptxas -v ${VA_EXTRA_FLAGS:-})
 OBJS=()
 mkdir -p "$BUILD"
-for f in va_logits va_upsample va_tail va_fused_tc va_nms va_contour va_api; do
+for f in va_logits va_upsample va_tail va_fused_tc va_nms va_api; do
   if [ ! -f "$BUILD/$f.o" ] || [ "$HERE/$f.cu" -nt "$BUILD/$f.o" ] || [ "$HERE/va_common.cuh" -nt "$BUILD/$f.o" ] || [ "$HERE/va_up_common.cuh" -nt "$BUILD/$f.o" ] \
      || [ "$HERE/va_contour_core.h" -nt "$BUILD/$f.o" ] || [ "$HERE/va_contour_lut.h" -nt "$BUILD/$f.o" ] \
      || [ "$HERE/../../include/vision_assist_b200.h" -nt "$BUILD/$f.o" ]; then

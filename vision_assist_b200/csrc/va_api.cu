@@ -171,24 +171,24 @@ extern "C" int va_create(va_ctx** out, const va_config* cfg) {
   VA_CREATE_CUDA(cudaMalloc(&c->scratch.lattice, ns * d.lat_rows * d.lat_words * sizeof(unsigned)));
   VA_CREATE_CUDA(launch_init_scratch(d, cfg->max_batch, c->scratch.stats, c->scratch.lattice, 0));
   {
-    // contour step (va_contour.cu): per-row summaries, per-instance results, work list and the general path's slabs
+    // contour step (tail kernel, va_contour_core.h): per-row summaries and the general path's global slabs
     int sms = 0;
     VA_CREATE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     c->num_sms = sms;
     c->d.num_sms = sms;
     VA_CREATE_CUDA(cudaMalloc(&c->scratch.rowsum, ns * d.H * d.nblk * sizeof(uint32_t)));
     VA_CREATE_CUDA(cudaMemset(c->scratch.rowsum, 0, ns * d.H * d.nblk * sizeof(uint32_t)));
-    VA_CREATE_CUDA(cudaMalloc(&c->scratch.contour, ns * sizeof(cc::InstContour)));
-    VA_CREATE_CUDA(cudaMemset(c->scratch.contour, 0, ns * sizeof(cc::InstContour)));
-    VA_CREATE_CUDA(cudaMalloc(&c->scratch.worklist, (2 + ns) * sizeof(int)));
-    VA_CREATE_CUDA(cudaMemset(c->scratch.worklist, 0, (2 + ns) * sizeof(int)));
     // run capacity: a 4x-upsampled mask row has at most W / 8 runs (one sign change per proto cell)
     int cap = (int)(((size_t)d.H * d.W) / 8);
     if (cap < 4096) cap = 4096;
     c->scratch.cc_cap = cap;
-    c->scratch.cc_ctas = (int)((ns < (size_t)sms) ? ns : (size_t)sms);
+    // one slab per frame of a batch, at most two per SM (a frame's tail CTA takes the slab's lock only when the batch
+    // has more frames than slabs)
+    c->scratch.nslab = cfg->max_batch < 2 * sms ? cfg->max_batch : 2 * sms;
     c->scratch.cc_slab_bytes = (contour_slab_bytes(d, cap) + 255) & ~(size_t)255;
-    VA_CREATE_CUDA(cudaMalloc(&c->scratch.cc_slab, c->scratch.cc_slab_bytes * c->scratch.cc_ctas));
+    VA_CREATE_CUDA(cudaMalloc(&c->scratch.cc_slab, c->scratch.cc_slab_bytes * c->scratch.nslab));
+    VA_CREATE_CUDA(cudaMalloc(&c->scratch.slab_lock, sizeof(int) * c->scratch.nslab));
+    VA_CREATE_CUDA(cudaMemset(c->scratch.slab_lock, 0, sizeof(int) * c->scratch.nslab));
   }
   // logits scratch for the CUDA-core path: keep one chunk (<= ~48 MB) so that it stays L2-resident
   const size_t per_frame = (size_t)d.max_n * d.mh * d.mw * sizeof(float);
@@ -250,9 +250,8 @@ extern "C" void va_destroy(va_ctx* c) {
   cudaFree(c->scratch.logits);
   cudaFree(c->scratch.rowsum);
   cudaFree(c->scratch.bits);
-  cudaFree(c->scratch.contour);
-  cudaFree(c->scratch.worklist);
   cudaFree(c->scratch.cc_slab);
+  cudaFree(c->scratch.slab_lock);
   cudaFree(const_cast<double*>(c->d.ratio));
   if (c->prof_ev[0][0])
     for (int i = 0; i < kProfMax; ++i)
@@ -478,10 +477,9 @@ extern "C" int va_run_fused(va_ctx* c, const float* protos, const float* coefs, 
   rc = assemble(c, protos, coefs, boxes, counts, B, masks_out, nullptr, st);
   if (rc != VA_OK) return rc;
   if (prof) VA_CUDA(c, cudaEventRecord(ev[1], st));
-  VA_CUDA(c, launch_contour(c->d, counts, B, c->scratch, masks_out, st));
-  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, c->scratch.contour, nullptr, nullptr, records_out, st));
+  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch, masks_out, nullptr, nullptr, records_out, st));
   if (prof) { VA_CUDA(c, cudaEventRecord(ev[2], st)); c->prof_count++; }
-  c->last_launches += 3;
+  c->last_launches += 1;
   return VA_OK;
 }
 
@@ -497,9 +495,8 @@ extern "C" int va_mask_to_records(va_ctx* c, const uint8_t* masks, const int32_t
   MaskSinks sinks;
   sinks.stats = c->scratch.stats; sinks.lattice = c->scratch.lattice; sinks.rowsum = c->scratch.rowsum; sinks.bits = nullptr;
   VA_CUDA(c, launch_mask_stats(c->d, masks, counts, B, sinks, st));
-  VA_CUDA(c, launch_contour(c->d, counts, B, c->scratch, masks, st));
-  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch.stats, c->scratch.lattice, c->scratch.contour, rects, sel, records_out, st));
-  c->last_launches = 4;
+  VA_CUDA(c, launch_tail(c->d, counts, B, c->scratch, masks, rects, sel, records_out, st));
+  c->last_launches = 2;
   return VA_OK;
 }
 
@@ -590,10 +587,9 @@ extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* 
       cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->s_compute); cudaStreamSynchronize(c->s_out);
       return rc;
     }
-    VA_CUDA(c, launch_contour(d, c->d_counts[s], nb, c->scratch, h_masks_out ? c->d_masks[s] : nullptr, c->s_compute));
-    VA_CUDA(c, launch_tail(d, c->d_counts[s], nb, c->scratch.stats, c->scratch.lattice, c->scratch.contour, nullptr, nullptr,
+    VA_CUDA(c, launch_tail(d, c->d_counts[s], nb, c->scratch, h_masks_out ? c->d_masks[s] : nullptr, nullptr, nullptr,
                            c->d_records[s], c->s_compute));
-    launches += c->last_launches + 3;
+    launches += c->last_launches + 1;
     VA_CUDA(c, cudaEventRecord(c->ev_done[s], c->s_compute));
     VA_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_done[s], 0));
     VA_CUDA(c, cudaMemcpyAsync(h_records_out + (size_t)b0 * d.record_bytes, c->d_records[s], (size_t)d.record_bytes * nb,

@@ -47,12 +47,11 @@ struct Scratch {
   uint32_t* rowsum;        // [max_batch][max_n][H][nblk] per-(row, 128 px block) summaries of the masks
   uint32_t* bits;          // [max_batch][max_n][H][bit_words] bit-packed masks, written INSTEAD of the u8 masks in
                            // grid-only mode (allocated on first use)
-  void* contour;           // [max_batch][max_n] cc::InstContour - result of the contour step
-  int* worklist;           // [0] entries, [1] finished CTAs, [2 ...] (frame * max_n + instance) of the general path
-  unsigned char* cc_slab;  // general-path scratch, one slab per CTA of the contour kernel
+  unsigned char* cc_slab;  // [nslab][cc_slab_bytes] global scratch of the contour step's general path (tail kernel)
   size_t cc_slab_bytes;
   int cc_cap;              // run capacity per instance
-  int cc_ctas;
+  int nslab;
+  int* slab_lock;          // [nslab]
 };
 
 // Where the mask kernels leave their by-products (besides the u8 masks).
@@ -83,15 +82,14 @@ cudaError_t launch_upsample(const Dims& d, const float* logits, const float* box
 // stats / lattice / row summaries from caller-provided binary masks
 cudaError_t launch_mask_stats(const Dims& d, const uint8_t* masks, const int* counts, int B, const MaskSinks& sinks,
                               cudaStream_t st);
-// contour step (va_contour.cu): per instance the polygon the reference keeps - doubled contourArea, bounding box,
-// lattice samples of its fillPoly raster.  masks may be nullptr (then scratch.bits holds the pixels).
-cudaError_t launch_contour(const Dims& d, const int* counts, int B, const Scratch& sc, const uint8_t* masks, cudaStream_t st);
 size_t contour_slab_bytes(const Dims& d, int cap);
 cudaError_t launch_init_scratch(const Dims& d, int max_batch, InstStats* stats, unsigned int* lattice,
                                 cudaStream_t st);
-// selection -> grid -> penalties -> peaks -> record; resets stats / lattice
-cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned int* lattice, const void* contour,
-                        const int* rects, const int* sel, uint8_t* records, cudaStream_t st);
+// contour step (per instance the polygon the reference keeps: doubled contourArea, bounding box, lattice samples of
+// its fillPoly raster) -> selection -> grid -> penalties -> peaks -> record; resets stats / lattice / row summaries.
+// masks may be nullptr (then scratch.bits holds the pixels).
+cudaError_t launch_tail(const Dims& d, const int* counts, int B, const Scratch& sc, const uint8_t* masks, const int* rects,
+                        const int* sel, uint8_t* records, cudaStream_t st);
 cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,
                              const uint8_t* occ, const int* plane_y, const uint8_t* plane_occ, int B,
                              uint8_t* records, cudaStream_t st);

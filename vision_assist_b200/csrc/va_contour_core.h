@@ -1,5 +1,5 @@
 // Contour semantics of the reference without contour tracing - the algorithm shared by the CUDA kernels
-// (va_contour.cu) and a host build that the CPU tests drive (tests/native/contour_host.cpp).
+// (va_tail.cu: the tail kernel runs both paths per frame) and a host build that the CPU tests drive (tests/native/contour_host.cpp).
 //
 // Reference behaviour reproduced (bit-exact, see oracle/contour.py for the model and its OpenCV pin):
 //   masks2segments          vendored ultralytics ops.py:837-859   findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE),
@@ -13,7 +13,7 @@
 // one with the most points (ties: last in raster order = OpenCV's first); its pixels ARE the fillPoly raster.
 //
 // Two paths:
-//   * certificate (contour_certify): every mask row of the instance is ONE run and consecutive rows touch -> one
+//   * certificate (cert_row): every mask row of the instance is ONE run and consecutive rows touch -> one
 //     hole-free component; its doubled area follows in closed form from the per-row run ends (2N - L - 2 with L the
 //     number of border moves).  Input: the per-row summaries the mask kernels emit - no pixel is re-read.
 //   * general (Work / phase_*): run-based connected components on a bit image of the mask's bounding box:

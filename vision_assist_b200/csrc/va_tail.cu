@@ -25,6 +25,7 @@
 
 #include "va_common.cuh"
 #include "va_contour_core.h"
+#include "va_contour_lut.h"
 
 namespace va {
 
@@ -554,9 +555,86 @@ __device__ void finish_record(const Dims& d, const TailSmem& s, uint8_t* rec) {
 // ---------------------------------------------------------------------------------------------
 // mask-driven tail
 // ---------------------------------------------------------------------------------------------
+// What the contour step needs besides the per-instance reductions (va_contour_core.h).
+struct TailContour {
+  uint32_t* rowsum;          // [B][max_n][H][nblk] per-(row, 128 px block) summaries (read, then reset to 0)
+  const uint8_t* masks;      // [B][max_n][H][W] u8 masks, or nullptr ...
+  const uint32_t* bits;      // ... then [B][max_n][H][bit_words] bit-packed masks
+  unsigned char* slab;       // [nslab][slab_bytes] global scratch of the general path (word part, big run tables)
+  size_t slab_bytes;
+  int nslab;
+  int* slab_lock;            // [nslab] taken only when the batch has more frames than slabs
+  int cap;                   // run capacity of a slab
+  int smem_off;              // offset of the general path's shared-memory scratch behind the tail's own
+  int smem_bytes;            // its size
+};
+
+__device__ const uint16_t g_contour_lut[256] = {VA_CONTOUR_LUT_VALUES};
+
+// Contour step of one instance with the whole CTA (va_contour_core.h): run-based components with hole filling on the
+// instance's bounding box, table sums, selection of the kept component; overwrites the instance's lattice samples.
+// Per-row scratch and (when they fit) the run table live in shared memory, the bit rows of the few multi-run rows in
+// the CTA's global slab.
+__device__ void contour_general(const Dims& d, const TailContour& tc, size_t inst, const InstStats& st, unsigned* lattice_inst,
+                                unsigned char* smem, unsigned char* slab, const uint16_t* lut, int* sc, unsigned long long* best,
+                                cc::InstContour* out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  cc::Work w;
+  w.H = d.H; w.W = d.W;
+  w.fmt = tc.masks ? 0 : 1;
+  w.px = tc.masks ? tc.masks + inst * (size_t)d.H * d.W : nullptr;
+  w.bits = tc.masks ? nullptr : tc.bits + inst * (size_t)d.H * d.bit_words;
+  w.bit_words = d.bit_words;
+  w.rowsum = tc.rowsum + inst * (size_t)d.H * d.nblk; w.nblk = d.nblk;
+  w.y0 = st.miny; w.x0w = st.minx >> 5;
+  w.R = st.maxy - st.miny + 1; w.Wd = (st.maxx >> 5) - w.x0w + 1;
+  w.gs = d.gs; w.lat_rows = d.lat_rows; w.lat_cols = d.lat_cols; w.lat_words = d.lat_words;
+  w.cap = tc.cap;
+  w.sc = sc; w.best = best;
+  w.lattice = lattice_inst;
+  w.out = out;
+  w.dbg = nullptr;
+  const cc::RowLayout wl = cc::row_layout(w.R);
+  const cc::GridLayout gl = cc::grid_layout(w.R, w.Wd);
+  const cc::RowLayout wl_full = cc::row_layout(d.H);
+  const cc::GridLayout gl_full = cc::grid_layout(d.H, d.bit_words);
+  size_t used = 0;
+  const bool rows_in_smem = wl.total <= (size_t)tc.smem_bytes;
+  cc::bind_rows(w, rows_in_smem ? smem : slab, wl);
+  if (rows_in_smem) used += wl.total;
+  cc::bind_grid(w, slab + wl_full.total, gl);
+  cc::bind_runs(w, slab + wl_full.total + gl_full.total, cc::run_layout(tc.cap));
+  __syncthreads();
+  cc::phase_init(w, tid, nt);       __syncthreads();
+  cc::phase_lists(w, tid, nt);      __syncthreads();
+  cc::phase_load(w, tid, nt);       __syncthreads();
+  cc::phase_count(w, tid, nt);      __syncthreads();
+  cc::phase_scan_a(w, tid, nt);     __syncthreads();
+  cc::phase_scan_b(w, tid, nt);     __syncthreads();
+  cc::phase_scan_c(w, tid, nt);     __syncthreads();
+  {
+    const int NR = sc[cc::W_NR];
+    const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
+    if (NR <= tc.cap && used + rl.total <= (size_t)tc.smem_bytes) {
+      w.cap = NR > 0 ? NR : 1;
+      cc::bind_runs(w, smem + used, rl);
+    }
+  }
+  cc::phase_runs(w, tid, nt);       __syncthreads();
+  cc::phase_gaps(w, tid, nt);       __syncthreads();
+  cc::phase_holes(w, tid, nt);      __syncthreads();
+  cc::phase_link(w, tid, nt);       __syncthreads();
+  cc::phase_flatten_a(w, tid, nt);  __syncthreads();
+  cc::phase_flatten_b(w, tid, nt);  __syncthreads();
+  cc::phase_sums(w, lut, tid, nt);  __syncthreads();
+  cc::phase_select(w, tid, nt);     __syncthreads();
+  cc::phase_bbox(w, tid, nt);       __syncthreads();
+  cc::phase_output(w, tid, nt);     __syncthreads();
+}
+
 __global__ void __launch_bounds__(kTailMaxThreads)
 tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stats, unsigned* __restrict__ lattice,
-            const cc::InstContour* __restrict__ contour, const int* __restrict__ rects, const int* __restrict__ sel_in,
+            TailContour tc, const int* __restrict__ rects, const int* __restrict__ sel_in,
             uint8_t* __restrict__ records) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TailSmem s;
@@ -572,23 +650,128 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   __shared__ unsigned s_area[kMaxInst];
   __shared__ int s_area2[kMaxInst], s_state[kMaxInst];
   __shared__ int s_bbox[kMaxInst][4];
+  __shared__ int s_cert[kMaxInst][5];              // certificate partials: ok, pixels, border moves, min x, max x
+  __shared__ InstStats s_stats[kMaxInst];
+  __shared__ int s_cc[cc::W_COUNT];
+  __shared__ unsigned long long s_best;
+  __shared__ uint16_t s_lut[256];
+  __shared__ cc::InstContour s_out;
   for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
   for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
-  // Programmatic dependent launch: this kernel may become resident while the kernels before it are still draining;
-  // everything above touched only shared memory and kernel inputs.  Wait here for their writes (contour results,
-  // lattice bits, statistics).
+  if (threadIdx.x < kMaxInst) {
+    const int i = threadIdx.x;
+    s_cert[i][0] = 1; s_cert[i][1] = 0; s_cert[i][2] = 0; s_cert[i][3] = INT_MAX; s_cert[i][4] = -1;
+  }
+  // Programmatic dependent launch: this kernel may become resident while the mask kernel is still draining;
+  // everything above touched only shared memory and kernel inputs.  Wait here for its writes (statistics, lattice
+  // bits, row summaries, masks).
   asm volatile("griddepcontrol.wait;" ::: "memory");
   TT(1);
-  if (threadIdx.x < kMaxInst) {      // all per-instance results in one parallel round of global loads
+  if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
     const int i = threadIdx.x;
-    cc::InstContour v;
-    v.area2 = 0; v.state = cc::kEmpty; v.minx = 0; v.miny = 0; v.maxx = -1; v.maxy = -1;
-    unsigned area = 0;
-    if (i < n) { v = contour[(size_t)b * d.max_n + i]; area = st[i].area; }
-    s_area[i] = area;
-    s_area2[i] = (v.state == cc::kSimple || v.state == cc::kGeneral) ? v.area2 : 0;
-    s_state[i] = v.state;
-    s_bbox[i][0] = v.minx; s_bbox[i][1] = v.miny; s_bbox[i][2] = v.maxx; s_bbox[i][3] = v.maxy;
+    InstStats v;
+    v.area = 0; v.minx = 0; v.miny = 0; v.maxx = -1; v.maxy = -1;
+    if (i < n) v = st[i];
+    s_stats[i] = v;
+    s_area[i] = v.area;
+  }
+  __syncthreads();
+  // ---- contour step, part 1: certificate (va_contour_core.h) - every mask row of an instance one run, consecutive
+  //      rows touching => one hole-free component whose polygon area follows from the run ends in closed form.
+  //      Reads only the per-(row, block) summaries the mask kernel wrote.  Thread groups of >= 32 share the instances. ----
+  {
+    const int tpi = max(32, ((int)blockDim.x / max(n, 1)) & ~31);      // threads per instance
+    const int group = (int)threadIdx.x / tpi, ngroups = (int)blockDim.x / tpi, gt = (int)threadIdx.x % tpi;
+    const int lane = threadIdx.x & 31;
+    for (int i = group; i < n; i += ngroups) {
+      const InstStats v = s_stats[i];
+      if (v.area == 0) continue;
+      uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
+      int ok = 1, npx = 0, l = 0, minx = INT_MAX, maxx = -1;
+      for (int y0 = v.miny; y0 <= v.maxy; y0 += tpi) {
+        const int y = y0 + gt;
+        const bool live = y <= v.maxy;
+        cc::RowRun cur; cur.cnt = 0; cur.a = 0; cur.b = -1;
+        if (live) cur = cc::rowsum_combine(rs + (size_t)y * d.nblk, d.nblk);
+        cc::RowRun prev;
+        prev.cnt = __shfl_up_sync(0xffffffffu, cur.cnt, 1);
+        prev.a = __shfl_up_sync(0xffffffffu, cur.a, 1);
+        prev.b = __shfl_up_sync(0xffffffffu, cur.b, 1);
+        if (live && lane == 0 && y > v.miny) prev = cc::rowsum_combine(rs + (size_t)(y - 1) * d.nblk, d.nblk);
+        if (live) {
+          const cc::CertTerms t = cc::cert_row(cur, prev, y == v.miny, y == v.maxy);
+          ok &= t.ok; npx += t.n; l += t.l;
+          minx = min(minx, t.minx); maxx = max(maxx, t.maxx);
+        }
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      npx = (int)__reduce_add_sync(0xffffffffu, (unsigned)npx);
+      l = (int)__reduce_add_sync(0xffffffffu, (unsigned)l);
+      minx = __reduce_min_sync(0xffffffffu, minx);
+      maxx = __reduce_max_sync(0xffffffffu, maxx);
+      if (lane == 0) {
+        if (!ok) atomicAnd(&s_cert[i][0], 0);
+        atomicAdd(&s_cert[i][1], npx); atomicAdd(&s_cert[i][2], l);
+        atomicMin(&s_cert[i][3], minx); atomicMax(&s_cert[i][4], maxx);
+      }
+    }
+    __syncthreads();
+    int n_pending = 0;
+    for (int i = group; i < n; i += ngroups) {
+      const InstStats v = s_stats[i];
+      if (v.area == 0) continue;
+      if (s_cert[i][0]) {
+        // certified: put the instance's summaries back to their resting state (all zero)
+        uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk + (size_t)v.miny * d.nblk;
+        for (int t = gt; t < (v.maxy - v.miny + 1) * d.nblk; t += tpi) rs[t] = 0u;
+      }
+    }
+    if (threadIdx.x < kMaxInst) {
+      const int i = threadIdx.x;
+      int state = cc::kEmpty, area2 = 0;
+      int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;
+      if (i < n && s_stats[i].area) {
+        if (s_cert[i][0]) {
+          state = cc::kSimple;
+          area2 = 2 * s_cert[i][1] - s_cert[i][2] - 2;
+          bx0 = s_cert[i][3]; bx1 = s_cert[i][4]; by0 = s_stats[i].miny; by1 = s_stats[i].maxy;
+        } else {
+          state = cc::kPending;
+        }
+      }
+      s_state[i] = state; s_area2[i] = area2;
+      s_bbox[i][0] = bx0; s_bbox[i][1] = by0; s_bbox[i][2] = bx1; s_bbox[i][3] = by1;
+      n_pending = (state == cc::kPending);
+    }
+    n_pending = __syncthreads_or(n_pending);
+    // ---- contour step, part 2: the general path for every instance the certificate did not cover ----
+    if (n_pending) {
+      for (int t = threadIdx.x; t < 256; t += (int)blockDim.x) s_lut[t] = g_contour_lut[t];
+      const int slot = b % tc.nslab;
+      if (threadIdx.x == 0 && (int)gridDim.x > tc.nslab) {          // more frames than slabs: frames b and b + nslab share one
+        while (atomicCAS(&tc.slab_lock[slot], 0, 1) != 0) __nanosleep(200);
+        __threadfence();
+      }
+      __syncthreads();
+      unsigned char* slab = tc.slab + (size_t)slot * tc.slab_bytes;
+      for (int i = 0; i < n; ++i) {
+        if (s_state[i] != cc::kPending) continue;                   // CTA-uniform
+        const size_t inst = (size_t)b * d.max_n + i;
+        contour_general(d, tc, inst, s_stats[i], lattice + inst * d.lat_rows * d.lat_words, smem_raw + tc.smem_off, slab, s_lut,
+                        s_cc, &s_best, &s_out);
+        if (threadIdx.x == 0) {
+          const cc::InstContour o = s_out;
+          s_state[i] = o.state;
+          s_area2[i] = (o.state == cc::kSimple || o.state == cc::kGeneral) ? o.area2 : 0;
+          s_bbox[i][0] = o.minx; s_bbox[i][1] = o.miny; s_bbox[i][2] = o.maxx; s_bbox[i][3] = o.maxy;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0 && (int)gridDim.x > tc.nslab) {
+        __threadfence();
+        atomicExch(&tc.slab_lock[slot], 0);
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -823,13 +1006,24 @@ static int tail_threads(const Dims& d, int B) {
   return (2 * B <= sms) ? kTailMaxThreads : 512;
 }
 
-cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stats, unsigned* lattice, const void* contour,
-                        const int* rects, const int* sel, uint8_t* records, cudaStream_t st) {
-  const size_t smem = tail_smem_bytes(d);
+size_t contour_slab_bytes(const Dims& d, int cap) {
+  return cc::row_layout(d.H).total + cc::grid_layout(d.H, d.bit_words).total + cc::run_layout(cap).total + 256;
+}
+
+cudaError_t launch_tail(const Dims& d, const int* counts, int B, const Scratch& sc, const uint8_t* masks, const int* rects,
+                        const int* sel, uint8_t* records, cudaStream_t st) {
+  // shared memory: the tail's own tables, then the contour step's per-row scratch (+ the run table when it fits)
+  const size_t own = (tail_smem_bytes(d) + 15) & ~(size_t)15;
+  const size_t cc_smem = cc::row_layout(d.H).total + cc::run_layout(2048).total;
+  const size_t smem = own + cc_smem;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
+  TailContour tc;
+  tc.rowsum = sc.rowsum; tc.masks = masks; tc.bits = sc.bits;
+  tc.slab = sc.cc_slab; tc.slab_bytes = sc.cc_slab_bytes; tc.nslab = sc.nslab; tc.slab_lock = sc.slab_lock;
+  tc.cap = sc.cc_cap; tc.smem_off = (int)own; tc.smem_bytes = (int)cc_smem;
   // launched with programmatic stream serialization: see griddepcontrol.wait in the kernel
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B);
@@ -842,7 +1036,7 @@ cudaError_t launch_tail(const Dims& d, const int* counts, int B, InstStats* stat
   cfg.attrs = attr;
   static const bool no_pdl = getenv("VA_NO_PDL") != nullptr;   // tuning aid: plain stream-ordered launch
   cfg.numAttrs = no_pdl ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, tail_kernel, d, counts, stats, lattice, reinterpret_cast<const cc::InstContour*>(contour), rects, sel, records);
+  return cudaLaunchKernelEx(&cfg, tail_kernel, d, counts, sc.stats, sc.lattice, tc, rects, sel, records);
 }
 
 cudaError_t launch_grid_mode(const Dims& d, const va_grid_input* hdr, const int* row_y, const int* row_attr,
