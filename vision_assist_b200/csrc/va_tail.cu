@@ -680,51 +680,77 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   //      rows touching => one hole-free component whose polygon area follows from the run ends in closed form.
   //      Reads only the per-(row, block) summaries the mask kernel wrote.  Thread groups of >= 32 share the instances. ----
   {
-    const int tpi = max(32, ((int)blockDim.x / max(n, 1)) & ~31);      // threads per instance
-    const int group = (int)threadIdx.x / tpi, ngroups = (int)blockDim.x / tpi, gt = (int)threadIdx.x % tpi;
-    const int lane = threadIdx.x & 31;
-    for (int i = group; i < n; i += ngroups) {
+    // Work items = (instance, block of 32 consecutive mask rows), numbered through a prefix sum over the instances and
+    // dealt to the warps round-robin: a frame with one tall mask and many small ones keeps every warp busy.
+    __shared__ int s_task0[kMaxInst + 1];
+    if (threadIdx.x < 32) {
+      const int i = threadIdx.x;
       const InstStats v = s_stats[i];
-      if (v.area == 0) continue;
-      uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
-      int ok = 1, npx = 0, l = 0, minx = INT_MAX, maxx = -1;
-      for (int y0 = v.miny; y0 <= v.maxy; y0 += tpi) {
-        const int y = y0 + gt;
-        const bool live = y <= v.maxy;
-        cc::RowRun cur; cur.cnt = 0; cur.a = 0; cur.b = -1;
-        if (live) cur = cc::rowsum_combine(rs + (size_t)y * d.nblk, d.nblk);
-        cc::RowRun prev;
-        prev.cnt = __shfl_up_sync(0xffffffffu, cur.cnt, 1);
-        prev.a = __shfl_up_sync(0xffffffffu, cur.a, 1);
-        prev.b = __shfl_up_sync(0xffffffffu, cur.b, 1);
-        if (live && lane == 0 && y > v.miny) prev = cc::rowsum_combine(rs + (size_t)(y - 1) * d.nblk, d.nblk);
-        if (live) {
-          const cc::CertTerms t = cc::cert_row(cur, prev, y == v.miny, y == v.maxy);
-          ok &= t.ok; npx += t.n; l += t.l;
-          minx = min(minx, t.minx); maxx = max(maxx, t.maxx);
-        }
+      int cnt = (i < n && v.area) ? (v.maxy - v.miny + 32) >> 5 : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (i >= o) incl += u; }
+      s_task0[i] = incl - cnt;
+      if (i == 31) s_task0[32] = incl;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = (int)threadIdx.x >> 5, nwarps = (int)blockDim.x >> 5;
+    const int ntask = s_task0[kMaxInst];
+    constexpr int kU = 4;                                              // work items in flight per warp: their loads overlap
+    for (int t0 = warp; t0 < ntask; t0 += kU * nwarps) {
+      int inst_i[kU], yy[kU];
+      bool live[kU];
+      cc::RowRun cur[kU], prv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int t = t0 + u * nwarps;
+        int i = 0;
+        while (i + 1 < n && s_task0[i + 1] <= t) ++i;                  // instance of task t (n <= 32: a short scan)
+        inst_i[u] = i;
+        const InstStats v = s_stats[i];
+        yy[u] = v.miny + 32 * (t - s_task0[i]) + lane;
+        live[u] = t < ntask && yy[u] <= v.maxy;
+        cur[u].cnt = 0; cur[u].a = 0; cur[u].b = -1;
+        prv[u] = cur[u];
+        const uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
+        if (live[u]) cur[u] = cc::rowsum_combine(rs + (size_t)yy[u] * d.nblk, d.nblk);
+        if (live[u] && lane == 0 && yy[u] > v.miny) prv[u] = cc::rowsum_combine(rs + (size_t)(yy[u] - 1) * d.nblk, d.nblk);
       }
-      ok = __all_sync(0xffffffffu, ok);
-      npx = (int)__reduce_add_sync(0xffffffffu, (unsigned)npx);
-      l = (int)__reduce_add_sync(0xffffffffu, (unsigned)l);
-      minx = __reduce_min_sync(0xffffffffu, minx);
-      maxx = __reduce_max_sync(0xffffffffu, maxx);
-      if (lane == 0) {
-        if (!ok) atomicAnd(&s_cert[i][0], 0);
-        atomicAdd(&s_cert[i][1], npx); atomicAdd(&s_cert[i][2], l);
-        atomicMin(&s_cert[i][3], minx); atomicMax(&s_cert[i][4], maxx);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (t0 + u * nwarps >= ntask) break;                           // warp-uniform
+        const int i = inst_i[u];
+        const InstStats v = s_stats[i];
+        cc::RowRun prev;
+        prev.cnt = __shfl_up_sync(0xffffffffu, cur[u].cnt, 1);
+        prev.a = __shfl_up_sync(0xffffffffu, cur[u].a, 1);
+        prev.b = __shfl_up_sync(0xffffffffu, cur[u].b, 1);
+        if (lane == 0) prev = prv[u];
+        int ok = 1, npx = 0, l = 0, minx = INT_MAX, maxx = -1;
+        if (live[u]) {
+          const cc::CertTerms ct = cc::cert_row(cur[u], prev, yy[u] == v.miny, yy[u] == v.maxy);
+          ok = ct.ok; npx = ct.n; l = ct.l; minx = ct.minx; maxx = ct.maxx;
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        npx = (int)__reduce_add_sync(0xffffffffu, (unsigned)npx);
+        l = (int)__reduce_add_sync(0xffffffffu, (unsigned)l);
+        minx = __reduce_min_sync(0xffffffffu, minx);
+        maxx = __reduce_max_sync(0xffffffffu, maxx);
+        if (lane == 0) {
+          if (!ok) atomicAnd(&s_cert[i][0], 0);
+          atomicAdd(&s_cert[i][1], npx); atomicAdd(&s_cert[i][2], l);
+          atomicMin(&s_cert[i][3], minx); atomicMax(&s_cert[i][4], maxx);
+        }
       }
     }
     __syncthreads();
     int n_pending = 0;
-    for (int i = group; i < n; i += ngroups) {
+    for (int i = 0; i < n; ++i) {
       const InstStats v = s_stats[i];
-      if (v.area == 0) continue;
-      if (s_cert[i][0]) {
-        // certified: put the instance's summaries back to their resting state (all zero)
-        uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk + (size_t)v.miny * d.nblk;
-        for (int t = gt; t < (v.maxy - v.miny + 1) * d.nblk; t += tpi) rs[t] = 0u;
-      }
+      if (v.area == 0 || !s_cert[i][0]) continue;
+      // certified: put the instance's summaries back to their resting state (all zero)
+      uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk + (size_t)v.miny * d.nblk;
+      for (int t = threadIdx.x; t < (v.maxy - v.miny + 1) * d.nblk; t += (int)blockDim.x) rs[t] = 0u;
     }
     if (threadIdx.x < kMaxInst) {
       const int i = threadIdx.x;
