@@ -93,7 +93,7 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       bind_runs(w, scratch2.data(), rl);
       int sc[W_COUNT];
       unsigned long long best = 0;
-      w.sc = sc; w.best = &best; w.lattice = lattice; w.out = &res; w.dbg = nullptr;
+      w.sc = sc; w.best = &best; w.lattice = lattice; w.out = &res;
       const int nt = nthreads;
 #define PHASE(call) for (int tid = 0; tid < nt; ++tid) { call; }
       PHASE(phase_init(w, tid, nt));
@@ -110,6 +110,7 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       PHASE(phase_flatten_a(w, tid, nt));
       PHASE(phase_flatten_b(w, tid, nt));
       PHASE(phase_sums(w, kContourLutHost, tid, nt));
+      PHASE(phase_sums_long(w, kContourLutHost, tid, nt));
       PHASE(phase_select(w, tid, nt));
       PHASE(phase_bbox(w, tid, nt));
       PHASE(phase_output(w, tid, nt));

@@ -29,8 +29,12 @@
 
 #if defined(__CUDACC__)
 #define VA_HD __host__ __device__ __forceinline__
+// The phases run once per mask, mostly a row or a run per thread: unrolled loops only add to the instruction
+// footprint of the kernel that inlines all of them (instruction fetch, not issue, bounds the single-thread sections).
+#define VA_ROLL _Pragma("unroll 1")
 #else
 #define VA_HD inline
+#define VA_ROLL
 #endif
 
 namespace va {
@@ -131,6 +135,7 @@ struct RowRun { int cnt, a, b; };   // pixels set in the row, first and last set
 
 VA_HD RowRun rowsum_combine(const uint32_t* e, int nblk) {
   RowRun r; r.cnt = 0; r.a = 1 << 30; r.b = -1;
+  VA_ROLL
   for (int k = 0; k < nblk; ++k) {
     const uint32_t v = e[k];
     const int c = (int)(v & 0xffu);
@@ -187,13 +192,14 @@ struct Work {
   int R, Wd;                // region rows / words (covers the pixel bbox of the mask)
   int gs, lat_rows, lat_cols, lat_words;
   // ---- scratch (shared or global memory) ----
-  uint32_t* Mfg;            // [R][Wd] foreground bits
-  uint32_t* G;              // [R][Wd] foreground + holes
-  uint16_t* S;              // [R][Wd] runs of the row that start before word k (rows with several runs only)
+  uint32_t* Mfg;            // [NM][Wd] foreground bits of the rows with several runs (slot = position in mlist)
+  uint32_t* G;              // [NM][Wd] foreground + holes
+  uint16_t* S;              // [NM][Wd] runs of the row that start before word k
   int16_t* one_a;           // [R] first pixel of the row's only run (region-relative); kRowEmpty / kRowMulti otherwise
-  int16_t* one_b;           // [R] last pixel of the row's only run
+  int16_t* one_b;           // [R] last pixel of the row's only run; rows with several runs: their slot in Mfg / G / S
   int16_t* mlist;           // [R] rows with several runs (sc[W_NM] entries, any order)
-  int16_t* nplist;          // [R] non-empty rows that are not "plain" (sc[W_NNP] entries): summed word by word
+  int16_t* nplist;          // [R] from the front: non-empty rows that are not "plain" (sc[W_NNP] entries), summed word by word;
+                            //     from the back: plain rows with long candidate ranges (sc[W_NLONG] entries)
   int* rowoff;              // [R + 1] first run id of the row
   int cap;                  // run capacity
   uint16_t* rs;             // [cap] first / last pixel (region-relative) and row of a run; ids are in raster order
@@ -210,9 +216,8 @@ struct Work {
   // ---- output ----
   unsigned* lattice;        // [lat_rows][lat_words] of this instance (overwritten)
   InstContour* out;
-  unsigned long long* dbg;  // developer diagnostic (device only): per-section maximum cycles over the threads, or nullptr
 };
-enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_NM, W_NNP, W_COUNT };
+enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_NM, W_NNP, W_NLONG, W_COUNT };
 constexpr int kRowEmpty = -1, kRowMulti = -2;
 
 // bits [a, b] of word k (pixels 32k .. 32k+31), a <= b
@@ -221,11 +226,13 @@ VA_HD uint32_t span_bits(int a, int b, int k) {
   if (lo > hi) return 0u;
   return (0xffffffffu << (lo & 31)) & (0xffffffffu >> (31 - (hi & 31)));
 }
+// first word of a row with several runs in Mfg / G / S
+VA_HD int slot_base(const Work& w, int r) { return (int)w.one_b[r] * w.Wd; }
 // word k of row r of a bit image: stored for rows with several runs, made up from the run ends otherwise
 VA_HD uint32_t word_at(const uint32_t* bm, const Work& w, int r, int k) {
   if (r < 0 || r >= w.R || k < 0 || k >= w.Wd) return 0u;
   const int a = w.one_a[r];
-  if (a == kRowMulti) return bm[r * w.Wd + k];
+  if (a == kRowMulti) return bm[slot_base(w, r) + k];
   return (a >= 0) ? span_bits(a, (int)w.one_b[r], k) : 0u;
 }
 VA_HD uint32_t rise_at(const Work& w, int r, int k) {      // bits where a foreground run starts
@@ -240,7 +247,7 @@ VA_HD bool fg_at(const Work& w, int r, int x) {
   if (x < 0 || x >= 32 * w.Wd) return false;
   const int a = w.one_a[r];
   if (a != kRowMulti) return a >= 0 && x >= a && x <= (int)w.one_b[r];
-  return (w.Mfg[r * w.Wd + (x >> 5)] >> (x & 31)) & 1u;
+  return (w.Mfg[slot_base(w, r) + (x >> 5)] >> (x & 31)) & 1u;
 }
 VA_HD int row_runs(const Work& w, int r) { return w.rowoff[r + 1] - w.rowoff[r]; }
 // number of runs of row r that start at a pixel <= x
@@ -250,13 +257,14 @@ VA_HD int ns(const Work& w, int r, int x) {
   if (a != kRowMulti) return (a >= 0 && x >= a) ? 1 : 0;
   if (x >= 32 * w.Wd) return row_runs(w, r);
   const int k = x >> 5;
-  return (int)w.S[r * w.Wd + k] + popc32(rise_at(w, r, k) & (0xffffffffu >> (31 - (x & 31))));
+  return (int)w.S[slot_base(w, r) + k] + popc32(rise_at(w, r, k) & (0xffffffffu >> (31 - (x & 31))));
 }
 
 // find with path halving: every visited node is re-pointed at its grandparent.  The concurrent writes are benign -
 // a parent is only ever replaced by one of its ancestors, so chains only get shorter (a vertical stack of runs would
 // otherwise leave a chain as long as the mask is tall).
 VA_HD int uf_find(int* p, int x) {
+  VA_ROLL
   while (true) {
     const int q = p[x];
     if (q == x) return x;
@@ -267,6 +275,7 @@ VA_HD int uf_find(int* p, int x) {
 }
 // roots are the smallest ids: lock-free union by atomicMin on the larger root
 VA_HD void uf_union(int* p, int a, int b) {
+  VA_ROLL
   while (true) {
     a = uf_find(p, a);
     b = uf_find(p, b);
@@ -297,14 +306,17 @@ VA_HD bool row_is_plain(const Work& w, int r) { return w.one_a[r] >= 0 && !row_i
 // ---- phase 0: scalars + row classes from the summaries ----
 VA_HD void phase_init(Work& w, int tid, int nt) {
   if (tid == 0) {
+    VA_ROLL
     for (int q = 0; q < W_COUNT; ++q) w.sc[q] = 0;
     w.sc[W_MINX] = 1 << 30; w.sc[W_MINY] = 1 << 30; w.sc[W_MAXX] = -1; w.sc[W_MAXY] = -1;
     w.sc[W_CHOSEN] = -1;
     w.best[0] = 0ull;
   }
+  VA_ROLL
   for (int r = tid; r < w.R; r += nt) {
     uint32_t* e = w.rowsum + (size_t)(w.y0 + r) * w.nblk;
     const RowRun rr = rowsum_combine(e, w.nblk);
+    VA_ROLL
     for (int k = 0; k < w.nblk; ++k) e[k] = 0u;       // the summaries are all zero between calls: the mask kernels only write non-zero ones
     int a = kRowMulti, b = 0;
     if (rr.cnt == 0) { a = kRowEmpty; }
@@ -323,9 +335,14 @@ VA_HD int atom_inc(int* p) {
 #endif
 }
 VA_HD void phase_lists(Work& w, int tid, int nt) {
+  VA_ROLL
   for (int r = tid; r < w.R; r += nt) {
     const int a = w.one_a[r];
-    if (a == kRowMulti) w.mlist[atom_inc(&w.sc[W_NM])] = (int16_t)r;
+    if (a == kRowMulti) {
+      const int slot = atom_inc(&w.sc[W_NM]);
+      w.mlist[slot] = (int16_t)r;
+      w.one_b[r] = (int16_t)slot;
+    }
     if (a != kRowEmpty && !row_is_plain(w, r)) w.nplist[atom_inc(&w.sc[W_NNP])] = (int16_t)r;
   }
 }
@@ -333,8 +350,9 @@ VA_HD void phase_lists(Work& w, int tid, int nt) {
 // ---- phase 1: bit rows of the rows with several runs (every other row is made up from its run ends on demand) ----
 VA_HD void phase_load(Work& w, int tid, int nt) {
   const int ntask = w.sc[W_NM] * w.Wd;
+  VA_ROLL
   for (int q = tid; q < ntask; q += nt) {
-    const int r = w.mlist[q / w.Wd], k = q % w.Wd, t = r * w.Wd + k;
+    const int r = w.mlist[q / w.Wd], k = q % w.Wd, t = q;      // slot * Wd + k
     const int y = w.y0 + r, xw = w.x0w + k;
     uint32_t m = 0;
     if (w.fmt == 1) {
@@ -354,6 +372,7 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
           m |= ((u * 0x01020408u) >> 24) << (4 * j);          // 4 byte flags -> 4 bits
         }
       } else {
+        VA_ROLL
         for (int j = 0; j < 32 && j < rem; ++j) m |= (uint32_t)(p[j] != 0) << j;
       }
     }
@@ -364,15 +383,21 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
 
 // ---- phase 2: runs per word / row ----
 VA_HD void phase_count(Work& w, int tid, int nt) {
+  VA_ROLL
   for (int r = tid; r < w.R; r += nt) {
     const int a = w.one_a[r];
     int acc = 0;
     if (a != kRowMulti) {
       acc = (a >= 0) ? 1 : 0;
     } else {
+      const int base = slot_base(w, r);
+      uint32_t carry = 0u;                              // last pixel of the previous word
+      VA_ROLL
       for (int k = 0; k < w.Wd; ++k) {
-        w.S[r * w.Wd + k] = (uint16_t)acc;
-        acc += popc32(rise_at(w, r, k));
+        const uint32_t m = w.Mfg[base + k];
+        w.S[base + k] = (uint16_t)acc;
+        acc += popc32(m & ~((m << 1) | carry));
+        carry = m >> 31;
       }
     }
     w.rowoff[r] = acc;
@@ -381,8 +406,10 @@ VA_HD void phase_count(Work& w, int tid, int nt) {
 // ---- phase 3a-c: exclusive scan of the row counts (32 segments) ----
 VA_HD void phase_scan_a(Work& w, int tid, int nt) {
   const int segl = (w.R + 31) / 32;
+  VA_ROLL
   for (int s = tid; s < 32; s += nt) {
     int acc = 0;
+    VA_ROLL
     for (int r = s * segl; r < imin((s + 1) * segl, w.R); ++r) acc += w.rowoff[r];
     w.seg[s] = acc;
   }
@@ -391,6 +418,7 @@ VA_HD void phase_scan_b(Work& w, int tid, int nt) {
   (void)nt;
   if (tid == 0) {
     int acc = 0;
+    VA_ROLL
     for (int s = 0; s < 32; ++s) { const int v = w.seg[s]; w.seg[s] = acc; acc += v; }
     w.seg[32] = acc;
     w.sc[W_NR] = acc;
@@ -399,8 +427,10 @@ VA_HD void phase_scan_b(Work& w, int tid, int nt) {
 }
 VA_HD void phase_scan_c(Work& w, int tid, int nt) {
   const int segl = (w.R + 31) / 32;
+  VA_ROLL
   for (int s = tid; s < 32; s += nt) {
     int acc = w.seg[s];
+    VA_ROLL
     for (int r = s * segl; r < imin((s + 1) * segl, w.R); ++r) { const int v = w.rowoff[r]; w.rowoff[r] = acc; acc += v; }
   }
   if (tid == 0) w.rowoff[w.R] = w.seg[32];
@@ -419,6 +449,7 @@ VA_HD void run_init(Work& w, int id, int start, int r, bool last_in_row) {
 VA_HD void phase_runs(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   if (tid == 0) w.pG[0] = 0;                          // the outside
+  VA_ROLL
   for (int r = tid; r < w.R; r += nt) {               // rows with one run
     const int a = w.one_a[r];
     if (a < 0) continue;
@@ -427,11 +458,13 @@ VA_HD void phase_runs(Work& w, int tid, int nt) {
     w.re[id] = (uint16_t)w.one_b[r];
   }
   const int ntask = w.sc[W_NM] * w.Wd;
+  VA_ROLL
   for (int q = tid; q < ntask; q += nt) {              // rows with several runs
-    const int r = w.mlist[q / w.Wd], k = q % w.Wd, t = r * w.Wd + k;
+    const int r = w.mlist[q / w.Wd], k = q % w.Wd, t = q;      // slot * Wd + k
     const int base = w.rowoff[r], last_id = w.rowoff[r + 1] - 1;
     uint32_t rise = rise_at(w, r, k);
     int id = base + (int)w.S[t];
+    VA_ROLL
     while (rise) {
       const int b = ffs32(rise) - 1;
       rise &= rise - 1;
@@ -442,6 +475,7 @@ VA_HD void phase_runs(Work& w, int tid, int nt) {
     uint32_t fall = fall_at(w, r, k);
     const int open = (k > 0) ? (int)(w.Mfg[t - 1] >> 31) & (int)(w.Mfg[t] & 1u) : 0;
     int ie = base + (int)w.S[t] - open;
+    VA_ROLL
     while (fall) {
       const int b = ffs32(fall) - 1;
       fall &= fall - 1;
@@ -455,10 +489,12 @@ VA_HD void phase_runs(Work& w, int tid, int nt) {
 VA_HD void phase_gaps(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
+  VA_ROLL
   for (int id = tid; id < NR; id += nt) {
     const int r = w.ry[id];
     if (id == w.rowoff[r + 1] - 1) continue;            // no gap to the right
     const int g0 = w.re[id] + 1, g1 = w.rs[id + 1] - 1;
+    VA_ROLL
     for (int dr = -1; dr <= 1; dr += 2) {
       const int rr = r + dr;
       if (rr < 0 || rr >= w.R) { uf_union(w.pG, id + 1, 0); continue; }
@@ -469,6 +505,7 @@ VA_HD void phase_gaps(Work& w, int tid, int nt) {
       if (fg_at(w, rr, xb)) xb = w.rs[o2 + ns(w, rr, xb) - 1] - 1;       // last background pixel <= g1
       if (xa > xb) continue;
       const int qa = ns(w, rr, xa), qb = ns(w, rr, xb);                  // gap q lies between runs q-1 and q
+      VA_ROLL
       for (int q = qa; q <= qb; ++q) uf_union(w.pG, id + 1, (q == 0 || q == n2) ? 0 : o2 + q);
     }
   }
@@ -477,6 +514,7 @@ VA_HD void phase_gaps(Work& w, int tid, int nt) {
 VA_HD void phase_holes(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
+  VA_ROLL
   for (int id = tid; id < NR; id += nt) {
     const int r = w.ry[id];
     if (id == w.rowoff[r + 1] - 1) continue;
@@ -485,7 +523,8 @@ VA_HD void phase_holes(Work& w, int tid, int nt) {
       atom_add(&w.sc[W_HOLES], 1);
       // fill the hole pixels into G
       const int g0 = w.re[id] + 1, g1 = w.rs[id + 1] - 1;
-      for (int k = g0 >> 5; k <= (g1 >> 5); ++k) atom_or(&w.G[r * w.Wd + k], span_bits(g0, g1, k));
+      VA_ROLL
+      for (int k = g0 >> 5; k <= (g1 >> 5); ++k) atom_or(&w.G[slot_base(w, r) + k], span_bits(g0, g1, k));
     }
   }
 }
@@ -493,13 +532,18 @@ VA_HD void phase_holes(Work& w, int tid, int nt) {
 VA_HD void phase_link(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
-  for (int id = tid; id < NR; id += nt) {
+  // consecutive ids per thread: a strided second pass would start from the id - 1 chains the first pass left behind
+  // (a vertical stack of runs links into one list as long as the mask is tall) and walk them alone
+  const int per = (NR + nt - 1) / nt;
+  VA_ROLL
+  for (int id = tid * per; id < imin(NR, (tid + 1) * per); ++id) {
     const int r = w.ry[id];
     if (r == 0) continue;
     const int lo = (int)w.rs[id] - 1, hi = imin((int)w.re[id] + 1, 32 * w.Wd - 1);
     const int o2 = w.rowoff[r - 1];
     const int jlo = (lo >= 0 && fg_at(w, r - 1, lo)) ? ns(w, r - 1, lo) - 1 : ns(w, r - 1, lo);
     const int jhi = ns(w, r - 1, hi) - 1;
+    VA_ROLL
     for (int j = jlo; j <= jhi; ++j) uf_union(w.pF, id, o2 + j);
   }
 }
@@ -508,11 +552,13 @@ VA_HD void phase_link(Work& w, int tid, int nt) {
 VA_HD void phase_flatten_a(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
+  VA_ROLL
   for (int id = tid; id < NR; id += nt) w.accA[id] = uf_find(w.pF, id);
 }
 VA_HD void phase_flatten_b(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
+  VA_ROLL
   for (int id = tid; id < NR; id += nt) {
     const int root = w.accA[id];
     if (root == id) atom_add(&w.sc[W_ROOTS], 1);
@@ -537,116 +583,171 @@ VA_HD uint32_t span_code(const Span& u, const Span& c, const Span& d, int x) {
   return in(u, x - 1) | (in(u, x) << 1) | (in(u, x + 1) << 2) | (in(c, x - 1) << 3) | (in(c, x + 1) << 4) |
          (in(d, x - 1) << 5) | (in(d, x) << 6) | (in(d, x + 1) << 7);
 }
+// per-thread running sums, flushed to the component's accumulators when the component changes
+struct SumAcc {
+  int root, pts, a2;
+  VA_HD SumAcc() : root(-1), pts(0), a2(0) {}
+  VA_HD void add(Work& w, int r, int p, int v) {
+    if (r != root) { sums_flush(w, root, pts, a2); root = r; pts = 0; a2 = 0; }
+    pts += p; a2 += v;
+  }
+  // last flush: aggregated over the warp when all its threads hold the same component (the usual case)
+  VA_HD void finish(Work& w, int tid) {
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+    const int rmax = __reduce_max_sync(0xffffffffu, root);
+    if (__all_sync(0xffffffffu, root == rmax || root < 0)) {
+      const int sp = (int)__reduce_add_sync(0xffffffffu, (unsigned)(root >= 0 ? pts : 0));
+      const int sa = (int)__reduce_add_sync(0xffffffffu, (unsigned)(root >= 0 ? a2 : 0));
+      if ((tid & 31) == 0) sums_flush(w, rmax, sp, sa);
+      return;
+    }
+#endif
+    (void)tid;
+    sums_flush(w, root, pts, a2);
+  }
+};
+// the two pixel ranges of a plain row that can hold border pixels: [c.a, la] and [lb, c.b] (second one possibly empty)
+struct PlainRanges { Span c, u, d; int la, lb, n1, n2; };
+VA_HD PlainRanges plain_ranges(const Work& w, int r) {
+  PlainRanges g;
+  g.c = row_span(w, r); g.u = row_span(w, r - 1); g.d = row_span(w, r + 1);
+  const bool both = (g.u.a <= g.u.b) && (g.d.a <= g.d.b);
+  g.la = both ? imin(g.c.b, imax(g.c.a, imax(g.u.a, g.d.a)) + 1) : g.c.b;
+  g.lb = both ? imax(g.la + 1, imax(g.c.a, imin(g.c.b, imin(g.u.b, g.d.b)) - 1)) : g.c.b + 1;
+  g.n1 = g.la - g.c.a + 1; g.n2 = g.c.b - g.lb + 1;
+  return g;
+}
+VA_HD void plain_pixel(Work& w, const uint16_t* lut, const PlainRanges& g, int r, int root, int j, SumAcc& acc) {
+  const int x = (j < g.n1) ? g.c.a + j : g.lb + (j - g.n1);
+  const uint32_t e = lut[span_code(g.u, g.c, g.d, x)];
+  const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+  if (p | dxs | dys) acc.add(w, root, p, x * dys - r * dxs);
+}
+// a word of G and its eight neighbour words, then the six shifted images whose bit b is a neighbour of pixel b
+struct WordNb {
+  uint32_t Up, U, Un, Mp, M, Mn, Dp, D, Dn, Ul, Ur, Ml, Mr, Dl, Dr;
+  VA_HD void shift() {
+    Ul = (U << 1) | (Up >> 31); Ur = (U >> 1) | (Un << 31);
+    Ml = (M << 1) | (Mp >> 31); Mr = (M >> 1) | (Mn << 31);
+    Dl = (D << 1) | (Dp >> 31); Dr = (D >> 1) | (Dn << 31);
+  }
+  VA_HD uint32_t border() const { return M & ~(Ul & U & Ur & Ml & Mr & Dl & D & Dr); }
+  VA_HD uint32_t code(int b) const {
+    return ((Ul >> b) & 1u) | (((U >> b) & 1u) << 1) | (((Ur >> b) & 1u) << 2) | (((Ml >> b) & 1u) << 3) |
+           (((Mr >> b) & 1u) << 4) | (((Dl >> b) & 1u) << 5) | (((D >> b) & 1u) << 6) | (((Dr >> b) & 1u) << 7);
+  }
+};
+// the run a pixel of word (r, k) belongs to: the row's only run, or the run starts up to the pixel (it lies in that
+// run or in the hole after it) - fetched once per word
+struct WordRuns {
+  bool multi; const int* pF; int id0, before, root1; uint32_t rise;
+  VA_HD WordRuns(const Work& w, int r, int k) {
+    multi = w.one_a[r] == kRowMulti;
+    pF = w.pF;
+    id0 = w.rowoff[r];
+    rise = multi ? rise_at(w, r, k) : 0u;
+    before = multi ? (int)w.S[slot_base(w, r) + k] : 0;
+    root1 = multi ? -1 : pF[id0];
+  }
+  VA_HD int root(int b) const { return multi ? pF[id0 + before + popc32(rise & (0xffffffffu >> (31 - b))) - 1] : root1; }
+};
+constexpr int kPlainInline = 8;   // plain rows with more candidate pixels than this go to the long list
+VA_HD void word_pixel(Work& w, const uint16_t* lut, const WordNb& nb, const WordRuns& wr, int r, int k, int b, SumAcc& acc) {
+  const uint32_t e = lut[nb.code(b)];
+  const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+  if (!(p | dxs | dys)) return;                         // a hole pixel touching the outside diagonally: no visit
+  acc.add(w, wr.root(b), p, (32 * k + b) * dys - r * dxs);    // region-relative coordinates: the area is translation invariant
+}
 VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
-#ifdef __CUDA_ARCH__
-  long long tdbg0 = w.dbg ? clock64() : 0;
-#define VA_DBG(slot) do { if (w.dbg) { const long long n__ = clock64(); atomicMax(w.dbg + (slot), (unsigned long long)(n__ - tdbg0)); tdbg0 = n__; } } while (0)
-#else
-#define VA_DBG(slot) do { } while (0)
-#endif
-  int cur_root = -1, pts = 0, a2 = 0;
-  auto add = [&](int root, int p, int v) {
-    if (root != cur_root) { sums_flush(w, cur_root, pts, a2); cur_root = root; pts = 0; a2 = 0; }
-    pts += p; a2 += v;
-  };
+  SumAcc acc;
   // (a) plain rows.  All pixels of [a, b] that miss a neighbour lie in [a, la] and [lb, b] with la = max(a, ua, da) + 1,
   //     lb = min(b, ub, db) - 1 (the whole run when a neighbour row is empty).  Slanted outlines make both ranges a
-  //     few pixels long: evaluated pixel by pixel.  Long ranges (flat edges) are evaluated at the pixels next to a run
-  //     end of the three rows and once per stretch in between, where the 3x3 code is constant (count * table entry,
-  //     sum of x in closed form).
+  //     few pixels long: one thread per row.  Rows with long ranges (flat edges) are listed at the back of nplist
+  //     and summed by phase_sums_long, 32 threads per row.
+  VA_ROLL
   for (int r = tid; r < w.R; r += nt) {
     if (!row_is_plain(w, r)) continue;
-    const Span c = row_span(w, r), u = row_span(w, r - 1), d = row_span(w, r + 1);
+    const PlainRanges g = plain_ranges(w, r);
+    if (g.n1 + g.n2 > kPlainInline) { w.nplist[w.R - 1 - atom_inc(&w.sc[W_NLONG])] = (int16_t)r; continue; }
     const int root = w.pF[w.rowoff[r]];
-    auto pixel = [&](int x) {
-      const uint32_t e = lut[span_code(u, c, d, x)];
-      const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
-      if (p | dxs | dys) add(root, p, x * dys - r * dxs);
-    };
-    const bool both = (u.a <= u.b) && (d.a <= d.b);
-    const int la = both ? imin(c.b, imax(c.a, imax(u.a, d.a)) + 1) : c.b;
-    const int lb = both ? imax(c.a, imin(c.b, imin(u.b, d.b)) - 1) : c.a;
-    if (both && la - c.a < 8 && c.b - lb < 8) {
-      for (int x = c.a; x <= la; ++x) pixel(x);
-      for (int x = imax(lb, la + 1); x <= c.b; ++x) pixel(x);
-      continue;
-    }
-    int bp[14], n = 0;
-    bp[n++] = c.a; bp[n++] = c.b;
-    if (u.a <= u.b) { for (int q = -1; q <= 1; ++q) { bp[n++] = u.a + q; bp[n++] = u.b + q; } }
-    if (d.a <= d.b) { for (int q = -1; q <= 1; ++q) { bp[n++] = d.a + q; bp[n++] = d.b + q; } }
-    for (int i = 1; i < n; ++i) {                       // insertion sort (<= 14 values)
-      const int v = bp[i];
-      int j = i - 1;
-      while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
-      bp[j + 1] = v;
-    }
-    int prev = c.a - 1;                                 // last pixel already accounted for
-    for (int i = 0; i < n; ++i) {
-      const int x = bp[i];
-      if (x < c.a || x > c.b || x <= prev) continue;
-      if (x - 1 > prev) {                               // stretch prev+1 .. x-1: constant code
-        const int lo = prev + 1, hi = x - 1, cnt = hi - lo + 1;
-        const uint32_t e = lut[span_code(u, c, d, lo)];
-        const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
-        if (p | dxs | dys) add(root, p * cnt, dys * ((lo + hi) * cnt / 2) - r * dxs * cnt);
-      }
-      pixel(x);
-      prev = x;
-    }
-    // c.b is a breakpoint, so the row is complete here
+    VA_ROLL
+    for (int j = 0; j < g.n1 + g.n2; ++j) plain_pixel(w, lut, g, r, root, j, acc);
   }
-  VA_DBG(0);
   // (b) every other non-empty row (rows with several runs and their neighbours), word by word on the bit image
   const int ntask = w.sc[W_NNP] * w.Wd;
-  for (int q = tid; q < ntask; q += nt) {
-    const int r = w.nplist[q / w.Wd], k = q % w.Wd;
-    const uint32_t M = word_at(w.G, w, r, k);
-    if (!M) continue;
-    const uint32_t U = word_at(w.G, w, r - 1, k), D = word_at(w.G, w, r + 1, k);
-    const uint32_t Up = word_at(w.G, w, r - 1, k - 1), Un = word_at(w.G, w, r - 1, k + 1);
-    const uint32_t Mp = word_at(w.G, w, r, k - 1), Mn = word_at(w.G, w, r, k + 1);
-    const uint32_t Dp = word_at(w.G, w, r + 1, k - 1), Dn = word_at(w.G, w, r + 1, k + 1);
-    const uint32_t Ul = (U << 1) | (Up >> 31), Ur = (U >> 1) | (Un << 31);
-    const uint32_t Ml = (M << 1) | (Mp >> 31), Mr = (M >> 1) | (Mn << 31);
-    const uint32_t Dl = (D << 1) | (Dp >> 31), Dr = (D >> 1) | (Dn << 31);
-    uint32_t border = M & ~(Ul & U & Ur & Ml & Mr & Dl & D & Dr);
-    while (border) {
-      const int b = ffs32(border) - 1;
-      border &= border - 1;
-      const uint32_t code = ((Ul >> b) & 1u) | (((U >> b) & 1u) << 1) | (((Ur >> b) & 1u) << 2) | (((Ml >> b) & 1u) << 3) |
-                            (((Mr >> b) & 1u) << 4) | (((Dl >> b) & 1u) << 5) | (((D >> b) & 1u) << 6) | (((Dr >> b) & 1u) << 7);
-      const uint32_t e = lut[code];
-      const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
-      if (!(p | dxs | dys)) continue;                   // a hole pixel touching the outside diagonally: no visit
-      const int lx = 32 * k + b;
-      add(w.pF[w.rowoff[r] + ns(w, r, lx) - 1], p, lx * dys - r * dxs);   // region-relative coordinates: the area is translation invariant
-    }
-  }
-  VA_DBG(1);
 #ifdef __CUDA_ARCH__
-  __syncwarp();
-  const int rmax = __reduce_max_sync(0xffffffffu, cur_root);
-  if (__all_sync(0xffffffffu, cur_root == rmax || cur_root < 0)) {     // one component in this warp (the usual case)
-    const int sp = (int)__reduce_add_sync(0xffffffffu, (unsigned)(cur_root >= 0 ? pts : 0));
-    const int sa = (int)__reduce_add_sync(0xffffffffu, (unsigned)(cur_root >= 0 ? a2 : 0));
-    if ((tid & 31) == 0) sums_flush(w, rmax, sp, sa);
-    VA_DBG(2);
+  if ((nt & 31) == 0 && ntask <= 8 * (nt >> 5)) {
+    // few words (a notch in an otherwise row-convex outline): one word per warp and one pixel per lane - a single
+    // thread walking the up to 32 border pixels of its word would be the whole mask's critical path
+    const int lane = tid & 31;
+    VA_ROLL
+    for (int q = tid >> 5; q < ntask; q += nt >> 5) {
+      const int r = w.nplist[q / w.Wd], k = q % w.Wd;
+      const uint32_t mine = (lane < 9) ? word_at(w.G, w, r - 1 + lane / 3, k - 1 + lane % 3) : 0u;   // the 3x3 words
+      WordNb nb;
+      nb.Up = __shfl_sync(0xffffffffu, mine, 0); nb.U = __shfl_sync(0xffffffffu, mine, 1); nb.Un = __shfl_sync(0xffffffffu, mine, 2);
+      nb.Mp = __shfl_sync(0xffffffffu, mine, 3); nb.M = __shfl_sync(0xffffffffu, mine, 4); nb.Mn = __shfl_sync(0xffffffffu, mine, 5);
+      nb.Dp = __shfl_sync(0xffffffffu, mine, 6); nb.D = __shfl_sync(0xffffffffu, mine, 7); nb.Dn = __shfl_sync(0xffffffffu, mine, 8);
+      if (!nb.M) continue;
+      nb.shift();
+      if (!((nb.border() >> lane) & 1u)) continue;
+      const WordRuns wr(w, r, k);
+      word_pixel(w, lut, nb, wr, r, k, lane, acc);
+    }
+    acc.finish(w, tid);
     return;
   }
 #endif
-  sums_flush(w, cur_root, pts, a2);
-  VA_DBG(2);
-#undef VA_DBG
+  VA_ROLL
+  for (int q = tid; q < ntask; q += nt) {
+    const int r = w.nplist[q / w.Wd], k = q % w.Wd;
+    WordNb nb;
+    nb.M = word_at(w.G, w, r, k);
+    if (!nb.M) continue;
+    nb.U = word_at(w.G, w, r - 1, k); nb.D = word_at(w.G, w, r + 1, k);
+    nb.Up = word_at(w.G, w, r - 1, k - 1); nb.Un = word_at(w.G, w, r - 1, k + 1);
+    nb.Mp = word_at(w.G, w, r, k - 1); nb.Mn = word_at(w.G, w, r, k + 1);
+    nb.Dp = word_at(w.G, w, r + 1, k - 1); nb.Dn = word_at(w.G, w, r + 1, k + 1);
+    nb.shift();
+    uint32_t border = nb.border();
+    if (!border) continue;
+    const WordRuns wr(w, r, k);
+    VA_ROLL
+    while (border) {
+      const int b = ffs32(border) - 1;
+      border &= border - 1;
+      word_pixel(w, lut, nb, wr, r, k, b, acc);
+    }
+  }
+  acc.finish(w, tid);
+}
+// ---- phase 9b: the plain rows with long candidate ranges, one row per group of 32 threads ----
+VA_HD void phase_sums_long(Work& w, const uint16_t* lut, int tid, int nt) {
+  if (w.sc[W_OVERFLOW]) return;
+  SumAcc acc;
+  const int L = (nt % 32 == 0) ? 32 : 1;
+  const int nlong = w.sc[W_NLONG];
+  VA_ROLL
+  for (int q = tid / L; q < nlong; q += nt / L) {
+    const int r = w.nplist[w.R - 1 - q];
+    const PlainRanges g = plain_ranges(w, r);
+    const int root = w.pF[w.rowoff[r]];
+    VA_ROLL
+    for (int j = tid % L; j < g.n1 + g.n2; j += L) plain_pixel(w, lut, g, r, root, j, acc);
+  }
+  acc.finish(w, tid);
 }
 // ---- phase 10: the component whose contour has the most points; ties: the last in raster order ----
 VA_HD void phase_select(Work& w, int tid, int nt) {
+  VA_ROLL
   for (int t = tid; t < w.lat_rows * w.lat_words; t += nt) w.lattice[t] = 0u;     // rebuilt by phase_output
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
   unsigned long long best = 0ull;
   bool any = false;
+  VA_ROLL
   for (int id = tid; id < NR; id += nt) {
     if (w.pF[id] != id) continue;
     const unsigned long long key = ((unsigned long long)(unsigned)w.accP[id] << 32) | (unsigned)(id + 1);
@@ -662,6 +763,7 @@ VA_HD void phase_bbox(Work& w, int tid, int nt) {
   if (tid == 0) w.sc[W_CHOSEN] = chosen;
   if (chosen < 0) return;
   int minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
+  VA_ROLL
   for (int id = tid; id < NR; id += nt) {
     if (w.pF[id] != chosen) continue;
     minx = imin(minx, (int)w.rs[id]); maxx = imax(maxx, (int)w.re[id]);
@@ -683,6 +785,7 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
     const int lx0 = imax(0, (32 * w.x0w - half + w.gs - 1) / w.gs), lx1 = imin(w.lat_cols - 1, (32 * (w.x0w + w.Wd) - 1 - half) / w.gs);
     const int nly = ly1 - ly0 + 1, nlx = lx1 - lx0 + 1;
     if (w.y0 + w.R - 1 >= half && nly > 0 && nlx > 0) {
+      VA_ROLL
       for (int t = tid; t < nly * nlx; t += nt) {
         const int ly = ly0 + t / nlx, lx = lx0 + t % nlx;
         const int r = w.gs * ly + half - w.y0;

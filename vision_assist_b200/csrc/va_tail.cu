@@ -31,6 +31,7 @@ namespace va {
 
 constexpr int kTailThreads = 256;       // smallest CTA size (tuning aid VA_TAIL_THREADS); the launch uses kTailMaxThreads
 constexpr int kTailMaxThreads = 1024;
+constexpr size_t kContourGridSmem = 16 * 1024;   // contour step: bit rows of the rows with several runs
 
 // developer diagnostic (VA_TAIL_TIMING=1): cycle stamps of block 0 at the phase boundaries, printed by the kernel
 constexpr int kTailDebugFlag = 1 << 30;
@@ -96,6 +97,7 @@ __device__ __forceinline__ int run_left(const unsigned* row, int c) {
   int w = c >> 5;
   // zeros strictly below c in word w
   unsigned z = ~row[w] & ((c & 31) ? (0xffffffffu >> (32 - (c & 31))) : 0u);
+  VA_ROLL
   while (true) {
     if (z) return (w << 5) + (32 - __clz(z));
     if (w == 0) return 0;
@@ -108,6 +110,7 @@ __device__ __forceinline__ int run_right(const unsigned* row, int c, int C) {
   int w = c >> 5;
   const int nw = (C + 31) >> 5;
   unsigned z = ~row[w] & (((c & 31) == 31) ? 0u : (0xffffffffu << ((c & 31) + 1)));
+  VA_ROLL
   while (true) {
     if (z) return min((w << 5) + (__ffs(z) - 1) - 1, C - 1);
     if (w == nw - 1) return C - 1;
@@ -143,6 +146,7 @@ __device__ __forceinline__ double blend_penalty(double rp, double cp) {
 // ---------------------------------------------------------------------------------------------
 __device__ void easy_segments(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords;
+  VA_ROLL
   for (int id = threadIdx.x; id < s.sc[S_NCREATED]; id += (int)blockDim.x) s.row_ly[id] = s.row_y[id] / d.gs;
   {
     // grid_lookup occupancy by column: the vertical traversal of PenaltyCalculator.py:73-95 becomes the same
@@ -150,6 +154,7 @@ __device__ void easy_segments(const Dims& d, const TailSmem& s) {
     const int PL = plane_cap(d), plw = (PL + 31) >> 5;
     // 32 x 32 bit blocks transposed with ballots: lane = lookup row of the block, bit q of its word = column q
     const int lane = threadIdx.x & 31, nwarps = (int)blockDim.x >> 5;
+    VA_ROLL
     for (int blk = nwarps - 1 - ((int)threadIdx.x >> 5); blk < plw * cw; blk += nwarps) {   // last warps first: the first ones scan rows / columns below
       const int w = blk / cw, cwd = blk - w * cw;
       const int ly = 32 * w + lane;
@@ -166,10 +171,12 @@ __device__ void easy_segments(const Dims& d, const TailSmem& s) {
     }
   }
   const bool use = s.sc[S_USE_EASY] != 0;
+  VA_ROLL
   for (int k = threadIdx.x; k < d.rmax; k += (int)blockDim.x) {
     int first = -1, last = -1, cnt = 0;
     if (use && k < R) {
       const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
+      VA_ROLL
       for (int w = 0; w < cw; ++w) {
         const unsigned v = row[w];
         if (v) {
@@ -183,9 +190,11 @@ __device__ void easy_segments(const Dims& d, const TailSmem& s) {
     s.erow_first[k] = first;
     s.erow_last[k] = last;
   }
+  VA_ROLL
   for (int c = threadIdx.x; c < d.cmax; c += (int)blockDim.x) {
     int first = -1, last = -1, cnt = 0;
     if (use && c < C) {
+      VA_ROLL
       for (int k = 0; k < R; ++k) {
         if (bit_at(s.occ + (size_t)s.list_ids[k] * cw, c)) {
           if (first < 0) first = k;
@@ -214,6 +223,7 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   const int dk = nt / d.cmax, dc = nt - dk * d.cmax;
   int k = tid / d.cmax, c0 = tid - k * d.cmax, kmod = k % d.cmax;
   const int dkmod = dk % d.cmax;
+  VA_ROLL
   for (int u = tid; u < cells; u += nt, k += dk, c0 += dc, kmod += dkmod) {
     if (c0 >= d.cmax) { c0 -= d.cmax; ++k; ++kmod; }
     if (kmod >= d.cmax) kmod -= d.cmax;
@@ -260,6 +270,7 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
   }
   int* ry = reinterpret_cast<int*>(rec + d.off_row_y);
   int* ra = reinterpret_cast<int*>(rec + d.off_row_attr);
+  VA_ROLL
   for (int k = tid; k < d.rmax; k += nt) {
     int y = 0, a = 0;
     if (k < R + norph) {
@@ -271,8 +282,11 @@ __device__ void penalties_and_record(const Dims& d, const TailSmem& s, uint8_t* 
     ra[k] = a;
   }
   // alignment padding: keep every byte of the record deterministic
+  VA_ROLL
   for (int t = d.off_row_attr + 4 * d.rmax + tid; t < d.off_penalty; t += nt) rec[t] = 0;
+  VA_ROLL
   for (int t = d.off_occ + d.rmax * d.cmax + tid; t < d.off_goals; t += nt) rec[t] = 0;
+  VA_ROLL
   for (int t = d.off_lookup + 8 * d.rmax + tid; t < d.record_bytes; t += nt) rec[t] = 0;
 }
 
@@ -283,17 +297,21 @@ __device__ void find_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
   const int R = s.sc[S_R], C = s.sc[S_C], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
   const int lane = threadIdx.x & 31;
   int ytop = INT_MAX;
+  VA_ROLL
   for (int k = lane; k < R; k += 32) {
     const unsigned* row = s.occ + (size_t)s.list_ids[k] * cw;
     unsigned any = 0;
+    VA_ROLL
     for (int w = 0; w < cw; ++w) any |= row[w];
     if (any) ytop = min(ytop, s.row_y[s.list_ids[k]]);
   }
   ytop = __reduce_min_sync(0xffffffffu, ytop);
   __shared__ unsigned uni[kMaxColWords];
   if (ytop != INT_MAX) {
+    VA_ROLL
     for (int w = 0; w < cw; ++w) {
       unsigned v = 0;
+      VA_ROLL
       for (int k = lane; k < R; k += 32)
         if (s.row_y[s.list_ids[k]] == ytop) v |= s.occ[(size_t)s.list_ids[k] * cw + w];
       v = __reduce_or_sync(0xffffffffu, v);
@@ -305,9 +323,11 @@ __device__ void find_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
   int np = 0;
   if (ytop != INT_MAX) {
     int c = 0;
+    VA_ROLL
     while (c < C) {
       int w = c >> 5;                                   // next set bit at or after c
       unsigned v = uni[w] & (0xffffffffu << (c & 31));
+      VA_ROLL
       while (!v && ++w < cw) v = uni[w];
       if (!v) break;
       c = (w << 5) + __ffs(v) - 1;
@@ -324,6 +344,7 @@ __device__ void find_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) {
     }
   }
   if (np > d.pmax) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW; np = d.pmax; }
+  VA_ROLL
   for (int q = np; q < d.pmax; ++q) { peaks[2 * q] = 0; peaks[2 * q + 1] = 0; }
   s.sc[S_NPEAKS] = np;
 }
@@ -343,10 +364,13 @@ __device__ void write_header(const TailSmem& s, uint8_t* rec) {
 __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   const int R = s.sc[S_R], n = s.sc[S_NCREATED];
   int* s_flags = s.oflag;
+  VA_ROLL
   for (int id = threadIdx.x; id < n; id += (int)blockDim.x) s_flags[id] = 0;
   __syncthreads();
+  VA_ROLL
   for (int k = threadIdx.x; k < R; k += (int)blockDim.x) s_flags[s.list_ids[k]] = 1;      // rows still in the list
   __syncthreads();
+  VA_ROLL
   for (int id = threadIdx.x; id < n; id += (int)blockDim.x) {
     const bool in_list = s_flags[id] != 0;
     const int ly = s.row_y[id] / d.gs;
@@ -355,9 +379,11 @@ __device__ void collect_orphans(const Dims& d, const TailSmem& s) {
   __syncthreads();
   if (threadIdx.x == 0) {
     int no = 0;
+    VA_ROLL
     for (int id = 0; id < n; ++id) {
       if (!s_flags[id] || R + no >= d.rmax) continue;
       int pos = no++;
+      VA_ROLL
       while (pos > 0 && s.row_y[s.orphan_ids[pos - 1]] > s.row_y[id]) { s.orphan_ids[pos] = s.orphan_ids[pos - 1]; --pos; }
       s.orphan_ids[pos] = id;
     }
@@ -374,11 +400,13 @@ __device__ __forceinline__ unsigned long long row_best_key(const unsigned* row, 
   int cfl = floor_div(px - x0 - half, gs);               // column whose centre is at or left of px
   cfl = max(-1, min(cfl, C - 1));
   int cl = -1, cr = -1;
+  VA_ROLL
   for (int w = cfl >> 5; w >= 0 && cfl >= 0; --w) {      // nearest set bit <= cfl
     unsigned v = row[w];
     if (w == (cfl >> 5) && (cfl & 31) != 31) v &= (2u << (cfl & 31)) - 1u;
     if (v) { cl = (w << 5) + 31 - __clz(v); break; }
   }
+  VA_ROLL
   for (int w = (cfl + 1) >> 5; w < cw; ++w) {            // nearest set bit > cfl
     unsigned v = row[w];
     if (w == ((cfl + 1) >> 5)) v &= 0xffffffffu << ((cfl + 1) & 31);
@@ -409,9 +437,11 @@ __device__ void closest_cells(const Dims& d, const TailSmem& s, uint8_t* rec, in
   const int R = s.sc[S_R], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0];
   const int* peaks = reinterpret_cast<const int*>(rec + d.off_peaks);     // written by lane 0 in find_peaks
   int* goals = reinterpret_cast<int*>(rec + d.off_goals);
+  VA_ROLL
   for (int pt = first_pt; pt <= last_pt; ++pt) {
     const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
     unsigned long long best = ~0ull;
+    VA_ROLL
     for (int k = lane; k < R; k += 32) {
       const int id = s.list_ids[k];
       best = min(best, row_best_key(s.occ + (size_t)id * cw, cw, s.sc[S_C], k, d.cmax, px, py, x0, s.row_y[id], gs));
@@ -434,6 +464,7 @@ __device__ void goals_for_peaks(const Dims& d, const TailSmem& s, uint8_t* rec) 
   const int npk = s.sc[S_NPEAKS];
   closest_cells(d, s, rec, 1, npk);
   int* goals = reinterpret_cast<int*>(rec + d.off_goals);
+  VA_ROLL
   for (int q = npk + lane; q < d.pmax; q += 32) { goals[2 * q] = 0; goals[2 * q + 1] = 0; }
 }
 
@@ -443,12 +474,16 @@ __device__ void start_and_lookup(const Dims& d, const TailSmem& s, uint8_t* rec)
   const int R = s.sc[S_R], norph = s.sc[S_NORPH], T = 2 * d.rmax, PL = plane_cap(d);
   closest_cells(d, s, rec, 0, 0);
   // created id -> record row (first list position, or R + j for the j-th orphan)
+  VA_ROLL
   for (int t = lane; t < T; t += 32) s.oflag[t] = INT_MAX;
   __syncwarp();
+  VA_ROLL
   for (int k = lane; k < R; k += 32) atomicMin(&s.oflag[s.list_ids[k]], k);
+  VA_ROLL
   for (int j = lane; j < norph; j += 32) s.oflag[s.orphan_ids[j]] = R + j;
   __syncwarp();
   int* lookup = reinterpret_cast<int*>(rec + d.off_lookup);
+  VA_ROLL
   for (int ly = lane; ly < PL; ly += 32) {
     const int owner = (R > 0) ? s.plane_owner[ly] : -1;
     const int v = (owner >= 0) ? s.oflag[owner] : -1;
@@ -462,12 +497,16 @@ __device__ void start_goals_lookup_block(const Dims& d, const TailSmem& s, uint8
   const int R = s.sc[S_R], cw = d.cwords, gs = d.gs, x0 = s.sc[S_X0], half = gs >> 1;
   const int npk = s.sc[S_NPEAKS], P = 1 + npk, norph = s.sc[S_NORPH], T = 2 * d.rmax, PL = plane_cap(d);
   const int* peaks = reinterpret_cast<const int*>(rec + d.off_peaks);     // written by warp 0 before the barrier
+  VA_ROLL
   for (int t = threadIdx.x; t < d.pmax + 1; t += (int)blockDim.x) s.best[t] = ~0ull;
+  VA_ROLL
   for (int t = threadIdx.x; t < T; t += (int)blockDim.x) s.oflag[t] = INT_MAX;
   __syncthreads();
+  VA_ROLL
   for (int pt = 0; pt < P; ++pt) {           // per point: per-thread minimum, warp minimum, one shared atomic per warp
     const int px = pt ? peaks[2 * (pt - 1)] : d.W / 2, py = pt ? peaks[2 * (pt - 1) + 1] : d.H;
     unsigned long long best = ~0ull;
+    VA_ROLL
     for (int k = threadIdx.x; k < R; k += (int)blockDim.x) {
       const int id = s.list_ids[k];
       best = min(best, row_best_key(s.occ + (size_t)id * cw, cw, s.sc[S_C], k, d.cmax, px, py, x0, s.row_y[id], gs));
@@ -476,10 +515,13 @@ __device__ void start_goals_lookup_block(const Dims& d, const TailSmem& s, uint8
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&s.best[pt], best);
   }
+  VA_ROLL
   for (int k = threadIdx.x; k < R; k += (int)blockDim.x) atomicMin(&s.oflag[s.list_ids[k]], k);
+  VA_ROLL
   for (int j = threadIdx.x; j < norph; j += (int)blockDim.x) s.oflag[s.orphan_ids[j]] = R + j;
   __syncthreads();
   int* goals = reinterpret_cast<int*>(rec + d.off_goals);
+  VA_ROLL
   for (int q = threadIdx.x; q < d.pmax; q += (int)blockDim.x) {
     int gk = 0, gc = 0;
     if (q < npk) {
@@ -492,6 +534,7 @@ __device__ void start_goals_lookup_block(const Dims& d, const TailSmem& s, uint8
     goals[2 * q + 1] = gc;
   }
   int* lookup = reinterpret_cast<int*>(rec + d.off_lookup);
+  VA_ROLL
   for (int ly = threadIdx.x; ly < PL; ly += (int)blockDim.x) {
     const int owner = (R > 0) ? s.plane_owner[ly] : -1;
     const int v = (owner >= 0) ? s.oflag[owner] : -1;
@@ -593,25 +636,35 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
   w.sc = sc; w.best = best;
   w.lattice = lattice_inst;
   w.out = out;
-  w.dbg = nullptr;
   const cc::RowLayout wl = cc::row_layout(w.R);
-  const cc::GridLayout gl = cc::grid_layout(w.R, w.Wd);
   const cc::RowLayout wl_full = cc::row_layout(d.H);
   const cc::GridLayout gl_full = cc::grid_layout(d.H, d.bit_words);
   size_t used = 0;
   const bool rows_in_smem = wl.total <= (size_t)tc.smem_bytes;
   cc::bind_rows(w, rows_in_smem ? smem : slab, wl);
   if (rows_in_smem) used += wl.total;
-  cc::bind_grid(w, slab + wl_full.total, gl);
+  cc::bind_grid(w, slab + wl_full.total, gl_full);
   cc::bind_runs(w, slab + wl_full.total + gl_full.total, cc::run_layout(tc.cap));
   __syncthreads();
-  cc::phase_init(w, tid, nt);       __syncthreads();
-  cc::phase_lists(w, tid, nt);      __syncthreads();
-  cc::phase_load(w, tid, nt);       __syncthreads();
-  cc::phase_count(w, tid, nt);      __syncthreads();
-  cc::phase_scan_a(w, tid, nt);     __syncthreads();
-  cc::phase_scan_b(w, tid, nt);     __syncthreads();
-  cc::phase_scan_c(w, tid, nt);     __syncthreads();
+  const bool ptime = (d.flags & kTailDebugFlag) && tid == 0 && blockIdx.x < 64;
+  long long pt[20]; int npt = 0;
+#define PT(k) do { if (ptime) pt[npt++] = clock64(); } while (0)
+  PT(0);
+  cc::phase_init(w, tid, nt);       __syncthreads(); PT(1);
+  cc::phase_lists(w, tid, nt);      __syncthreads(); PT(2);
+  {
+    // bit rows of the rows with several runs (usually a handful): shared memory when they fit
+    const cc::GridLayout gl = cc::grid_layout(sc[cc::W_NM] > 0 ? sc[cc::W_NM] : 1, w.Wd);
+    if (used + gl.total <= (size_t)tc.smem_bytes) {
+      cc::bind_grid(w, smem + used, gl);
+      used += gl.total;
+    }
+  }
+  cc::phase_load(w, tid, nt);       __syncthreads(); PT(3);
+  cc::phase_count(w, tid, nt);      __syncthreads(); PT(4);
+  cc::phase_scan_a(w, tid, nt);     __syncthreads(); PT(5);
+  cc::phase_scan_b(w, tid, nt);     __syncthreads(); PT(6);
+  cc::phase_scan_c(w, tid, nt);     __syncthreads(); PT(7);
   {
     const int NR = sc[cc::W_NR];
     const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
@@ -620,16 +673,24 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
       cc::bind_runs(w, smem + used, rl);
     }
   }
-  cc::phase_runs(w, tid, nt);       __syncthreads();
-  cc::phase_gaps(w, tid, nt);       __syncthreads();
-  cc::phase_holes(w, tid, nt);      __syncthreads();
-  cc::phase_link(w, tid, nt);       __syncthreads();
-  cc::phase_flatten_a(w, tid, nt);  __syncthreads();
-  cc::phase_flatten_b(w, tid, nt);  __syncthreads();
-  cc::phase_sums(w, lut, tid, nt);  __syncthreads();
-  cc::phase_select(w, tid, nt);     __syncthreads();
-  cc::phase_bbox(w, tid, nt);       __syncthreads();
-  cc::phase_output(w, tid, nt);     __syncthreads();
+  cc::phase_runs(w, tid, nt);       __syncthreads(); PT(8);
+  cc::phase_gaps(w, tid, nt);       __syncthreads(); PT(9);
+  cc::phase_holes(w, tid, nt);      __syncthreads(); PT(10);
+  cc::phase_link(w, tid, nt);       __syncthreads(); PT(11);
+  cc::phase_flatten_a(w, tid, nt);  __syncthreads(); PT(12);
+  cc::phase_flatten_b(w, tid, nt);  __syncthreads(); PT(13);
+  cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
+  cc::phase_sums_long(w, lut, tid, nt);  __syncthreads();
+  cc::phase_select(w, tid, nt);     __syncthreads(); PT(15);
+  cc::phase_bbox(w, tid, nt);       __syncthreads(); PT(16);
+  cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
+  if (ptime) {
+    printf("[va tail] frame %d phases (R=%d Wd=%d NR=%d NM=%d): init %lld lists %lld load %lld count %lld scan %lld %lld %lld runs %lld gaps %lld holes %lld link %lld flat %lld %lld sums %lld select %lld bbox %lld out %lld\n",
+           (int)blockIdx.x, w.R, w.Wd, sc[cc::W_NR], sc[cc::W_NM], pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3],
+           pt[5] - pt[4], pt[6] - pt[5], pt[7] - pt[6], pt[8] - pt[7], pt[9] - pt[8], pt[10] - pt[9], pt[11] - pt[10],
+           pt[12] - pt[11], pt[13] - pt[12], pt[14] - pt[13], pt[15] - pt[14], pt[16] - pt[15], pt[17] - pt[16]);
+  }
+#undef PT
 }
 
 __global__ void __launch_bounds__(kTailMaxThreads)
@@ -656,7 +717,9 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   __shared__ unsigned long long s_best;
   __shared__ uint16_t s_lut[256];
   __shared__ cc::InstContour s_out;
+  VA_ROLL
   for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
+  VA_ROLL
   for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
   if (threadIdx.x < kMaxInst) {
     const int i = threadIdx.x;
@@ -697,6 +760,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     const int lane = threadIdx.x & 31, warp = (int)threadIdx.x >> 5, nwarps = (int)blockDim.x >> 5;
     const int ntask = s_task0[kMaxInst];
     constexpr int kU = 4;                                              // work items in flight per warp: their loads overlap
+    VA_ROLL
     for (int t0 = warp; t0 < ntask; t0 += kU * nwarps) {
       int inst_i[kU], yy[kU];
       bool live[kU];
@@ -705,6 +769,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       for (int u = 0; u < kU; ++u) {
         const int t = t0 + u * nwarps;
         int i = 0;
+        VA_ROLL
         while (i + 1 < n && s_task0[i + 1] <= t) ++i;                  // instance of task t (n <= 32: a short scan)
         inst_i[u] = i;
         const InstStats v = s_stats[i];
@@ -745,11 +810,13 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     }
     __syncthreads();
     int n_pending = 0;
+    VA_ROLL
     for (int i = 0; i < n; ++i) {
       const InstStats v = s_stats[i];
       if (v.area == 0 || !s_cert[i][0]) continue;
       // certified: put the instance's summaries back to their resting state (all zero)
       uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk + (size_t)v.miny * d.nblk;
+      VA_ROLL
       for (int t = threadIdx.x; t < (v.maxy - v.miny + 1) * d.nblk; t += (int)blockDim.x) rs[t] = 0u;
     }
     if (threadIdx.x < kMaxInst) {
@@ -772,14 +839,17 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     n_pending = __syncthreads_or(n_pending);
     // ---- contour step, part 2: the general path for every instance the certificate did not cover ----
     if (n_pending) {
+      VA_ROLL
       for (int t = threadIdx.x; t < 256; t += (int)blockDim.x) s_lut[t] = g_contour_lut[t];
       const int slot = b % tc.nslab;
       if (threadIdx.x == 0 && (int)gridDim.x > tc.nslab) {          // more frames than slabs: frames b and b + nslab share one
+        VA_ROLL
         while (atomicCAS(&tc.slab_lock[slot], 0, 1) != 0) __nanosleep(200);
         __threadfence();
       }
       __syncthreads();
       unsigned char* slab = tc.slab + (size_t)slot * tc.slab_bytes;
+      VA_ROLL
       for (int i = 0; i < n; ++i) {
         if (s_state[i] != cc::kPending) continue;                   // CTA-uniform
         const size_t inst = (size_t)b * d.max_n + i;
@@ -801,6 +871,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    VA_ROLL
     for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
     s.sc[S_USE_EASY] = 1;
     // ---- instance selection (FrameProcessor.py:71-73): the polygon with the largest cv2.contourArea, first maximum;
@@ -812,6 +883,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       if (sel < 0 || sel >= n) sel = -1;
     } else if (n > 0) {
       sel = 0;
+      VA_ROLL
       for (int i = 1; i < n; ++i) if (s_area2[i] > s_area2[sel]) sel = i;
     }
     s.sc[S_SEL] = sel;
@@ -854,6 +926,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     const int lx0 = s.sc[S_X0] / gs, ly0 = s.sc[S_Y0] / gs;
     const unsigned* lat = lattice + ((size_t)b * d.max_n + sel) * d.lat_rows * d.lat_words;
     int any = 0;
+    VA_ROLL
     for (int t = threadIdx.x; t < Rm * cw; t += (int)blockDim.x) {
       const int r = t / cw, w = t - r * cw;
       const unsigned* lrow = lat + (size_t)(ly0 + r) * d.lat_words;
@@ -867,6 +940,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       s.occ[(size_t)r * cw + w] = v;
       any |= (v != 0);
     }
+    VA_ROLL
     for (int r = threadIdx.x; r < Rm; r += (int)blockDim.x) {
       s.row_y[r] = s.sc[S_Y0] + r * gs;
       s.row_attr[r] = r;
@@ -878,6 +952,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       // band row: one column per thread, one ballot per 32 columns (erow_last is scratch until easy_segments runs)
       unsigned* am = reinterpret_cast<unsigned*>(s.erow_last);
       const int base = d.W / 2 - 8 * gs;
+      VA_ROLL
       for (int c0 = threadIdx.x & ~31; c0 < 32 * cw; c0 += (int)blockDim.x) {
         const int c = c0 + (threadIdx.x & 31);
         const int delta = s.sc[S_X0] + c * gs - base;
@@ -895,12 +970,14 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
         // ---- artificial band (FrameProcessor.py:126-165), replayed literally ----
         int list_len = Rm, ncreated = Rm;
         const unsigned* am = reinterpret_cast<const unsigned*>(s.erow_last);   // built by all warps above
+        VA_ROLL
         for (int i = d.band_start; i < d.H; i += gs) {
           const int ly = i / gs;
           const int row_idx = floor_div(i - s.sc[S_Y0], gs);
           if (ncreated >= T || ly >= PL) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW; break; }
           const int id = ncreated++;
           const int prev = s.plane_owner[ly];
+          VA_ROLL
           for (int w = 0; w < cw; ++w) {
             const unsigned pv = (prev >= 0) ? s.occ[(size_t)prev * cw + w] : 0u;
             s.occ[(size_t)id * cw + w] = pv | am[w];
@@ -934,6 +1011,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   __syncthreads();
   TT(9);
   TT(115);
+  VA_ROLL
   for (int i = threadIdx.x; i < d.max_n; i += (int)blockDim.x) {
     InstStats z;
     z.area = 0; z.minx = INT_MAX; z.miny = INT_MAX; z.maxx = -1; z.maxy = -1; z.euler4 = 0; z.pad0 = 0; z.pad1 = 0;
@@ -941,6 +1019,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   }
   TT(11);
   unsigned* latb = lattice + (size_t)b * d.max_n * d.lat_rows * d.lat_words;
+  VA_ROLL
   for (int t = threadIdx.x; t < d.max_n * d.lat_rows * d.lat_words; t += (int)blockDim.x) latb[t] = 0u;
   TT(12);
   if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -972,9 +1051,12 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
   const int R = min(max(h.n_rows, 0), d.rmax), C = min(max(h.n_cols, 0), d.cmax);
   const int NP = (plane_y && plane_occ) ? min(max(h.n_plane, 0), d.rmax) : 0;
 
+  VA_ROLL
   for (int t = threadIdx.x; t < PL; t += (int)blockDim.x) s.plane_owner[t] = -1;
+  VA_ROLL
   for (int t = threadIdx.x; t < T * cw; t += (int)blockDim.x) { s.occ[t] = 0; s.art[t] = 0; }
   if (threadIdx.x == 0) {
+    VA_ROLL
     for (int q = 0; q < S_COUNT; ++q) s.sc[q] = 0;
     s.sc[S_USE_EASY] = h.use_easy;
     s.sc[S_SEL] = -1;
@@ -986,11 +1068,13 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
   }
   __syncthreads();
   // bit-pack rows: one thread per (row, word)
+  VA_ROLL
   for (int t = threadIdx.x; t < (R + NP) * cw; t += (int)blockDim.x) {
     const int id = t / cw, w = t - id * cw;
     const uint8_t* src = (id < R) ? occ + ((size_t)b * d.rmax + id) * d.cmax
                                   : plane_occ + ((size_t)b * d.rmax + (id - R)) * d.cmax;
     unsigned vo = 0, va_ = 0;
+    VA_ROLL
     for (int q = 0; q < 32; ++q) {
       const int c = 32 * w + q;
       if (c >= C) break;
@@ -1001,6 +1085,7 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
     s.occ[t] = vo;
     s.art[t] = va_;
   }
+  VA_ROLL
   for (int id = threadIdx.x; id < R + NP; id += (int)blockDim.x) {
     s.row_y[id] = (id < R) ? row_y[(size_t)b * d.rmax + id] : plane_y[(size_t)b * d.rmax + (id - R)];
     s.row_attr[id] = (id < R) ? row_attr[(size_t)b * d.rmax + id] : -1;
@@ -1010,11 +1095,13 @@ grid_mode_kernel(Dims d, const va_grid_input* __restrict__ hdr, const int* __res
   if (threadIdx.x == 0) {
     // grid_lookup rows: explicit plane rows, else the list rows in order (later rows override)
     const int lo = NP ? R : 0, hi = NP ? R + NP : R;
+    VA_ROLL
     for (int id = lo; id < hi; ++id) {
       const int y = s.row_y[id];
       if (y < 0 || y % gs != 0 || y / gs >= PL) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW | VA_FLAG_EMPTY; break; }
       s.plane_owner[y / gs] = id;
     }
+    VA_ROLL
     for (int id = 0; id < R && NP; ++id) {   // every list row must have a lookup row
       const int y = s.row_y[id];
       if (y < 0 || y % gs != 0 || y / gs >= PL || s.plane_owner[y / gs] < 0) { s.sc[S_FLAGS] |= VA_FLAG_OVERFLOW | VA_FLAG_EMPTY; break; }
@@ -1040,7 +1127,7 @@ cudaError_t launch_tail(const Dims& d, const int* counts, int B, const Scratch& 
                         const int* sel, uint8_t* records, cudaStream_t st) {
   // shared memory: the tail's own tables, then the contour step's per-row scratch (+ the run table when it fits)
   const size_t own = (tail_smem_bytes(d) + 15) & ~(size_t)15;
-  const size_t cc_smem = cc::row_layout(d.H).total + cc::run_layout(2048).total;
+  const size_t cc_smem = cc::row_layout(d.H).total + kContourGridSmem + cc::run_layout(2048).total;
   const size_t smem = own + cc_smem;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
