@@ -510,7 +510,7 @@ def run_ours(args, wl):
     if world == 1 and args.workload == "cfg1" and not args.no_extras:
         line["cfg2"] = measure_cfg2(local, peak)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=96)
+        line["cpu_baseline"] = cpu_baseline(wl, frames_per_core=768)      # about 10-15 s of work on every host core
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -599,6 +599,26 @@ def measure_latency(wl, device, iters: int = 1000):
     except Exception as e:  # graph capture is an optimisation of the measurement, not of the path
         out["cuda_graph"] = {"error": str(e)[:120]}
     out["what"] = "B=1, grid-only, launch -> record in pinned host memory (perf_counter around run + D2H + sync)"
+    # the drop-in FrameProcessor.__call__ (reference FrameProcessor.py:301-360) on the same frame: model shim returning the
+    # head tensors already on the GPU, record -> peaks -> array A* on the host; Grid objects are built on first access only
+    try:
+        import numpy as np
+        from vision_assist_b200.FrameProcessor import FrameProcessor, HeadOutputModel
+        p1, c1, b1 = protos[0], coefs[0, :n].contiguous(), boxes[0, :n].contiguous()
+        FrameProcessor._instance, FrameProcessor._initialized = None, False
+        fp = FrameProcessor(HeadOutputModel(lambda frame: (p1, c1, b1)))
+        frame = np.zeros((H, W, 3), np.uint8)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            lazy = stats(lambda: fp(frame))
+            full = stats(lambda: (fp(frame), fp.grids))
+        out["dropin_call"] = {"p50_us": lazy["p50_us"], "p99_us": lazy["p99_us"],
+                              "with_grid_objects_p50_us": full["p50_us"],
+                              "what": "FrameProcessor(frame) -> peaks + A* paths (array port), no Grid objects; "
+                                      "with_grid_objects also reads .grids (the reference's pydantic object view)"}
+        FrameProcessor._instance, FrameProcessor._initialized = None, False
+    except Exception as e:
+        out["dropin_call"] = {"error": str(e)[:160]}
     return out
 
 

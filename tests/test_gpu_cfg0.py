@@ -76,8 +76,11 @@ def test_cfg0_mockcamera_clip_through_dropin(tmp_path):
                 case = golden_case(z, k)
                 goldenio.assert_result_matches(rec.as_dict(), case, f"cfg0 frame {idx}")
                 assert [(p.x, p.y) for p in peaks] == [tuple(int(v) for v in q) for q in case["peaks"]]
-                # the object view the reference's host stages consume
-                assert len(fp.grids) == case["R"] and np.array_equal(fp.np_grids, case["occ"] & 1)
+                # the object view the reference's host stages consume is built on first access only
+                assert fp._pending_record is rec and np.array_equal(fp.np_grids, case["occ"] & 1)
+                assert len(fp.grids) == case["R"] and fp._pending_record is None
+                assert fp.protrusion_detector.grids is fp.grids
+                assert all(fp.grid_lookup[(g.coords.x, g.coords.y)].col == g.col for g in fp.grids[-1])
                 # A* paths and costs: array port on the GPU record vs the reference's PathFinder + similarity filter
                 assert_paths_match(z, k, fp.array_paths, f"cfg0 frame {idx}")
                 k += 1

@@ -81,8 +81,9 @@ class FrameProcessor:
             self.debug = debug
             self.imshow = imshow
             self.frame: Optional[np.ndarray] = None
-            self.grids: list = []
-            self.grid_lookup: dict = {}
+            self._pending_record: FrameRecord | None = None   # record whose Grid objects have not been built yet
+            self._grids: list = []
+            self._grid_lookup: dict = {}
             self.np_grids: np.ndarray = np.empty((0, 0), dtype=np.uint8)
             self.protrusion_detector = ProtrusionDetector(debug=debug, imshow=imshow)
             self.frame_record: FrameRecord | None = None
@@ -94,6 +95,38 @@ class FrameProcessor:
             self.get_closest_grid_to_point = None
             self.Path = None
             self.array_paths: list = []          # [(cells [(x, y), ...], cost)] of the last frame (array A*, no host stages)
+
+    # -- grids / grid_lookup: the reference's object view of the last frame, built from the GPU record on first access
+    #    (about a thousand validated Grid / Coordinate objects per frame cost milliseconds, the record 60 us) ---------
+    def _materialise(self) -> None:
+        rec = self._pending_record
+        if rec is not None:
+            self._pending_record = None
+            self._grids, self._grid_lookup, _ = record_to_objects(rec, config.grid_size)
+            self.protrusion_detector.set_precomputed(self._grids, rec.peaks)
+
+    @property
+    def grids(self) -> list:
+        self._materialise()
+        return self._grids
+
+    @grids.setter
+    def grids(self, value: list) -> None:
+        self._pending_record = None
+        self._grids = value
+
+    @property
+    def grid_lookup(self) -> dict:
+        self._materialise()
+        return self._grid_lookup
+
+    @grid_lookup.setter
+    def grid_lookup(self, value: dict) -> None:
+        self._pending_record = None
+        self._grid_lookup = value
+
+    def _has_grid(self) -> bool:
+        return self._pending_record is not None or bool(self._grids)
 
     def bind_host_stages(self, path_finder=None, path_analyser=None, path_visualiser=None,
                          get_closest_grid_to_point=None, Path=None) -> None:
@@ -171,9 +204,9 @@ class FrameProcessor:
             if rec.R == 0:
                 return                                                                       # :99-101
             self.frame_record = rec
-            self.grids, self.grid_lookup, self.np_grids = record_to_objects(rec, gs)
+            self.np_grids = rec.np_grids
+            self._pending_record = rec                  # grids / grid_lookup are built on first access
             self._penalties_ready = True
-            self.protrusion_detector.set_precomputed(self.grids, rec.peaks)
 
     # -- FrameProcessor.py:173-182 ---------------------------------------------------------------
     def _calculate_penalties(self) -> None:
@@ -296,17 +329,25 @@ class FrameProcessor:
         self.frame = frame
         results = self.model.predict(frame, conf=0.5, verbose=self.verbose)
         self._extract_grid_information(results)
-        if not self.grids:
+        if not self._has_grid():
             return (self.frame, []) if self.debug else []
         self._calculate_penalties()
+        if self.path_finder is None or self.path_analyser is None:
+            # no host stages bound: the peaks of the record go back to the caller, the paths come from the array A*
+            # (kept in self.array_paths) - no Grid object is built unless somebody reads .grids / .grid_lookup
+            rec = self.frame_record
+            if self._pending_record is not None and rec is not None:
+                protrusion_peaks = self.protrusion_detector.from_record(frame, rec.peaks, lambda: self.grids)
+            else:
+                protrusion_peaks = self.protrusion_detector(frame, self.grids, self.grid_lookup)
+            if not protrusion_peaks:
+                print("No protrusions detected.")
+            self.array_paths = self._find_paths_arrays()
+            return (self.frame, protrusion_peaks) if self.debug else protrusion_peaks
         graph = self._create_graph()
         protrusion_peaks = self.protrusion_detector(frame, self.grids, self.grid_lookup)
         if not protrusion_peaks:
             print("No protrusions detected.")
-        if self.path_finder is None or self.path_analyser is None:
-            # no host stages bound: paths from the array A* (kept in self.array_paths), the peaks go back to the caller
-            self.array_paths = self._find_paths_arrays()
-            return (self.frame, protrusion_peaks) if self.debug else protrusion_peaks
         paths = self._find_paths(protrusion_peaks, graph)
         final_answer = self.path_analyser(frame.shape[0], frame.shape[1], paths)
         if self.debug:

@@ -28,7 +28,7 @@ class ProtrusionDetector:
         if not self._initialized:
             self._initialized = True
             self.frame = None
-            self.grids = None
+            self._grids = None                   # list[list[Grid]], or a callable that builds it (lazy object view)
             self.height = 0
             self.width = 0
             self.binary = None
@@ -38,6 +38,27 @@ class ProtrusionDetector:
 
     def bind_engine(self, engine: MaskGridEngine) -> None:
         self._engine = engine
+
+    @property
+    def grids(self):
+        if callable(self._grids):
+            self._grids = self._grids()
+        return self._grids
+
+    @grids.setter
+    def grids(self, value) -> None:
+        self._grids = value
+
+    def from_record(self, frame: np.ndarray, peaks: np.ndarray, grids_source) -> list:
+        """__call__ for a frame whose peaks the fused kernel already produced; `.grids` is built from `grids_source()`
+        only if somebody reads it."""
+        Coordinate, _, _ = models.classes()
+        self.frame = frame
+        self._grids = grids_source
+        self.height, self.width = frame.shape[:2]
+        self.frames_processed += 1
+        self._precomputed = None
+        return [Coordinate(x=int(x), y=int(y)) for x, y in peaks]
 
     def set_precomputed(self, grids, peaks: np.ndarray) -> None:
         """FrameProcessor hands over the peaks the fused kernel already produced for `grids`."""
