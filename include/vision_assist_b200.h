@@ -197,9 +197,11 @@ VA_API int va_grid_to_penalty_peaks(va_ctx* ctx, const va_grid_input* hdr, const
  *   pred [B][4 + nc + K][A] f32: rows cx, cy, w, h, nc class confidences, K mask coefficients; A anchors
  *   outputs in the layout va_run_fused takes: coefs_out [B][max_n][K], boxes_out [B][max_n][4] (xyxy, input pixels),
  *   counts_out [B]; conf_out [B][max_n] f32 and cls_out [B][max_n] i32 may be NULL.  Slots >= counts are zero.
- *   max_det <= max_n survivors are kept (the reference's max_det is 300: choose max_n accordingly).
- *   The kernel holds 512 candidates per image.  When more anchors pass conf_thres it keeps the 512 best by (score,
- *   anchor order) - exact whenever max_det of them survive; otherwise counts_out[b] = -(number of candidates). */
+ *   max_det <= max_n <= 32 survivors are kept: the mask path carries at most 32 instances per frame (the reference's
+ *   max_det default is 300; a frame with more than max_n survivors keeps the max_n best, like max_det = max_n).
+ *   Any number of candidates: they are visited in tiles of 512 in order of (score descending, anchor ascending), each
+ *   tile thinned by the survivors of the earlier ones, until max_det survive or the best 30000 (ops.py max_nms) are
+ *   used up - the reference's result, not an approximation.  counts_out[b] is never negative. */
 typedef struct va_nms_params {
   float conf_thres;   /* 0.5 in FrameProcessor.py:322 */
   float iou_thres;    /* ultralytics predict default 0.7 */
@@ -210,6 +212,13 @@ typedef struct va_nms_params {
 } va_nms_params;
 VA_API int va_nms(va_ctx* ctx, const float* pred, int32_t A, const va_nms_params* prm, int32_t B, float* coefs_out,
                   float* boxes_out, float* conf_out, int32_t* cls_out, int32_t* counts_out, void* stream);
+
+/* ops.scale_boxes(img1_shape, boxes, img0_shape) + clip_boxes (ops.py:139-174, :367-385; padding = True, xyxy): the
+ * kept boxes of va_nms, moved from the letterboxed model input (img1) back to the original frame (img0) as
+ * SegmentationPredictor.postprocess does for Results.boxes AFTER process_mask has used the unscaled ones.
+ *   boxes [B][max_n][4] f32, counts [B] -> boxes_out [B][max_n][4] (may alias boxes); slots >= counts are zero. */
+VA_API int va_scale_boxes(va_ctx* ctx, const float* boxes, const int32_t* counts, int32_t B, int32_t img1_h, int32_t img1_w,
+                          int32_t img0_h, int32_t img0_w, float* boxes_out, void* stream);
 
 /* Multi-GPU record sink (frames are sharded across the GPUs of one box, only the per-frame records are
  * gathered).  Instead of a collective, every rank's tail kernel stores its records straight into the gathering

@@ -65,3 +65,17 @@ def nms_image(pred: np.ndarray, conf_thres: float, iou_thres: float, nc: int, ma
 
 def nms_batch(pred: np.ndarray, **kw) -> list:
     return [nms_image(p, **kw) for p in pred]
+
+
+def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape) -> np.ndarray:
+    """ops.scale_boxes (ops.py:139-174; ratio_pad None, padding True, xyxy) + clip_boxes (:367-385) on fp32 rows [n, 4]:
+    gain / pad in Python arithmetic, the tensor arithmetic in fp32 (torch CPU: boxes -= pad; boxes /= fp32(gain); clamp)."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    out = np.array(boxes, F, copy=True)
+    out[..., 0] -= F(pad[0]); out[..., 2] -= F(pad[0])
+    out[..., 1] -= F(pad[1]); out[..., 3] -= F(pad[1])
+    out[..., :4] /= F(gain)
+    out[..., 0] = out[..., 0].clip(0, img0_shape[1]); out[..., 2] = out[..., 2].clip(0, img0_shape[1])
+    out[..., 1] = out[..., 1].clip(0, img0_shape[0]); out[..., 3] = out[..., 3].clip(0, img0_shape[0])
+    return out

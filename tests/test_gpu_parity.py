@@ -414,21 +414,34 @@ def test_nms_golden_and_oracle():
         b2[b, :k] = torch.from_numpy(rows[:, :4]).cuda(); c2[b, :k] = torch.from_numpy(rows[:, 6:]).cuda()
     rec_b, masks_b = eng.run(protos, c2, b2, torch.tensor([r.shape[0] for r in want], dtype=torch.int32).cuda())
     assert torch.equal(rec_a, rec_b)
-    # more candidates than the kernel holds (512): the best 512 by (score, anchor order) are enough whenever max_det
-    # of them survive - exact; otherwise the overflow is reported, not guessed
+    # more candidates than one 512-candidate tile: tiles in order of (score, anchor order), each thinned by the survivors
+    # of the earlier ones - the reference's result for any number of candidates
     g = torch.Generator().manual_seed(99)
-    dense = torch.rand(3, 37, 4000, generator=g)
+    dense = torch.rand(5, 37, 4000, generator=g)
     dense[:, :2] *= 600
     dense[:, 2:4] = 8 + dense[:, 2:4] * 60
     dense[0, 4] = 0.9                                        # all tied: anchor order decides
     dense[1, 4] = 0.5 + 0.5 * torch.rand(4000, generator=g)  # distinct scores
-    dense[2, 4] = torch.round((0.5 + 0.5 * torch.rand(4000, generator=g)) * 64) / 64   # many ties on the threshold key
+    dense[2, 4] = torch.round((0.5 + 0.5 * torch.rand(4000, generator=g)) * 64) / 64   # many ties on the tile boundaries
+    dense[3, :4] = torch.tensor([300., 300., 100., 100.])[:, None]                      # every box identical: one survivor,
+    dense[3, 4] = 0.9                                                                   # found after visiting every tile
+    dense[4, :2] = 300 + 40 * torch.rand(2, 4000, generator=g)                          # one crowded spot: few survivors,
+    dense[4, 2:4] = 80 + 40 * torch.rand(2, 4000, generator=g)                          # spread over many tiles
+    dense[4, 4] = torch.round((0.5 + 0.5 * torch.rand(4000, generator=g)) * 16) / 16
     want = onms.nms_batch(dense.numpy(), conf_thres=0.5, iou_thres=0.7, nc=1, max_det=32)
+    assert want[3].shape[0] == 1 and 1 < want[4].shape[0] < 32
     check(dense, want, 0.5, 0.7, 1, 32)
-    same = torch.rand(1, 37, 4000, generator=g)
-    same[:, :4] = torch.tensor([300., 300., 100., 100.])[None, :, None]        # every box identical: one survivor
-    same[:, 4] = 0.9
-    assert int(eng.nms(same.cuda())[4][0]) == -4000
+    check(dense, onms.nms_batch(dense.numpy(), conf_thres=0.5, iou_thres=0.3, nc=1, max_det=32), 0.5, 0.3, 1, 32)
+    check(dense, onms.nms_batch(dense.numpy(), conf_thres=0.5, iou_thres=0.7, nc=1, max_det=5), 0.5, 0.7, 1, 5)
+    # scale_boxes: the kept boxes back in original-frame pixels (ops.py:139-174)
+    coefs, boxes, conf, cls, counts = eng.nms(dense.cuda(), conf_thres=0.5, iou_thres=0.7, nc=1)
+    for img1, img0 in [((640, 640), (720, 1280)), ((640, 640), (480, 640)), ((640, 640), (333, 517)), ((384, 640), (1080, 1920))]:
+        got = eng.scale_boxes(boxes, counts, img1, img0).cpu().numpy()
+        for b in range(dense.shape[0]):
+            k = int(counts[b])
+            want_b = onms.scale_boxes(img1, boxes[b, :k].cpu().numpy(), img0)
+            assert np.array_equal(got[b, :k].view(np.uint32), want_b.view(np.uint32)), (img1, img0, b)
+            assert not got[b, k:].any()
 
 
 @pytest.mark.parametrize("H,W,mh,mw,n,B", [(640, 640, 160, 160, 8, 256), (640, 640, 160, 160, 32, 48), (1080, 1920, 160, 160, 32, 8)])

@@ -142,3 +142,15 @@ def test_nms_matches_vendored_ops(ref):
         for w, m in zip(want, got):
             assert tuple(w.shape) == m.shape, seed
             assert np.array_equal(w.numpy().view(np.uint32), m.view(np.uint32)), seed
+
+
+def test_scale_boxes_matches_vendored_ops(ref):
+    """oracle.nms.scale_boxes against ops.scale_boxes + clip_boxes (ops.py:139-174): letterboxed 640x640 input back to
+    frames of several shapes (gain < 1, > 1, pads that round either way), boxes partly outside the frame - bit-exact."""
+    g = torch.Generator().manual_seed(5)
+    for (h1, w1), (h0, w0) in [((640, 640), (720, 1280)), ((640, 640), (1080, 1920)), ((640, 640), (480, 640)), ((384, 640), (1080, 1920)),
+                               ((640, 640), (640, 640)), ((640, 640), (333, 517)), ((640, 480), (1000, 601)), ((320, 320), (97, 131))]:
+        boxes = torch.rand(64, 4, generator=g) * torch.tensor([w1, h1, w1, h1]) * 1.2 - 0.1 * max(h1, w1)
+        want = ref.ops.scale_boxes((h1, w1), boxes.clone(), (h0, w0)).numpy()
+        got = onms.scale_boxes((h1, w1), boxes.numpy(), (h0, w0))
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), ((h1, w1), (h0, w0))

@@ -163,8 +163,6 @@ class FrameProcessor:
                 coefs, boxes, _, _, counts = eng.nms(result.pred.contiguous()[None], conf_thres=result.conf,
                                                      iou_thres=result.iou, nc=result.nc)
                 n = int(counts[0])
-                if n < 0:
-                    raise RuntimeError(f"va_nms: {-n} candidates above the confidence threshold exceed the kernel's capacity")
                 if n == 0:
                     continue
                 records, _ = eng.run(result.protos.contiguous()[None], coefs, boxes, counts, write_masks=False)

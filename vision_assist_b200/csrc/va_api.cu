@@ -309,8 +309,26 @@ extern "C" int va_nms(va_ctx* c, const float* pred, int32_t A, const va_nms_para
   if (B == 0) return VA_OK;
   VA_ON_DEVICE(c);
   const float off = prm->agnostic ? 0.f : (float)prm->max_wh;
-  VA_CUDA(c, launch_nms(pred, A, prm->nc, c->cfg.K, prm->conf_thres, prm->iou_thres, off, prm->max_det, c->cfg.max_n, B,
+  constexpr int kMaxNms = 30000;      // ops.non_max_suppression's max_nms default (ops.py:225); predict does not change it
+  VA_CUDA(c, launch_nms(pred, A, prm->nc, c->cfg.K, prm->conf_thres, prm->iou_thres, off, prm->max_det, c->cfg.max_n, kMaxNms, B,
                         coefs_out, boxes_out, conf_out, cls_out, counts_out, (cudaStream_t)stream));
+  c->last_launches = 1;
+  return VA_OK;
+}
+
+extern "C" int va_scale_boxes(va_ctx* c, const float* boxes, const int32_t* counts, int32_t B, int32_t img1_h, int32_t img1_w,
+                              int32_t img0_h, int32_t img0_w, float* boxes_out, void* stream) {
+  if (!c) return VA_ERR_INVALID;
+  if (!boxes || !counts || !boxes_out) { set_err(c, "va_scale_boxes: null pointer"); return VA_ERR_INVALID; }
+  if (B < 0 || B > c->cfg.max_batch) { set_err(c, "batch %d exceeds max_batch %d", B, c->cfg.max_batch); return VA_ERR_CAPACITY; }
+  if (img1_h < 1 || img1_w < 1 || img0_h < 1 || img0_w < 1) { set_err(c, "va_scale_boxes: image shapes must be positive"); return VA_ERR_INVALID; }
+  if (B == 0) return VA_OK;
+  VA_ON_DEVICE(c);
+  // ops.py:158-163 in Python arithmetic: doubles, round() = round half to even
+  const double gain = std::min((double)img1_h / img0_h, (double)img1_w / img0_w);
+  const double pad_x = std::nearbyint((img1_w - img0_w * gain) / 2 - 0.1), pad_y = std::nearbyint((img1_h - img0_h * gain) / 2 - 0.1);
+  VA_CUDA(c, launch_scale_boxes(boxes, counts, c->cfg.max_n, B, (float)pad_x, (float)pad_y, (float)gain, (float)img0_w, (float)img0_h,
+                                boxes_out, (cudaStream_t)stream));
   c->last_launches = 1;
   return VA_OK;
 }

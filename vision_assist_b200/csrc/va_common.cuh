@@ -97,8 +97,10 @@ size_t tail_smem_bytes(const Dims& d);
 
 // candidate filter + NMS on raw head output (va_nms.cu); counts_out[b] < 0: more than the 512 candidates it holds
 cudaError_t launch_nms(const float* pred, int A, int nc, int nm, float conf_thres, float iou_thres, float class_offset,
-                       int max_det, int max_n, int B, float* coefs_out, float* boxes_out, float* conf_out, int* cls_out,
+                       int max_det, int max_n, int max_nms, int B, float* coefs_out, float* boxes_out, float* conf_out, int* cls_out,
                        int* counts_out, cudaStream_t st);
+cudaError_t launch_scale_boxes(const float* boxes, const int* counts, int max_n, int B, float pad_x, float pad_y, float gain,
+                               float w0, float h0, float* out, cudaStream_t st);
 
 // tcgen05 / TMA fused kernel (va_fused_tc.cu)
 struct FusedPlan;  // opaque, owned by the context

@@ -178,7 +178,7 @@ class MaskGridEngine:
             max_det: int | None = None, agnostic: bool = False, max_wh: int = 7680):
         """ops.non_max_suppression (+ torchvision nms) on the raw head output `pred` [B, 4 + nc + K, A] ->
         (coefs [B,max_n,K], boxes [B,max_n,4] xyxy, conf [B,max_n], cls [B,max_n] i32, counts [B] i32): the first
-        three in exactly the layout `run()` takes.  Raises if an image has more candidates than the kernel holds."""
+        three in exactly the layout `run()` takes.  Any number of candidates (tiles of 512 in score order)."""
         if not (pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3):
             raise ValueError("expected a contiguous float32 CUDA tensor [B, 4 + nc + K, A]")
         B, Cc, A = pred.shape
@@ -197,6 +197,20 @@ class MaskGridEngine:
                                     C.c_void_p(boxes.data_ptr()), C.c_void_p(conf.data_ptr()), C.c_void_p(cls.data_ptr()),
                                     C.c_void_p(counts.data_ptr()), self._stream()))
         return coefs, boxes, conf, cls, counts
+
+    def scale_boxes(self, boxes: torch.Tensor, counts: torch.Tensor, img1_shape, img0_shape) -> torch.Tensor:
+        """ops.scale_boxes(img1_shape, boxes, img0_shape) + clip_boxes (ops.py:139-174) on `nms()`'s boxes [B,max_n,4]:
+        letterboxed model input (h, w) -> original frame (h, w).  Returns a new tensor; slots >= counts are zero."""
+        if not (boxes.is_cuda and boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.shape[1:] == (self.max_n, 4)):
+            raise ValueError(f"expected a contiguous float32 CUDA tensor [B, {self.max_n}, 4]")
+        B = boxes.shape[0]
+        if counts.shape != (B,) or counts.dtype != torch.int32 or not counts.is_cuda:
+            raise ValueError("counts must be an int32 CUDA tensor [B]")
+        out = torch.empty_like(boxes)
+        self._check(self.lib.va_scale_boxes(self._ctx, C.c_void_p(boxes.data_ptr()), C.c_void_p(counts.data_ptr()), B,
+                                            int(img1_shape[0]), int(img1_shape[1]), int(img0_shape[0]), int(img0_shape[1]),
+                                            C.c_void_p(out.data_ptr()), self._stream()))
+        return out
 
     def run(self, protos, coefs, boxes, counts, masks_out: torch.Tensor | None = None,
             records_out: torch.Tensor | None = None, write_masks: bool = True, records_ptr: int | None = None):
