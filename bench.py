@@ -362,8 +362,9 @@ def run_stream(eng, wl, rank, world, sink_factory):
             dist.barrier()
             sink.close()
     out["non_simple_frames_sampled"] = non_simple
-    out["gather"] = ("tail kernels store into rank 0's peer-mapped buffer (NVLink), one flag per rank and chunk; rank 0 waits for the "
-                     "last flags inside the clock") if world > 1 else "single GPU: records written to the full-stream buffer"
+    out["gather"] = ("every chunk's records are put into rank 0's peer-mapped buffer by a copy engine over NVLink (side stream), one "
+                     "flag per rank and chunk; rank 0 waits for the last flags inside the clock") if world > 1 else \
+        "single GPU: records written to the full-stream buffer"
     return out
 
 
