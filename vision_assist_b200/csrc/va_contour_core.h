@@ -133,17 +133,28 @@ VA_HD uint32_t rowsum_pack(int cnt, int first, int last) { return (uint32_t)cnt 
 
 struct RowRun { int cnt, a, b; };   // pixels set in the row, first and last set pixel (a > b when empty)
 
+// fold block k's summary into the row's (blocks in ascending order)
+VA_HD void rowsum_accumulate(RowRun& r, uint32_t v, int k) {
+  const int c = (int)(v & 0xffu);
+  if (c) {
+    if (r.cnt == 0) r.a = k * kRowBlock + (int)((v >> 8) & 0x7fu);
+    r.b = k * kRowBlock + (int)((v >> 15) & 0x7fu);
+    r.cnt += c;
+  }
+}
 VA_HD RowRun rowsum_combine(const uint32_t* e, int nblk) {
   RowRun r; r.cnt = 0; r.a = 1 << 30; r.b = -1;
   VA_ROLL
-  for (int k = 0; k < nblk; ++k) {
-    const uint32_t v = e[k];
-    const int c = (int)(v & 0xffu);
-    if (c) {
-      if (r.cnt == 0) r.a = k * kRowBlock + (int)((v >> 8) & 0x7fu);
-      r.b = k * kRowBlock + (int)((v >> 15) & 0x7fu);
-      r.cnt += c;
-    }
+  for (int k0 = 0; k0 < nblk; k0 += 8) {
+    uint32_t v[8];                                     // all loads of a batch are issued before the first use
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < nblk) ? e[k0 + j] : 0u;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; ++j) rowsum_accumulate(r, v[j], k0 + j);
   }
   return r;
 }

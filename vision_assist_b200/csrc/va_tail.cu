@@ -35,7 +35,7 @@ constexpr size_t kContourGridSmem = 16 * 1024;   // contour step: bit rows of th
 
 // developer diagnostic (VA_TAIL_TIMING=1): cycle stamps of block 0 at the phase boundaries, printed by the kernel
 constexpr int kTailDebugFlag = 1 << 30;
-__device__ long long g_tail_t[16];
+__device__ long long g_tail_t[24];
 #define TT(k) do { if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 64))) g_tail_t[(k) % 100] = clock64(); } while (0)
 
 struct TailSmem {
@@ -739,17 +739,19 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     s_area[i] = v.area;
   }
   __syncthreads();
+  TT(16);
   // ---- contour step, part 1: certificate (va_contour_core.h) - every mask row of an instance one run, consecutive
   //      rows touching => one hole-free component whose polygon area follows from the run ends in closed form.
   //      Reads only the per-(row, block) summaries the mask kernel wrote.  Thread groups of >= 32 share the instances. ----
   {
-    // Work items = (instance, block of 32 consecutive mask rows), numbered through a prefix sum over the instances and
-    // dealt to the warps round-robin: a frame with one tall mask and many small ones keeps every warp busy.
+    // Work items = (instance, block of 31 consecutive mask rows), numbered through a prefix sum over the instances and
+    // dealt to the warps round-robin: a frame with one tall mask and many small ones keeps every warp busy.  Lane 0 of
+    // an item holds the row ABOVE the block (every lane gets its previous row by one shuffle), lanes 1..31 are certified.
     __shared__ int s_task0[kMaxInst + 1];
     if (threadIdx.x < 32) {
       const int i = threadIdx.x;
       const InstStats v = s_stats[i];
-      int cnt = (i < n && v.area) ? (v.maxy - v.miny + 32) >> 5 : 0;
+      int cnt = (i < n && v.area) ? (v.maxy - v.miny + 31) / 31 : 0;
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (i >= o) incl += u; }
@@ -759,12 +761,16 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = (int)threadIdx.x >> 5, nwarps = (int)blockDim.x >> 5;
     const int ntask = s_task0[kMaxInst];
-    constexpr int kU = 4;                                              // work items in flight per warp: their loads overlap
+    TT(17);
+    // kU work items in flight per warp and all summary words of a chunk loaded before the first is used: the pass is a
+    // chain of global round trips, so their number per warp is what counts
+    constexpr int kU = 3, kChunk = 8;
     VA_ROLL
     for (int t0 = warp; t0 < ntask; t0 += kU * nwarps) {
       int inst_i[kU], yy[kU];
       bool live[kU];
-      cc::RowRun cur[kU], prv[kU];
+      cc::RowRun cur[kU];
+      const uint32_t* rowp[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int t = t0 + u * nwarps;
@@ -773,13 +779,24 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
         while (i + 1 < n && s_task0[i + 1] <= t) ++i;                  // instance of task t (n <= 32: a short scan)
         inst_i[u] = i;
         const InstStats v = s_stats[i];
-        yy[u] = v.miny + 32 * (t - s_task0[i]) + lane;
-        live[u] = t < ntask && yy[u] <= v.maxy;
+        yy[u] = v.miny + 31 * (t - s_task0[i]) + lane - 1;
+        live[u] = t < ntask && yy[u] >= v.miny && yy[u] <= v.maxy;
         cur[u].cnt = 0; cur[u].a = 0; cur[u].b = -1;
-        prv[u] = cur[u];
-        const uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
-        if (live[u]) cur[u] = cc::rowsum_combine(rs + (size_t)yy[u] * d.nblk, d.nblk);
-        if (live[u] && lane == 0 && yy[u] > v.miny) prv[u] = cc::rowsum_combine(rs + (size_t)(yy[u] - 1) * d.nblk, d.nblk);
+        rowp[u] = tc.rowsum + (((size_t)b * d.max_n + i) * d.H + (live[u] ? yy[u] : 0)) * d.nblk;
+      }
+      VA_ROLL
+      for (int k0 = 0; k0 < d.nblk; k0 += kChunk) {
+        uint32_t raw[kU][kChunk];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) raw[u][j] = (live[u] && k0 + j < d.nblk) ? rowp[u][k0 + j] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) cc::rowsum_accumulate(cur[u], raw[u][j], k0 + j);
+        }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
@@ -790,9 +807,8 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
         prev.cnt = __shfl_up_sync(0xffffffffu, cur[u].cnt, 1);
         prev.a = __shfl_up_sync(0xffffffffu, cur[u].a, 1);
         prev.b = __shfl_up_sync(0xffffffffu, cur[u].b, 1);
-        if (lane == 0) prev = prv[u];
         int ok = 1, npx = 0, l = 0, minx = INT_MAX, maxx = -1;
-        if (live[u]) {
+        if (live[u] && lane > 0) {
           const cc::CertTerms ct = cc::cert_row(cur[u], prev, yy[u] == v.miny, yy[u] == v.maxy);
           ok = ct.ok; npx = ct.n; l = ct.l; minx = ct.minx; maxx = ct.maxx;
         }
@@ -809,16 +825,27 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
       }
     }
     __syncthreads();
+    TT(18);
     int n_pending = 0;
     VA_ROLL
     for (int i = 0; i < n; ++i) {
       const InstStats v = s_stats[i];
       if (v.area == 0 || !s_cert[i][0]) continue;
       // certified: put the instance's summaries back to their resting state (all zero)
-      uint32_t* rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk + (size_t)v.miny * d.nblk;
-      VA_ROLL
-      for (int t = threadIdx.x; t < (v.maxy - v.miny + 1) * d.nblk; t += (int)blockDim.x) rs[t] = 0u;
+      uint32_t* inst_rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
+      if (((d.H * d.nblk) & 3) == 0 && (d.H & 3) == 0) {
+        // groups of 4 rows are 16-byte aligned: vector stores (the rows added by the rounding are zero already)
+        const int y_lo = v.miny & ~3, y_hi = (v.maxy + 4) & ~3;
+        uint4* rs4 = reinterpret_cast<uint4*>(inst_rs + (size_t)y_lo * d.nblk);
+        VA_ROLL
+        for (int t = threadIdx.x; t < (y_hi - y_lo) * d.nblk / 4; t += (int)blockDim.x) rs4[t] = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        uint32_t* rs = inst_rs + (size_t)v.miny * d.nblk;
+        VA_ROLL
+        for (int t = threadIdx.x; t < (v.maxy - v.miny + 1) * d.nblk; t += (int)blockDim.x) rs[t] = 0u;
+      }
     }
+    TT(19);
     if (threadIdx.x < kMaxInst) {
       const int i = threadIdx.x;
       int state = cc::kEmpty, area2 = 0;
@@ -1026,6 +1053,8 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     const long long t0 = g_tail_t[0], te = clock64();
     printf("[va tail] reset: stats %lld lattice %lld rest %lld | t0 before barrier %lld t32 before %lld t32 after %lld (from t6)\n", g_tail_t[11] - g_tail_t[9], g_tail_t[12] - g_tail_t[11], te - g_tail_t[12],
            g_tail_t[13] - g_tail_t[6], g_tail_t[14] - g_tail_t[6], g_tail_t[15] - g_tail_t[6]);
+    printf("[va tail] certificate: stats %lld tasks %lld rows %lld (%d tasks) zero %lld rest %lld\n", g_tail_t[16] - g_tail_t[1], g_tail_t[17] - g_tail_t[16],
+           g_tail_t[18] - g_tail_t[17], 0, g_tail_t[19] - g_tail_t[18], g_tail_t[2] - g_tail_t[19]);
     printf("[va tail] cycles: wait %lld select %lld sample %lld band %lld | orphans %lld easy %lld | warp0: peaks %lld cells %lld"
            " | warp1 penalties %lld | end barrier %lld total %lld\n",
            g_tail_t[1] - t0, g_tail_t[2] - g_tail_t[1], g_tail_t[3] - g_tail_t[2], g_tail_t[4] - g_tail_t[3],
