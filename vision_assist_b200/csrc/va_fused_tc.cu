@@ -886,6 +886,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           const bool active = (g < NG) && (pair < npairs);
           const size_t inst = (size_t)it.b * d.max_n + it.i0 + i;
           RowPats<kGeneric> rp;                         // this lane's 16-pixel patterns of its dst rows (slot = row - Yfirst)
+          bool touched = false;                         // rp may hold a set pixel
           if (active) {
             uint8_t* M = kWriteMasks ? p.masks + inst * (size_t)d.H * d.W + 16 * g : nullptr;
             unsigned* lat = p.lattice + inst * (size_t)d.lat_rows * d.lat_words;
@@ -928,11 +929,13 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                   }
                   if (uni_pos) {
                     rp.fill(nrows);
+                    touched = true;
                     if (laty >= 0 && laty < Yfirst + nrows) lattice_row(ones, laty, 16 * g, d, lat);
                   }
                 } else {
                   // mixed signs: the exact 4-tap blend.  One compact, rolled loop (code size matters: the roles
                   // share the instruction cache).
+                  touched = true;
                   float hA[16], hB[16];
                   hinterp4(sA, hA, left);
                   hinterp4(sB, hB, left);
@@ -984,6 +987,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                   }
                   if (uni_pos) {
                     rp.fill(nrows);
+                    touched = true;
 #pragma unroll 1
                     for (int j = 0; j < nrows; ++j) {
                       const int tl = Yfirst + j - half;
@@ -993,6 +997,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
                 } else {
                   // horizontal pass for both proto rows (ATen: top = fma(a, l0x, fl(b * l1x))), then one vertical
                   // blend per dst row of the pair (out = fma(top, l0y, fl(bot * l1y)))
+                  touched = true;
                   float hA[16], hB[16];
 #pragma unroll
                   for (int px = 0; px < 16; ++px) {
@@ -1024,7 +1029,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
           // that are all ones / all zeros and their summaries are constants; only tasks that cross the outline
           // gather the 128-bit block patterns (four shuffles per row, the rows' chains interleaved).
           __syncwarp();
-          if (p.rowsum != nullptr) {                      // nullptr: developer A/B switch (VA_NO_ROWSUM=1), records are then meaningless
+          if (p.rowsum != nullptr && !kWriteMasks) {
+            const int nrow = active ? nrows : 0;
+#pragma unroll 1
+            for (int sidx = 0; sidx < nrow; ++sidx)
+              p.bits16[(inst * d.H + Yfirst + sidx) * (size_t)(2 * d.bit_words) + g] = (uint16_t)rp.get(sidx);
+          }
+          // a task with no set pixel at all (most of them: outside the box or below the threshold) leaves the summaries
+          // in their resting state - one vote instead of the classification below
+          if (p.rowsum != nullptr && __any_sync(0xffffffffu, touched)) {   // nullptr: developer A/B switch (VA_NO_ROWSUM=1), records are then meaningless
             const int nrow = active ? nrows : 0;
             const bool is_zero = rp.is_zero();
             const bool is_full = active && rp.is_full(nrow);
@@ -1037,11 +1050,6 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
             const bool ragged = (NG & 7) != 0;
             uint32_t* rs_inst = p.rowsum + inst * (size_t)d.H * d.nblk;
             LeaderStats ls;
-            if (!kWriteMasks) {
-#pragma unroll 1
-              for (int sidx = 0; sidx < nrow; ++sidx)
-                p.bits16[(inst * d.H + Yfirst + sidx) * (size_t)(2 * d.bit_words) + g] = (uint16_t)rp.get(sidx);
-            }
             if (!ragged && ((gzall | gfall) == 0x01010101u)) {
               if (gl == 0 && nrow > 0 && ((gfall >> (lane & 24)) & 1u)) {     // all-zero blocks: nothing to store (resting state)
                 const int blk = g >> 3;
