@@ -451,6 +451,27 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = B * world * e2e_steps / e2e_s
+    # separately labelled: the same call with fp16 prototypes in host memory (model run with half=True; the reference
+    # computes on protos.float(), ops.py:724).  Different input values than the fp32 line - not the headline.
+    e2e_f16 = None
+    if not args.no_extras:
+        ph = hp.half().pin_memory()
+        eng.run_host(ph, pc, pb, pn, records_out=hrec)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.run_host(ph, pc, pb, pn, records_out=hrec)
+        f16_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([f16_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            f16_s = float(t.item())
+        e2e_f16 = {"value": B * world * e2e_steps / f16_s, "unit": "frames/s",
+                   "h2d_bytes_per_step": hp.numel() * 2 + hc.numel() * 4 + hb.numel() * 4 + B * 4,
+                   "note": "va_run_fused_host_f16: fp16 prototypes in pinned host memory, widened exactly on the device "
+                           "(= protos.float()), then the fp32 path; inputs are the fp32 line's prototypes rounded to fp16"}
+        del ph
     ceiling_gbs = pcie_ceiling(256 << 20, world)
     e2e_ceiling = world * ceiling_gbs * 1e9 / ((in_bytes + B * 4) / B)      # frames/s if the copies ran at the ceiling
 
@@ -496,6 +517,7 @@ def run_ours(args, wl):
                                  "how": "pinned cudaMemcpyAsync of 256 MB x4, all ranks at once, slowest rank"},
                 "note": "va_run_fused_host: pinned host tensors in, records in host memory out; grid-only instantiation (h_masks_out = "
                         "NULL: the u8 masks are neither written nor returned); PCIe-bound: 3.3 MB of fp32 prototypes per frame"},
+        "e2e_fp16_protos": e2e_f16,
         "gpu_launches": m["launches_per_step"] * args.steps,
         "roofline": {"bound": "hbm", "kernel": "fused_tc_kernel" if eng.uses_tensor_core else "logits+upsample",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

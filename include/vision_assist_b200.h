@@ -173,6 +173,13 @@ VA_API int va_run_fused(va_ctx* ctx, const float* protos, const float* coefs, co
 VA_API int va_run_fused_host(va_ctx* ctx, const float* h_protos, const float* h_coefs, const float* h_boxes,
                       const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out);
 
+/* va_run_fused_host with fp16 prototypes in host memory (a model run with half = True emits them; the reference then
+ * computes on protos.float(), ops.py:724).  Half the host -> device bytes of the fp32 entry point - the path is
+ * PCIe-bound - and the same arithmetic: the prototypes are widened exactly on the device, everything after that is
+ * va_run_fused.  h_protos_f16 [B][K][mh][mw] IEEE binary16; K*mh*mw must be a multiple of 8. */
+VA_API int va_run_fused_host_f16(va_ctx* ctx, const uint16_t* h_protos_f16, const float* h_coefs, const float* h_boxes,
+                          const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out);
+
 /* Binary masks -> records.  Replaces FrameProcessor._extract_grid_information (+ penalties, peaks)
  * when the masks come from elsewhere (e.g. cv2.fillPoly of a polygon model output).
  *   masks [B][max_n][H][W] u8 (non-zero = inside), counts [B]

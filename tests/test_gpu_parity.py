@@ -524,6 +524,19 @@ def test_host_buffer_path_matches_device_path():
     _, masks_d = eng.run(*to_dev(protos, coefs, boxes, counts))
     assert np.array_equal(rec_host2.numpy(), rec_dev.cpu().numpy())
     assert np.array_equal(masks_h.numpy(), masks_d.cpu().numpy())
+    # fp16 prototypes in host memory (model run with half=True): widened exactly on the device, i.e. the fp32 path on
+    # protos.half().float() - what the reference computes (protos.float(), ops.py:724) - with half the PCIe bytes
+    ph = protos.half().pin_memory()
+    rec_f16 = eng.run_host(ph, coefs, boxes, counts)
+    rec_ref, _ = eng.run(*to_dev(ph.float(), coefs, boxes, counts), write_masks=False)
+    assert np.array_equal(rec_f16.numpy(), rec_ref.cpu().numpy())
+    for b_ in (0, 33, 69):                      # and against the oracle's process_mask on the widened prototypes
+        m_ = oma.process_mask(ph[b_].float(), coefs[b_], boxes[b_], (H, W)).numpy().astype(np.uint8)
+        up_ = oma.upsampled_logits(ph[b_].float(), coefs[b_], boxes[b_], (H, W)).numpy()
+        masks_b = eng.run(*to_dev(ph[b_:b_ + 1].float(), coefs[b_:b_ + 1], boxes[b_:b_ + 1], counts[b_:b_ + 1]))[1][0].cpu().numpy()
+        nd, nout = band_mismatch_report(masks_b, up_)
+        assert nout == 0
+        assert_record_equals_oracle(eng.decode(rec_f16[b_:b_ + 1])[0], opl.frame_from_masks(masks_b, 20, "contour"), f"f16 frame {b_}")
 
 
 def test_polygon_route_golden():

@@ -18,7 +18,7 @@ VA_IPC_HANDLE_BYTES = 64
 VA_FLAG_EMPTY, VA_FLAG_CENTRE_OOB, VA_FLAG_LIST_OOB, VA_FLAG_NON_SIMPLE, VA_FLAG_OVERFLOW, VA_FLAG_NO_POLYGON = 1, 2, 4, 8, 16, 32
 
 EXPORTS = ["va_abi_version", "va_create", "va_destroy", "va_last_error", "va_get_layout", "va_assemble_masks",
-           "va_run_fused", "va_run_fused_host", "va_mask_to_records", "va_grid_to_penalty_peaks", "va_nms", "va_scale_boxes",
+           "va_run_fused", "va_run_fused_host", "va_run_fused_host_f16", "va_mask_to_records", "va_grid_to_penalty_peaks", "va_nms", "va_scale_boxes",
            "va_last_launch_count", "va_uses_tensor_core", "va_profile_enable", "va_profile_read",
            "va_peer_alloc", "va_peer_open", "va_peer_close", "va_peer_free", "va_peer_put", "va_signal", "va_wait_flags"]
 
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     lib.va_assemble_masks.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.va_run_fused.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.va_run_fused_host.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.va_run_fused_host_f16.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     lib.va_mask_to_records.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.va_grid_to_penalty_peaks.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.va_nms.argtypes = [vp, vp, i32, C.POINTER(VaNmsParams), i32, vp, vp, vp, vp, vp, vp]

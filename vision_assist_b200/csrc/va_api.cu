@@ -1,4 +1,5 @@
 // C ABI of libva_sm100.so (include/vision_assist_b200.h): context, record layout, launch plumbing.
+#include <cuda_fp16.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -32,6 +33,7 @@ struct va_ctx {
   cudaStream_t s_in, s_compute, s_out;
   cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
   float* d_protos[2];
+  uint16_t* d_protos_h[2];     // fp16 staging of va_run_fused_host_f16 (allocated on first use)
   float* d_coefs[2];
   float* d_boxes[2];
   int* d_counts[2];
@@ -227,6 +229,7 @@ static void host_pipeline_destroy(va_ctx* c) {
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_protos[i]); cudaFree(c->d_coefs[i]); cudaFree(c->d_boxes[i]); cudaFree(c->d_counts[i]);
     cudaFree(c->d_records[i]); cudaFree(c->d_masks[i]);
+    cudaFree(c->d_protos_h[i]); c->d_protos_h[i] = nullptr;
     c->d_protos[i] = c->d_coefs[i] = c->d_boxes[i] = nullptr; c->d_counts[i] = nullptr; c->d_records[i] = c->d_masks[i] = nullptr;
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -562,13 +565,40 @@ static int host_pipeline_init_impl(va_ctx* c) {
     VA_CUDA(c, cudaMalloc(&c->d_counts[i], sizeof(int) * chunk));
     VA_CUDA(c, cudaMalloc(&c->d_records[i], (size_t)d.record_bytes * chunk));
     c->d_masks[i] = nullptr;
+    c->d_protos_h[i] = nullptr;
   }
   c->host_ready = true;
   return VA_OK;
 }
 
+// protos.float() (ops.py:724) of fp16 prototypes: exact widening, 8 values per thread
+__global__ void half_to_float_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, size_t n8) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n8; t += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[t];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), e = __half22float2(h[3]);
+    dst[2 * t] = make_float4(a.x, a.y, b.x, b.y);
+    dst[2 * t + 1] = make_float4(c.x, c.y, e.x, e.y);
+  }
+}
+
+static int run_fused_host_impl(va_ctx* c, const void* h_protos_any, bool f16, const float* h_coefs, const float* h_boxes,
+                               const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out);
+
 extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* h_coefs, const float* h_boxes,
                                  const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out) {
+  return run_fused_host_impl(c, h_protos, false, h_coefs, h_boxes, h_counts, B, h_masks_out, h_records_out);
+}
+
+extern "C" int va_run_fused_host_f16(va_ctx* c, const uint16_t* h_protos_f16, const float* h_coefs, const float* h_boxes,
+                                     const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out) {
+  return run_fused_host_impl(c, h_protos_f16, true, h_coefs, h_boxes, h_counts, B, h_masks_out, h_records_out);
+}
+
+static int run_fused_host_impl(va_ctx* c, const void* h_protos_any, bool f16, const float* h_coefs, const float* h_boxes,
+                               const int32_t* h_counts, int32_t B, uint8_t* h_masks_out, uint8_t* h_records_out) {
+  const float* h_protos = static_cast<const float*>(h_protos_any);
+  const uint16_t* h_protos_h = static_cast<const uint16_t*>(h_protos_any);
   int rc = check_batch(c, B, h_protos, h_coefs, h_boxes, h_counts);
   if (rc != VA_OK) return rc;
   if (!h_records_out) { set_err(c, "h_records_out is null"); return VA_ERR_INVALID; }
@@ -585,19 +615,34 @@ extern "C" int va_run_fused_host(va_ctx* c, const float* h_protos, const float* 
     for (int i = 0; i < 2; ++i)
       if (!c->d_masks[i]) VA_CUDA(c, cudaMalloc(&c->d_masks[i], fr_masks * chunk));
   }
+  if (f16) {
+    if ((fr_protos & 7) != 0) { set_err(c, "fp16 prototypes need K*mh*mw to be a multiple of 8"); return VA_ERR_INVALID; }
+    for (int i = 0; i < 2; ++i)
+      if (!c->d_protos_h[i]) VA_CUDA(c, cudaMalloc(&c->d_protos_h[i], fr_protos * 2 * chunk));
+  }
   int launches = 0;
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
     const int nb = (B - b0 < chunk) ? B - b0 : chunk;
     const int s = k & 1;
     if (k >= 2) VA_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_done[s], 0));     // input slot consumed
-    VA_CUDA(c, cudaMemcpyAsync(c->d_protos[s], h_protos + b0 * fr_protos, fr_protos * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
+    if (f16)
+      VA_CUDA(c, cudaMemcpyAsync(c->d_protos_h[s], h_protos_h + b0 * fr_protos, fr_protos * 2 * nb, cudaMemcpyHostToDevice, c->s_in));
+    else
+      VA_CUDA(c, cudaMemcpyAsync(c->d_protos[s], h_protos + b0 * fr_protos, fr_protos * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
     VA_CUDA(c, cudaMemcpyAsync(c->d_coefs[s], h_coefs + b0 * fr_coefs, fr_coefs * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
     VA_CUDA(c, cudaMemcpyAsync(c->d_boxes[s], h_boxes + b0 * fr_boxes, fr_boxes * 4 * nb, cudaMemcpyHostToDevice, c->s_in));
     VA_CUDA(c, cudaMemcpyAsync(c->d_counts[s], h_counts + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, c->s_in));
     VA_CUDA(c, cudaEventRecord(c->ev_in[s], c->s_in));
     VA_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_in[s], 0));
     if (k >= 2) VA_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_out[s], 0)); // output slot drained
+    if (f16) {
+      const size_t n8 = fr_protos * nb / 8;
+      half_to_float_kernel<<<c->d.num_sms * 8, 256, 0, c->s_compute>>>(reinterpret_cast<const uint4*>(c->d_protos_h[s]),
+                                                                       reinterpret_cast<float4*>(c->d_protos[s]), n8);
+      VA_CUDA(c, cudaGetLastError());
+      ++launches;
+    }
     c->last_launches = 0;
     rc = assemble(c, c->d_protos[s], c->d_coefs[s], c->d_boxes[s], c->d_counts[s], nb,
                   h_masks_out ? c->d_masks[s] : nullptr, nullptr, c->s_compute);

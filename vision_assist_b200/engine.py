@@ -310,16 +310,21 @@ class MaskGridEngine:
     # -- host-buffer API -----------------------------------------------------------------------
     def run_host(self, protos, coefs, boxes, counts, records_out: torch.Tensor | None = None,
                  masks_out: torch.Tensor | None = None):
-        """Host tensors in (pinned recommended), records (and optionally masks) back in host memory."""
-        for t, dt in ((protos, torch.float32), (coefs, torch.float32), (boxes, torch.float32), (counts, torch.int32)):
+        """Host tensors in (pinned recommended), records (and optionally masks) back in host memory.  `protos` may be
+        float16 (a model run with half=True; the reference computes on protos.float(), ops.py:724): half the PCIe bytes,
+        widened exactly on the device."""
+        f16 = protos.dtype == torch.float16
+        for t, dt in ((protos, torch.float16 if f16 else torch.float32), (coefs, torch.float32), (boxes, torch.float32),
+                      (counts, torch.int32)):
             if t.is_cuda or t.dtype != dt or not t.is_contiguous():
-                raise ValueError("run_host expects contiguous CPU tensors (f32 / i32)")
+                raise ValueError("run_host expects contiguous CPU tensors (f32 or f16 prototypes, f32, f32, i32)")
         B = protos.shape[0]
         if B > self.max_batch:
             raise ValueError(f"batch {B} > max_batch {self.max_batch}")
         if records_out is None:
             records_out = torch.empty((B, self.record_bytes), dtype=torch.uint8, pin_memory=True)
-        self._check(self.lib.va_run_fused_host(
+        fn = self.lib.va_run_fused_host_f16 if f16 else self.lib.va_run_fused_host
+        self._check(fn(
             self._ctx, C.c_void_p(protos.data_ptr()), C.c_void_p(coefs.data_ptr()), C.c_void_p(boxes.data_ptr()),
             C.c_void_p(counts.data_ptr()), B, C.c_void_p(masks_out.data_ptr()) if masks_out is not None else None,
             C.c_void_p(records_out.data_ptr())))
