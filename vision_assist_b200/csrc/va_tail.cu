@@ -761,6 +761,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = (int)threadIdx.x >> 5, nwarps = (int)blockDim.x >> 5;
     const int ntask = s_task0[kMaxInst];
+    const int my_task0 = s_task0[lane];                                // lane i: first task of instance i
     TT(17);
     // kU work items in flight per warp and all summary words of a chunk loaded before the first is used: the pass is a
     // chain of global round trips, so their number per warp is what counts
@@ -774,9 +775,9 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int t = t0 + u * nwarps;
-        int i = 0;
-        VA_ROLL
-        while (i + 1 < n && s_task0[i + 1] <= t) ++i;                  // instance of task t (n <= 32: a short scan)
+        // instance of task t: the last one whose first task is <= t (empty instances share their successor's start)
+        const unsigned le = __ballot_sync(0xffffffffu, lane < n && my_task0 <= t);
+        const int i = le ? 31 - __clz(le) : 0;
         inst_i[u] = i;
         const InstStats v = s_stats[i];
         yy[u] = v.miny + 31 * (t - s_task0[i]) + lane - 1;
@@ -827,22 +828,28 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     __syncthreads();
     TT(18);
     int n_pending = 0;
-    VA_ROLL
-    for (int i = 0; i < n; ++i) {
-      const InstStats v = s_stats[i];
-      if (v.area == 0 || !s_cert[i][0]) continue;
-      // certified: put the instance's summaries back to their resting state (all zero)
-      uint32_t* inst_rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
-      if (((d.H * d.nblk) & 3) == 0 && (d.H & 3) == 0) {
-        // groups of 4 rows are 16-byte aligned: vector stores (the rows added by the rounding are zero already)
-        const int y_lo = v.miny & ~3, y_hi = (v.maxy + 4) & ~3;
-        uint4* rs4 = reinterpret_cast<uint4*>(inst_rs + (size_t)y_lo * d.nblk);
-        VA_ROLL
-        for (int t = threadIdx.x; t < (y_hi - y_lo) * d.nblk / 4; t += (int)blockDim.x) rs4[t] = make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        uint32_t* rs = inst_rs + (size_t)v.miny * d.nblk;
-        VA_ROLL
-        for (int t = threadIdx.x; t < (v.maxy - v.miny + 1) * d.nblk; t += (int)blockDim.x) rs[t] = 0u;
+    {
+      // certified instances: put their summaries back to the resting state (all zero).  The warps are split over the
+      // instances so that all of them are reset at once (one instance after the other is a chain of short loops).
+      const int per = max(1, nwarps / max(n, 1));                     // warps per instance
+      const bool vec = ((d.H * d.nblk) & 3) == 0 && (d.H & 3) == 0;   // groups of 4 rows are 16-byte aligned
+      VA_ROLL
+      for (int i = warp / per; i < n; i += max(1, nwarps / per)) {
+        const InstStats v = s_stats[i];
+        if (v.area == 0 || !s_cert[i][0]) continue;
+        const int sub = warp % per;
+        uint32_t* inst_rs = tc.rowsum + ((size_t)b * d.max_n + i) * d.H * d.nblk;
+        if (vec) {
+          // vector stores; the rows added by rounding to groups of 4 are zero already
+          const int y_lo = v.miny & ~3, y_hi = (v.maxy + 4) & ~3;
+          uint4* rs4 = reinterpret_cast<uint4*>(inst_rs + (size_t)y_lo * d.nblk);
+          VA_ROLL
+          for (int t = sub * 32 + lane; t < (y_hi - y_lo) * d.nblk / 4; t += per * 32) rs4[t] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          uint32_t* rs = inst_rs + (size_t)v.miny * d.nblk;
+          VA_ROLL
+          for (int t = sub * 32 + lane; t < (v.maxy - v.miny + 1) * d.nblk; t += per * 32) rs[t] = 0u;
+        }
       }
     }
     TT(19);
