@@ -171,6 +171,10 @@ class FrameProcessor:
                 n = int(result.coefs.shape[0])
                 if n == 0:
                     continue
+                if n > 32:
+                    raise ValueError(f"{n} instances in one frame: the GPU path carries at most 32 per frame "
+                                     "(DESIGN.md section 6); pass the raw head output (RawHeadResult) to get the 32 best "
+                                     "survivors of NMS, or keep the 32 highest-confidence rows")
                 K, mh, mw = result.protos.shape
                 eng = self._engine_for(H, W, mh, mw, n)
                 dev = result.protos.device

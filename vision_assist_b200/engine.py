@@ -169,7 +169,8 @@ class MaskGridEngine:
         """ops.process_mask for a batch -> masks u8 [B,max_n,H,W] (+ cropped logits [B,max_n,mh,mw])."""
         B, p, c, b, n = self._inputs(protos, coefs, boxes, counts)
         masks = torch.empty((B, self.max_n, self.H, self.W), dtype=torch.uint8, device=protos.device)
-        logits = torch.empty((B, self.max_n, self.mh, self.mw), dtype=torch.float32, device=protos.device) if want_logits else None
+        # zeros: the kernels only write the rows of live instances (slots >= counts[b] stay 0)
+        logits = torch.zeros((B, self.max_n, self.mh, self.mw), dtype=torch.float32, device=protos.device) if want_logits else None
         self._check(self.lib.va_assemble_masks(self._ctx, p, c, b, n, B, C.c_void_p(masks.data_ptr()),
                                                C.c_void_p(logits.data_ptr()) if want_logits else None, self._stream()))
         return (masks, logits) if want_logits else masks
