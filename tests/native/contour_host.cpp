@@ -110,7 +110,6 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       PHASE(phase_flatten_a(w, tid, nt));
       PHASE(phase_flatten_b(w, tid, nt));
       PHASE(phase_sums(w, kContourLutHost, tid, nt));
-      PHASE(phase_sums_long(w, kContourLutHost, tid, nt));
       PHASE(phase_select(w, tid, nt));
       PHASE(phase_bbox(w, tid, nt));
       PHASE(phase_output(w, tid, nt));

@@ -337,6 +337,24 @@ VA_HD void phase_init(Work& w, int tid, int nt) {
   }
 }
 
+struct Span { int a, b; };     // a > b: empty
+VA_HD Span row_span(const Work& w, int r) {
+  Span s; s.a = 1; s.b = 0;
+  if (r >= 0 && r < w.R && w.one_a[r] >= 0) { s.a = w.one_a[r]; s.b = w.one_b[r]; }
+  return s;
+}
+// the two pixel ranges of a plain row that can hold border pixels: [c.a, la] and [lb, c.b] (second one possibly empty)
+struct PlainRanges { Span c, u, d; int la, lb, n1, n2; };
+VA_HD PlainRanges plain_ranges(const Work& w, int r) {
+  PlainRanges g;
+  g.c = row_span(w, r); g.u = row_span(w, r - 1); g.d = row_span(w, r + 1);
+  const bool both = (g.u.a <= g.u.b) && (g.d.a <= g.d.b);
+  g.la = both ? imin(g.c.b, imax(g.c.a, imax(g.u.a, g.d.a)) + 1) : g.c.b;
+  g.lb = both ? imax(g.la + 1, imax(g.c.a, imin(g.c.b, imin(g.u.b, g.d.b)) - 1)) : g.c.b + 1;
+  g.n1 = g.la - g.c.a + 1; g.n2 = g.c.b - g.lb + 1;
+  return g;
+}
+constexpr int kPlainInline = 8;   // plain rows with more candidate pixels than this go to the long list
 // ---- phase 0b: the (few) rows that need word-level work ----
 VA_HD int atom_inc(int* p) {
 #ifdef __CUDA_ARCH__
@@ -354,7 +372,14 @@ VA_HD void phase_lists(Work& w, int tid, int nt) {
       w.mlist[slot] = (int16_t)r;
       w.one_b[r] = (int16_t)slot;
     }
-    if (a != kRowEmpty && !row_is_plain(w, r)) w.nplist[atom_inc(&w.sc[W_NNP])] = (int16_t)r;
+    if (a == kRowEmpty) continue;
+    if (!row_is_plain(w, r)) {
+      w.nplist[atom_inc(&w.sc[W_NNP])] = (int16_t)r;
+    } else {
+      // plain rows with long candidate ranges (flat edges) are summed by a whole warp: listed from the back
+      const PlainRanges g = plain_ranges(w, r);
+      if (g.n1 + g.n2 > kPlainInline) w.nplist[w.R - 1 - atom_inc(&w.sc[W_NLONG])] = (int16_t)r;
+    }
   }
 }
 
@@ -583,12 +608,6 @@ VA_HD void phase_flatten_b(Work& w, int tid, int nt) {
 VA_HD void sums_flush(Work& w, int root, int pts, int a2) {
   if (root >= 0) { atom_add(&w.accP[root], pts); atom_add(&w.accA[root], a2); }
 }
-struct Span { int a, b; };     // a > b: empty
-VA_HD Span row_span(const Work& w, int r) {
-  Span s; s.a = 1; s.b = 0;
-  if (r >= 0 && r < w.R && w.one_a[r] >= 0) { s.a = w.one_a[r]; s.b = w.one_b[r]; }
-  return s;
-}
 VA_HD uint32_t span_code(const Span& u, const Span& c, const Span& d, int x) {
   auto in = [](const Span& s, int v) -> uint32_t { return (v >= s.a && v <= s.b) ? 1u : 0u; };
   return in(u, x - 1) | (in(u, x) << 1) | (in(u, x + 1) << 2) | (in(c, x - 1) << 3) | (in(c, x + 1) << 4) |
@@ -618,17 +637,6 @@ struct SumAcc {
     sums_flush(w, root, pts, a2);
   }
 };
-// the two pixel ranges of a plain row that can hold border pixels: [c.a, la] and [lb, c.b] (second one possibly empty)
-struct PlainRanges { Span c, u, d; int la, lb, n1, n2; };
-VA_HD PlainRanges plain_ranges(const Work& w, int r) {
-  PlainRanges g;
-  g.c = row_span(w, r); g.u = row_span(w, r - 1); g.d = row_span(w, r + 1);
-  const bool both = (g.u.a <= g.u.b) && (g.d.a <= g.d.b);
-  g.la = both ? imin(g.c.b, imax(g.c.a, imax(g.u.a, g.d.a)) + 1) : g.c.b;
-  g.lb = both ? imax(g.la + 1, imax(g.c.a, imin(g.c.b, imin(g.u.b, g.d.b)) - 1)) : g.c.b + 1;
-  g.n1 = g.la - g.c.a + 1; g.n2 = g.c.b - g.lb + 1;
-  return g;
-}
 VA_HD void plain_pixel(Work& w, const uint16_t* lut, const PlainRanges& g, int r, int root, int j, SumAcc& acc) {
   const int x = (j < g.n1) ? g.c.a + j : g.lb + (j - g.n1);
   const uint32_t e = lut[span_code(g.u, g.c, g.d, x)];
@@ -663,7 +671,20 @@ struct WordRuns {
   }
   VA_HD int root(int b) const { return multi ? pF[id0 + before + popc32(rise & (0xffffffffu >> (31 - b))) - 1] : root1; }
 };
-constexpr int kPlainInline = 8;   // plain rows with more candidate pixels than this go to the long list
+// the plain rows with long candidate ranges, one row per group of 32 threads (warps from the back: the word tasks
+// below are dealt from the front)
+VA_HD void sums_long_rows(Work& w, const uint16_t* lut, int tid, int nt, SumAcc& acc) {
+  const int L = (nt % 32 == 0) ? 32 : 1;
+  const int nlong = w.sc[W_NLONG], ngroups = nt / L;
+  VA_ROLL
+  for (int q = ngroups - 1 - tid / L; q < nlong; q += ngroups) {
+    const int r = w.nplist[w.R - 1 - q];
+    const PlainRanges g = plain_ranges(w, r);
+    const int root = w.pF[w.rowoff[r]];
+    VA_ROLL
+    for (int j = tid % L; j < g.n1 + g.n2; j += L) plain_pixel(w, lut, g, r, root, j, acc);
+  }
+}
 VA_HD void word_pixel(Work& w, const uint16_t* lut, const WordNb& nb, const WordRuns& wr, int r, int k, int b, SumAcc& acc) {
   const uint32_t e = lut[nb.code(b)];
   const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
@@ -681,11 +702,12 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   for (int r = tid; r < w.R; r += nt) {
     if (!row_is_plain(w, r)) continue;
     const PlainRanges g = plain_ranges(w, r);
-    if (g.n1 + g.n2 > kPlainInline) { w.nplist[w.R - 1 - atom_inc(&w.sc[W_NLONG])] = (int16_t)r; continue; }
+    if (g.n1 + g.n2 > kPlainInline) continue;          // on the long list (phase_lists)
     const int root = w.pF[w.rowoff[r]];
     VA_ROLL
     for (int j = 0; j < g.n1 + g.n2; ++j) plain_pixel(w, lut, g, r, root, j, acc);
   }
+  sums_long_rows(w, lut, tid, nt, acc);
   // (b) every other non-empty row (rows with several runs and their neighbours), word by word on the bit image
   const int ntask = w.sc[W_NNP] * w.Wd;
 #ifdef __CUDA_ARCH__
@@ -734,26 +756,14 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   }
   acc.finish(w, tid);
 }
-// ---- phase 9b: the plain rows with long candidate ranges, one row per group of 32 threads ----
-VA_HD void phase_sums_long(Work& w, const uint16_t* lut, int tid, int nt) {
-  if (w.sc[W_OVERFLOW]) return;
-  SumAcc acc;
-  const int L = (nt % 32 == 0) ? 32 : 1;
-  const int nlong = w.sc[W_NLONG];
-  VA_ROLL
-  for (int q = tid / L; q < nlong; q += nt / L) {
-    const int r = w.nplist[w.R - 1 - q];
-    const PlainRanges g = plain_ranges(w, r);
-    const int root = w.pF[w.rowoff[r]];
-    VA_ROLL
-    for (int j = tid % L; j < g.n1 + g.n2; j += L) plain_pixel(w, lut, g, r, root, j, acc);
-  }
-  acc.finish(w, tid);
-}
 // ---- phase 10: the component whose contour has the most points; ties: the last in raster order ----
+// the lattice samples the mask kernel left are those of the kept component when the mask is one hole-free component
+VA_HD bool lattice_stands(const Work& w) { return !w.sc[W_OVERFLOW] && w.sc[W_ROOTS] == 1 && w.sc[W_HOLES] == 0; }
 VA_HD void phase_select(Work& w, int tid, int nt) {
-  VA_ROLL
-  for (int t = tid; t < w.lat_rows * w.lat_words; t += nt) w.lattice[t] = 0u;     // rebuilt by phase_output
+  if (!lattice_stands(w)) {
+    VA_ROLL
+    for (int t = tid; t < w.lat_rows * w.lat_words; t += nt) w.lattice[t] = 0u;   // rebuilt by phase_output
+  }
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
   unsigned long long best = 0ull;
@@ -790,7 +800,7 @@ VA_HD void phase_output(Work& w, int tid, int nt) {
   const int half = w.gs >> 1;
   const bool ok = !w.sc[W_OVERFLOW] && w.sc[W_CHOSEN] >= 0;
   const int chosen = w.sc[W_CHOSEN];
-  if (ok) {
+  if (ok && !lattice_stands(w)) {
     // lattice points inside the region only: rows ly0 .. ly1, columns lx0 .. lx1
     const int ly0 = imax(0, (w.y0 - half + w.gs - 1) / w.gs), ly1 = imin(w.lat_rows - 1, (w.y0 + w.R - 1 - half) / w.gs);
     const int lx0 = imax(0, (32 * w.x0w - half + w.gs - 1) / w.gs), lx1 = imin(w.lat_cols - 1, (32 * (w.x0w + w.Wd) - 1 - half) / w.gs);

@@ -680,7 +680,6 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
   cc::phase_flatten_a(w, tid, nt);  __syncthreads(); PT(12);
   cc::phase_flatten_b(w, tid, nt);  __syncthreads(); PT(13);
   cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
-  cc::phase_sums_long(w, lut, tid, nt);  __syncthreads();
   cc::phase_select(w, tid, nt);     __syncthreads(); PT(15);
   cc::phase_bbox(w, tid, nt);       __syncthreads(); PT(16);
   cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
