@@ -565,9 +565,44 @@ VA_HD void phase_holes(Work& w, int tid, int nt) {
   }
 }
 // ---- phase 7: foreground runs, 8-connectivity with the row above ----
+// all runs of the row above that touch run id (its pixels and the two diagonal neighbours)
+VA_HD void link_row_above(Work& w, int id, int r) {
+  const int lo = (int)w.rs[id] - 1, hi = imin((int)w.re[id] + 1, 32 * w.Wd - 1);
+  const int o2 = w.rowoff[r - 1];
+  const int jlo = (lo >= 0 && fg_at(w, r - 1, lo)) ? ns(w, r - 1, lo) - 1 : ns(w, r - 1, lo);
+  const int jhi = ns(w, r - 1, hi) - 1;
+  VA_ROLL
+  for (int j = jlo; j <= jhi; ++j) uf_union(w.pF, id, o2 + j);
+}
 VA_HD void phase_link(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
+#ifdef __CUDA_ARCH__
+  if ((nt & 31) == 0) {
+    // A mask is mostly a vertical stack of single-run rows: run id sits on run id - 1.  Linking every run to the one
+    // above at the same time leaves one list as long as the mask is tall, which the finds then walk.  Within a warp
+    // (32 consecutive ids) the stack links are resolved by a vote instead: every run of a stretch of stack links is
+    // united with the stretch's first run directly, only the first run of a stretch looks at the row above.
+    const int lane = tid & 31;
+    VA_ROLL
+    for (int base = 0; base < NR; base += nt) {
+      const int id = base + tid;
+      const bool valid = id < NR;
+      const int r = valid ? (int)w.ry[id] : 0;
+      bool stack = false;
+      if (valid && r > 0) {
+        const int a = w.one_a[r], ap = w.one_a[r - 1];
+        stack = a >= 0 && ap >= 0 && a - 1 <= (int)w.one_b[r - 1] && (int)w.one_b[r] + 1 >= ap;   // both rows one run, touching
+      }
+      const unsigned heads = __ballot_sync(0xffffffffu, !stack || lane == 0);
+      const int head_lane = 31 - clz32(heads & (0xffffffffu >> (31 - lane)));
+      if (!valid || r == 0) continue;
+      if (lane != head_lane) uf_union(w.pF, id, id - (lane - head_lane));
+      else link_row_above(w, id, r);
+    }
+    return;
+  }
+#endif
   // consecutive ids per thread: a strided second pass would start from the id - 1 chains the first pass left behind
   // (a vertical stack of runs links into one list as long as the mask is tall) and walk them alone
   const int per = (NR + nt - 1) / nt;
@@ -575,12 +610,7 @@ VA_HD void phase_link(Work& w, int tid, int nt) {
   for (int id = tid * per; id < imin(NR, (tid + 1) * per); ++id) {
     const int r = w.ry[id];
     if (r == 0) continue;
-    const int lo = (int)w.rs[id] - 1, hi = imin((int)w.re[id] + 1, 32 * w.Wd - 1);
-    const int o2 = w.rowoff[r - 1];
-    const int jlo = (lo >= 0 && fg_at(w, r - 1, lo)) ? ns(w, r - 1, lo) - 1 : ns(w, r - 1, lo);
-    const int jhi = ns(w, r - 1, hi) - 1;
-    VA_ROLL
-    for (int j = jlo; j <= jhi; ++j) uf_union(w.pF, id, o2 + j);
+    link_row_above(w, id, r);
   }
 }
 // ---- phase 8: flatten, in two barrier-separated steps: the finds of step a still re-point nodes (path halving) and
@@ -637,11 +667,17 @@ struct SumAcc {
     sums_flush(w, root, pts, a2);
   }
 };
-VA_HD void plain_pixel(Work& w, const uint16_t* lut, const PlainRanges& g, int r, int root, int j, SumAcc& acc) {
-  const int x = (j < g.n1) ? g.c.a + j : g.lb + (j - g.n1);
+// table terms of pixel x of plain row r added to (p, v); a pixel the border does not visit adds zeros
+VA_HD void plain_term(const uint16_t* lut, const PlainRanges& g, int r, int x, int& p, int& v) {
   const uint32_t e = lut[span_code(g.u, g.c, g.d, x)];
-  const int p = (int)(e & 7u), dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
-  if (p | dxs | dys) acc.add(w, root, p, x * dys - r * dxs);
+  const int dxs = (int)((e >> 3) & 7u) - 2, dys = (int)((e >> 6) & 7u) - 2;
+  p += (int)(e & 7u);
+  v += x * dys - r * dxs;
+}
+VA_HD void plain_pixel(Work& w, const uint16_t* lut, const PlainRanges& g, int r, int root, int j, SumAcc& acc) {
+  int p = 0, v = 0;
+  plain_term(lut, g, r, (j < g.n1) ? g.c.a + j : g.lb + (j - g.n1), p, v);
+  if (p | v) acc.add(w, root, p, v);
 }
 // a word of G and its eight neighbour words, then the six shifted images whose bit b is a neighbour of pixel b
 struct WordNb {
@@ -704,8 +740,13 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
     const PlainRanges g = plain_ranges(w, r);
     if (g.n1 + g.n2 > kPlainInline) continue;          // on the long list (phase_lists)
     const int root = w.pF[w.rowoff[r]];
+    int p1 = 0, v1 = 0, p2 = 0, v2 = 0;                // the two ranges side by side: two independent dependency chains
     VA_ROLL
-    for (int j = 0; j < g.n1 + g.n2; ++j) plain_pixel(w, lut, g, r, root, j, acc);
+    for (int j = 0; j < imax(g.n1, g.n2); ++j) {
+      if (j < g.n1) plain_term(lut, g, r, g.c.a + j, p1, v1);
+      if (j < g.n2) plain_term(lut, g, r, g.lb + j, p2, v2);
+    }
+    acc.add(w, root, p1 + p2, v1 + v2);
   }
   sums_long_rows(w, lut, tid, nt, acc);
   // (b) every other non-empty row (rows with several runs and their neighbours), word by word on the bit image
