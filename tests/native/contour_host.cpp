@@ -99,20 +99,29 @@ extern "C" int contour_host_instance(const uint8_t* mask, int H, int W, int gs, 
       PHASE(phase_init(w, tid, nt));
       PHASE(phase_lists(w, tid, nt));
       PHASE(phase_load(w, tid, nt));
-      PHASE(phase_count(w, tid, nt));
-      PHASE(phase_scan_a(w, tid, nt));
-      PHASE(phase_scan_b(w, tid, nt));
-      PHASE(phase_scan_c(w, tid, nt));
-      PHASE(phase_runs(w, tid, nt));
-      PHASE(phase_gaps(w, tid, nt));
-      PHASE(phase_holes(w, tid, nt));
-      PHASE(phase_link(w, tid, nt));
-      PHASE(phase_flatten_a(w, tid, nt));
-      PHASE(phase_flatten_b(w, tid, nt));
-      PHASE(phase_sums(w, kContourLutHost, tid, nt));
-      PHASE(phase_select(w, tid, nt));
-      PHASE(phase_bbox(w, tid, nt));
-      PHASE(phase_output(w, tid, nt));
+      PHASE(phase_light_check(w, tid, nt));
+      if (sc[W_LIGHT] && force_general != 2) {          // force_general == 2: the full path even where the light one applies
+        out[8] = 2;
+        PHASE(phase_light_setup(w, tid, bbox[0], bbox[2]));
+        PHASE(phase_sums(w, kContourLutHost, tid, nt));
+        PHASE(phase_output(w, tid, nt));
+      } else {
+        sc[W_LIGHT] = 0;
+        PHASE(phase_count(w, tid, nt));
+        PHASE(phase_scan_a(w, tid, nt));
+        PHASE(phase_scan_b(w, tid, nt));
+        PHASE(phase_scan_c(w, tid, nt));
+        PHASE(phase_runs(w, tid, nt));
+        PHASE(phase_gaps(w, tid, nt));
+        PHASE(phase_holes(w, tid, nt));
+        PHASE(phase_link(w, tid, nt));
+        PHASE(phase_flatten_a(w, tid, nt));
+        PHASE(phase_flatten_b(w, tid, nt));
+        PHASE(phase_sums(w, kContourLutHost, tid, nt));
+        PHASE(phase_select(w, tid, nt));
+        PHASE(phase_bbox(w, tid, nt));
+        PHASE(phase_output(w, tid, nt));
+      }
 #undef PHASE
     }
   }

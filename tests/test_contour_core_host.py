@@ -42,7 +42,7 @@ def run(lib, mask, gs=20, fmt=0, force_general=0, nthreads=64, cap=None):
     for x in range(lc):
         bits[:, x] = (lat[:, x >> 5] >> np.uint32(x & 31)) & 1
     return dict(state=int(out[0]), area2=int(out[1]), bbox=tuple(int(v) for v in out[2:6]), points=int(out[6]),
-                n_components=int(out[7]), general=bool(out[8]), lattice=bits)
+                n_components=int(out[7]), general=bool(out[8]), light=int(out[8]) == 2, lattice=bits)
 
 
 def check(lib, mask, gs, **kw):
@@ -81,8 +81,57 @@ def test_random_masks_general_and_certificate(lib):
         g = check(lib, m, gs, fmt=it % 2, nthreads=int(rng.choice([1, 7, 64, 256])))
         n_general += g["general"]
         n_cert += (not g["general"]) and g["state"] == 1
-        check(lib, m, gs, fmt=(it + 1) % 2, force_general=1, nthreads=33)     # the general path must agree on simple masks too
+        check(lib, m, gs, fmt=(it + 1) % 2, force_general=1, nthreads=33)     # the light / general path must agree on simple masks too
+        g2 = check(lib, m, gs, fmt=it % 2, force_general=2, nthreads=64)      # ... and the full path where the light one applies
+        assert not g2["light"]
     assert n_general > 100
+
+
+def test_notched_masks_take_the_light_path(lib):
+    """Row-convex blobs with a few isolated rows of several runs (notches, bumps, slits): one component without holes
+    decided from the run ends (phase_light_check).  The same masks with a covered gap (a hole), an island row or a
+    run that hangs in the air must fall through to the full path - every result is checked against the OpenCV model."""
+    rng = np.random.default_rng(8)
+    n_light = n_full = 0
+    for it in range(400):
+        H, W = int(rng.integers(16, 70)), int(rng.integers(40, 300))
+        m = np.zeros((H, W), np.uint8)
+        y0 = int(rng.integers(0, H // 3)); y1 = int(rng.integers(2 * H // 3, H))
+        a, b = sorted(int(v) for v in rng.integers(0, W, 2))
+        b = max(b, min(W - 1, a + 12))
+        spans = {}
+        for y in range(y0, y1 + 1):
+            a = int(np.clip(a + rng.integers(-3, 4), 0, W - 13)); b = int(np.clip(b + rng.integers(-3, 4), a + 12, W - 1))
+            m[y, a:b + 1] = 1
+            spans[y] = (a, b)
+        kind = it % 5
+        # notches in the top / bottom row (never holes: one neighbour row is missing)
+        for y in ([y0] if kind in (0, 3) else [y1] if kind == 1 else [y0, y1]):
+            a, b = spans[y]
+            for _ in range(int(rng.integers(1, 4))):
+                c0 = int(rng.integers(a + 1, b)); c1 = min(b - 1, c0 + int(rng.integers(0, 6)))
+                m[y, c0:c1 + 1] = 0
+        # interior rows: a stub beside the main run (a notch when a neighbour row leaves the gap open, a hole when both
+        # cover it, an island when the stub touches neither neighbour), sometimes a slit inside the run (a hole)
+        rows = [y for y in range(y0 + 2, y1 - 1, int(rng.integers(2, 9)))][:int(rng.integers(0, 4))]
+        for y in rows:
+            a, b = spans[y]
+            if rng.random() < 0.75:
+                gap = int(rng.integers(1, 4)); ln = int(rng.integers(1, 5))
+                if rng.random() < 0.5 and a - gap - ln >= 0:
+                    m[y, a - gap - ln:a - gap] = 1
+                elif b + gap + ln < W:
+                    m[y, b + gap + 1:b + gap + 1 + ln] = 1
+            else:
+                c0 = int(rng.integers(a + 1, b))
+                m[y, c0:min(b - 1, c0 + 2) + 1] = 0
+        if kind == 3 and rows:                              # two adjacent rows with several runs: never light
+            a, b = spans[rows[0] + 1]
+            m[rows[0] + 1, (a + b) // 2] = 0
+        g = check(lib, m, int(rng.choice([4, 8, 20])), fmt=it % 2, force_general=1, nthreads=int(rng.choice([1, 32, 64, 256])))
+        n_light += g["light"]; n_full += g["general"] and not g["light"]
+        check(lib, m, 20, fmt=it % 2, force_general=2, nthreads=64)
+    assert n_light > 60 and n_full > 60, (n_light, n_full)
 
 
 def test_row_convex_shapes_take_the_certificate(lib):

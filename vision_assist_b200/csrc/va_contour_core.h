@@ -228,7 +228,7 @@ struct Work {
   unsigned* lattice;        // [lat_rows][lat_words] of this instance (overwritten)
   InstContour* out;
 };
-enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_NM, W_NNP, W_NLONG, W_COUNT };
+enum { W_NR, W_OVERFLOW, W_HOLES, W_ROOTS, W_MINX, W_MINY, W_MAXX, W_MAXY, W_CHOSEN, W_NM, W_NNP, W_NLONG, W_LIGHT, W_COUNT };
 constexpr int kRowEmpty = -1, kRowMulti = -2;
 
 // bits [a, b] of word k (pixels 32k .. 32k+31), a <= b
@@ -321,6 +321,7 @@ VA_HD void phase_init(Work& w, int tid, int nt) {
     for (int q = 0; q < W_COUNT; ++q) w.sc[q] = 0;
     w.sc[W_MINX] = 1 << 30; w.sc[W_MINY] = 1 << 30; w.sc[W_MAXX] = -1; w.sc[W_MAXY] = -1;
     w.sc[W_CHOSEN] = -1;
+    w.sc[W_LIGHT] = 1;                                  // cleared by phase_light_check
     w.best[0] = 0ull;
   }
   VA_ROLL
@@ -417,6 +418,69 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
   }
 }
 
+// ---- phase 1b: the light check.  Most masks that miss the certificate are row-convex except for a few rows with a
+//      notch (two or more runs).  When every row is non-empty, consecutive single-run rows touch, and every row with
+//      several runs stands alone between two single-run rows (or at the top / bottom of the mask) with
+//        - each of its runs touching the run above or the run below,
+//        - no gap covered by both neighbour runs (such a gap would be a hole),
+//        - some run touching both neighbours when both exist (the parts above and below meet only in this row),
+//      the mask is ONE component WITHOUT holes: no run table, union-find or lattice rebuild is needed, the table sums
+//      over the border pixels (phase_sums) give points and area, the pixel bounding box is the component's.
+//      Clears sc[W_LIGHT] otherwise; the full path then continues from phase_count. ----
+VA_HD void phase_light_check(Work& w, int tid, int nt) {
+  VA_ROLL
+  for (int r = tid; r < w.R; r += nt) {
+    const int a = w.one_a[r];
+    bool ok = true;
+    if (a == kRowEmpty) {
+      ok = false;
+    } else if (a >= 0) {
+      if (r > 0 && w.one_a[r - 1] >= 0) ok = a - 1 <= (int)w.one_b[r - 1] && (int)w.one_b[r] + 1 >= (int)w.one_a[r - 1];
+    } else {                                            // several runs
+      if (row_is_multi(w, r - 1) || row_is_multi(w, r + 1)) {
+        ok = false;
+      } else {
+        const Span u = row_span(w, r - 1), d = row_span(w, r + 1);
+        const bool hasu = u.a <= u.b, hasd = d.a <= d.b;
+        const int base = slot_base(w, r);
+        bool both = false, open = false;               // a run touches both neighbours; inside a run
+        int start = 0, prev_end = -1;
+        uint32_t carry = 0u;
+        VA_ROLL
+        for (int k = 0; k <= w.Wd && ok; ++k) {          // one word past the end closes a run that reaches the last pixel
+          const uint32_t m = (k < w.Wd) ? w.Mfg[base + k] : 0u;
+          uint32_t edges = m ^ ((m << 1) | carry);      // bit x: pixel x differs from pixel x - 1
+          carry = m >> 31;
+          VA_ROLL
+          while (edges && ok) {
+            const int x = 32 * k + ffs32(edges) - 1;
+            edges &= edges - 1;
+            if (!open) { start = x; open = true; continue; }
+            open = false;
+            const int end = x - 1;                      // run [start, end]
+            const bool tu = hasu && start - 1 <= u.b && end + 1 >= u.a, td = hasd && start - 1 <= d.b && end + 1 >= d.a;
+            if (!tu && !td) ok = false;
+            both = both || (tu && td);
+            if (prev_end >= 0) {                        // gap [prev_end + 1, start - 1]
+              const int g0 = prev_end + 1, g1 = start - 1;
+              if (hasu && u.a <= g0 && u.b >= g1 && hasd && d.a <= g0 && d.b >= g1) ok = false;
+            }
+            prev_end = end;
+          }
+        }
+        if (hasu && hasd && !both) ok = false;
+      }
+    }
+    if (!ok) w.sc[W_LIGHT] = 0;
+  }
+}
+// ---- phase 1c (light path only): one component, no holes - the state the later phases read ----
+VA_HD void phase_light_setup(Work& w, int tid, int minx, int maxx) {
+  if (tid != 0) return;
+  w.sc[W_NR] = 1; w.sc[W_ROOTS] = 1; w.sc[W_HOLES] = 0; w.sc[W_CHOSEN] = 0;
+  w.sc[W_MINX] = minx - 32 * w.x0w; w.sc[W_MAXX] = maxx - 32 * w.x0w; w.sc[W_MINY] = 0; w.sc[W_MAXY] = w.R - 1;
+  w.pF[0] = 0; w.accP[0] = 0; w.accA[0] = 0;
+}
 // ---- phase 2: runs per word / row ----
 VA_HD void phase_count(Work& w, int tid, int nt) {
   VA_ROLL
@@ -698,6 +762,10 @@ struct WordNb {
 struct WordRuns {
   bool multi; const int* pF; int id0, before, root1; uint32_t rise;
   VA_HD WordRuns(const Work& w, int r, int k) {
+    if (w.sc[W_LIGHT]) {                               // light path: one component, run 0 stands for it
+      multi = false; pF = w.pF; id0 = 0; rise = 0u; before = 0; root1 = 0;
+      return;
+    }
     multi = w.one_a[r] == kRowMulti;
     pF = w.pF;
     id0 = w.rowoff[r];
@@ -716,7 +784,7 @@ VA_HD void sums_long_rows(Work& w, const uint16_t* lut, int tid, int nt, SumAcc&
   for (int q = ngroups - 1 - tid / L; q < nlong; q += ngroups) {
     const int r = w.nplist[w.R - 1 - q];
     const PlainRanges g = plain_ranges(w, r);
-    const int root = w.pF[w.rowoff[r]];
+    const int root = w.sc[W_LIGHT] ? 0 : w.pF[w.rowoff[r]];
     VA_ROLL
     for (int j = tid % L; j < g.n1 + g.n2; j += L) plain_pixel(w, lut, g, r, root, j, acc);
   }
@@ -739,7 +807,7 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
     if (!row_is_plain(w, r)) continue;
     const PlainRanges g = plain_ranges(w, r);
     if (g.n1 + g.n2 > kPlainInline) continue;          // on the long list (phase_lists)
-    const int root = w.pF[w.rowoff[r]];
+    const int root = w.sc[W_LIGHT] ? 0 : w.pF[w.rowoff[r]];
     int p1 = 0, v1 = 0, p2 = 0, v2 = 0;                // the two ranges side by side: two independent dependency chains
     VA_ROLL
     for (int j = 0; j < imax(g.n1, g.n2); ++j) {

@@ -35,7 +35,9 @@ constexpr size_t kContourGridSmem = 16 * 1024;   // contour step: bit rows of th
 
 // developer diagnostic (VA_TAIL_TIMING=1): cycle stamps of block 0 at the phase boundaries, printed by the kernel
 constexpr int kTailDebugFlag = 1 << 30;
+constexpr int kTailTimelineFlag = 1 << 28;   // VA_TAIL_TIMING=2: one line per CTA (SM, start, end of the dependency wait, end)
 __device__ long long g_tail_t[24];
+__device__ __forceinline__ unsigned __smid() { unsigned v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
 #define TT(k) do { if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 64))) g_tail_t[(k) % 100] = clock64(); } while (0)
 
 struct TailSmem {
@@ -661,28 +663,40 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
     }
   }
   cc::phase_load(w, tid, nt);       __syncthreads(); PT(3);
-  cc::phase_count(w, tid, nt);      __syncthreads(); PT(4);
-  cc::phase_scan_a(w, tid, nt);     __syncthreads(); PT(5);
-  cc::phase_scan_b(w, tid, nt);     __syncthreads(); PT(6);
-  cc::phase_scan_c(w, tid, nt);     __syncthreads(); PT(7);
-  {
-    const int NR = sc[cc::W_NR];
-    const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
-    if (NR <= tc.cap && used + rl.total <= (size_t)tc.smem_bytes) {
-      w.cap = NR > 0 ? NR : 1;
-      cc::bind_runs(w, smem + used, rl);
+  cc::phase_light_check(w, tid, nt); __syncthreads();
+  if (sc[cc::W_LIGHT]) {
+    // one component without holes, decided from the run ends: no run table, no union-find, the mask kernel's lattice
+    // samples stand
+    cc::bind_runs(w, smem + used, cc::run_layout(1));
+    cc::phase_light_setup(w, tid, st.minx, st.maxx);  __syncthreads();
+    PT(4); PT(5); PT(6); PT(7); PT(8); PT(9); PT(10); PT(11); PT(12); PT(13);
+    cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
+    PT(15); PT(16);
+    cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
+  } else {
+    cc::phase_count(w, tid, nt);      __syncthreads(); PT(4);
+    cc::phase_scan_a(w, tid, nt);     __syncthreads(); PT(5);
+    cc::phase_scan_b(w, tid, nt);     __syncthreads(); PT(6);
+    cc::phase_scan_c(w, tid, nt);     __syncthreads(); PT(7);
+    {
+      const int NR = sc[cc::W_NR];
+      const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
+      if (NR <= tc.cap && used + rl.total <= (size_t)tc.smem_bytes) {
+        w.cap = NR > 0 ? NR : 1;
+        cc::bind_runs(w, smem + used, rl);
+      }
     }
+    cc::phase_runs(w, tid, nt);       __syncthreads(); PT(8);
+    cc::phase_gaps(w, tid, nt);       __syncthreads(); PT(9);
+    cc::phase_holes(w, tid, nt);      __syncthreads(); PT(10);
+    cc::phase_link(w, tid, nt);       __syncthreads(); PT(11);
+    cc::phase_flatten_a(w, tid, nt);  __syncthreads(); PT(12);
+    cc::phase_flatten_b(w, tid, nt);  __syncthreads(); PT(13);
+    cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
+    cc::phase_select(w, tid, nt);     __syncthreads(); PT(15);
+    cc::phase_bbox(w, tid, nt);       __syncthreads(); PT(16);
+    cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
   }
-  cc::phase_runs(w, tid, nt);       __syncthreads(); PT(8);
-  cc::phase_gaps(w, tid, nt);       __syncthreads(); PT(9);
-  cc::phase_holes(w, tid, nt);      __syncthreads(); PT(10);
-  cc::phase_link(w, tid, nt);       __syncthreads(); PT(11);
-  cc::phase_flatten_a(w, tid, nt);  __syncthreads(); PT(12);
-  cc::phase_flatten_b(w, tid, nt);  __syncthreads(); PT(13);
-  cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
-  cc::phase_select(w, tid, nt);     __syncthreads(); PT(15);
-  cc::phase_bbox(w, tid, nt);       __syncthreads(); PT(16);
-  cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
   if (ptime) {
     printf("[va tail] frame %d phases (R=%d Wd=%d NR=%d NM=%d): init %lld lists %lld load %lld count %lld scan %lld %lld %lld runs %lld gaps %lld holes %lld link %lld flat %lld %lld sums %lld select %lld bbox %lld out %lld\n",
            (int)blockIdx.x, w.R, w.Wd, sc[cc::W_NR], sc[cc::W_NM], pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3],
@@ -706,6 +720,8 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   const int gs = d.gs, cw = d.cwords;
   const int T = 2 * d.rmax, PL = plane_cap(d);
   TT(0);
+  unsigned long long gt_start = 0, gt_wait = 0;
+  if ((d.flags & kTailTimelineFlag) && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_start));
 
   __shared__ unsigned s_area[kMaxInst];
   __shared__ int s_area2[kMaxInst], s_state[kMaxInst];
@@ -728,6 +744,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   // everything above touched only shared memory and kernel inputs.  Wait here for its writes (statistics, lattice
   // bits, row summaries, masks).
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if ((d.flags & kTailTimelineFlag) && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_wait));
   TT(1);
   if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
     const int i = threadIdx.x;
@@ -1055,6 +1072,11 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   VA_ROLL
   for (int t = threadIdx.x; t < d.max_n * d.lat_rows * d.lat_words; t += (int)blockDim.x) latb[t] = 0u;
   TT(12);
+  if ((d.flags & kTailTimelineFlag) && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    printf("[va tail] block %d on sm %d: starts %llu waited %llu ends %llu ns\n", (int)blockIdx.x, (int)__smid(), gt_start, gt_wait, gt);
+  }
   if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long t0 = g_tail_t[0], te = clock64();
     printf("[va tail] reset: stats %lld lattice %lld rest %lld | t0 before barrier %lld t32 before %lld t32 after %lld (from t6)\n", g_tail_t[11] - g_tail_t[9], g_tail_t[12] - g_tail_t[11], te - g_tail_t[12],
