@@ -1193,8 +1193,10 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
   pl->num_sms = prop.multiProcessorCount;
   // Instances are processed in groups of `ni` (8 or 16 accumulator columns); a frame with more instances becomes
   // several work items per band that re-read the same prototype rows (from L2).  Pick the group size, the row pairs
-  // per chunk and the number of chunk buffers that fit next to the tile rings; measured: groups of 16 beat groups of 8
-  // whenever they fit (half the prototype re-reads and splits per mask byte).
+  // per chunk and the number of chunk buffers that fit next to the tile rings.  Groups of 16 halve the prototype
+  // re-reads and splits per mask byte, but their instantiation sits at the 128-register cap and spills since the
+  // per-row by-products were added: groups of 8 are tried first (measured at 640^2: n = 16 0.342 -> 0.288 ms,
+  // n = 32 0.285 -> 0.254 ms; cfg2 0.60 -> 0.51 ms at equal band counts).
   const size_t limit = (size_t)prop.sharedMemPerBlockOptin - 1024;
   int pr = 0, nbuf = 0, ni = 0;
   int force_ni = 0;
@@ -1206,11 +1208,9 @@ FusedPlan* fused_plan_create(const Dims& d, int device, char* err, size_t errlen
     return (exact4 || want <= fit) ? want : fit;
   };
   int zrows = 0;
-  // measured (cfg2, 1080p, n = 32): with the generic blend groups of 8 beat groups of 16 (0.60 -> 0.51 ms at equal band
-  // counts: the 16-column instantiation spills), so the generic plan tries 8 first
-  const int order_exact[2] = {16, 8}, order_generic[2] = {8, 16};
+  const int order[2] = {8, 16};
   for (int gi = 0; gi < 2; ++gi) {
-    const int g = exact4 ? order_exact[gi] : order_generic[gi];
+    const int g = order[gi];
     if (g == 16 && d.max_n <= 8) continue;
     if (force_ni && g != force_ni && d.max_n > 8) continue;
     for (int cand : {4, 2}) {
