@@ -53,6 +53,34 @@ def _adversarial_frames(H, W, n):
             if rng.random() < 0.8:
                 f[i] = _rand_mask(rng, H, W)
         frames.append(f)
+    # row-convex blobs with a few rows of several runs: notches in the top / bottom row and stubs beside the outline
+    # (light path: one component without holes decided from the run ends), slits inside the blob (holes), stubs that
+    # touch nothing (islands) and adjacent notched rows (full path) - and a tall one (more rows than threads)
+    for k in range(10):
+        f = blank()
+        for i in range(min(n, 3)):
+            y0 = int(rng.integers(5, H // 4)); y1 = int(rng.integers(H // 2, H - 5)) if k != 9 else H - 3
+            a, b_ = int(rng.integers(20, W // 3)), int(rng.integers(2 * W // 3, W - 20))
+            spans = {}
+            for y in range(y0, y1 + 1):
+                a = int(np.clip(a + rng.integers(-3, 4), 8, W // 2 - 10)); b_ = int(np.clip(b_ + rng.integers(-3, 4), W // 2 + 10, W - 9))
+                f[i, y, a:b_ + 1] = 1
+                spans[y] = (a, b_)
+            for y in ([y0], [y1], [y0, y1])[k % 3]:
+                a, b_ = spans[y]
+                for _ in range(int(rng.integers(1, 4))):
+                    c0 = int(rng.integers(a + 1, b_)); f[i, y, c0:min(b_ - 1, c0 + int(rng.integers(0, 9))) + 1] = 0
+            for y in range(y0 + 3, y1 - 3, int(rng.integers(17, 60))):
+                a, b_ = spans[y]
+                r_ = rng.random()
+                if r_ < 0.6:
+                    gap, ln = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+                    f[i, y, a - gap - ln:a - gap] = 1
+                elif r_ < 0.8:
+                    f[i, y, (a + b_) // 2:(a + b_) // 2 + 3] = 0                      # a hole
+                else:
+                    f[i, y:y + 2, b_ - 4] = 0                                        # adjacent rows with several runs
+        frames.append(f)
     return frames
 
 
