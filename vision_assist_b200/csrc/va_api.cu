@@ -90,7 +90,8 @@ static bool compute_dims(const va_config& c, Dims& d, va_layout& L, char* why, s
   memset(&d, 0, sizeof(d));
   d.H = c.H; d.W = c.W; d.mh = c.mh; d.mw = c.mw; d.K = c.K; d.max_n = c.max_n; d.gs = c.gs;
   d.flags = c.flags;
-  if (const char* e = getenv("VA_TAIL_TIMING")) { if (e[0] == '1') d.flags |= 1 << 30; if (e[0] == '2') d.flags |= 1 << 28; }   // developer diagnostics (va_tail.cu)
+  if (const char* e = getenv("VA_TAIL_TIMING")) { if (e[0] == '1') d.flags |= 1 << 30; if (e[0] == '2') d.flags |= 1 << 28; if (e[0] == '3') d.flags |= 1 << 27; }
+  if (const char* e = getenv("VA_TAIL_BLOCK")) d.flags |= (atoi(e) & 0xfff) << 8;                 // which frame VA_TAIL_TIMING=1 clocks   // developer diagnostics (va_tail.cu)
   if (const char* e = getenv("VA_TAIL_ROLES")) { if (e[0] == '3') d.flags |= 1 << 29; }    // tuning aid (va_tail.cu)
   const int half = c.gs / 2;
   d.lat_rows = ceil_div(c.H - half, c.gs);

@@ -38,7 +38,7 @@ constexpr int kTailDebugFlag = 1 << 30;
 constexpr int kTailTimelineFlag = 1 << 28;   // VA_TAIL_TIMING=2: one line per CTA (SM, start, end of the dependency wait, end)
 __device__ long long g_tail_t[24];
 __device__ __forceinline__ unsigned __smid() { unsigned v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
-#define TT(k) do { if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 64))) g_tail_t[(k) % 100] = clock64(); } while (0)
+#define TT(k) do { if ((d.flags & kTailDebugFlag) && (int)blockIdx.x == ((d.flags >> 8) & 0xfff) && (threadIdx.x == 0 || ((k) >= 100 && threadIdx.x == 64))) g_tail_t[(k) % 100] = clock64(); } while (0)
 
 struct TailSmem {
   // "created rows" table: ids [0, 2*rmax)
@@ -648,9 +648,15 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
   cc::bind_grid(w, slab + wl_full.total, gl_full);
   cc::bind_runs(w, slab + wl_full.total + gl_full.total, cc::run_layout(tc.cap));
   __syncthreads();
-  const bool ptime = (d.flags & kTailDebugFlag) && tid == 0 && blockIdx.x < 64;
+  // per-phase clocks: compiled in with -DVA_TAIL_PHASE_TIMING only (VA_EXTRA_FLAGS of build.sh) - the array and the
+  // printf would otherwise sit in the production kernel's stack frame and instruction footprint
+#ifdef VA_TAIL_PHASE_TIMING
+  const bool ptime = (d.flags & kTailDebugFlag) && tid == 0;
   long long pt[20]; int npt = 0;
 #define PT(k) do { if (ptime) pt[npt++] = clock64(); } while (0)
+#else
+#define PT(k) do { } while (0)
+#endif
   PT(0);
   cc::phase_init(w, tid, nt);       __syncthreads(); PT(1);
   cc::phase_lists(w, tid, nt);      __syncthreads(); PT(2);
@@ -664,15 +670,13 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
   }
   cc::phase_load(w, tid, nt);       __syncthreads(); PT(3);
   cc::phase_light_check(w, tid, nt); __syncthreads();
-  if (sc[cc::W_LIGHT]) {
+  const bool light = sc[cc::W_LIGHT] != 0;
+  if (light) {
     // one component without holes, decided from the run ends: no run table, no union-find, the mask kernel's lattice
     // samples stand
     cc::bind_runs(w, smem + used, cc::run_layout(1));
     cc::phase_light_setup(w, tid, st.minx, st.maxx);  __syncthreads();
     PT(4); PT(5); PT(6); PT(7); PT(8); PT(9); PT(10); PT(11); PT(12); PT(13);
-    cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
-    PT(15); PT(16);
-    cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
   } else {
     cc::phase_count(w, tid, nt);      __syncthreads(); PT(4);
     cc::phase_scan_a(w, tid, nt);     __syncthreads(); PT(5);
@@ -692,17 +696,23 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
     cc::phase_link(w, tid, nt);       __syncthreads(); PT(11);
     cc::phase_flatten_a(w, tid, nt);  __syncthreads(); PT(12);
     cc::phase_flatten_b(w, tid, nt);  __syncthreads(); PT(13);
-    cc::phase_sums(w, lut, tid, nt);  __syncthreads(); PT(14);
+  }
+  cc::phase_sums(w, lut, tid, nt);    __syncthreads(); PT(14);
+  if (!light) {
     cc::phase_select(w, tid, nt);     __syncthreads(); PT(15);
     cc::phase_bbox(w, tid, nt);       __syncthreads(); PT(16);
-    cc::phase_output(w, tid, nt);     __syncthreads(); PT(17);
+  } else {
+    PT(15); PT(16);
   }
+  cc::phase_output(w, tid, nt);       __syncthreads(); PT(17);
+#ifdef VA_TAIL_PHASE_TIMING
   if (ptime) {
     printf("[va tail] frame %d phases (R=%d Wd=%d NR=%d NM=%d): init %lld lists %lld load %lld count %lld scan %lld %lld %lld runs %lld gaps %lld holes %lld link %lld flat %lld %lld sums %lld select %lld bbox %lld out %lld\n",
            (int)blockIdx.x, w.R, w.Wd, sc[cc::W_NR], sc[cc::W_NM], pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3],
            pt[5] - pt[4], pt[6] - pt[5], pt[7] - pt[6], pt[8] - pt[7], pt[9] - pt[8], pt[10] - pt[9], pt[11] - pt[10],
            pt[12] - pt[11], pt[13] - pt[12], pt[14] - pt[13], pt[15] - pt[14], pt[16] - pt[15], pt[17] - pt[16]);
   }
+#endif
 #undef PT
 }
 
@@ -746,6 +756,7 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((d.flags & kTailTimelineFlag) && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_wait));
   TT(1);
+  if (d.flags & (1 << 27)) return;      // VA_TAIL_TIMING=3: floor of the stage (launch + dependency wait), records are not written
   if (threadIdx.x < kMaxInst) {      // all per-instance reductions in one parallel round of global loads
     const int i = threadIdx.x;
     InstStats v;
@@ -1077,12 +1088,13 @@ tail_kernel(Dims d, const int* __restrict__ counts, InstStats* __restrict__ stat
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     printf("[va tail] block %d on sm %d: starts %llu waited %llu ends %llu ns\n", (int)blockIdx.x, (int)__smid(), gt_start, gt_wait, gt);
   }
-  if ((d.flags & kTailDebugFlag) && blockIdx.x == 0 && threadIdx.x == 0) {
+  if ((d.flags & kTailDebugFlag) && (int)blockIdx.x == ((d.flags >> 8) & 0xfff) && threadIdx.x == 0) {
     const long long t0 = g_tail_t[0], te = clock64();
     printf("[va tail] reset: stats %lld lattice %lld rest %lld | t0 before barrier %lld t32 before %lld t32 after %lld (from t6)\n", g_tail_t[11] - g_tail_t[9], g_tail_t[12] - g_tail_t[11], te - g_tail_t[12],
            g_tail_t[13] - g_tail_t[6], g_tail_t[14] - g_tail_t[6], g_tail_t[15] - g_tail_t[6]);
     printf("[va tail] certificate: stats %lld tasks %lld rows %lld (%d tasks) zero %lld rest %lld\n", g_tail_t[16] - g_tail_t[1], g_tail_t[17] - g_tail_t[16],
            g_tail_t[18] - g_tail_t[17], 0, g_tail_t[19] - g_tail_t[18], g_tail_t[2] - g_tail_t[19]);
+    printf("[va tail] block %d ", (int)blockIdx.x);
     printf("[va tail] cycles: wait %lld select %lld sample %lld band %lld | orphans %lld easy %lld | warp0: peaks %lld cells %lld"
            " | warp1 penalties %lld | end barrier %lld total %lld\n",
            g_tail_t[1] - t0, g_tail_t[2] - g_tail_t[1], g_tail_t[3] - g_tail_t[2], g_tail_t[4] - g_tail_t[3],
