@@ -536,6 +536,29 @@ VA_HD void phase_scan_c(Work& w, int tid, int nt) {
   if (tid == 0) w.rowoff[w.R] = w.seg[32];
 }
 
+#if defined(__CUDACC__)
+// phases 3a-c in one: the first warp scans the row counts (a segment per lane, one shuffle scan across the lanes)
+__device__ __forceinline__ void phase_scan_warp(Work& w, int tid) {
+  if (tid >= 32) return;
+  const int segl = (w.R + 31) / 32;
+  const int r0 = tid * segl, r1 = imin(r0 + segl, w.R);
+  int acc = 0;
+  VA_ROLL
+  for (int r = r0; r < r1; ++r) acc += w.rowoff[r];
+  int incl = acc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += u; }
+  int run = incl - acc;
+  VA_ROLL
+  for (int r = r0; r < r1; ++r) { const int v = w.rowoff[r]; w.rowoff[r] = run; run += v; }
+  if (tid == 31) {
+    w.rowoff[w.R] = incl;
+    w.sc[W_NR] = incl;
+    if (incl > w.cap) w.sc[W_OVERFLOW] = 1;
+  }
+}
+#endif
+
 VA_HD void run_init(Work& w, int id, int start, int r, bool last_in_row) {
   w.rs[id] = (uint16_t)start;
   w.ry[id] = (uint16_t)r;
@@ -590,13 +613,13 @@ VA_HD void phase_gaps(Work& w, int tid, int nt) {
   if (w.sc[W_OVERFLOW]) return;
   const int NR = w.sc[W_NR];
   VA_ROLL
-  for (int id = tid; id < NR; id += nt) {
+  for (int t = tid; t < 2 * NR; t += nt) {              // (gap, direction) tasks: the two neighbour rows side by side
+    const int id = t >> 1;
     const int r = w.ry[id];
     if (id == w.rowoff[r + 1] - 1) continue;            // no gap to the right
     const int g0 = w.re[id] + 1, g1 = w.rs[id + 1] - 1;
-    VA_ROLL
-    for (int dr = -1; dr <= 1; dr += 2) {
-      const int rr = r + dr;
+    {
+      const int rr = r + ((t & 1) ? 1 : -1);
       if (rr < 0 || rr >= w.R) { uf_union(w.pG, id + 1, 0); continue; }
       const int n2 = row_runs(w, rr), o2 = w.rowoff[rr];
       int xa = g0, xb = g1;

@@ -679,9 +679,7 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
     PT(4); PT(5); PT(6); PT(7); PT(8); PT(9); PT(10); PT(11); PT(12); PT(13);
   } else {
     cc::phase_count(w, tid, nt);      __syncthreads(); PT(4);
-    cc::phase_scan_a(w, tid, nt);     __syncthreads(); PT(5);
-    cc::phase_scan_b(w, tid, nt);     __syncthreads(); PT(6);
-    cc::phase_scan_c(w, tid, nt);     __syncthreads(); PT(7);
+    cc::phase_scan_warp(w, tid);      __syncthreads(); PT(5); PT(6); PT(7);
     {
       const int NR = sc[cc::W_NR];
       const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
