@@ -537,24 +537,37 @@ VA_HD void phase_scan_c(Work& w, int tid, int nt) {
 }
 
 #if defined(__CUDACC__)
-// phases 3a-c in one: the first warp scans the row counts (a segment per lane, one shuffle scan across the lanes)
-__device__ __forceinline__ void phase_scan_warp(Work& w, int tid) {
-  if (tid >= 32) return;
-  const int segl = (w.R + 31) / 32;
-  const int r0 = tid * segl, r1 = imin(r0 + segl, w.R);
+// phases 3a-c on the GPU, two barrier-separated steps: consecutive rows per thread, one shuffle scan per warp and the
+// warp totals in seg[]; then every warp scans the totals again for its own offset
+__device__ __forceinline__ void phase_scan_rows_a(Work& w, int tid, int nt, int& first, int& excl) {
+  const int per = (w.R + nt - 1) / nt;
+  const int r0 = imin(tid * per, w.R), r1 = imin(r0 + per, w.R);
   int acc = 0;
   VA_ROLL
   for (int r = r0; r < r1; ++r) acc += w.rowoff[r];
   int incl = acc;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += u; }
-  int run = incl - acc;
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += u; }
+  if ((tid & 31) == 31) w.seg[tid >> 5] = incl;       // nt <= 1024: at most 32 warps, seg holds 33 entries
+  first = r0;
+  excl = incl - acc;                                   // exclusive prefix inside the warp
+}
+__device__ __forceinline__ void phase_scan_rows_b(Work& w, int tid, int nt, int first, int excl) {
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int mine = lane < nwarps ? w.seg[lane] : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int base = __shfl_sync(0xffffffffu, incl - mine, warp);   // sum of the warps below this one
+  const int per = (w.R + nt - 1) / nt;
+  int run = base + excl;
   VA_ROLL
-  for (int r = r0; r < r1; ++r) { const int v = w.rowoff[r]; w.rowoff[r] = run; run += v; }
-  if (tid == 31) {
-    w.rowoff[w.R] = incl;
-    w.sc[W_NR] = incl;
-    if (incl > w.cap) w.sc[W_OVERFLOW] = 1;
+  for (int r = first; r < imin(first + per, w.R); ++r) { const int v = w.rowoff[r]; w.rowoff[r] = run; run += v; }
+  if (tid == 0) {
+    w.rowoff[w.R] = total;
+    w.sc[W_NR] = total;
+    if (total > w.cap) w.sc[W_OVERFLOW] = 1;
   }
 }
 #endif

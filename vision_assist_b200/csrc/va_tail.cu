@@ -679,7 +679,11 @@ __device__ void contour_general(const Dims& d, const TailContour& tc, size_t ins
     PT(4); PT(5); PT(6); PT(7); PT(8); PT(9); PT(10); PT(11); PT(12); PT(13);
   } else {
     cc::phase_count(w, tid, nt);      __syncthreads(); PT(4);
-    cc::phase_scan_warp(w, tid);      __syncthreads(); PT(5); PT(6); PT(7);
+    {
+      int first, excl;
+      cc::phase_scan_rows_a(w, tid, nt, first, excl);          __syncthreads(); PT(5);
+      cc::phase_scan_rows_b(w, tid, nt, first, excl);          __syncthreads(); PT(6); PT(7);
+    }
     {
       const int NR = sc[cc::W_NR];
       const cc::RunLayout rl = cc::run_layout(NR > 0 ? NR : 1);
