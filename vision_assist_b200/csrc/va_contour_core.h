@@ -856,23 +856,29 @@ VA_HD void phase_sums(Work& w, const uint16_t* lut, int tid, int nt) {
   // (b) every other non-empty row (rows with several runs and their neighbours), word by word on the bit image
   const int ntask = w.sc[W_NNP] * w.Wd;
 #ifdef __CUDA_ARCH__
-  if ((nt & 31) == 0 && ntask <= 8 * (nt >> 5)) {
-    // few words (a notch in an otherwise row-convex outline): one word per warp and one pixel per lane - a single
-    // thread walking the up to 32 border pixels of its word would be the whole mask's critical path
-    const int lane = tid & 31;
+  if ((nt & 31) == 0 && ntask <= 2 * (nt >> 3)) {
+    // few words (notches in an otherwise row-convex outline): one word per group of 8 lanes and four pixels per lane -
+    // a single thread walking the up to 32 border pixels of its word would be the whole mask's critical path.  The
+    // eight lanes fetch the 3x3 words around the task's word (lane 0 two of them) and exchange them by shuffles.
+    const int lane = tid & 31, gl = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
     VA_ROLL
-    for (int q = tid >> 5; q < ntask; q += nt >> 5) {
+    for (int q = tid >> 3; q < ntask; q += nt >> 3) {
       const int r = w.nplist[q / w.Wd], k = q % w.Wd;
-      const uint32_t mine = (lane < 9) ? word_at(w.G, w, r - 1 + lane / 3, k - 1 + lane % 3) : 0u;   // the 3x3 words
+      const uint32_t mine = word_at(w.G, w, r - 1 + gl / 3, k - 1 + gl % 3);           // words 0..7 of the 3x3 block
+      const uint32_t last = (gl == 0) ? word_at(w.G, w, r + 1, k + 1) : 0u;            // word 8
       WordNb nb;
-      nb.Up = __shfl_sync(0xffffffffu, mine, 0); nb.U = __shfl_sync(0xffffffffu, mine, 1); nb.Un = __shfl_sync(0xffffffffu, mine, 2);
-      nb.Mp = __shfl_sync(0xffffffffu, mine, 3); nb.M = __shfl_sync(0xffffffffu, mine, 4); nb.Mn = __shfl_sync(0xffffffffu, mine, 5);
-      nb.Dp = __shfl_sync(0xffffffffu, mine, 6); nb.D = __shfl_sync(0xffffffffu, mine, 7); nb.Dn = __shfl_sync(0xffffffffu, mine, 8);
+      nb.Up = __shfl_sync(gmask, mine, 0, 8); nb.U = __shfl_sync(gmask, mine, 1, 8); nb.Un = __shfl_sync(gmask, mine, 2, 8);
+      nb.Mp = __shfl_sync(gmask, mine, 3, 8); nb.M = __shfl_sync(gmask, mine, 4, 8); nb.Mn = __shfl_sync(gmask, mine, 5, 8);
+      nb.Dp = __shfl_sync(gmask, mine, 6, 8); nb.D = __shfl_sync(gmask, mine, 7, 8); nb.Dn = __shfl_sync(gmask, last, 0, 8);
       if (!nb.M) continue;
       nb.shift();
-      if (!((nb.border() >> lane) & 1u)) continue;
+      const uint32_t border = nb.border() & (0x01010101u << gl);                       // this lane's pixels: gl, gl + 8, ...
+      if (!border) continue;
       const WordRuns wr(w, r, k);
-      word_pixel(w, lut, nb, wr, r, k, lane, acc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((border >> (gl + 8 * j)) & 1u) word_pixel(w, lut, nb, wr, r, k, gl + 8 * j, acc);
     }
     acc.finish(w, tid);
     return;
