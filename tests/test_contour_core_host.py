@@ -88,9 +88,11 @@ def test_random_masks_general_and_certificate(lib):
 
 
 def test_notched_masks_take_the_light_path(lib):
-    """Row-convex blobs with a few isolated rows of several runs (notches, bumps, slits): one component without holes
-    decided from the run ends (phase_light_check).  The same masks with a covered gap (a hole), an island row or a
-    run that hangs in the air must fall through to the full path - every result is checked against the OpenCV model."""
+    """Row-convex blobs with notches one or several rows deep, stubs beside the outline, bumps and slits: one component
+    without holes decided from the run ends (phase_light_check follows bands of adjacent multi-run rows while they stay
+    parallel).  The same masks with a covered gap (a hole), an island, a run that hangs in the air or notches of
+    different depths side by side must fall through to the full path - every result is checked against the OpenCV
+    model."""
     rng = np.random.default_rng(8)
     n_light = n_full = 0
     for it in range(400):
@@ -108,9 +110,17 @@ def test_notched_masks_take_the_light_path(lib):
         # notches in the top / bottom row (never holes: one neighbour row is missing)
         for y in ([y0] if kind in (0, 3) else [y1] if kind == 1 else [y0, y1]):
             a, b = spans[y]
-            for _ in range(int(rng.integers(1, 4))):
-                c0 = int(rng.integers(a + 1, b)); c1 = min(b - 1, c0 + int(rng.integers(0, 6)))
-                m[y, c0:c1 + 1] = 0
+            step = 1 if y == y0 else -1
+            same_depth = int(rng.integers(1, 7))
+            for _ in range(int(rng.choice([1, 1, 1, 2, 3]))):
+                c0 = int(rng.integers(a + 1, b)); c1 = min(b - 1, c0 + int(rng.integers(0, 9)))
+                depth = same_depth if rng.random() < 0.5 else int(rng.integers(1, 7))                 # a notch several rows deep, narrowing or drifting as it goes in
+                for k in range(depth):
+                    yy = y + step * k
+                    if not (y0 <= yy <= y1) or c0 > c1:
+                        break
+                    m[yy, c0:c1 + 1] = 0
+                    c0 += int(rng.integers(-1, 2)); c1 -= int(rng.integers(0, 2))
         # interior rows: a stub beside the main run (a notch when a neighbour row leaves the gap open, a hole when both
         # cover it, an island when the stub touches neither neighbour), sometimes a slit inside the run (a hole)
         rows = [y for y in range(y0 + 2, y1 - 1, int(rng.integers(2, 9)))][:int(rng.integers(0, 4))]

@@ -419,14 +419,38 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
 }
 
 // ---- phase 1b: the light check.  Most masks that miss the certificate are row-convex except for a few rows with a
-//      notch (two or more runs).  When every row is non-empty, consecutive single-run rows touch, and every row with
-//      several runs stands alone between two single-run rows (or at the top / bottom of the mask) with
-//        - each of its runs touching the run above or the run below,
-//        - no gap covered by both neighbour runs (such a gap would be a hole),
-//        - some run touching both neighbours when both exist (the parts above and below meet only in this row),
-//      the mask is ONE component WITHOUT holes: no run table, union-find or lattice rebuild is needed, the table sums
-//      over the border pixels (phase_sums) give points and area, the pixel bounding box is the component's.
+//      notch (two or more runs).  When every row is non-empty, consecutive single-run rows touch, and every band of
+//      adjacent rows with several runs passes the test spelled out below, the mask is ONE component WITHOUT holes: no
+//      run table, union-find or lattice rebuild is needed, the table sums over the border pixels (phase_sums) give
+//      points and area, the pixel bounding box is the component's.
 //      Clears sc[W_LIGHT] otherwise; the full path then continues from phase_count. ----
+constexpr int kLightRuns = 8;      // runs per row the light check follows
+constexpr int kLightBand = 16;     // adjacent rows with several runs it follows
+// runs of a row with several runs -> starts / ends (region-relative pixels); their number, or -1 when more than kLightRuns
+VA_HD int light_row_runs(const Work& w, int r, int* rs, int* re) {
+  const int base = slot_base(w, r);
+  int n = 0;
+  bool open = false;
+  uint32_t carry = 0u;
+  VA_ROLL
+  for (int k = 0; k <= w.Wd; ++k) {                     // one word past the end closes a run that reaches the last pixel
+    const uint32_t m = (k < w.Wd) ? w.Mfg[base + k] : 0u;
+    uint32_t edges = m ^ ((m << 1) | carry);            // bit x: pixel x differs from pixel x - 1
+    carry = m >> 31;
+    VA_ROLL
+    while (edges) {
+      const int x = 32 * k + ffs32(edges) - 1;
+      edges &= edges - 1;
+      if (!open) {
+        if (n == kLightRuns) return -1;
+        rs[n] = x; open = true;
+      } else {
+        re[n++] = x - 1; open = false;
+      }
+    }
+  }
+  return n;
+}
 VA_HD void phase_light_check(Work& w, int tid, int nt) {
   VA_ROLL
   for (int r = tid; r < w.R; r += nt) {
@@ -436,37 +460,48 @@ VA_HD void phase_light_check(Work& w, int tid, int nt) {
       ok = false;
     } else if (a >= 0) {
       if (r > 0 && w.one_a[r - 1] >= 0) ok = a - 1 <= (int)w.one_b[r - 1] && (int)w.one_b[r] + 1 >= (int)w.one_a[r - 1];
-    } else {                                            // several runs
-      if (row_is_multi(w, r - 1) || row_is_multi(w, r + 1)) {
-        ok = false;
-      } else {
-        const Span u = row_span(w, r - 1), d = row_span(w, r + 1);
-        const bool hasu = u.a <= u.b, hasd = d.a <= d.b;
-        const int base = slot_base(w, r);
-        bool both = false, open = false;               // a run touches both neighbours; inside a run
-        int start = 0, prev_end = -1;
-        uint32_t carry = 0u;
+    } else if (!row_is_multi(w, r - 1)) {
+      // first row of a band of adjacent rows with several runs (a notch is usually a few rows deep).  The band is
+      // followed only while it stays "parallel": the same number of runs in every row, run j touching run j of the
+      // row above and gap j sharing a column with gap j of the row above - so run j forms a vertical strip and gap j a
+      // vertical slit.  Then: a strip belongs to the component iff it touches the run above the band or the run
+      // below it; a slit is open (not a hole) iff the run above or the run below does not cover its end; the parts
+      // above and below the band meet iff some strip touches both.  Anything else goes to the full path.
+      const Span u = row_span(w, r - 1);
+      const bool hasu = u.a <= u.b;
+      int ps[kLightRuns], pe[kLightRuns], cs[kLightRuns], ce[kLightRuns];
+      const int m = light_row_runs(w, r, ps, pe);
+      ok = m >= 2;
+      unsigned tu = 0u, open_top = 0u;                  // bit j: strip j touches the run above / slit j is open at the top
+      VA_ROLL
+      for (int j = 0; j < m && ok; ++j) {
+        if (hasu && ps[j] - 1 <= u.b && pe[j] + 1 >= u.a) tu |= 1u << j;
+        if (j + 1 < m && !(hasu && u.a <= pe[j] + 1 && u.b >= ps[j + 1] - 1)) open_top |= 1u << j;
+      }
+      int rr = r;
+      VA_ROLL
+      while (ok && row_is_multi(w, rr + 1)) {            // follow the band downwards
+        ++rr;
+        if (rr - r >= kLightBand || light_row_runs(w, rr, cs, ce) != m) { ok = false; break; }
         VA_ROLL
-        for (int k = 0; k <= w.Wd && ok; ++k) {          // one word past the end closes a run that reaches the last pixel
-          const uint32_t m = (k < w.Wd) ? w.Mfg[base + k] : 0u;
-          uint32_t edges = m ^ ((m << 1) | carry);      // bit x: pixel x differs from pixel x - 1
-          carry = m >> 31;
-          VA_ROLL
-          while (edges && ok) {
-            const int x = 32 * k + ffs32(edges) - 1;
-            edges &= edges - 1;
-            if (!open) { start = x; open = true; continue; }
-            open = false;
-            const int end = x - 1;                      // run [start, end]
-            const bool tu = hasu && start - 1 <= u.b && end + 1 >= u.a, td = hasd && start - 1 <= d.b && end + 1 >= d.a;
-            if (!tu && !td) ok = false;
-            both = both || (tu && td);
-            if (prev_end >= 0) {                        // gap [prev_end + 1, start - 1]
-              const int g0 = prev_end + 1, g1 = start - 1;
-              if (hasu && u.a <= g0 && u.b >= g1 && hasd && d.a <= g0 && d.b >= g1) ok = false;
-            }
-            prev_end = end;
-          }
+        for (int j = 0; j < m; ++j) {
+          if (!(cs[j] <= pe[j] + 1 && ce[j] >= ps[j] - 1)) ok = false;                                    // strip j continues
+          if (j + 1 < m && imax(ce[j] + 1, pe[j] + 1) > imin(cs[j + 1] - 1, ps[j + 1] - 1)) ok = false;   // slit j continues
+        }
+        VA_ROLL
+        for (int j = 0; j < m; ++j) { ps[j] = cs[j]; pe[j] = ce[j]; }
+      }
+      if (ok) {
+        const Span d = row_span(w, rr + 1);
+        const bool hasd = d.a <= d.b;
+        bool both = false;
+        VA_ROLL
+        for (int j = 0; j < m; ++j) {
+          const bool td = hasd && ps[j] - 1 <= d.b && pe[j] + 1 >= d.a;
+          const bool tuj = (tu >> j) & 1u;
+          if (!tuj && !td) ok = false;                  // a strip that hangs in the air: another component
+          both = both || (tuj && td);
+          if (j + 1 < m && !((open_top >> j) & 1u) && hasd && d.a <= pe[j] + 1 && d.b >= ps[j + 1] - 1) ok = false;   // a hole
         }
         if (hasu && hasd && !both) ok = false;
       }
