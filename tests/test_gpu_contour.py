@@ -68,8 +68,16 @@ def _adversarial_frames(H, W, n):
                 spans[y] = (a, b_)
             for y in ([y0], [y1], [y0, y1])[k % 3]:
                 a, b_ = spans[y]
-                for _ in range(int(rng.integers(1, 4))):
-                    c0 = int(rng.integers(a + 1, b_)); f[i, y, c0:min(b_ - 1, c0 + int(rng.integers(0, 9))) + 1] = 0
+                step = 1 if y == y0 else -1
+                depth = int(rng.integers(1, 7))                 # notches several rows deep (bands of adjacent multi-run rows)
+                for _ in range(int(rng.choice([1, 1, 2, 3]))):
+                    c0 = int(rng.integers(a + 1, b_)); c1 = min(b_ - 1, c0 + int(rng.integers(0, 9)))
+                    dd = depth if rng.random() < 0.6 else int(rng.integers(1, 7))
+                    for q in range(dd):
+                        if c0 > c1:
+                            break
+                        f[i, y + step * q, c0:c1 + 1] = 0
+                        c0 += int(rng.integers(-1, 2)); c1 -= int(rng.integers(0, 2))
             for y in range(y0 + 3, y1 - 3, int(rng.integers(17, 60))):
                 a, b_ = spans[y]
                 r_ = rng.random()
