@@ -210,6 +210,9 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
     import torch
     import torch.distributed as dist
     protos, coefs, boxes, counts = tensors
+    # diagnostic only (VA_BENCH_COMMIT_EVERY=k): move the records of every k-th step only - what the per-step put costs
+    commit_every = max(1, int(os.environ.get("VA_BENCH_COMMIT_EVERY", "1")))
+    state = {"i": 0}
 
     def step():
         if gatherer is not None:          # fallback: NCCL gather of every step's records, overlapped with the next step
@@ -220,7 +223,9 @@ def measure_device_resident(eng, tensors, masks, records, steps, warmup, sink=No
             eng.run(protos, coefs, boxes, counts, masks_out=masks, records_out=records, write_masks=masks is not None)
         else:
             eng.run(protos, coefs, boxes, counts, masks_out=masks, write_masks=masks is not None, records_ptr=sink.records_ptr())
-            sink.commit()
+            state["i"] += 1
+            if state["i"] % commit_every == 0:
+                sink.commit()
 
     for _ in range(max(warmup, 3)):
         step()
