@@ -425,7 +425,8 @@ VA_HD void phase_load(Work& w, int tid, int nt) {
 //      points and area, the pixel bounding box is the component's.
 //      Clears sc[W_LIGHT] otherwise; the full path then continues from phase_count. ----
 constexpr int kLightRuns = 8;      // runs per row the light check follows
-constexpr int kLightBand = 16;     // adjacent rows with several runs it follows
+constexpr int kLightBand = 16;     // adjacent rows with several runs it follows ...
+constexpr int kLightWords = 256;   // ... as long as the band has at most this many bit words (one thread walks it)
 // runs of a row with several runs -> starts / ends (region-relative pixels); their number, or -1 when more than kLightRuns
 VA_HD int light_row_runs(const Work& w, int r, int* rs, int* re) {
   const int base = slot_base(w, r);
@@ -469,8 +470,11 @@ VA_HD void phase_light_check(Work& w, int tid, int nt) {
       // above and below the band meet iff some strip touches both.  Anything else goes to the full path.
       const Span u = row_span(w, r - 1);
       const bool hasu = u.a <= u.b;
+      int depth = 1;                                    // size the band first: a deep or wide one is the full path's job
+      VA_ROLL
+      while (depth <= kLightBand && row_is_multi(w, r + depth)) ++depth;
       int ps[kLightRuns], pe[kLightRuns], cs[kLightRuns], ce[kLightRuns];
-      const int m = light_row_runs(w, r, ps, pe);
+      const int m = (depth <= kLightBand && depth * w.Wd <= kLightWords) ? light_row_runs(w, r, ps, pe) : -1;
       ok = m >= 2;
       unsigned tu = 0u, open_top = 0u;                  // bit j: strip j touches the run above / slit j is open at the top
       VA_ROLL
