@@ -444,26 +444,6 @@ def test_nms_golden_and_oracle():
             assert not got[b, k:].any()
 
 
-@pytest.mark.parametrize("H,W,mh,mw,n,B", [(640, 640, 160, 160, 8, 256), (640, 640, 160, 160, 32, 48), (1080, 1920, 160, 160, 32, 8)])
-def test_repeatability_soak(H, W, mh, mw, n, B):
-    """Work stealing, atomics into the reduction scratch and the self-resetting work counter must not make the
-    result depend on scheduling: 60 back-to-back calls on the same inputs give bit-identical records and masks."""
-    eng = MaskGridEngine(H=H, W=W, mh=mh, mw=mw, max_n=n, gs=20, max_batch=B)
-    uniq = min(B, 16)
-    hp, hc, hb, hn = synth.make_batch(4242, uniq, n, H, W, mh, mw, max_n=n)
-    r = (B + uniq - 1) // uniq
-    dev = [t.repeat(r, *([1] * (t.dim() - 1)))[:B].contiguous().cuda() for t in (hp, hc, hb, hn)]
-    rec0, masks0 = eng.run(*dev)
-    rec0, masks0 = rec0.clone(), masks0.clone()
-    rec = torch.empty_like(rec0)
-    masks = torch.empty_like(masks0)
-    for it in range(60):
-        eng.run(*dev, masks_out=masks, records_out=rec, write_masks=(it % 3 != 2))
-        assert torch.equal(rec, rec0), it
-        if it % 3 != 2 and it % 10 == 0:
-            assert torch.equal(masks, masks0), it
-
-
 @pytest.mark.parametrize("tc", PATHS)
 def test_cfg2_1080p_generic_scale(tc):
     H, W, B, n = 1080, 1920, 2, 32
@@ -628,3 +608,30 @@ def test_capacity_and_argument_errors():
         MaskGridEngine(H=640, W=640, mh=160, mw=160, max_n=64)
     r0, _ = eng.run(*[t[:0] for t in to_dev(protos, coefs, boxes, counts)])
     assert r0.shape[0] == 0
+
+
+# last in the file on purpose: the longest-running test of the suite
+@pytest.mark.parametrize("H,W,mh,mw,n,B", [(640, 640, 160, 160, 8, 256), (640, 640, 160, 160, 32, 48), (1080, 1920, 160, 160, 32, 8)])
+def test_repeatability_soak(H, W, mh, mw, n, B):
+    """Work stealing, atomics into the reduction scratch and the self-resetting work counter must not make the
+    result depend on scheduling: 60 back-to-back calls on the same inputs give bit-identical records and masks."""
+    eng = MaskGridEngine(H=H, W=W, mh=mh, mw=mw, max_n=n, gs=20, max_batch=B)
+    uniq = min(B, 16)
+    hp, hc, hb, hn = synth.make_batch(4242, uniq, n, H, W, mh, mw, max_n=n)
+    r = (B + uniq - 1) // uniq
+    dev = [t.repeat(r, *([1] * (t.dim() - 1)))[:B].contiguous().cuda() for t in (hp, hc, hb, hn)]
+    rec0, masks0 = eng.run(*dev)
+    rec0, masks0 = rec0.clone(), masks0.clone()
+    rec = torch.empty_like(rec0)
+    masks = torch.empty_like(masks0)
+    for it in range(60):
+        eng.run(*dev, masks_out=masks, records_out=rec, write_masks=(it % 3 != 2))
+        if not torch.equal(rec, rec0):              # say what moved: frame, byte offsets, the decoded fields
+            d = (rec != rec0).cpu().numpy()
+            fr = int(np.nonzero(d.any(1))[0][0])
+            a_, g_ = eng.decode(rec0[fr:fr + 1])[0], eng.decode(rec[fr:fr + 1])[0]
+            raise AssertionError(f"call {it}: record of frame {fr} differs at byte offsets {np.nonzero(d[fr])[0][:8].tolist()} "
+                                 f"({int(d[fr].sum())} bytes): sel {a_.sel}->{g_.sel} flags {a_.flags}->{g_.flags} "
+                                 f"area2 {a_.contour_area2}->{g_.contour_area2} bbox {a_.bbox}->{g_.bbox} R {a_.R}->{g_.R}")
+        if it % 3 != 2 and it % 10 == 0:
+            assert torch.equal(masks, masks0), it
