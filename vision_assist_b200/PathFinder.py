@@ -29,31 +29,6 @@ class ArrayPathFinder:
     def __init__(self):
         self.angle_cache: dict = {}
 
-    # PathFinder.py:49-99
-    def _angle_between_grids(self, path, segment_size: int):
-        if len(path) < segment_size:
-            return 0
-        angles = []
-        half = segment_size // 2
-        for i in range(half, len(path) - half - 1):
-            prev_points = path[i - half:i + 1]
-            next_points = path[i + 1:i + half + 1]
-            prev_vector = (prev_points[-1][0] - prev_points[0][0], prev_points[-1][1] - prev_points[0][1])
-            next_vector = (next_points[-1][0] - next_points[0][0], next_points[-1][1] - next_points[0][1])
-            key = (tuple(prev_vector), tuple(next_vector))
-            if key in self.angle_cache:
-                angles.append(self.angle_cache[key])
-                continue
-            dot_product = prev_vector[0] * next_vector[0] + prev_vector[1] * next_vector[1]
-            magnitude_prev = (prev_vector[0] ** 2 + prev_vector[1] ** 2) ** 0.5
-            magnitude_next = (next_vector[0] ** 2 + next_vector[1] ** 2) ** 0.5
-            if magnitude_prev == 0 or magnitude_next == 0:
-                continue
-            angle = np.arccos(np.clip(dot_product / (magnitude_prev * magnitude_next), -1.0, 1.0))
-            angles.append(np.degrees(angle))
-            self.angle_cache[key] = angle
-        return max(angles) if angles else 0
-
     @staticmethod
     def graph_arrays(rec, gs: int):
         """-> (adjacency {(x, y): [((nx, ny), distance), ...]} built on demand, penalty-of-lookup-cell function).
