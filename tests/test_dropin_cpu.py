@@ -139,3 +139,40 @@ def test_reference_host_stages_on_materialised_objects():
     finally:
         vmodels.bind_models(vmodels)
         VFP._instance, VFP._initialized = None, False
+
+
+def test_lazy_object_view_of_the_dropin():
+    """FrameProcessor.grids / grid_lookup are built from the pending record on first access only, and the protrusion
+    detector's `.grids` follows them (no GPU: the record comes from the oracle)."""
+    rng = np.random.default_rng(9)
+    rec = None
+    while rec is None:
+        try:
+            st = og.extract_grid_from_polygons([polygen.random_polygon(rng, 640, 640, kind="blob")], 640, 640, 20)
+        except IndexError:
+            continue
+        if st.grids:
+            rec = record_from_oracle(opl.state_to_result(st))
+    VFP._instance, VFP._initialized = None, False
+    try:
+        fp = VFP(model=None)
+        fp.frame = np.zeros((640, 640, 3), np.uint8)
+        assert fp.grids == [] and fp.grid_lookup == {} and not fp._has_grid()
+        fp.frame_record, fp.np_grids, fp._pending_record = rec, rec.np_grids, rec          # what _extract_grid_information leaves
+        assert fp._has_grid() and fp._grids == []                                          # nothing built yet
+        peaks = fp.protrusion_detector.from_record(fp.frame, rec.peaks, lambda: fp.grids)
+        assert [(p.x, p.y) for p in peaks] == [tuple(int(v) for v in q) for q in rec.peaks]
+        assert fp._pending_record is rec                                                   # still nothing built
+        want_grids, want_lookup, _ = record_to_objects(rec, 20)
+        got = fp.grids                                                                     # first access builds the objects
+        assert fp._pending_record is None and len(got) == rec.R
+        assert [[(g.coords.x, g.coords.y, g.empty, g.artificial, g.penalty) for g in row] for row in got] == \
+               [[(g.coords.x, g.coords.y, g.empty, g.artificial, g.penalty) for g in row] for row in want_grids]
+        assert set(fp.grid_lookup) == set(want_lookup)
+        assert fp.protrusion_detector.grids is got                                         # the detector's lazy view resolves to the same list
+        fp.grids = []                                                                      # assigning drops any pending record
+        fp._pending_record = rec
+        fp.grid_lookup = {}
+        assert fp._pending_record is None and fp.grids == []
+    finally:
+        VFP._instance, VFP._initialized = None, False
