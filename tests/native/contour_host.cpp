@@ -1,6 +1,6 @@
 // Host build of the contour algorithm (vision_assist_b200/csrc/va_contour_core.h) for the CPU tests: the same
 // phase functions the CUDA kernel runs, driven by a loop over emulated thread ids.  TEST INFRASTRUCTURE ONLY - the
-// product path is the CUDA kernel (va_contour.cu); nothing under vision_assist_b200/ links this file.
+// product path is the CUDA tail kernel (va_tail.cu, which runs the same phases); nothing under vision_assist_b200/ links this file.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
