@@ -95,7 +95,7 @@ def test_notched_masks_take_the_light_path(lib):
     model."""
     rng = np.random.default_rng(8)
     n_light = n_full = 0
-    for it in range(400):
+    for it in range(700):
         H, W = int(rng.integers(16, 70)), int(rng.integers(40, 300))
         m = np.zeros((H, W), np.uint8)
         y0 = int(rng.integers(0, H // 3)); y1 = int(rng.integers(2 * H // 3, H))
@@ -141,7 +141,7 @@ def test_notched_masks_take_the_light_path(lib):
         g = check(lib, m, int(rng.choice([4, 8, 20])), fmt=it % 2, force_general=1, nthreads=int(rng.choice([1, 32, 64, 256])))
         n_light += g["light"]; n_full += g["general"] and not g["light"]
         check(lib, m, 20, fmt=it % 2, force_general=2, nthreads=64)
-    assert n_light > 60 and n_full > 60, (n_light, n_full)
+    assert n_light > 100 and n_full > 100, (n_light, n_full)
 
 
 def test_row_convex_shapes_take_the_certificate(lib):
